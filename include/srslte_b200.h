@@ -1,0 +1,103 @@
+/*
+ * srslte_b200 — C ABI of the B200-native receive-side PHY hot path.
+ *
+ * Two groups of entry points live in libsrslte_b200.so:
+ *
+ *  1. The reference's own per-object API for this path (srsran_ofdm_*, srsran_dft_*, srsran_rm_turbo_*,
+ *     srsran_tdec_*, ...), declared in srslte_b200_srsran_api.h with the reference's names, argument meaning and
+ *     error behaviour, so existing callers (sch.c, enb_ul.c, ue_dl.c and the reference's unit tests) link unchanged.
+ *
+ *  2. The batched entries declared HERE.  They are what a maintainer binds to move the hot loops of
+ *     lib/src/phy/phch/sch.c:370-492 (decode_tb_cb) and lib/src/phy/enb/enb_ul.c:151-154 (srsran_enb_ul_fft) onto the
+ *     GPU a whole batch of code blocks / subframes at a time.  See INTEGRATION.md.
+ *
+ * Conventions: plain pointers and sizes only; every function returns SRSRAN_SUCCESS (0), SRSRAN_ERROR (-1) or
+ * SRSRAN_ERROR_INVALID_INPUTS (-2) like lib/include/srsran/config.h:57-64 and prints a one-line reason on stderr.
+ * There is NO CPU fallback: without a usable CUDA device every entry fails with SRSRAN_ERROR.
+ * "pass" below means one SISO half-iteration, exactly what the reference calls an iteration
+ * (turbodecoder_iter.h:104-140): expert.pusch_max_its = 8 is 8 passes = 4 full turbo iterations.
+ */
+#ifndef SRSLTE_B200_H
+#define SRSLTE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SRSRAN_B200_API __attribute__((visibility("default")))
+
+/* flags */
+#define SRSRAN_B200_FLAG_DEVICE_PTRS 0x1u /* data pointers are device memory on the object's GPU (else host memory) */
+
+/* CRC the per-pass early-stop check uses (sch.c:437-444) */
+#define SRSRAN_B200_CRC_NONE 0
+#define SRSRAN_B200_CRC24A 1 /* single-code-block transport block: CRC24A over the K = tbs+24 bits */
+#define SRSRAN_B200_CRC24B 2 /* segmented transport block: CRC24B over the K bits of each code block */
+
+SRSRAN_B200_API int srsran_b200_device_count(void);
+
+/* Number of CUDA kernels this library has launched so far in this process (all objects, all devices). */
+SRSRAN_B200_API uint64_t srsran_b200_kernel_launches(void);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Batched turbo decoding.  Replaces the loop  srsran_tdec_new_cb(); do { srsran_tdec_iteration(); crc } while (..)
+ * of sch.c:420-454 for many code blocks at once, bit-exact with the reference's generic int16 decoder
+ * (lib/src/phy/fec/turbo/turbodecoder_gen.c).
+ */
+typedef struct srsran_b200_tdec srsran_b200_tdec_t; /* opaque; one per host thread, not thread-safe (like srsran_tdec_t) */
+
+/* max_cb_hint: expected batch size, used to pre-size device memory (it still grows on demand). */
+SRSRAN_B200_API int  srsran_b200_tdec_init(srsran_b200_tdec_t** h, int device, uint32_t max_cb_hint);
+SRSRAN_B200_API void srsran_b200_tdec_free(srsran_b200_tdec_t* h);
+
+/*
+ * Decode ncb code blocks of equal length K.
+ *   llr        [ncb][3K+12] int16, the natural decoder input layout of turbodecoder_gen.c:238-258
+ *              (what srsran_rm_turbo_rx_lut_(.., enable_input_tdec=false) leaves in the soft buffer)
+ *   max_passes upper bound on SISO passes per block (q->max_iterations, sch.c:454); >= 1
+ *   crc_kind   SRSRAN_B200_CRC_*; the syndrome is evaluated after every pass
+ *   early_stop non-zero: a block stops at its first CRC match (sch.c:446-449); zero: every block runs max_passes
+ *   out        [ncb][K/8] decided bits of each block's LAST pass, MSB first (tdec_decision_byte)
+ *   crc_ok     [ncb] 1 if the CRC matched after some pass (may be NULL)
+ *   npass      [ncb] pass count at the first CRC match, else the passes spent — cb_noi of sch.c:431 (may be NULL)
+ *   stream     cudaStream_t to enqueue on when SRSRAN_B200_FLAG_DEVICE_PTRS is set (NULL = default stream); the
+ *              call then returns without synchronising.  With host pointers the call is synchronous.
+ */
+SRSRAN_B200_API int srsran_b200_tdec_run(srsran_b200_tdec_t* h,
+                                         const int16_t*      llr,
+                                         uint32_t            ncb,
+                                         uint32_t            K,
+                                         uint32_t            max_passes,
+                                         int                 crc_kind,
+                                         int                 early_stop,
+                                         uint8_t*            out,
+                                         uint8_t*            crc_ok,
+                                         uint8_t*            npass,
+                                         uint32_t            flags,
+                                         void*               stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Synthetic workload (bench / tests only, never on the decode path): fills llr_dev[ncb][3K+12] (device memory) with
+ * the quantised channel output of randomly drawn, CRC24B-terminated, turbo-encoded blocks:
+ * llr = clip(rint(scale * ((2c-1) + sigma*n)), +-clip), the recipe of turbodecoder_test.c:211-255 plus a clip.
+ * truth_dev (optional) receives the transmitted K bits of every block, packed MSB first, [ncb][K/8].
+ */
+SRSRAN_B200_API int srsran_b200_synth_llr(int      device,
+                                          int16_t* llr_dev,
+                                          uint8_t* truth_dev,
+                                          uint32_t ncb,
+                                          uint32_t K,
+                                          float    sigma,
+                                          float    scale,
+                                          int      clip,
+                                          uint64_t seed,
+                                          int      attach_crc,
+                                          void*    stream);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* SRSLTE_B200_H */

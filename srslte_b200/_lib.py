@@ -1,0 +1,54 @@
+"""ctypes binding of libsrslte_b200.so (the C ABI of include/srslte_b200.h).
+
+There is no Python or CPU fallback: if the shared library is missing or cannot be loaded this module raises, so a
+GPU box can never silently run something else.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from functools import lru_cache
+
+from .build import LIB_PATH
+
+SUCCESS = 0
+ERROR = -1
+ERROR_INVALID_INPUTS = -2
+
+FLAG_DEVICE_PTRS = 0x1
+CRC_NONE, CRC24A, CRC24B = 0, 1, 2
+
+vp = C.c_void_p
+u32 = C.c_uint32
+
+
+class LibraryMissing(RuntimeError):
+    pass
+
+
+@lru_cache(maxsize=None)
+def lib() -> C.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise LibraryMissing(
+            f"{LIB_PATH} not built: run `python -m srslte_b200.build` (or __graft_entry__.build()). "
+            "srslte_b200 has no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    L.srsran_b200_device_count.restype = C.c_int
+    L.srsran_b200_kernel_launches.restype = C.c_uint64
+    L.srsran_b200_tdec_init.argtypes = [C.POINTER(vp), C.c_int, u32]
+    L.srsran_b200_tdec_free.argtypes = [vp]
+    L.srsran_b200_tdec_free.restype = None
+    L.srsran_b200_tdec_run.argtypes = [vp, vp, u32, u32, u32, C.c_int, C.c_int, vp, vp, vp, u32, vp]
+    L.srsran_b200_synth_llr.argtypes = [C.c_int, vp, vp, u32, u32, C.c_float, C.c_float, C.c_int, C.c_uint64, C.c_int, vp]
+    return L
+
+
+# every symbol include/srslte_b200.h declares; tests check the built library exports all of them
+EXPORTED_SYMBOLS = [
+    "srsran_b200_device_count",
+    "srsran_b200_kernel_launches",
+    "srsran_b200_tdec_init",
+    "srsran_b200_tdec_free",
+    "srsran_b200_tdec_run",
+    "srsran_b200_synth_llr",
+]

@@ -1,0 +1,115 @@
+#include "b200_runtime.h"
+
+#include <memory>
+
+#include "lte_tables.h"
+
+namespace b200 {
+
+int DeviceArena::reserve(size_t bytes)
+{
+  if (bytes <= cap) {
+    return B200_SUCCESS;
+  }
+  if (base) {
+    B200_CUDA_TRY(cudaFree(base));
+    base = nullptr;
+    cap  = 0;
+  }
+  // round up so that slowly growing batches do not reallocate every call
+  size_t want = (bytes + (size_t(64) << 20)) & ~((size_t(64) << 20) - 1);
+  B200_CUDA_TRY(cudaMalloc(&base, want));
+  cap = want;
+  return B200_SUCCESS;
+}
+
+void* DeviceArena::take(size_t bytes)
+{
+  size_t off = (used + 255) & ~size_t(255);
+  if (off + bytes > cap) {
+    return nullptr;
+  }
+  used = off + bytes;
+  return static_cast<char*>(base) + off;
+}
+
+void DeviceArena::release()
+{
+  if (base) {
+    cudaFree(base);
+  }
+  base = nullptr;
+  cap = used = 0;
+}
+
+int DeviceContext::init(int dev)
+{
+  device = dev;
+  B200_CUDA_TRY(cudaSetDevice(dev));
+
+  std::vector<uint16_t> fwd_all, rev_all, f, r;
+  qpp_off.resize(NOF_CB_SIZES);
+  for (int i = 0; i < NOF_CB_SIZES; i++) {
+    qpp_tables(i, f, r);
+    while (fwd_all.size() % 8) { // 16-byte alignment of every table start
+      fwd_all.push_back(0);
+      rev_all.push_back(0);
+    }
+    qpp_off[i] = fwd_all.size();
+    fwd_all.insert(fwd_all.end(), f.begin(), f.end());
+    rev_all.insert(rev_all.end(), r.begin(), r.end());
+  }
+  B200_CUDA_TRY(cudaMalloc(&qpp_fwd_all, fwd_all.size() * sizeof(uint16_t)));
+  B200_CUDA_TRY(cudaMalloc(&qpp_rev_all, rev_all.size() * sizeof(uint16_t)));
+  B200_CUDA_TRY(cudaMemcpy(qpp_fwd_all, fwd_all.data(), fwd_all.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+  B200_CUDA_TRY(cudaMemcpy(qpp_rev_all, rev_all.data(), rev_all.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+
+  const uint32_t polys[2] = {CRC24A_POLY, CRC24B_POLY};
+  for (int k = 0; k < 2; k++) {
+    std::vector<CrcPow> pw;
+    crc_pow_table(polys[k], MAX_CB_LEN, pw);
+    B200_CUDA_TRY(cudaMalloc(&crc_pow[k], pw.size() * sizeof(CrcPow)));
+    B200_CUDA_TRY(cudaMemcpy(crc_pow[k], pw.data(), pw.size() * sizeof(CrcPow), cudaMemcpyHostToDevice));
+  }
+  return B200_SUCCESS;
+}
+
+const uint16_t* DeviceContext::rm_table(int cb_idx, int rv)
+{
+  std::lock_guard<std::mutex> lock(rm_mutex);
+  RmTableKey                  key{cb_idx, rv};
+  auto                        it = rm_gather.find(key);
+  if (it != rm_gather.end()) {
+    return it->second;
+  }
+  std::vector<uint16_t> inv;
+  rm_gather_table(cb_idx, rv, inv);
+  uint16_t* d = nullptr;
+  if (cudaSetDevice(device) != cudaSuccess || cudaMalloc(&d, inv.size() * sizeof(uint16_t)) != cudaSuccess ||
+      cudaMemcpy(d, inv.data(), inv.size() * sizeof(uint16_t), cudaMemcpyHostToDevice) != cudaSuccess) {
+    B200_LOG_ERROR("could not upload rate-matching table cb_idx=%d rv=%d", cb_idx, rv);
+    return nullptr;
+  }
+  rm_gather[key] = d;
+  return d;
+}
+
+DeviceContext* device_context(int device)
+{
+  static std::mutex                                    m;
+  static std::map<int, std::unique_ptr<DeviceContext>> ctxs;
+  std::lock_guard<std::mutex>                          lock(m);
+  auto                                                 it = ctxs.find(device);
+  if (it != ctxs.end()) {
+    return it->second.get();
+  }
+  std::unique_ptr<DeviceContext> c(new DeviceContext());
+  if (c->init(device) != B200_SUCCESS) {
+    return nullptr;
+  }
+  DeviceContext* raw = c.get();
+  ctxs[device]       = std::move(c);
+  return raw;
+}
+
+} // namespace b200

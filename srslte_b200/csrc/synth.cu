@@ -1,0 +1,162 @@
+// Synthetic workload generator (device side), used by bench.py and the full-size GPU tests so that a 65,536-block
+// batch (2.4 GB of LLRs) does not have to be produced on the host: random payload + CRC24B, LTE turbo encoding,
+// BPSK over AWGN, quantisation to int16.  This is the recipe of SURVEY.md section 8(d) config 2 and follows what
+// lib/src/phy/fec/turbo/test/turbodecoder_test.c:211-255 does on the CPU (encode -> +-1 + noise -> scale to int16),
+// with an explicit clip so the inputs stay inside the range where the reference's generic decoder never wraps.
+// Not on the decode path; nothing here is timed.
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include "../../include/srslte_b200.h"
+#include "b200_runtime.h"
+#include "lte_tables.h"
+#include "tdec_engine.h"
+
+namespace b200 {
+
+__device__ __forceinline__ uint64_t mix64(uint64_t z)
+{
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+// One thread per code block: payload bits, CRC24B in the last 24 positions, both constituent encoders.
+// coded[cb][3K+12] one bit per byte in the order of turbocoder.c:77-185.
+__global__ void synth_encode_kernel(uint8_t* __restrict__ bits,  // [ncb][K] scratch, one bit per byte
+                                    uint8_t* __restrict__ coded, // [ncb][3K+12]
+                                    uint8_t* __restrict__ truth, // [ncb][K/8] packed payload+CRC (may be null)
+                                    const uint16_t* __restrict__ qpp_fwd,
+                                    uint32_t ncb,
+                                    int      K,
+                                    uint64_t seed,
+                                    int      attach_crc)
+{
+  const uint32_t cb = blockIdx.x * blockDim.x + threadIdx.x;
+  if (cb >= ncb) return;
+  uint8_t* b = bits + (size_t)cb * K;
+  uint8_t* c = coded + (size_t)cb * (3 * (size_t)K + 12);
+
+  uint32_t  crc     = 0;
+  const int payload = attach_crc ? K - 24 : K;
+  for (int i = 0; i < payload; i += 64) {
+    uint64_t r = mix64(seed ^ ((uint64_t)cb << 20) ^ (uint64_t)i);
+    for (int j = 0; j < 64 && i + j < payload; j++) {
+      uint32_t bit = (uint32_t)(r >> j) & 1u;
+      b[i + j]     = (uint8_t)bit;
+      uint32_t top = ((crc >> 23) & 1u) ^ bit;
+      crc          = (crc << 1) & 0xFFFFFFu;
+      if (top) crc ^= (CRC24B_POLY & 0xFFFFFFu);
+    }
+  }
+  if (attach_crc) {
+    for (int j = 0; j < 24; j++) b[payload + j] = (uint8_t)((crc >> (23 - j)) & 1u);
+  }
+  if (truth) {
+    for (int i = 0; i < K / 8; i++) {
+      uint32_t v = 0;
+      for (int j = 0; j < 8; j++) v = (v << 1) | b[8 * i + j];
+      truth[(size_t)cb * (K / 8) + i] = (uint8_t)v;
+    }
+  }
+  uint32_t a0 = 0, a1 = 0, a2 = 0, e0 = 0, e1 = 0, e2 = 0; // shift registers of encoder 1 and 2
+  for (int i = 0; i < K; i++) {
+    uint32_t x  = b[i];
+    uint32_t fb = x ^ a2 ^ a1;
+    c[3 * i]    = (uint8_t)x;
+    c[3 * i + 1] = (uint8_t)(a2 ^ a0 ^ fb);
+    a2 = a1; a1 = a0; a0 = fb;
+    uint32_t xi = b[qpp_fwd[i]];
+    uint32_t fi = xi ^ e2 ^ e1;
+    c[3 * i + 2] = (uint8_t)(e2 ^ e0 ^ fi);
+    e2 = e1; e1 = e0; e0 = fi;
+  }
+  int k = 3 * K;
+  for (int t = 0; t < 3; t++) {
+    uint32_t x = a2 ^ a1, fb = 0;
+    c[k++]     = (uint8_t)x;
+    c[k++]     = (uint8_t)(a2 ^ a0 ^ fb);
+    a2 = a1; a1 = a0; a0 = fb;
+  }
+  for (int t = 0; t < 3; t++) {
+    uint32_t x = e2 ^ e1, fb = 0;
+    c[k++]     = (uint8_t)x;
+    c[k++]     = (uint8_t)(e2 ^ e0 ^ fb);
+    e2 = e1; e1 = e0; e0 = fb;
+  }
+}
+
+// One thread per LLR: y = (2c-1) + sigma*n ; llr = clip(rint(scale*y), +-clip)
+__global__ void synth_channel_kernel(const uint8_t* __restrict__ coded,
+                                     int16_t* __restrict__ llr,
+                                     size_t   n,
+                                     float    sigma,
+                                     float    scale,
+                                     int      clip,
+                                     uint64_t seed)
+{
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t r  = mix64(seed ^ (0xA5A5ull << 48) ^ (uint64_t)i);
+  float    u1 = ((float)(uint32_t)(r >> 40) + 1.0f) * (1.0f / 16777217.0f); // (0,1)
+  float    u2 = (float)(uint32_t)((r >> 8) & 0xFFFFFFu) * (1.0f / 16777216.0f);
+  float    g  = sqrtf(-2.0f * __logf(u1)) * __cosf(6.28318530718f * u2);
+  float    y  = (coded[i] ? 1.0f : -1.0f) + sigma * g;
+  int      q  = __float2int_rn(scale * y);
+  q           = max(-clip, min(clip, q));
+  llr[i]      = (int16_t)q;
+}
+
+} // namespace b200
+
+using namespace b200;
+
+extern "C" SRSRAN_B200_API int srsran_b200_synth_llr(int      device,
+                                                     int16_t* llr_dev,
+                                                     uint8_t* truth_dev,
+                                                     uint32_t ncb,
+                                                     uint32_t K,
+                                                     float    sigma,
+                                                     float    scale,
+                                                     int      clip,
+                                                     uint64_t seed,
+                                                     int      attach_crc,
+                                                     void*    stream)
+{
+  const int cb_idx = cb_index_exact(K);
+  if (cb_idx < 0 || !llr_dev) {
+    return B200_ERROR_INVALID_INPUTS;
+  }
+  DeviceContext* ctx = device_context(device);
+  if (!ctx) {
+    return B200_ERROR;
+  }
+  B200_CUDA_TRY(cudaSetDevice(device));
+  cudaStream_t st   = (cudaStream_t)stream;
+  const size_t nllr = 3 * (size_t)K + 12;
+  uint8_t *    bits = nullptr, *coded = nullptr;
+  // generate in slabs so the byte-per-bit scratch stays small next to a multi-GB LLR batch
+  const uint32_t slab = 8192;
+  B200_CUDA_TRY(cudaMalloc(&bits, (size_t)slab * K));
+  B200_CUDA_TRY(cudaMalloc(&coded, (size_t)slab * nllr));
+  for (uint32_t first = 0; first < ncb; first += slab) {
+    const uint32_t n = (ncb - first) < slab ? (ncb - first) : slab;
+    synth_encode_kernel<<<(n + 63) / 64, 64, 0, st>>>(bits,
+                                                      coded,
+                                                      truth_dev ? truth_dev + (size_t)first * (K / 8) : nullptr,
+                                                      ctx->qpp_fwd(cb_idx),
+                                                      n,
+                                                      (int)K,
+                                                      seed + 0x1000003ull * first,
+                                                      attach_crc);
+    const size_t tot = (size_t)n * nllr;
+    synth_channel_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(
+        coded, llr_dev + (size_t)first * nllr, tot, sigma, scale, clip, seed + 0x9E37ull * (first + 1));
+  }
+  B200_CUDA_TRY(cudaStreamSynchronize(st));
+  B200_CUDA_TRY(cudaFree(bits));
+  B200_CUDA_TRY(cudaFree(coded));
+  B200_CUDA_TRY(cudaGetLastError());
+  return B200_SUCCESS;
+}

@@ -1,0 +1,54 @@
+// Host-side engine of the batched turbo decoder (see tdec_host.cu).
+#pragma once
+#include <atomic>
+
+#include "b200_runtime.h"
+
+namespace b200 {
+
+extern std::atomic<uint64_t> g_kernel_launches;
+
+struct TdecEngine {
+  // code blocks per pipeline chunk on the host-pointer path: ~300 MB of LLRs at K=6144, big enough to run PCIe at
+  // full rate and to fill the GPU (128 tiles), small enough that two chunks in flight stay modest
+  static constexpr uint32_t kPipeChunkCb = 8192;
+
+  DeviceContext* ctx = nullptr;
+  DeviceArena    arena;          // device-pointer path
+  cudaStream_t   pipe_stream[2] = {nullptr, nullptr};
+  DeviceArena    pipe_arena[2];  // host-pointer path: decoder workspace per stream
+  DeviceArena    pipe_io[2];     // host-pointer path: staged inputs/outputs per stream
+
+  static size_t workspace_bytes(int K, uint32_t ncb);
+  int           carve(DeviceArena& a, int K, uint32_t ncb, TdecView& v) const;
+
+  int  init(int device, uint32_t max_cb_hint);
+  void destroy();
+
+  int run_device(DeviceArena&   ws,
+                 const int16_t* llr_dev,
+                 uint32_t       ncb,
+                 int            K,
+                 int            cb_idx,
+                 uint32_t       max_passes,
+                 int            crc_kind,
+                 int            early_stop,
+                 uint8_t*       out_dev,
+                 uint8_t*       crc_ok_dev,
+                 uint8_t*       npass_dev,
+                 cudaStream_t   stream);
+
+  int run(const int16_t* llr,
+          uint32_t       ncb,
+          uint32_t       K,
+          uint32_t       max_passes,
+          int            crc_kind,
+          int            early_stop,
+          uint8_t*       out,
+          uint8_t*       crc_ok,
+          uint8_t*       npass,
+          uint32_t       flags,
+          cudaStream_t   stream);
+};
+
+} // namespace b200

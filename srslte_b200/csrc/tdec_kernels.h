@@ -1,0 +1,21 @@
+// Launchers of the turbo-decoder kernels (tdec_kernels.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "tdec_core.h"
+
+namespace b200 {
+
+void launch_load_natural(const TdecView& v, const int16_t* llr_dev, uint32_t ncb, cudaStream_t stream);
+void launch_siso_pass(const TdecView& v, int pass_idx, cudaStream_t stream);
+void launch_decide(const TdecView& v,
+                   const uint16_t* qpp_rev_dev,
+                   uint8_t*        out_dev,
+                   uint8_t*        crc_ok_dev,
+                   uint8_t*        npass_dev,
+                   uint8_t*        npass_run_dev,
+                   uint32_t        ncb,
+                   cudaStream_t    stream);
+
+} // namespace b200

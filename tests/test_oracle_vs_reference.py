@@ -1,0 +1,107 @@
+"""Pins the oracle port to the reference itself: every function of oracle/oracle_port.c against the same call into
+oracle/_ref/libsrsref.so (the reference's unmodified sources, compiled in place by oracle/Makefile)."""
+import numpy as np
+import pytest
+
+from helpers import coded_llrs
+
+
+def test_tables(port, ref):
+    assert (port.cb_sizes() == ref.cb_sizes()).all()
+    for K in (40, 48, 104, 512, 528, 1024, 2048, 5824, 6144):
+        a, b = port.interleaver(K)
+        c, d = ref.interleaver(K)
+        assert (a == c).all() and (b == d).all()
+    for K in (1, 39, 40, 41, 513, 6144, 6145):
+        assert port.cbindex(K) == ref.cbindex(K)
+    for tbs in list(range(16, 6300, 97)) + [6120, 6121, 6144, 12960, 36696, 75376, 97896]:
+        assert port.cbsegm(tbs) == ref.cbsegm(tbs), tbs
+
+
+def test_rm_tables_all(port, ref):
+    for i in range(188):
+        for rv in range(4):
+            assert (port.rm_table(i, rv) == ref.rm_table(i, rv)).all(), (i, rv)
+
+
+def test_rm_matches_float_spec_implementation(port, ref):
+    """rm_turbo_test.c:172-188: the LUT path must equal the float spec implementation srsran_rm_turbo_rx exactly."""
+    import ctypes as C
+
+    rng = np.random.default_rng(5)
+    for cb_idx in (0, 7, 59, 100, 187):
+        K = int(port.cb_sizes()[cb_idx])
+        n = 3 * K + 12
+        for rv in range(4):
+            for E in (n // 2, n, n + 500):
+                e = rng.integers(-50, 50, E).astype(np.int16)
+                soft = np.zeros(n + 64, np.int16)
+                port.rm_rx(e, soft, cb_idx, rv)
+                ef = e.astype(np.float32)
+                of = np.zeros(n, np.float32)
+                assert ref.lib.ref_rm_rx_float(ef.ctypes.data_as(C.c_void_p), C.c_uint32(E), of.ctypes.data_as(C.c_void_p),
+                                               C.c_uint32(n), C.c_uint32(rv)) == 0
+                assert (soft[:n] == of.astype(np.int16)).all(), (cb_idx, rv, E)
+
+
+@pytest.mark.parametrize("K", [40, 504, 1024, 6144])
+def test_encode_rm_decode(port, ref, K):
+    rng = np.random.default_rng(K)
+    bits = rng.integers(0, 2, K).astype(np.uint8)
+    cw = port.tcod_encode(bits)
+    assert (cw == ref.tcod_encode(bits)).all()
+    n = 3 * K + 12
+    for rv in range(4):
+        for E in (int(0.4 * n), n, int(1.7 * n)):
+            assert (port.rm_tx(cw, K, E, rv) == ref.rm_tx(cw, K, E, rv)).all()
+            e = rng.integers(-40, 40, E).astype(np.int16)
+            s1 = rng.integers(-100, 100, n + 64).astype(np.int16)
+            s2 = s1.copy()
+            port.rm_rx(e, s1, port.cbindex(K), rv)
+            ref.rm_rx(e, s2, port.cbindex(K), rv)
+            assert (s1 == s2).all()
+
+
+@pytest.mark.parametrize("K,sigma,scale,clip", [(40, 0.8, 16, 31), (504, 0.95, 16, 31), (1024, 1.0, 16, 31), (6144, 0.93, 16, 31),
+                                                (6144, 1.3, 32, 63), (2048, 0.8, 500, 2000), (1024, 3.0, 8000, 30000)])
+def test_generic_decoder_bit_exact_including_wraparound(port, ref, K, sigma, scale, clip):
+    """Every pass's decision equals the reference's generic int16 decoder, also where its arithmetic wraps (|LLR| >= 100,
+    SURVEY.md section 0.2)."""
+    llr, _ = coded_llrs(port, K, 3, sigma, scale, clip, seed=K + clip)
+    for c in range(3):
+        assert (port.tdec_passes(llr[c], K, 8) == ref.tdec_passes(llr[c], K, 8)).all()
+    for es in (True, False):
+        a = port.decode_batch(llr, K, 8, "B", 0, es)
+        b = ref.decode_batch(llr, K, 8, "B", 0, es)
+        for x, y in zip(a[:3], b[:3]):
+            assert (x == y).all()
+
+
+def test_crc(port, ref):
+    rng = np.random.default_rng(9)
+    d = rng.integers(0, 256, 4096).astype(np.uint8)
+    for n in (8, 16, 24, 32, 6144, 32768):
+        for k in "AB":
+            assert port.crc24(k, d, n) == ref.crc24(k, d, n)
+
+
+@pytest.mark.parametrize("prb,N,cp,fs,wo,nm,kd", [(6, 0, 0, 0.0, 0.0, 0, 0), (25, 0, 0, -0.5, 0.5, 0, 0), (100, 2048, 0, -0.5, 0.5, 0, 0),
+                                                  (50, 0, 1, 0.0, 0.0, 1, 0), (100, 0, 0, 0.5, 0.0, 0, 1), (15, 0, 0, 0.0, 0.3, 0, 0),
+                                                  (75, 1536, 1, -0.5, 0.5, 1, 0), (6, 4096, 0, 0.0, 0.0, 0, 0)])
+def test_ofdm_rx(port, ref, prb, N, cp, fs, wo, nm, kd):
+    """ofdm_test.c:170-179 accepts < 1e-4; same bound between the float64 restatement and the reference's ofdm.c."""
+    n = N or port.symbol_sz(prb)
+    rng = np.random.default_rng(prb + n)
+    x = (rng.normal(size=2 * 15 * n) + 1j * rng.normal(size=2 * 15 * n)).astype(np.complex64)
+    a, _ = port.ofdm_rx(x, prb, bool(cp), N, fs, wo, bool(nm), bool(kd))
+    b, _ = ref.ofdm_rx(x, prb, bool(cp), N, fs, wo, bool(nm), bool(kd))
+    assert np.linalg.norm(a - b) / np.linalg.norm(b) < 1e-4
+
+
+def test_demod(port, ref):
+    rng = np.random.default_rng(11)
+    for mod in (2, 3):
+        for n in (1, 4, 7, 1000, 14401):
+            s = ((rng.normal(size=n) + 1j * rng.normal(size=n)) * 0.8).astype(np.complex64)
+            s[:1] = 47.0 - 46.9j
+            assert (port.demod_s(mod, s) == ref.demod_s(mod, s)).all()
