@@ -64,13 +64,27 @@ int DeviceContext::init(int dev)
   B200_CUDA_TRY(cudaMemcpy(qpp_fwd_all, fwd_all.data(), fwd_all.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
   B200_CUDA_TRY(cudaMemcpy(qpp_rev_all, rev_all.data(), rev_all.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
 
-  const uint32_t polys[2] = {CRC24A_POLY, CRC24B_POLY};
-  for (int k = 0; k < 2; k++) {
-    std::vector<CrcPow> pw;
-    crc_pow_table(polys[k], MAX_CB_LEN, pw);
-    B200_CUDA_TRY(cudaMalloc(&crc_pow[k], pw.size() * sizeof(CrcPow)));
-    B200_CUDA_TRY(cudaMemcpy(crc_pow[k], pw.data(), pw.size() * sizeof(CrcPow), cudaMemcpyHostToDevice));
+  return B200_SUCCESS;
+}
+
+int DeviceContext::crc_visit(int cb_idx, int kind, const CrcPow** nat, const CrcPow** perm)
+{
+  std::lock_guard<std::mutex> lock(crc_mutex);
+  RmTableKey                  key{cb_idx, kind};
+  auto                        it = crc_tables.find(key);
+  if (it == crc_tables.end()) {
+    std::vector<CrcPow> n, p;
+    crc_visit_tables(kind == 0 ? CRC24A_POLY : CRC24B_POLY, cb_idx, n, p);
+    CrcTables t;
+    B200_CUDA_TRY(cudaSetDevice(device));
+    B200_CUDA_TRY(cudaMalloc(&t.nat, n.size() * sizeof(CrcPow)));
+    B200_CUDA_TRY(cudaMalloc(&t.perm, p.size() * sizeof(CrcPow)));
+    B200_CUDA_TRY(cudaMemcpy(t.nat, n.data(), n.size() * sizeof(CrcPow), cudaMemcpyHostToDevice));
+    B200_CUDA_TRY(cudaMemcpy(t.perm, p.data(), p.size() * sizeof(CrcPow), cudaMemcpyHostToDevice));
+    it = crc_tables.emplace(key, t).first;
   }
+  *nat  = it->second.nat;
+  *perm = it->second.perm;
   return B200_SUCCESS;
 }
 

@@ -61,7 +61,14 @@ struct DeviceContext {
   uint16_t*           qpp_rev_all = nullptr;
   std::vector<size_t> qpp_off;
 
-  CrcPow* crc_pow[2] = {nullptr, nullptr}; // [0] CRC24A, [1] CRC24B; MAX_CB_LEN entries each
+  // CRC syndrome weights in visiting order (TdecView::crc_nat / crc_perm), built per (size, polynomial) on first use
+  struct CrcTables {
+    CrcPow* nat  = nullptr;
+    CrcPow* perm = nullptr;
+  };
+  std::mutex                        crc_mutex;
+  std::map<RmTableKey, CrcTables>   crc_tables; // key = (cb_idx, kind) with kind 0 = CRC24A, 1 = CRC24B
+  int crc_visit(int cb_idx, int kind, const CrcPow** nat, const CrcPow** perm);
 
   std::mutex                      rm_mutex;
   std::map<RmTableKey, uint16_t*> rm_gather; // device copies of the gather-form de-matching tables

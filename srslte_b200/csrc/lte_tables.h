@@ -87,6 +87,22 @@ inline void crc_pow_table(uint32_t poly, int n, std::vector<CrcPow>& out)
   }
 }
 
+// Syndrome weights in the order each constituent decoder visits the bits (see TdecView::crc_nat / crc_perm)
+inline void crc_visit_tables(uint32_t poly, int cb_idx, std::vector<CrcPow>& nat, std::vector<CrcPow>& perm)
+{
+  const int             K = g_qpp_rows[cb_idx].K;
+  std::vector<CrcPow>   pw;
+  std::vector<uint16_t> fwd, rev;
+  crc_pow_table(poly, K, pw);
+  qpp_tables(cb_idx, fwd, rev);
+  nat.resize(K);
+  perm.resize(K);
+  for (int j = 0; j < K; j++) {
+    nat[j]  = pw[K - 1 - j];
+    perm[j] = pw[K - 1 - fwd[j]];
+  }
+}
+
 // ---- rate matching geometry (36.212 5.1.4.1, rm_turbo.c:175-248) -------------------------------------------------
 static const uint8_t g_rm_colperm[32] = {0, 16, 8, 24, 4, 20, 12, 28, 2, 18, 10, 26, 6, 22, 14, 30,
                                          1, 17, 9, 25, 5, 21, 13, 29, 3, 19, 11, 27, 7, 23, 15, 31};

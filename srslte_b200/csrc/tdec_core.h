@@ -68,7 +68,9 @@ struct TdecView {
   uint16_t*       HB;
   CbStatus*       status; // [ntiles*64]
   const uint16_t* qpp_fwd; // PI(i), K entries (tc_interl_lte.c:89-93)
-  const CrcPow*   crc_pow; // x^m mod g for m in [0, K), for the CRC this bucket uses; nullptr = no CRC
+  // CRC syndrome weights in VISITING order, nullptr = no CRC:
+  const CrcPow*   crc_nat;  // [j] = x^(K-1-j) mod g        (DEC1 visits natural position j)
+  const CrcPow*   crc_perm; // [i] = x^(K-1-PI(i)) mod g    (DEC2 visits natural position PI(i) at step i)
   int             early_stop; // stop a block at its first CRC match (sch.c:446-449)
   int             max_pass;
 };
@@ -301,6 +303,7 @@ B200_HD void alpha_window(const TdecView&    v,
                           const WinIn<DEC2>& cur,
                           const u4&          c0,
                           const u4&          c1,
+                          const CrcPow*      cw, // the 8 syndrome weights of this window's steps, or nullptr
                           uint32_t           A[8],
                           LaneResult&        res,
                           bool               act_lo,
@@ -335,8 +338,8 @@ B200_HD void alpha_window(const TdecView&    v,
     p.E[pos * 32u] = sub2(L, cur.e[t]);
     uint32_t one   = pos2(L); // turbodecoder_gen.c:266: LLR > 0 -> 1
     bits           = (bits << 1) | one;
-    if (v.crc_pow) {
-      const CrcPow   c    = v.crc_pow[K - 1u - pos];
+    if (cw) {
+      const CrcPow   c    = cw[t];
       const uint32_t mask = one * 0xFFFFu;
       res.crc_lo16x2 ^= (c.lo16x2 & mask);
       res.crc_hi8x2 ^= (c.hi8x2 & mask);
@@ -358,6 +361,7 @@ B200_HD LaneResult alpha_sweep_lane(const TdecView& v, int tile, int lane, bool 
 {
   const uint32_t nw = (uint32_t)v.K / 8u;
   const LanePtrs p  = lane_ptrs<DEC2>(v, tile, lane);
+  const CrcPow*  cbase = DEC2 ? v.crc_perm : v.crc_nat;
   uint32_t       A[8];
   LaneResult     res = {0u, 0u};
   A[0]               = 0;
@@ -377,20 +381,55 @@ B200_HD LaneResult alpha_sweep_lane(const TdecView& v, int tile, int lane, bool 
       ckB0 = p.CK[(2u * (w + 1)) * 32u];
       ckB1 = p.CK[(2u * (w + 1) + 1u) * 32u];
     }
-    alpha_window<DEC2>(v, p, w, inA, ckA0, ckA1, A, res, act_lo, act_hi);
+    alpha_window<DEC2>(v, p, w, inA, ckA0, ckA1, cbase ? cbase + 8u * w : nullptr, A, res, act_lo, act_hi);
     if (w + 1 < nw) {
       if (w + 2 < nw) {
         load_window<DEC2, FIRST>(inA, p, w + 2);
         ckA0 = p.CK[(2u * (w + 2)) * 32u];
         ckA1 = p.CK[(2u * (w + 2) + 1u) * 32u];
       }
-      alpha_window<DEC2>(v, p, w + 1, inB, ckB0, ckB1, A, res, act_lo, act_hi);
+      alpha_window<DEC2>(v, p, w + 1, inB, ckB0, ckB1, cbase ? cbase + 8u * (w + 1) : nullptr, A, res, act_lo, act_hi);
     }
   }
   return res;
 }
 
-// ---- one full pass for one lane (two code blocks) ----------------------------------------------------------
+// ---- end of a pass: CRC verdict, pass counters, stop flag (sch.c:431-452) ---------------------------------------
+B200_HD void finish_pass(const TdecView&   v,
+                         CbStatus*         st,
+                         CbStatus          s_lo,
+                         CbStatus          s_hi,
+                         bool              act_lo,
+                         bool              act_hi,
+                         const LaneResult& r,
+                         int               pass_idx)
+{
+  const bool last = (pass_idx + 1 >= v.max_pass);
+  if (act_lo) {
+    bool ok        = v.crc_nat && ((r.crc_lo16x2 & 0xFFFFu) == 0) && ((r.crc_hi8x2 & 0xFFu) == 0);
+    s_lo.npass_run = (uint8_t)(pass_idx + 1);
+    if (ok && !s_lo.crc_ok) {
+      s_lo.crc_ok    = 1;
+      s_lo.npass_crc = (uint8_t)(pass_idx + 1);
+    }
+    if (last || (ok && v.early_stop)) s_lo.active = 0;
+    st[0] = s_lo;
+  }
+  if (act_hi) {
+    bool ok        = v.crc_nat && ((r.crc_lo16x2 >> 16) == 0) && (((r.crc_hi8x2 >> 16) & 0xFFu) == 0);
+    s_hi.npass_run = (uint8_t)(pass_idx + 1);
+    if (ok && !s_hi.crc_ok) {
+      s_hi.crc_ok    = 1;
+      s_hi.npass_crc = (uint8_t)(pass_idx + 1);
+    }
+    if (last || (ok && v.early_stop)) s_hi.active = 0;
+    st[1] = s_hi;
+  }
+}
+
+// ---- one full pass for one lane (two code blocks), direct-from-global variant ------------------------------------
+// Used by the CPU emulation (and kept as the reference structure of the pass); the GPU kernel in tdec_kernels.cu runs
+// the same steps but feeds the windows through a TMA-filled shared-memory ring.
 template <bool DEC2, bool FIRST, int PF>
 B200_HD void siso_pass_lane(const TdecView& v, int tile, int lane, int pass_idx)
 {
@@ -403,28 +442,7 @@ B200_HD void siso_pass_lane(const TdecView& v, int tile, int lane, int pass_idx)
   }
   beta_sweep_lane<DEC2, FIRST, PF>(v, tile, lane);
   LaneResult r = alpha_sweep_lane<DEC2, FIRST>(v, tile, lane, act_lo, act_hi);
-
-  const bool last = (pass_idx + 1 >= v.max_pass);
-  if (act_lo) {
-    bool ok        = v.crc_pow && ((r.crc_lo16x2 & 0xFFFFu) == 0) && ((r.crc_hi8x2 & 0xFFu) == 0);
-    s_lo.npass_run = (uint8_t)(pass_idx + 1);
-    if (ok && !s_lo.crc_ok) {
-      s_lo.crc_ok    = 1;
-      s_lo.npass_crc = (uint8_t)(pass_idx + 1);
-    }
-    if (last || (ok && v.early_stop)) s_lo.active = 0;
-    st[0] = s_lo;
-  }
-  if (act_hi) {
-    bool ok        = v.crc_pow && ((r.crc_lo16x2 >> 16) == 0) && (((r.crc_hi8x2 >> 16) & 0xFFu) == 0);
-    s_hi.npass_run = (uint8_t)(pass_idx + 1);
-    if (ok && !s_hi.crc_ok) {
-      s_hi.crc_ok    = 1;
-      s_hi.npass_crc = (uint8_t)(pass_idx + 1);
-    }
-    if (last || (ok && v.early_stop)) s_hi.active = 0;
-    st[1] = s_hi;
-  }
+  finish_pass(v, st, s_lo, s_hi, act_lo, act_hi, r, pass_idx);
 }
 
 } // namespace b200

@@ -100,7 +100,13 @@ int TdecEngine::run_device(DeviceArena&   ws,
     return B200_ERROR;
   }
   v.qpp_fwd    = ctx->qpp_fwd(cb_idx);
-  v.crc_pow    = crc_kind == SRSRAN_B200_CRC24A ? ctx->crc_pow[0] : (crc_kind == SRSRAN_B200_CRC24B ? ctx->crc_pow[1] : nullptr);
+  v.crc_nat    = nullptr;
+  v.crc_perm   = nullptr;
+  if (crc_kind != SRSRAN_B200_CRC_NONE) {
+    if (ctx->crc_visit(cb_idx, crc_kind == SRSRAN_B200_CRC24A ? 0 : 1, &v.crc_nat, &v.crc_perm) != B200_SUCCESS) {
+      return B200_ERROR;
+    }
+  }
   v.early_stop = early_stop ? 1 : 0;
   v.max_pass   = (int)max_passes;
 

@@ -31,15 +31,15 @@ extern "C" int emu_tdec_batch(const int16_t* llr,
   std::vector<uint16_t> HB((size_t)ntiles * (K / 8) * 32, 0);
   std::vector<CbStatus> st((size_t)ntiles * TDEC_TILE_CB);
   std::vector<uint16_t> fwd, rev;
-  std::vector<CrcPow>   pw;
+  std::vector<CrcPow>   cnat, cperm;
   qpp_tables(cbi, fwd, rev);
-  if (crc_kind != 2) crc_pow_table(crc_kind == 1 ? CRC24A_POLY : CRC24B_POLY, (int)K, pw);
+  if (crc_kind != 2) crc_visit_tables(crc_kind == 1 ? CRC24A_POLY : CRC24B_POLY, cbi, cnat, cperm);
 
   TdecView v;
   v.K = (int)K; v.ntiles = ntiles;
   v.S = S.data(); v.P0 = P0.data(); v.P1 = P1.data(); v.S2T = S2T.data();
   v.E = E.data(); v.CK = CK.data(); v.HB = HB.data(); v.status = st.data();
-  v.qpp_fwd = fwd.data(); v.crc_pow = crc_kind != 2 ? pw.data() : nullptr;
+  v.qpp_fwd = fwd.data(); v.crc_nat = crc_kind != 2 ? cnat.data() : nullptr; v.crc_perm = crc_kind != 2 ? cperm.data() : nullptr;
   v.early_stop = early_stop; v.max_pass = (int)max_pass;
 
   const size_t nllr = 3 * (size_t)K + 12;
