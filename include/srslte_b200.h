@@ -78,6 +78,14 @@ SRSRAN_B200_API int srsran_b200_tdec_run(srsran_b200_tdec_t* h,
                                          uint32_t            flags,
                                          void*               stream);
 
+/*
+ * Optional kernel timing: with enable != 0 every kernel the object launches is bracketed by CUDA events on the
+ * launching stream; profile_get synchronises the device and returns accumulated milliseconds and launch counts for
+ * the three kernel classes [0] layout load, [1] SISO pass, [2] decision/pack.  Reset clears the history.
+ */
+SRSRAN_B200_API void srsran_b200_tdec_profile_reset(srsran_b200_tdec_t* h, int enable);
+SRSRAN_B200_API int  srsran_b200_tdec_profile_get(srsran_b200_tdec_t* h, double* ms_by_class, uint64_t* launches_by_class);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * Synthetic workload (bench / tests only, never on the decode path): fills llr_dev[ncb][3K+12] (device memory) with
  * the quantised channel output of randomly drawn, CRC24B-terminated, turbo-encoded blocks:

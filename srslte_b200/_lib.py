@@ -39,6 +39,9 @@ def lib() -> C.CDLL:
     L.srsran_b200_tdec_free.argtypes = [vp]
     L.srsran_b200_tdec_free.restype = None
     L.srsran_b200_tdec_run.argtypes = [vp, vp, u32, u32, u32, C.c_int, C.c_int, vp, vp, vp, u32, vp]
+    L.srsran_b200_tdec_profile_reset.argtypes = [vp, C.c_int]
+    L.srsran_b200_tdec_profile_reset.restype = None
+    L.srsran_b200_tdec_profile_get.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
     L.srsran_b200_synth_llr.argtypes = [C.c_int, vp, vp, u32, u32, C.c_float, C.c_float, C.c_int, C.c_uint64, C.c_int, vp]
     return L
 
@@ -50,5 +53,7 @@ EXPORTED_SYMBOLS = [
     "srsran_b200_tdec_init",
     "srsran_b200_tdec_free",
     "srsran_b200_tdec_run",
+    "srsran_b200_tdec_profile_reset",
+    "srsran_b200_tdec_profile_get",
     "srsran_b200_synth_llr",
 ]

@@ -1,6 +1,7 @@
 // Host-side engine of the batched turbo decoder (see tdec_host.cu).
 #pragma once
 #include <atomic>
+#include <vector>
 
 #include "b200_runtime.h"
 
@@ -18,6 +19,18 @@ struct TdecEngine {
   cudaStream_t   pipe_stream[2] = {nullptr, nullptr};
   DeviceArena    pipe_arena[2];  // host-pointer path: decoder workspace per stream
   DeviceArena    pipe_io[2];     // host-pointer path: staged inputs/outputs per stream
+
+  // Optional per-kernel-class timing with CUDA events on the launching stream (bench.py's roofline numbers).
+  struct ProfSpan {
+    cudaEvent_t a, b;
+    int         cls; // 0 load, 1 siso pass, 2 decide
+  };
+  bool                  profiling = false;
+  std::vector<ProfSpan> spans;
+  void prof_begin(int cls, cudaStream_t st);
+  void prof_end(cudaStream_t st);
+  void prof_reset(bool enable);
+  int  prof_get(double* ms_by_class, uint64_t* launches_by_class); // synchronises the device
 
   static size_t workspace_bytes(int K, uint32_t ncb);
   int           carve(DeviceArena& a, int K, uint32_t ncb, TdecView& v) const;

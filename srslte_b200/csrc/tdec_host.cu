@@ -78,6 +78,50 @@ void TdecEngine::destroy()
     pipe_io[i].release();
   }
   arena.release();
+  prof_reset(false);
+}
+
+void TdecEngine::prof_begin(int cls, cudaStream_t st)
+{
+  if (!profiling || spans.size() >= 8192) return;
+  ProfSpan s;
+  s.cls = cls;
+  if (cudaEventCreate(&s.a) != cudaSuccess || cudaEventCreate(&s.b) != cudaSuccess) return;
+  cudaEventRecord(s.a, st);
+  spans.push_back(s);
+}
+
+void TdecEngine::prof_end(cudaStream_t st)
+{
+  if (!profiling || spans.empty() || spans.size() > 8192) return;
+  cudaEventRecord(spans.back().b, st);
+}
+
+void TdecEngine::prof_reset(bool enable)
+{
+  for (auto& s : spans) {
+    cudaEventDestroy(s.a);
+    cudaEventDestroy(s.b);
+  }
+  spans.clear();
+  profiling = enable;
+}
+
+int TdecEngine::prof_get(double* ms_by_class, uint64_t* launches_by_class)
+{
+  for (int i = 0; i < 3; i++) {
+    ms_by_class[i]       = 0;
+    launches_by_class[i] = 0;
+  }
+  B200_CUDA_TRY(cudaDeviceSynchronize());
+  for (auto& s : spans) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) {
+      ms_by_class[s.cls] += ms;
+      launches_by_class[s.cls]++;
+    }
+  }
+  return B200_SUCCESS;
 }
 
 // Everything on `stream`, all pointers device memory.
@@ -110,13 +154,19 @@ int TdecEngine::run_device(DeviceArena&   ws,
   v.early_stop = early_stop ? 1 : 0;
   v.max_pass   = (int)max_passes;
 
+  prof_begin(0, stream);
   launch_load_natural(v, llr_dev, ncb, stream);
+  prof_end(stream);
   g_kernel_launches++;
   for (uint32_t p = 0; p < max_passes; p++) {
+    prof_begin(1, stream);
     launch_siso_pass(v, (int)p, stream);
+    prof_end(stream);
     g_kernel_launches++;
   }
+  prof_begin(2, stream);
   launch_decide(v, ctx->qpp_rev(cb_idx), out_dev, crc_ok_dev, npass_dev, nullptr, ncb, stream);
+  prof_end(stream);
   g_kernel_launches++;
   B200_CUDA_TRY(cudaGetLastError());
   return B200_SUCCESS;
@@ -260,6 +310,21 @@ int srsran_b200_tdec_run(srsran_b200_tdec_t* h,
     return B200_ERROR_INVALID_INPUTS;
   }
   return h->eng.run(llr, ncb, K, max_passes, crc_kind, early_stop, out, crc_ok, npass, flags, (cudaStream_t)stream);
+}
+
+void srsran_b200_tdec_profile_reset(srsran_b200_tdec_t* h, int enable)
+{
+  if (h) {
+    h->eng.prof_reset(enable != 0);
+  }
+}
+
+int srsran_b200_tdec_profile_get(srsran_b200_tdec_t* h, double* ms_by_class, uint64_t* launches_by_class)
+{
+  if (!h || !ms_by_class || !launches_by_class) {
+    return B200_ERROR_INVALID_INPUTS;
+  }
+  return h->eng.prof_get(ms_by_class, launches_by_class);
 }
 
 } // extern "C"

@@ -36,6 +36,19 @@ class TurboDecoderBatch:
         except Exception:
             pass
 
+    # -- kernel timing (CUDA events inside the library, on the launching stream) ----------------------------
+    def profile_reset(self, enable: bool = True):
+        self._lib.srsran_b200_tdec_profile_reset(self._h, int(enable))
+
+    def profile_get(self) -> dict:
+        ms = (C.c_double * 3)()
+        n = (C.c_uint64 * 3)()
+        rc = self._lib.srsran_b200_tdec_profile_get(self._h, ms, n)
+        if rc != _lib.SUCCESS:
+            raise RuntimeError(f"srsran_b200_tdec_profile_get failed ({rc})")
+        return {"load_ms": ms[0], "siso_ms": ms[1], "decide_ms": ms[2], "total_ms": ms[0] + ms[1] + ms[2],
+                "load_launches": int(n[0]), "siso_launches": int(n[1]), "decide_launches": int(n[2])}
+
     # -- host buffers ------------------------------------------------------------------------------------
     def decode(self, llr: np.ndarray, K: int, max_passes: int = 8, crc: str | None = "B", early_stop: bool = True):
         """llr: (ncb, 3K+12) int16 numpy.  Returns (bytes (ncb,K/8) uint8, crc_ok (ncb,), npass (ncb,))."""
