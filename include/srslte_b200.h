@@ -29,7 +29,11 @@ extern "C" {
 #define SRSRAN_B200_API __attribute__((visibility("default")))
 
 /* flags */
-#define SRSRAN_B200_FLAG_DEVICE_PTRS 0x1u /* data pointers are device memory on the object's GPU (else host memory) */
+#define SRSRAN_B200_FLAG_DEVICE_PTRS 0x1u    /* data pointers are device memory on the object's GPU (else host memory) */
+#define SRSRAN_B200_FLAG_SOFT_ON_DEVICE 0x2u /* only the HARQ soft-buffer pool is device memory (stays resident) */
+
+/* int16 values per code block in a soft-buffer pool: SOFTBUFFER_SIZE of lib/include/srsran/phy/fec/softbuffer.h:56 */
+#define SRSRAN_B200_SOFTBUFFER_SIZE 18600
 
 /* CRC the per-pass early-stop check uses (sch.c:437-444) */
 #define SRSRAN_B200_CRC_NONE 0
@@ -85,6 +89,83 @@ SRSRAN_B200_API int srsran_b200_tdec_run(srsran_b200_tdec_t* h,
  */
 SRSRAN_B200_API void srsran_b200_tdec_profile_reset(srsran_b200_tdec_t* h, int enable);
 SRSRAN_B200_API int  srsran_b200_tdec_profile_get(srsran_b200_tdec_t* h, double* ms_by_class, uint64_t* launches_by_class);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Shared-channel receive processing: batched rate de-matching and the transport-block decode loop.
+ *
+ * srsran_b200_sch_t plays the role of srsran_sch_t (lib/include/srsran/phy/phch/sch.h:60-85) for the receive side:
+ * it owns the decoder and the de-matching tables.  One per host thread.
+ */
+typedef struct srsran_b200_sch srsran_b200_sch_t;
+
+SRSRAN_B200_API int  srsran_b200_sch_init(srsran_b200_sch_t** q, int device);
+SRSRAN_B200_API void srsran_b200_sch_free(srsran_b200_sch_t* q);
+/* srsran_sch_set_max_noi (sch.c:222-229): maximum SISO passes per code block, 0 selects the default of 10 */
+SRSRAN_B200_API void srsran_b200_sch_set_max_noi(srsran_b200_sch_t* q, uint32_t max_iterations);
+
+/* One srsran_rm_turbo_rx_lut_(input, output, in_len, cb_idx, rv_idx, enable_input_tdec=false) call (rm_turbo.c:403) */
+typedef struct {
+  uint32_t cb_idx;      /* index into the 188 code block sizes (srsran_cbsegm_cbindex) */
+  uint32_t rv;          /* redundancy version 0..3 */
+  uint32_t E;           /* in_len: received soft bits of this code block */
+  uint32_t new_data;    /* non-zero: the soft buffer is taken as all-zero before combining (fresh HARQ process) */
+  uint64_t in_offset;   /* first soft bit inside e_bits, int16 units */
+  uint64_t soft_offset; /* this block's 3K+12 soft buffer inside soft_pool, int16 units, natural layout */
+} srsran_b200_rm_cb_t;
+
+/*
+ * soft_pool[soft_offset + table[i mod (3K+12)]] += e_bits[in_offset + i]  for i < E, int16 wrap-around, for n code
+ * blocks at once.  With SRSRAN_B200_FLAG_DEVICE_PTRS both buffers are device memory and the work is enqueued on
+ * `stream`; otherwise host memory, synchronous.  Invalid rv / cb_idx returns SRSRAN_ERROR_INVALID_INPUTS (rm_turbo.c:442).
+ */
+SRSRAN_B200_API int srsran_b200_rm_turbo_rx_batch(srsran_b200_sch_t*         q,
+                                                  const int16_t*             e_bits,
+                                                  uint64_t                   e_len,
+                                                  int16_t*                   soft_pool,
+                                                  uint64_t                   soft_len,
+                                                  const srsran_b200_rm_cb_t* cbs,
+                                                  uint32_t                   n,
+                                                  uint32_t                   flags,
+                                                  void*                      stream);
+
+/* One decode_tb() call (sch.c:507-572) */
+typedef struct {
+  /* in */
+  uint32_t tbs;         /* transport block size in bits (cb_segm->tbs) */
+  uint32_t Qm;          /* bits per modulation symbol (x layers) */
+  uint32_t rv;
+  uint32_t nof_e_bits;  /* G: soft bits of this transport block */
+  uint64_t e_offset;    /* first soft bit inside e_bits, int16 units */
+  uint64_t soft_offset; /* soft buffers of this HARQ process inside soft_pool: code block c at
+                           soft_offset + c * SRSRAN_B200_SOFTBUFFER_SIZE (softbuffer->buffer_f[c]) */
+  uint64_t data_offset; /* first output byte inside data; tbs/8 + 3 bytes are produced, keep 768 bytes of slack */
+  uint32_t new_data;    /* non-zero: srsran_softbuffer_rx_reset_tbs semantics, soft buffers start from zero */
+  /* in/out */
+  uint32_t cb_crc_mask; /* bit c: code block c is already decoded (in: skipped, its bytes must still be in data,
+                           sch.c:390,466-471; out: updated with the blocks that passed now) */
+  /* out */
+  int32_t  result;         /* SRSRAN_SUCCESS: every code block and the TB CRC24A matched; SRSRAN_ERROR: CRC failure;
+                              SRSRAN_ERROR_INVALID_INPUTS: filler bits / too many blocks / buffer overrun */
+  uint32_t nof_cb;         /* C */
+  float    avg_iterations; /* q->avg_iterations of sch.c:490 */
+} srsran_b200_tb_t;
+
+/*
+ * Decodes n_tb transport blocks: per code block rate de-matching into the soft pool, up to max_noi SISO passes with
+ * a CRC check after each (CRC24B per block, CRC24A when C == 1), payload assembly, TB CRC.  Synchronous.
+ * flags: 0 = e_bits/soft_pool/data are host memory; SRSRAN_B200_FLAG_SOFT_ON_DEVICE = the soft pool is device
+ * memory; SRSRAN_B200_FLAG_DEVICE_PTRS = all three are device memory.
+ */
+SRSRAN_B200_API int srsran_b200_sch_decode_batch(srsran_b200_sch_t* q,
+                                                 const int16_t*     e_bits,
+                                                 uint64_t           e_len,
+                                                 int16_t*           soft_pool,
+                                                 uint64_t           soft_len,
+                                                 uint8_t*           data,
+                                                 uint64_t           data_len,
+                                                 srsran_b200_tb_t*  tbs,
+                                                 uint32_t           n_tb,
+                                                 uint32_t           flags);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Synthetic workload (bench / tests only, never on the decode path): fills llr_dev[ncb][3K+12] (device memory) with

@@ -168,6 +168,17 @@ class _Api:
         assert r == 0
         return out, ok, npass, sec.value
 
+    def decode_tb(self, e_bits: np.ndarray, tbs: int, Qm: int, rv: int, max_iter: int, soft: np.ndarray, cb_crc: np.ndarray,
+                  data: np.ndarray):
+        """Port only: decode_tb/decode_tb_cb (sch.c:370-572).  soft (C*18600 int16), cb_crc (C uint8), data (bytes) are in/out.
+        Returns (ret, iter_sum)."""
+        assert self.which == "port"
+        e_bits = np.ascontiguousarray(e_bits, np.int16)
+        it = C.c_uint32(0)
+        r = self.lib.orc_decode_tb(_p(e_bits), C.c_uint32(e_bits.size), C.c_uint32(tbs), C.c_uint32(Qm), C.c_uint32(rv),
+                                   C.c_uint32(max_iter), _p(soft), _p(cb_crc), _p(data), C.byref(it))
+        return int(r), int(it.value)
+
     # -- OFDM / demap ---------------------------------------------------------------------------------
     def ofdm_rx(self, x: np.ndarray, nof_prb: int, cp_ext: bool = False, symbol_sz: int = 0, freq_shift: float = 0.0,
                 rx_window_offset: float = 0.0, normalize: bool = False, keep_dc: bool = False):

@@ -804,3 +804,71 @@ int orc_demod_s(int mod, const cf_t* sym, int16_t* llr, int n)
   }
   return -1;
 }
+
+/* ---------------------------------------------------------------- transport block decode (sch.c:370-572) */
+
+#define ORC_SOFTBUFFER_SIZE 18600 /* softbuffer.h:56 */
+
+/*
+ * decode_tb + decode_tb_cb for one transport block.
+ *   e_bits : G = nof_e_bits soft bits;  soft : C buffers of ORC_SOFTBUFFER_SIZE int16 (combined in place);
+ *   cb_crc : C flags, in/out (blocks already decoded are skipped and their bytes are expected in `data`);
+ *   data   : tbs/8 + 3 bytes (+ K/8 slack);  iter_sum : sum of passes run (avg_iterations * C).
+ * Returns 0 when every code block CRC and the transport block CRC24A match, -1 on CRC failure, -2 on invalid input.
+ */
+int orc_decode_tb(const int16_t* e_bits,
+                  uint32_t       nof_e_bits,
+                  uint32_t       tbs,
+                  uint32_t       Qm,
+                  uint32_t       rv,
+                  uint32_t       max_iter,
+                  int16_t*       soft,
+                  uint8_t*       cb_crc,
+                  uint8_t*       data,
+                  uint32_t*      iter_sum)
+{
+  uint32_t s[9];
+  if (!e_bits || !soft || !data || Qm == 0 || orc_cbsegm(tbs, s)) return -2;
+  uint32_t F = s[0], C = s[1], K1 = s[2], K2 = s[3], K1i = s[4], K2i = s[5], C1 = s[6];
+  if (iter_sum) *iter_sum = 0;
+  if (tbs == 0 || C == 0) return 0; /* sch.c:517-519 */
+  if (F) return -2;                 /* sch.c:521-524 */
+  if (C > 32) return -2;
+  data[tbs / 8] = data[tbs / 8 + 1] = data[tbs / 8 + 2] = 0; /* sch.c:537-539 */
+
+  tdec_t d;
+  tdec_alloc(&d);
+  uint32_t Gp = nof_e_bits / Qm, gamma = Gp % C, n_e = Qm * (Gp / C);
+  for (uint32_t cb = 0; cb < C; cb++) {
+    if (cb_crc[cb]) continue; /* sch.c:390 (the saved bytes are the caller's business here) */
+    uint32_t K    = cb < C1 ? K1 : K2;
+    uint32_t Ki   = cb < C1 ? K1i : K2i;
+    uint32_t rlen = C == 1 ? K : K - 24;
+    uint32_t rp = cb * n_e, n_e2 = n_e;
+    if (cb > C - gamma) { /* sch.c:403, the reference's own comparison */
+      n_e2 = n_e + Qm;
+      rp   = (C - gamma) * n_e + (cb - (C - gamma)) * n_e2;
+    }
+    int16_t* sb = soft + (size_t)cb * ORC_SOFTBUFFER_SIZE;
+    orc_rm_rx(&e_bits[rp], sb, n_e2, Ki, rv);
+    tdec_new_cb(&d, (int)K);
+    uint8_t* out = &data[cb * rlen / 8];
+    uint32_t noi = 0;
+    int      ok  = 0;
+    do {
+      tdec_pass(&d, sb);
+      tdec_decide(&d, out);
+      noi++;
+      if (iter_sum) (*iter_sum)++;
+      uint32_t len = C > 1 ? K : tbs + 24;
+      if (crc24_bits_msb(C > 1 ? ORC_CRC24B : ORC_CRC24A, out, (int)len) == 0) ok = 1;
+    } while (noi < max_iter && !ok);
+    cb_crc[cb] = (uint8_t)ok;
+  }
+  tdec_release(&d);
+  for (uint32_t cb = 0; cb < C; cb++)
+    if (!cb_crc[cb]) return -1;
+  uint32_t par_rx = crc24_bits_msb(ORC_CRC24A, data, (int)tbs);
+  uint32_t par_tx = ((uint32_t)data[tbs / 8] << 16) | ((uint32_t)data[tbs / 8 + 1] << 8) | data[tbs / 8 + 2];
+  return (par_rx == par_tx && par_rx) ? 0 : -1; /* sch.c:553 */
+}

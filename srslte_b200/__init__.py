@@ -4,6 +4,7 @@ The product is the shared library ``libsrslte_b200.so`` (hand-written sm_100a CU
 this package is only its Python mirror for tests and benchmarks.
 """
 from . import _lib  # noqa: F401
+from .sch import SchDecoder  # noqa: F401
 from .tdec import TurboDecoderBatch  # noqa: F401
 
-__all__ = ["TurboDecoderBatch"]
+__all__ = ["TurboDecoderBatch", "SchDecoder"]

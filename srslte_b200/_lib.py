@@ -42,6 +42,14 @@ def lib() -> C.CDLL:
     L.srsran_b200_tdec_profile_reset.argtypes = [vp, C.c_int]
     L.srsran_b200_tdec_profile_reset.restype = None
     L.srsran_b200_tdec_profile_get.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
+    u64 = C.c_uint64
+    L.srsran_b200_sch_init.argtypes = [C.POINTER(vp), C.c_int]
+    L.srsran_b200_sch_free.argtypes = [vp]
+    L.srsran_b200_sch_free.restype = None
+    L.srsran_b200_sch_set_max_noi.argtypes = [vp, u32]
+    L.srsran_b200_sch_set_max_noi.restype = None
+    L.srsran_b200_rm_turbo_rx_batch.argtypes = [vp, vp, u64, vp, u64, vp, u32, u32, vp]
+    L.srsran_b200_sch_decode_batch.argtypes = [vp, vp, u64, vp, u64, vp, u64, vp, u32, u32]
     L.srsran_b200_synth_llr.argtypes = [C.c_int, vp, vp, u32, u32, C.c_float, C.c_float, C.c_int, C.c_uint64, C.c_int, vp]
     return L
 
@@ -56,4 +64,9 @@ EXPORTED_SYMBOLS = [
     "srsran_b200_tdec_profile_reset",
     "srsran_b200_tdec_profile_get",
     "srsran_b200_synth_llr",
+    "srsran_b200_sch_init",
+    "srsran_b200_sch_free",
+    "srsran_b200_sch_set_max_noi",
+    "srsran_b200_rm_turbo_rx_batch",
+    "srsran_b200_sch_decode_batch",
 ]

@@ -14,6 +14,8 @@ SOURCES = [
     "b200_runtime.cu",
     "tdec_kernels.cu",
     "tdec_host.cu",
+    "rm_kernels.cu",
+    "sch_host.cu",
     "synth.cu",
 ]
 

@@ -53,6 +53,46 @@ inline int cb_index_exact(uint32_t K)
   return (i >= 0 && g_qpp_rows[i].K == K) ? i : -1;
 }
 
+// 36.212 5.1.2 code block segmentation with the reference's conventions (cbsegm.c:48-117): B = tbs + 24,
+// Z = 6144, C = ceil(B / (Z - 24)) when B > Z, K1 = smallest table size >= B'/C, K2 the next smaller size.
+struct CbSegm {
+  uint32_t F, C, K1, K2, K1_idx, K2_idx, C1, C2, tbs;
+};
+
+inline int cb_segmentation(uint32_t tbs, CbSegm& s)
+{
+  s = CbSegm{0, 0, 0, 0, 0, 0, 0, 0, 0};
+  if (tbs == 0) {
+    return 0;
+  }
+  const uint32_t B = tbs + 24;
+  uint32_t       Bp;
+  s.tbs = tbs;
+  if (B <= (uint32_t)MAX_CB_LEN) {
+    s.C = 1;
+    Bp  = B;
+  } else {
+    s.C = (B + (MAX_CB_LEN - 24) - 1) / (MAX_CB_LEN - 24);
+    Bp  = B + 24 * s.C;
+  }
+  const int i1 = cb_index((Bp - 1) / s.C + 1);
+  if (i1 < 0) {
+    return -1;
+  }
+  s.K1     = g_qpp_rows[i1].K;
+  s.K1_idx = (uint32_t)i1;
+  if (s.C == 1) {
+    s.C1 = 1;
+  } else {
+    s.K2_idx = i1 > 0 ? (uint32_t)i1 - 1 : 0;
+    s.K2     = g_qpp_rows[s.K2_idx].K;
+    s.C2     = (s.K1 != s.K2) ? (s.C * s.K1 - Bp) / (s.K1 - s.K2) : 0;
+    s.C1     = s.C - s.C2;
+  }
+  s.F = s.C1 * s.K1 + s.C2 * s.K2 - Bp;
+  return 0;
+}
+
 inline void qpp_tables(int cb_idx, std::vector<uint16_t>& fwd, std::vector<uint16_t>& rev)
 {
   const uint64_t K = g_qpp_rows[cb_idx].K, f1 = g_qpp_rows[cb_idx].f1, f2 = g_qpp_rows[cb_idx].f2;

@@ -1,0 +1,458 @@
+// Batched shared-channel receive processing: rate de-matching and the transport-block decode loop.
+//
+// Replaces, a batch of transport blocks at a time, what the reference does per code block on one CPU thread:
+//   decode_tb     lib/src/phy/phch/sch.c:507-572   (filler check, TB CRC24A with the non-zero-parity rule)
+//   decode_tb_cb  lib/src/phy/phch/sch.c:370-492   (E split with its off-by-one, de-match into the HARQ soft buffer, up to
+//                                                   max_iterations passes with a CRC check after each, cb_crc bookkeeping)
+// Code blocks of all transport blocks are pooled, grouped by (K, CRC kind) and each group runs as ONE batched decode.
+#include <map>
+#include <new>
+#include <vector>
+
+#include "../../include/srslte_b200.h"
+#include "b200_runtime.h"
+#include "lte_tables.h"
+#include "rm_kernels.h"
+#include "tdec_engine.h"
+#include "tdec_kernels.h"
+
+namespace b200 {
+
+// Copies each code block's payload bytes from the per-group decision buffer into the transport block.  The reference
+// writes K/8 bytes per block at data[c * rlen/8] in block order, so every block but the last of its TB effectively
+// contributes rlen/8 bytes (its 3 CRC bytes are overwritten by the next block) -- reproduced without the overlap.
+struct ScatterJob {
+  uint64_t dst;    // byte offset in data
+  uint32_t src_cb; // index inside the group's decision buffer
+  uint32_t nbytes;
+};
+
+__global__ void sch_scatter_payload_kernel(const uint8_t* __restrict__ dec, uint32_t bytes_per_cb, uint8_t* __restrict__ data,
+                                           const ScatterJob* __restrict__ jobs, uint32_t n)
+{
+  const uint32_t j = blockIdx.x;
+  if (j >= n) return;
+  const ScatterJob  job = jobs[j];
+  const uint8_t*    src = dec + (size_t)job.src_cb * bytes_per_cb;
+  for (uint32_t i = threadIdx.x; i < job.nbytes; i += blockDim.x) data[job.dst + i] = src[i];
+}
+
+// One thread per transport block: CRC24A over tbs bits (byte table, crc.c:30-46,147-160) against the received parity.
+struct TbCrcJob {
+  uint64_t data_off;
+  uint32_t tbs;
+  uint32_t pad;
+};
+
+__global__ void sch_tb_crc_kernel(const uint8_t* __restrict__ data, const TbCrcJob* __restrict__ jobs, uint32_t n,
+                                  uint8_t* __restrict__ ok)
+{
+  __shared__ uint32_t table[256];
+  for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) {
+    uint32_t r = i << 16;
+    for (int b = 0; b < 8; b++) {
+      r = (r & 0x800000u) ? ((r << 1) ^ CRC24A_POLY) : (r << 1);
+    }
+    table[i] = r & 0xFFFFFFu;
+  }
+  __syncthreads();
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const TbCrcJob  j = jobs[t];
+  const uint8_t*  p = data + j.data_off;
+  uint32_t        crc = 0;
+  for (uint32_t i = 0; i < j.tbs / 8; i++) {
+    crc = ((crc << 8) ^ table[((crc >> 16) ^ p[i]) & 0xFFu]) & 0xFFFFFFu;
+  }
+  const uint32_t rx = ((uint32_t)p[j.tbs / 8] << 16) | ((uint32_t)p[j.tbs / 8 + 1] << 8) | (uint32_t)p[j.tbs / 8 + 2];
+  ok[t]             = (crc == rx && crc != 0) ? 1 : 0; // sch.c:553: parity must match AND be non-zero
+}
+
+struct SchEngine {
+  DeviceContext* ctx = nullptr;
+  TdecEngine     tdec;
+  cudaStream_t   stream = nullptr;
+  DeviceArena    io;   // staged e_bits / soft pool / data when the caller hands host memory
+  DeviceArena    meta; // descriptor arrays, per-group decision buffers
+  uint32_t       max_iterations = 10; // SRSRAN_PDSCH_MAX_TDEC_ITERS, sch.c:35
+
+  int init(int device)
+  {
+    if (tdec.init(device, 0) != B200_SUCCESS) return B200_ERROR;
+    ctx = tdec.ctx;
+    B200_CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    return B200_SUCCESS;
+  }
+  void destroy()
+  {
+    if (ctx) cudaSetDevice(ctx->device);
+    if (stream) cudaStreamDestroy(stream);
+    io.release();
+    meta.release();
+    tdec.destroy();
+  }
+
+  template <class T>
+  int upload(DeviceArena& a, const std::vector<T>& h, T** d, cudaStream_t st)
+  {
+    *d = (T*)a.take(h.size() * sizeof(T) + 16);
+    if (!*d) return B200_ERROR;
+    B200_CUDA_TRY(cudaMemcpyAsync(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+    return B200_SUCCESS;
+  }
+
+  int rm_batch(const int16_t* e_bits, uint64_t e_len, int16_t* soft_pool, uint64_t soft_len, const srsran_b200_rm_cb_t* cbs,
+               uint32_t n, uint32_t flags, cudaStream_t user_stream);
+  int decode_batch(const int16_t* e_bits, uint64_t e_len, int16_t* soft_pool, uint64_t soft_len, uint8_t* data, uint64_t data_len,
+                   srsran_b200_tb_t* tbs, uint32_t n_tb, uint32_t flags);
+};
+
+static int build_rm_descs(DeviceContext* ctx, const srsran_b200_rm_cb_t* cbs, uint32_t n, uint64_t e_len, uint64_t soft_len,
+                          std::vector<RmDescDev>& out)
+{
+  out.resize(n);
+  for (uint32_t i = 0; i < n; i++) {
+    const srsran_b200_rm_cb_t& c = cbs[i];
+    if (c.rv > 3 || c.cb_idx >= (uint32_t)NOF_CB_SIZES) {
+      // rm_turbo.c:442-444
+      fprintf(stderr, "Invalid inputs rv_idx=%u, cb_idx=%u\n", c.rv, c.cb_idx);
+      return B200_ERROR_INVALID_INPUTS;
+    }
+    const uint32_t n_out = 3 * (uint32_t)cb_size(c.cb_idx) + 12;
+    if (c.in_offset + c.E > e_len || c.soft_offset + n_out > soft_len) {
+      B200_LOG_ERROR("de-matching job %u exceeds its buffers", i);
+      return B200_ERROR_INVALID_INPUTS;
+    }
+    RmDescDev& d  = out[i];
+    d.inv         = ctx->rm_table((int)c.cb_idx, (int)c.rv);
+    d.in_offset   = c.in_offset;
+    d.soft_offset = c.soft_offset;
+    d.E           = c.E;
+    d.n_out       = n_out;
+    d.flags       = c.new_data ? 1u : 0u;
+    d.pad         = 0;
+    if (!d.inv) return B200_ERROR;
+  }
+  return B200_SUCCESS;
+}
+
+int SchEngine::rm_batch(const int16_t* e_bits, uint64_t e_len, int16_t* soft_pool, uint64_t soft_len, const srsran_b200_rm_cb_t* cbs,
+                        uint32_t n, uint32_t flags, cudaStream_t user_stream)
+{
+  if (!e_bits || !soft_pool || (!cbs && n)) return B200_ERROR_INVALID_INPUTS;
+  if (n == 0) return B200_SUCCESS;
+  B200_CUDA_TRY(cudaSetDevice(ctx->device));
+  std::vector<RmDescDev> descs;
+  int                    rc = build_rm_descs(ctx, cbs, n, e_len, soft_len, descs);
+  if (rc != B200_SUCCESS) return rc;
+  const bool   dev_ptrs = (flags & SRSRAN_B200_FLAG_DEVICE_PTRS) != 0;
+  cudaStream_t st       = dev_ptrs ? user_stream : stream;
+  if (meta.reserve(descs.size() * sizeof(RmDescDev) + 4096) != B200_SUCCESS) return B200_ERROR;
+  meta.reset();
+  RmDescDev* d_descs = nullptr;
+  if (upload(meta, descs, &d_descs, st) != B200_SUCCESS) return B200_ERROR;
+  if (dev_ptrs) {
+    rc = launch_rm_rx(e_bits, soft_pool, d_descs, n, st);
+    g_kernel_launches++;
+    // the descriptor upload came from a stack vector: make sure it has been consumed before returning
+    B200_CUDA_TRY(cudaStreamSynchronize(st));
+    return rc;
+  }
+  if (io.reserve((e_len + soft_len) * sizeof(int16_t) + 4096) != B200_SUCCESS) return B200_ERROR;
+  io.reset();
+  int16_t* d_e    = (int16_t*)io.take(e_len * sizeof(int16_t));
+  int16_t* d_soft = (int16_t*)io.take(soft_len * sizeof(int16_t));
+  B200_CUDA_TRY(cudaMemcpyAsync(d_e, e_bits, e_len * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+  B200_CUDA_TRY(cudaMemcpyAsync(d_soft, soft_pool, soft_len * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+  rc = launch_rm_rx(d_e, d_soft, d_descs, n, st);
+  g_kernel_launches++;
+  B200_CUDA_TRY(cudaMemcpyAsync(soft_pool, d_soft, soft_len * sizeof(int16_t), cudaMemcpyDeviceToHost, st));
+  B200_CUDA_TRY(cudaStreamSynchronize(st));
+  return rc;
+}
+
+struct CbRec {
+  uint32_t tb, c, K, cb_idx, E, rlen, crc_kind;
+  uint64_t in_off, soft_off;
+  bool     last_of_tb;
+};
+
+int SchEngine::decode_batch(const int16_t* e_bits, uint64_t e_len, int16_t* soft_pool, uint64_t soft_len, uint8_t* data,
+                            uint64_t data_len, srsran_b200_tb_t* tbs, uint32_t n_tb, uint32_t flags)
+{
+  if (!e_bits || !soft_pool || !data || (!tbs && n_tb)) return B200_ERROR_INVALID_INPUTS;
+  if (n_tb == 0) return B200_SUCCESS;
+  B200_CUDA_TRY(cudaSetDevice(ctx->device));
+  const bool   all_dev  = (flags & SRSRAN_B200_FLAG_DEVICE_PTRS) != 0;
+  const bool   soft_dev = all_dev || (flags & SRSRAN_B200_FLAG_SOFT_ON_DEVICE) != 0;
+  cudaStream_t st       = stream;
+
+  // ---- host-side bookkeeping: segmentation and the per-code-block E split of sch.c:392-406 ---------------------------
+  std::vector<CbRec>               cbs;
+  std::vector<srsran_b200_rm_cb_t> rm;
+  std::vector<TbCrcJob>            crc_jobs(n_tb);
+  bool                             any_skip = false;
+  for (uint32_t t = 0; t < n_tb; t++) {
+    srsran_b200_tb_t& tb = tbs[t];
+    tb.result            = B200_ERROR;
+    tb.nof_cb            = 0;
+    tb.avg_iterations    = 0;
+    CbSegm s;
+    if (tb.Qm == 0 || cb_segmentation(tb.tbs, s) != 0) {
+      tb.result = B200_ERROR_INVALID_INPUTS;
+      continue;
+    }
+    if (s.tbs == 0 || s.C == 0) {
+      tb.result = B200_SUCCESS; // sch.c:517-519
+      continue;
+    }
+    if (s.F) {
+      fprintf(stderr, "Error filler bits are not supported. Use standard TBS\n"); // sch.c:521-524
+      tb.result = B200_ERROR_INVALID_INPUTS;
+      continue;
+    }
+    if (s.C > 32) { // SRSRAN_MAX_CODEBLOCKS, sch.c:382-385
+      tb.result = B200_ERROR_INVALID_INPUTS;
+      continue;
+    }
+    if (tb.e_offset + tb.nof_e_bits > e_len || tb.soft_offset + (uint64_t)s.C * SRSRAN_B200_SOFTBUFFER_SIZE > soft_len ||
+        tb.data_offset + tb.tbs / 8 + 3 + MAX_CB_LEN / 8 > data_len) {
+      B200_LOG_ERROR("transport block %u exceeds its buffers", t);
+      tb.result = B200_ERROR_INVALID_INPUTS;
+      continue;
+    }
+    tb.nof_cb             = s.C;
+    crc_jobs[t].data_off  = tb.data_offset;
+    crc_jobs[t].tbs       = tb.tbs;
+    crc_jobs[t].pad       = 1; // valid
+    const uint32_t Gp     = tb.nof_e_bits / tb.Qm;
+    const uint32_t gamma  = Gp % s.C;
+    const uint32_t n_e    = tb.Qm * (Gp / s.C);
+    for (uint32_t c = 0; c < s.C; c++) {
+      if (tb.cb_crc_mask & (1u << c)) { // sch.c:390: already decoded in an earlier transmission
+        any_skip = true;
+        continue;
+      }
+      CbRec r;
+      r.tb     = t;
+      r.c      = c;
+      r.K      = c < s.C1 ? s.K1 : s.K2;           // sch.c:392 (decoder-side assignment)
+      r.cb_idx = c < s.C1 ? s.K1_idx : s.K2_idx;
+      r.rlen   = s.C == 1 ? r.K : r.K - 24;        // sch.c:395
+      uint32_t rp = c * n_e, n_e2 = n_e;
+      if (c > s.C - gamma) {                       // sch.c:403: '>' not '>=' -- the reference's off-by-one, kept
+        n_e2 = n_e + tb.Qm;
+        rp   = (s.C - gamma) * n_e + (c - (s.C - gamma)) * n_e2;
+      }
+      r.E          = n_e2;
+      r.in_off     = tb.e_offset + rp;
+      r.soft_off   = tb.soft_offset + (uint64_t)c * SRSRAN_B200_SOFTBUFFER_SIZE;
+      r.crc_kind   = s.C > 1 ? SRSRAN_B200_CRC24B : SRSRAN_B200_CRC24A; // sch.c:437-444
+      r.last_of_tb = (c == s.C - 1);
+      if (r.in_off + r.E > e_len) {
+        tb.result = B200_ERROR_INVALID_INPUTS;
+        continue;
+      }
+      cbs.push_back(r);
+      srsran_b200_rm_cb_t j;
+      j.cb_idx      = r.cb_idx;
+      j.rv          = tb.rv;
+      j.E           = r.E;
+      j.new_data    = tb.new_data;
+      j.in_offset   = r.in_off;
+      j.soft_offset = r.soft_off;
+      rm.push_back(j);
+    }
+  }
+
+  // ---- stage buffers ---------------------------------------------------------------------------------------------------
+  const int16_t* d_e    = e_bits;
+  int16_t*       d_soft = soft_pool;
+  uint8_t*       d_data = data;
+  if (!all_dev) {
+    size_t need = e_len * sizeof(int16_t) + data_len + 8192 + (soft_dev ? 0 : soft_len * sizeof(int16_t));
+    if (io.reserve(need) != B200_SUCCESS) return B200_ERROR;
+    io.reset();
+    int16_t* de = (int16_t*)io.take(e_len * sizeof(int16_t));
+    d_data      = (uint8_t*)io.take(data_len);
+    B200_CUDA_TRY(cudaMemcpyAsync(de, e_bits, e_len * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+    d_e = de;
+    if (any_skip) B200_CUDA_TRY(cudaMemcpyAsync(d_data, data, data_len, cudaMemcpyHostToDevice, st));
+    if (!soft_dev) {
+      d_soft = (int16_t*)io.take(soft_len * sizeof(int16_t));
+      B200_CUDA_TRY(cudaMemcpyAsync(d_soft, soft_pool, soft_len * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+    }
+  }
+
+  // ---- rate de-matching of every pending code block -------------------------------------------------------------------
+  std::vector<RmDescDev> descs;
+  int                    rc = build_rm_descs(ctx, rm.data(), (uint32_t)rm.size(), e_len, soft_len, descs);
+  if (rc != B200_SUCCESS) return rc;
+  size_t meta_need = descs.size() * sizeof(RmDescDev) + cbs.size() * (sizeof(uint64_t) + sizeof(ScatterJob) + 8) +
+                     n_tb * (sizeof(TbCrcJob) + 8) + (size_t(2) << 20);
+  for (const CbRec& r : cbs) meta_need += r.K / 8 + 64;
+  if (meta.reserve(meta_need) != B200_SUCCESS) return B200_ERROR;
+  meta.reset();
+  if (!descs.empty()) {
+    RmDescDev* d_descs = nullptr;
+    if (upload(meta, descs, &d_descs, st) != B200_SUCCESS) return B200_ERROR;
+    if (launch_rm_rx(d_e, d_soft, d_descs, (uint32_t)descs.size(), st) != B200_SUCCESS) return B200_ERROR;
+    g_kernel_launches++;
+  }
+
+  // ---- group by (K, CRC kind) and decode each group as one batch -----------------------------------------------------
+  std::map<std::pair<uint32_t, uint32_t>, std::vector<uint32_t>> groups;
+  for (uint32_t i = 0; i < cbs.size(); i++) groups[{cbs[i].K, cbs[i].crc_kind}].push_back(i);
+  std::vector<uint8_t> h_ok(cbs.size(), 0), h_np(cbs.size(), 0);
+  struct Pending {
+    uint8_t *d_ok, *d_np;
+    const std::vector<uint32_t>* idx;
+  };
+  std::vector<Pending> pend;
+  for (auto& g : groups) {
+    const uint32_t               K   = g.first.first;
+    const std::vector<uint32_t>& idx = g.second;
+    const uint32_t               n   = (uint32_t)idx.size();
+    std::vector<uint64_t>        offs(n);
+    std::vector<ScatterJob>      jobs(n);
+    bool                         al8 = (reinterpret_cast<uintptr_t>(d_soft) & 7u) == 0;
+    for (uint32_t j = 0; j < n; j++) {
+      const CbRec& r = cbs[idx[j]];
+      offs[j]        = r.soft_off;
+      al8            = al8 && (r.soft_off % 4 == 0);
+      jobs[j].dst    = tbs[r.tb].data_offset + (uint64_t)r.c * (r.rlen / 8);
+      jobs[j].src_cb = j;
+      jobs[j].nbytes = r.last_of_tb ? r.K / 8 : r.rlen / 8;
+    }
+    uint64_t*   d_offs = nullptr;
+    ScatterJob* d_jobs = nullptr;
+    if (upload(meta, offs, &d_offs, st) != B200_SUCCESS || upload(meta, jobs, &d_jobs, st) != B200_SUCCESS) return B200_ERROR;
+    uint8_t* d_dec = (uint8_t*)meta.take((size_t)n * (K / 8));
+    uint8_t* d_ok  = (uint8_t*)meta.take(n);
+    uint8_t* d_np  = (uint8_t*)meta.take(n);
+    if (!d_dec || !d_ok || !d_np) return B200_ERROR;
+    if (tdec.arena.reserve(TdecEngine::workspace_bytes((int)K, n)) != B200_SUCCESS) return B200_ERROR;
+    rc = tdec.run_device(tdec.arena, d_soft, n, (int)K, cb_index_exact(K), max_iterations, (int)g.first.second, 1, d_dec, d_ok,
+                         d_np, st, d_offs, al8);
+    if (rc != B200_SUCCESS) return rc;
+    sch_scatter_payload_kernel<<<n, 128, 0, st>>>(d_dec, K / 8, d_data, d_jobs, n);
+    g_kernel_launches++;
+    pend.push_back(Pending{d_ok, d_np, &idx});
+    // run_device reuses one workspace: the next group may only start once this one has drained (same stream: it has)
+  }
+
+  // ---- transport block CRC + results -------------------------------------------------------------------------------------
+  TbCrcJob* d_cj = nullptr;
+  if (upload(meta, crc_jobs, &d_cj, st) != B200_SUCCESS) return B200_ERROR;
+  uint8_t* d_tbok = (uint8_t*)meta.take(n_tb);
+  if (!d_tbok) return B200_ERROR;
+  sch_tb_crc_kernel<<<(n_tb + 63) / 64, 64, 0, st>>>(d_data, d_cj, n_tb, d_tbok);
+  g_kernel_launches++;
+  std::vector<uint8_t> h_tbok(n_tb, 0);
+  B200_CUDA_TRY(cudaMemcpyAsync(h_tbok.data(), d_tbok, n_tb, cudaMemcpyDeviceToHost, st));
+  std::vector<std::vector<uint8_t>> tmp_ok(pend.size()), tmp_np(pend.size());
+  for (size_t p = 0; p < pend.size(); p++) {
+    tmp_ok[p].resize(pend[p].idx->size());
+    tmp_np[p].resize(pend[p].idx->size());
+    B200_CUDA_TRY(cudaMemcpyAsync(tmp_ok[p].data(), pend[p].d_ok, tmp_ok[p].size(), cudaMemcpyDeviceToHost, st));
+    B200_CUDA_TRY(cudaMemcpyAsync(tmp_np[p].data(), pend[p].d_np, tmp_np[p].size(), cudaMemcpyDeviceToHost, st));
+  }
+  if (!all_dev) {
+    B200_CUDA_TRY(cudaMemcpyAsync(data, d_data, data_len, cudaMemcpyDeviceToHost, st));
+    if (!soft_dev) B200_CUDA_TRY(cudaMemcpyAsync(soft_pool, d_soft, soft_len * sizeof(int16_t), cudaMemcpyDeviceToHost, st));
+  }
+  B200_CUDA_TRY(cudaStreamSynchronize(st));
+  B200_CUDA_TRY(cudaGetLastError());
+  for (size_t p = 0; p < pend.size(); p++) {
+    for (size_t j = 0; j < pend[p].idx->size(); j++) {
+      h_ok[(*pend[p].idx)[j]] = tmp_ok[p][j];
+      h_np[(*pend[p].idx)[j]] = tmp_np[p][j];
+    }
+  }
+  std::vector<uint32_t> iters(n_tb, 0);
+  for (size_t i = 0; i < cbs.size(); i++) {
+    srsran_b200_tb_t& tb = tbs[cbs[i].tb];
+    iters[cbs[i].tb] += h_np[i];
+    if (h_ok[i]) tb.cb_crc_mask |= (1u << cbs[i].c);
+  }
+  for (uint32_t t = 0; t < n_tb; t++) {
+    srsran_b200_tb_t& tb = tbs[t];
+    if (tb.nof_cb == 0 || crc_jobs[t].pad == 0) continue;
+    if (tb.result == B200_ERROR_INVALID_INPUTS) continue;
+    tb.avg_iterations  = (float)iters[t] / (float)tb.nof_cb; // sch.c:490
+    const uint32_t all = tb.nof_cb >= 32 ? 0xFFFFFFFFu : ((1u << tb.nof_cb) - 1u);
+    tb.result          = ((tb.cb_crc_mask & all) == all && h_tbok[t]) ? B200_SUCCESS : B200_ERROR;
+  }
+  return B200_SUCCESS;
+}
+
+} // namespace b200
+
+using namespace b200;
+
+struct srsran_b200_sch {
+  SchEngine eng;
+};
+
+extern "C" {
+
+int srsran_b200_sch_init(srsran_b200_sch_t** q, int device)
+{
+  if (!q) return B200_ERROR_INVALID_INPUTS;
+  *q                   = nullptr;
+  srsran_b200_sch_t* h = new (std::nothrow) srsran_b200_sch_t();
+  if (!h) return B200_ERROR;
+  if (h->eng.init(device) != B200_SUCCESS) {
+    h->eng.destroy();
+    delete h;
+    return B200_ERROR;
+  }
+  *q = h;
+  return B200_SUCCESS;
+}
+
+void srsran_b200_sch_free(srsran_b200_sch_t* q)
+{
+  if (q) {
+    q->eng.destroy();
+    delete q;
+  }
+}
+
+void srsran_b200_sch_set_max_noi(srsran_b200_sch_t* q, uint32_t max_iterations)
+{
+  if (q) {
+    q->eng.max_iterations = max_iterations ? max_iterations : 10; // sch.c:222-229
+  }
+}
+
+int srsran_b200_rm_turbo_rx_batch(srsran_b200_sch_t*         q,
+                                  const int16_t*             e_bits,
+                                  uint64_t                   e_len,
+                                  int16_t*                   soft_pool,
+                                  uint64_t                   soft_len,
+                                  const srsran_b200_rm_cb_t* cbs,
+                                  uint32_t                   n,
+                                  uint32_t                   flags,
+                                  void*                      stream)
+{
+  if (!q) return B200_ERROR_INVALID_INPUTS;
+  return q->eng.rm_batch(e_bits, e_len, soft_pool, soft_len, cbs, n, flags, (cudaStream_t)stream);
+}
+
+int srsran_b200_sch_decode_batch(srsran_b200_sch_t* q,
+                                 const int16_t*     e_bits,
+                                 uint64_t           e_len,
+                                 int16_t*           soft_pool,
+                                 uint64_t           soft_len,
+                                 uint8_t*           data,
+                                 uint64_t           data_len,
+                                 srsran_b200_tb_t*  tbs,
+                                 uint32_t           n_tb,
+                                 uint32_t           flags)
+{
+  if (!q) return B200_ERROR_INVALID_INPUTS;
+  return q->eng.decode_batch(e_bits, e_len, soft_pool, soft_len, data, data_len, tbs, n_tb, flags);
+}
+
+} // extern "C"

@@ -49,7 +49,9 @@ struct TdecEngine {
                  uint8_t*       out_dev,
                  uint8_t*       crc_ok_dev,
                  uint8_t*       npass_dev,
-                 cudaStream_t   stream);
+                 cudaStream_t   stream,
+                 const uint64_t* llr_offsets_dev = nullptr, // optional: block cb's vector starts at llr_dev + offsets[cb]
+                 bool            offsets_aligned8 = false);
 
   int run(const int16_t* llr,
           uint32_t       ncb,

@@ -136,7 +136,9 @@ int TdecEngine::run_device(DeviceArena&   ws,
                            uint8_t*       out_dev,
                            uint8_t*       crc_ok_dev,
                            uint8_t*       npass_dev,
-                           cudaStream_t   stream)
+                           cudaStream_t   stream,
+                           const uint64_t* llr_offsets_dev,
+                           bool            offsets_aligned8)
 {
   TdecView v;
   ws.reset();
@@ -155,7 +157,7 @@ int TdecEngine::run_device(DeviceArena&   ws,
   v.max_pass   = (int)max_passes;
 
   prof_begin(0, stream);
-  launch_load_natural(v, llr_dev, ncb, stream);
+  launch_load_natural(v, llr_dev, llr_offsets_dev, llr_offsets_dev ? offsets_aligned8 : ((reinterpret_cast<uintptr_t>(llr_dev) & 7u) == 0), ncb, stream);
   prof_end(stream);
   g_kernel_launches++;
   for (uint32_t p = 0; p < max_passes; p++) {

@@ -304,7 +304,11 @@ void launch_siso_pass(const TdecView& v, int pass_idx, cudaStream_t stream)
 constexpr int LOAD_ROWS = 32;
 constexpr int LOAD_PITCH = 3 * LOAD_ROWS + 4; // int16 per staged block, +4 keeps 8-byte alignment and skews banks
 
-__global__ void __launch_bounds__(256) tdec_load_natural_kernel(TdecView v, const int16_t* __restrict__ llr, uint32_t ncb)
+// `offsets` (optional): int16 offset of each block's vector inside llr (soft buffers scattered in a HARQ pool); without it
+// the vectors are contiguous, block cb at cb*(3K+12).  ALIGNED8: every vector starts on an 8-byte boundary.
+template <bool ALIGNED8>
+__global__ void __launch_bounds__(256)
+    tdec_load_natural_kernel(TdecView v, const int16_t* __restrict__ llr, const uint64_t* __restrict__ offsets, uint32_t ncb)
 {
   __shared__ __align__(16) int16_t sm[TDEC_TILE_CB * LOAD_PITCH];
   const int    tile  = blockIdx.y;
@@ -322,7 +326,13 @@ __global__ void __launch_bounds__(256) tdec_load_natural_kernel(TdecView v, cons
       const uint32_t cb = (uint32_t)tile * TDEC_TILE_CB + c;
       uint2          val = make_uint2(0u, 0u);
       if (cb < ncb) {
-        val = __ldcs(reinterpret_cast<const uint2*>(llr + cb * nllr + 3 * (size_t)k0) + q);
+        const int16_t* src = llr + (offsets ? offsets[cb] : cb * nllr) + 3 * (size_t)k0 + 4 * (size_t)q;
+        if (ALIGNED8) {
+          val = __ldcs(reinterpret_cast<const uint2*>(src));
+        } else {
+          val.x = (uint32_t)(uint16_t)src[0] | ((uint32_t)(uint16_t)src[1] << 16);
+          val.y = (uint32_t)(uint16_t)src[2] | ((uint32_t)(uint16_t)src[3] << 16);
+        }
       }
       *reinterpret_cast<uint2*>(&sm[c * LOAD_PITCH + 4 * q]) = val;
     }
@@ -354,8 +364,8 @@ __global__ void __launch_bounds__(256) tdec_load_natural_kernel(TdecView v, cons
         for (int t = 0; t < 4; t++) {
           int16_t a = 0, b = 0;
           const uint32_t cb0 = (uint32_t)tile * TDEC_TILE_CB + 2 * lane;
-          if (cb0 < ncb) a = natural_pick(llr + cb0 * nllr, K, s, K + t);
-          if (cb0 + 1 < ncb) b = natural_pick(llr + (cb0 + 1) * nllr, K, s, K + t);
+          if (cb0 < ncb) a = natural_pick(llr + (offsets ? offsets[cb0] : cb0 * nllr), K, s, K + t);
+          if (cb0 + 1 < ncb) b = natural_pick(llr + (offsets ? offsets[cb0 + 1] : (cb0 + 1) * nllr), K, s, K + t);
           w[s][t] = pack2(a, b);
         }
       }
@@ -372,11 +382,20 @@ __global__ void __launch_bounds__(256) tdec_load_natural_kernel(TdecView v, cons
   }
 }
 
-void launch_load_natural(const TdecView& v, const int16_t* llr_dev, uint32_t ncb, cudaStream_t stream)
+void launch_load_natural(const TdecView& v,
+                         const int16_t*  llr_dev,
+                         const uint64_t* offsets_dev,
+                         bool            aligned8,
+                         uint32_t        ncb,
+                         cudaStream_t    stream)
 {
   const int chunks = (v.K + LOAD_ROWS - 1) / LOAD_ROWS + 1; // +1: the tail chunk
   dim3      grid((unsigned)chunks, (unsigned)v.ntiles), block(256);
-  tdec_load_natural_kernel<<<grid, block, 0, stream>>>(v, llr_dev, ncb);
+  if (aligned8) {
+    tdec_load_natural_kernel<true><<<grid, block, 0, stream>>>(v, llr_dev, offsets_dev, ncb);
+  } else {
+    tdec_load_natural_kernel<false><<<grid, block, 0, stream>>>(v, llr_dev, offsets_dev, ncb);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------

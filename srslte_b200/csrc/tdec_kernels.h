@@ -7,7 +7,12 @@
 
 namespace b200 {
 
-void launch_load_natural(const TdecView& v, const int16_t* llr_dev, uint32_t ncb, cudaStream_t stream);
+void launch_load_natural(const TdecView& v,
+                         const int16_t*  llr_dev,
+                         const uint64_t* offsets_dev, // optional per-block int16 offsets into llr_dev
+                         bool            aligned8,    // every block vector starts on an 8-byte boundary
+                         uint32_t        ncb,
+                         cudaStream_t    stream);
 void launch_siso_pass(const TdecView& v, int pass_idx, cudaStream_t stream);
 void launch_decide(const TdecView& v,
                    const uint16_t* qpp_rev_dev,

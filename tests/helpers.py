@@ -29,3 +29,35 @@ def coded_llrs(api, K: int, ncb: int, sigma: float, scale: float = 16.0, clip: i
 
 def npass_of(ok, npass_crc, npass_run):
     return np.where(ok == 1, npass_crc, npass_run)
+
+
+def make_tb(api, tbs: int, Qm: int, G: int, rv: int, sigma: float, scale: float = 16.0, clip: int = 31, seed: int = 0):
+    """One transport block through the transmit chain of sch.c:240-350 restated with the oracle's pieces: TB CRC24A,
+    segmentation (standard TBS only: F == 0, C2 == 0), CB CRC24B, turbo encoding, rate matching with the encoder-side
+    E split, BPSK-like +-1 mapping + AWGN, int16 quantisation.
+
+    Returns (e_bits int16 (G,), expected data bytes (tbs/8+3,), segm dict)."""
+    rng = np.random.default_rng(seed)
+    s = api.cbsegm(tbs)
+    assert s["F"] == 0 and s["C2"] == 0, "use a standard TBS"
+    C, K = s["C"], s["K1"]
+    payload = rng.integers(0, 2, tbs).astype(np.uint8)
+    par = api.crc24("A", np.packbits(payload), tbs)
+    tb = np.concatenate([payload, np.array([(par >> (23 - i)) & 1 for i in range(24)], np.uint8)])
+    Gp = G // Qm
+    gamma = Gp % C
+    rlen = K if C == 1 else K - 24
+    tx = []
+    for c in range(C):
+        bits = tb[c * rlen:(c + 1) * rlen]
+        if C > 1:
+            r = api.crc24("B", np.packbits(bits), rlen)
+            bits = np.concatenate([bits, np.array([(r >> (23 - i)) & 1 for i in range(24)], np.uint8)])
+        cw = api.tcod_encode(bits)
+        n_e = Qm * (Gp // C) if c <= C - gamma - 1 else Qm * -(-Gp // C)
+        tx.append(api.rm_tx(cw, K, n_e, rv))
+    tx = np.concatenate(tx)
+    tx = np.concatenate([tx, np.zeros(G - tx.size, np.uint8)])[:G]
+    y = (2.0 * tx - 1.0) + rng.normal(size=G) * sigma
+    e = np.clip(np.rint(scale * y), -clip, clip).astype(np.int16)
+    return e, np.packbits(tb), s
