@@ -168,6 +168,59 @@ SRSRAN_B200_API int srsran_b200_sch_decode_batch(srsran_b200_sch_t* q,
                                                  uint32_t           flags);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Batched OFDM demodulation: srsran_ofdm_rx_sf (lib/src/phy/dft/ofdm.c:453-466) for many subframes per call.
+ * The configuration mirrors srsran_ofdm_cfg_t (lib/include/srsran/phy/dft/ofdm.h:48-63) minus the buffer bindings.
+ */
+typedef struct srsran_b200_ofdm srsran_b200_ofdm_t;
+
+typedef struct {
+  uint32_t nof_prb;          /* number of resource blocks: 12*nof_prb elements are kept per symbol */
+  int      cp_ext;           /* 0: normal cyclic prefix (7 symbols/slot), 1: extended (6) */
+  uint32_t symbol_sz;        /* DFT size; 0 derives it from nof_prb like srsran_symbol_sz (phy_common.c:361-385) */
+  float    freq_shift_f;     /* frequency shift in subcarriers applied before the DFT (UL: -0.5), 0 = none */
+  float    rx_window_offset; /* fraction (0..1) of the CP the DFT window is advanced by, 0 = none */
+  int      normalize;        /* non-zero: scale the output by 1/sqrt(symbol_sz) */
+  int      keep_dc;          /* non-zero: keep the DC bin (it is dropped only when there is no frequency shift) */
+} srsran_b200_ofdm_cfg_t;
+
+/* srsran_use_standard_symbol_size / srsran_symbol_sz (phy_common.c:322,361): process-wide choice of the size table */
+SRSRAN_B200_API void srsran_b200_use_standard_symbol_size(int enabled);
+SRSRAN_B200_API int  srsran_b200_symbol_sz(uint32_t nof_prb);
+
+SRSRAN_B200_API int  srsran_b200_ofdm_rx_init(srsran_b200_ofdm_t** q, int device, const srsran_b200_ofdm_cfg_t* cfg);
+SRSRAN_B200_API int  srsran_b200_ofdm_rx_reconfigure(srsran_b200_ofdm_t* q, const srsran_b200_ofdm_cfg_t* cfg);
+SRSRAN_B200_API void srsran_b200_ofdm_rx_free(srsran_b200_ofdm_t* q);
+SRSRAN_B200_API int  srsran_b200_ofdm_rx_geometry(const srsran_b200_ofdm_t* q,
+                                                  uint32_t*                 symbol_sz,
+                                                  uint32_t*                 sf_sz,
+                                                  uint32_t*                 nof_symbols,
+                                                  uint32_t*                 nof_re);
+/*
+ * in : nsf subframes of sf_sz = 15*symbol_sz complex float samples (cf_t, interleaved re/im); NOT modified (the
+ *      reference multiplies the frequency shift into its input buffer in place, ofdm.c:455-457)
+ * out: nsf * nof_symbols * nof_re complex floats, symbol major, FFT-shifted, guards and (when applicable) DC removed
+ * Host pointers: synchronous.  SRSRAN_B200_FLAG_DEVICE_PTRS: enqueued on `stream`, returns immediately.
+ */
+SRSRAN_B200_API int srsran_b200_ofdm_rx_sf_batch(srsran_b200_ofdm_t* q, const void* in, void* out, uint32_t nsf, uint32_t flags,
+                                                 void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * int16 soft demapping: srsran_demod_soft_demodulate_s (lib/src/phy/modem/demod_soft.c:871-894) for QPSK (1), 16QAM (2)
+ * and 64QAM (3) -- srsran_mod_t numbering -- bit-exact with the reference's x86 (SSE/AVX2) build, whose vector body
+ * rounds to nearest and whose scalar tail truncates.  symbols_per_call is the nsymbols of each reference call this
+ * batch stands for (the body/tail split is per call); 0 means one call of nsymbols.
+ * symbols: nsymbols complex floats;  llr: nsymbols * {2,4,6} int16.
+ */
+SRSRAN_B200_API int srsran_b200_demod_soft_demodulate_s(int         device,
+                                                        int         modulation,
+                                                        const void* symbols,
+                                                        int16_t*    llr,
+                                                        uint32_t    nsymbols,
+                                                        uint32_t    symbols_per_call,
+                                                        uint32_t    flags,
+                                                        void*       stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Synthetic workload (bench / tests only, never on the decode path): fills llr_dev[ncb][3K+12] (device memory) with
  * the quantised channel output of randomly drawn, CRC24B-terminated, turbo-encoded blocks:
  * llr = clip(rint(scale * ((2c-1) + sigma*n)), +-clip), the recipe of turbodecoder_test.c:211-255 plus a clip.

@@ -777,6 +777,18 @@ int orc_demod_s(int mod, const cf_t* sym, int16_t* llr, int n)
     }
     return 0;
   }
+  if (mod == 1) {
+    /* demod_qpsk_lte_s (demod_soft.c:115-118) -> srsran_vec_convert_fi (vector_simd.c:436-472, AVX2 build): blocks of 16
+     * floats are scaled, truncated toward zero (cvttps, simd.h:1893) and saturated by the pack; the remaining floats take
+     * the plain C cast */
+    const float scale = (float)(-100 * M_SQRT2);
+    int         nf = 2 * n, body = 16 * (nf / 16);
+    for (int i = 0; i < nf; i++) {
+      float v = f[i] * scale;
+      llr[i]  = i < body ? sat16((int)v) : w16((int)v);
+    }
+    return 0;
+  }
   if (mod == 2) {
     const int16_t t  = (int16_t)(2 * 400 / sqrtf(10));
     int           n4 = 4 * (n / 4);

@@ -50,6 +50,16 @@ def lib() -> C.CDLL:
     L.srsran_b200_sch_set_max_noi.restype = None
     L.srsran_b200_rm_turbo_rx_batch.argtypes = [vp, vp, u64, vp, u64, vp, u32, u32, vp]
     L.srsran_b200_sch_decode_batch.argtypes = [vp, vp, u64, vp, u64, vp, u64, vp, u32, u32]
+    L.srsran_b200_use_standard_symbol_size.argtypes = [C.c_int]
+    L.srsran_b200_use_standard_symbol_size.restype = None
+    L.srsran_b200_symbol_sz.argtypes = [u32]
+    L.srsran_b200_ofdm_rx_init.argtypes = [C.POINTER(vp), C.c_int, vp]
+    L.srsran_b200_ofdm_rx_reconfigure.argtypes = [vp, vp]
+    L.srsran_b200_ofdm_rx_free.argtypes = [vp]
+    L.srsran_b200_ofdm_rx_free.restype = None
+    L.srsran_b200_ofdm_rx_geometry.argtypes = [vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), C.POINTER(u32)]
+    L.srsran_b200_ofdm_rx_sf_batch.argtypes = [vp, vp, vp, u32, u32, vp]
+    L.srsran_b200_demod_soft_demodulate_s.argtypes = [C.c_int, C.c_int, vp, vp, u32, u32, u32, vp]
     L.srsran_b200_synth_llr.argtypes = [C.c_int, vp, vp, u32, u32, C.c_float, C.c_float, C.c_int, C.c_uint64, C.c_int, vp]
     return L
 
@@ -69,4 +79,12 @@ EXPORTED_SYMBOLS = [
     "srsran_b200_sch_set_max_noi",
     "srsran_b200_rm_turbo_rx_batch",
     "srsran_b200_sch_decode_batch",
+    "srsran_b200_use_standard_symbol_size",
+    "srsran_b200_symbol_sz",
+    "srsran_b200_ofdm_rx_init",
+    "srsran_b200_ofdm_rx_reconfigure",
+    "srsran_b200_ofdm_rx_free",
+    "srsran_b200_ofdm_rx_geometry",
+    "srsran_b200_ofdm_rx_sf_batch",
+    "srsran_b200_demod_soft_demodulate_s",
 ]

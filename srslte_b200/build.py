@@ -16,6 +16,9 @@ SOURCES = [
     "tdec_host.cu",
     "rm_kernels.cu",
     "sch_host.cu",
+    "ofdm_kernels.cu",
+    "ofdm_host.cu",
+    "demod_kernels.cu",
     "synth.cu",
 ]
 

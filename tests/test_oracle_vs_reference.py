@@ -100,8 +100,8 @@ def test_ofdm_rx(port, ref, prb, N, cp, fs, wo, nm, kd):
 
 def test_demod(port, ref):
     rng = np.random.default_rng(11)
-    for mod in (2, 3):
-        for n in (1, 4, 7, 1000, 14401):
+    for mod in (1, 2, 3):
+        for n in (1, 4, 7, 9, 16, 1000, 14401):
             s = ((rng.normal(size=n) + 1j * rng.normal(size=n)) * 0.8).astype(np.complex64)
             s[:1] = 47.0 - 46.9j
             assert (port.demod_s(mod, s) == ref.demod_s(mod, s)).all()

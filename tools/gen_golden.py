@@ -94,7 +94,7 @@ def main():
         of[f"cfg{i}"] = np.array([prb, N, cp, fs, wo, nm, kd], np.float64)
         of[f"in{i}"] = x
         of[f"out{i}"] = y
-    for mod, name in ((2, "qam16"), (3, "qam64")):
+    for mod, name in ((1, "qpsk"), (2, "qam16"), (3, "qam64")):
         s = ((rng.normal(size=1003) + 1j * rng.normal(size=1003)) * 0.7).astype(np.complex64)
         s[:4] = [50 + 3j, -60 - 1j, 46.81 - 46.82j, 0.5 * 1j]
         of[f"{name}_sym"] = s
