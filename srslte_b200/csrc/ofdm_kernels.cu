@@ -162,6 +162,7 @@ __device__ __forceinline__ void fft_pass(const OfdmPlanDev& p,
       if (first) {
         float2 v = gin[idx];
         if (p.shift) v = cmul(v, p.shift[idx]);
+        if (p.inverse) v.y = -v.y;
         u[q] = v;
       } else {
         u[q] = sin_[pad_idx(idx)];
@@ -179,10 +180,11 @@ __device__ __forceinline__ void fft_pass(const OfdmPlanDev& p,
     for (int q = 0; q < RADIX; q++) {
       const int o = j0 + q * Ns;
       if (last) {
-        const int re = bin_to_re(o, N, p.R, p.dc);
+        const int re = p.generic ? o : bin_to_re(o, N, p.R, p.dc);
         if (re >= 0) {
           float2 v = u[q];
           if (p.ramp) v = cmul(v, p.ramp[re]);
+          if (p.inverse) v.y = -v.y;
           gout[re] = v;
         }
       } else {
@@ -205,16 +207,17 @@ __global__ void __launch_bounds__(OFDM_THREADS) ofdm_rx_kernel(OfdmPlanDev p, co
   const int      padN    = p.N + (p.N >> 4) + 1;
   float2*        bufA    = smem + (size_t)g * 2 * padN;
   float2*        bufB    = bufA + padN;
-  const uint32_t nsymtot = nsf * (uint32_t)p.nsym;
-  const int      half    = p.nsym / 2;
+  const uint32_t nsymtot = p.generic ? nsf : nsf * (uint32_t)p.nsym;
+  const int      half    = p.generic ? 1 : p.nsym / 2;
 
   for (uint32_t base = blockIdx.x * spb; base < nsymtot; base += gridDim.x * spb) {
     const uint32_t sidx   = base + g;
     const bool     active = !spare && sidx < nsymtot;
-    const uint32_t sf = active ? sidx / p.nsym : 0, l = active ? sidx % p.nsym : 0;
+    const uint32_t sf = (active && !p.generic) ? sidx / p.nsym : 0, l = (active && !p.generic) ? sidx % p.nsym : 0;
     const int      slot = (int)l / half, ls = (int)l % half;
-    const float2*  gin  = in + (size_t)sf * p.sf_sz + (size_t)slot * p.slot_sz + p.cp1 + (size_t)ls * (p.N + p.cp2) - p.noff;
-    float2*        gout = out + (size_t)sidx * p.R;
+    const float2*  gin  = p.generic ? in + (size_t)sidx * p.idist
+                                    : in + (size_t)sf * p.sf_sz + (size_t)slot * p.slot_sz + p.cp1 + (size_t)ls * (p.N + p.cp2) - p.noff;
+    float2*        gout = p.generic ? out + (size_t)sidx * p.odist : out + (size_t)sidx * p.R;
     int            Ns   = 1;
     float2 *       src = bufA, *dst = bufB;
     for (int ps = 0; ps < p.npass; ps++) {
@@ -252,7 +255,7 @@ int launch_ofdm_rx(const OfdmPlanDev& p, const float2* in_dev, float2* out_dev, 
   if (nsf == 0) return B200_SUCCESS;
   const int      spb     = OFDM_THREADS / p.tps;
   const size_t   smem    = (size_t)spb * 2 * (p.N + (p.N >> 4) + 1) * sizeof(float2);
-  const uint32_t nsymtot = nsf * (uint32_t)p.nsym;
+  const uint32_t nsymtot = p.generic ? nsf : nsf * (uint32_t)p.nsym;
   static size_t  attr_set = 0;
   if (smem > attr_set) {
     B200_CUDA_TRY(cudaFuncSetAttribute(ofdm_rx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

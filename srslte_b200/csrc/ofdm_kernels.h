@@ -22,6 +22,11 @@ struct OfdmPlanDev {
   int tps;     // threads cooperating on one symbol
   int npass;
   int radix[OFDM_MAX_PASSES];
+  // generic batched DFT mode (srsran_dft_* entries): transform h reads in + h*idist, writes all N bins to out + h*odist
+  int generic;
+  int idist;
+  int odist;
+  int inverse; // 1: e^{+2 pi i kn/N} (conjugate in, conjugate out)
   const float2* W;     // exp(-2 pi i m / N), m < N
   const float2* shift; // N entries: half-subcarrier rotation inside the FFT window, or nullptr
   const float2* ramp;  // R entries: window-offset phase fix x normalisation per output element, or nullptr
