@@ -154,9 +154,9 @@ def run_ours(args):
     from srslte_b200 import TurboDecoderBatch, _lib
     from srslte_b200.tdec import synth_llr
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
+    from srslte_b200 import shard
+
+    rank, world, local = shard.rank_info()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; srslte_b200 has no CPU fallback")
     torch.cuda.set_device(local)
@@ -173,24 +173,16 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def max_over_ranks(x: float) -> float:
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return shard.reduce_scalars([x], "max", dist, dev)[0]
 
     def sum_over_ranks(x: float) -> float:
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+        return shard.reduce_scalars([x], "sum", dist, dev)[0]
 
     ncb = NCB_PER_GPU
     sigma = sigma_of(EBN0_DB)
     lib = _lib.lib()
     dec = TurboDecoderBatch(local, ncb)
-    llr, truth = synth_llr(local, ncb, K, sigma=sigma, scale=SCALE, clip=CLIP, seed=0xB200 + rank)
+    llr, truth = synth_llr(local, ncb, K, sigma=sigma, scale=SCALE, clip=CLIP, seed=shard.shard_seed(0xB200, rank))
     out = torch.empty((ncb, K // 8), dtype=torch.uint8, device=dev)
     ok = torch.empty(ncb, dtype=torch.uint8, device=dev)
     npass = torch.empty(ncb, dtype=torch.uint8, device=dev)
@@ -255,7 +247,7 @@ def run_ours(args):
     step_e2e()
     barrier()
     t0 = time.perf_counter()
-    n_e2e = max(1, min(args.steps, 5))
+    n_e2e = max(1, min(args.steps, 8))
     for _ in range(n_e2e):
         step_e2e()
     barrier()
@@ -297,7 +289,8 @@ def run_ours(args):
             cores = os.cpu_count() or 1
             have_ref = loader.have_ref()
             api = loader.api("ref" if have_ref else "port")
-            n = cores * (768 if have_ref else 12)
+            # bounded sample: ~1.5 s of wall time on all cores (~20-25 core-seconds) for the AVX2 decoder at ~130 us/block
+            n = min(ncb, cores * (8192 if have_ref else 24))
             sub = llr[:n].cpu().numpy()
             api.decode_batch(sub[:cores], K, MAX_PASSES, "B", 0, False, nthreads=cores,
                              impl=loader.TDEC_AUTO if have_ref else loader.TDEC_GENERIC)
@@ -334,7 +327,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
