@@ -1,4 +1,4 @@
-// Batched max-log-MAP turbo decoder: memory layout and the per-lane SISO pass.
+// Batched max-log-MAP turbo decoder: memory layout and the per-lane SISO arithmetic.
 //
 // What it computes (bit-exactly): the reference's GENERIC int16 decoder
 //   lib/src/phy/fec/turbo/turbodecoder_gen.c:58-236   (map_gen_beta / map_gen_alpha, wrap-around int16)
@@ -8,33 +8,41 @@
 //
 // How it is mapped to the GPU (nothing like the reference's sub-block SIMD windows):
 //   * One CUDA thread decodes TWO code blocks, one in each int16 half of its 32-bit registers (packed16.h), with the
-//     exact sequential recursion of the generic decoder.  Parallelism comes from the batch: a warp owns a "tile" of
-//     64 code blocks of equal K.
-//   * Everything is stored k-major / code-block-minor so that one trellis step of a warp is one 128-byte row:
-//       S, P0, P1 : uint4 [tile][(K+4)/4][32 lanes]   4 consecutive trellis steps of a lane's block pair per 16 B
-//                   (rows K..K+2 hold the three tail steps; S2T holds encoder 2's systematic tail)
+//     exact sequential recursions of the generic decoder.  A "tile" is 64 code blocks of equal K = 32 lanes.
+//   * TWO warps work on a tile, from both ends of the trellis (the recursions are exact, so this is the only
+//     intra-block parallelism there is).  With ws = the split window:
+//       phase 1   warp F: forward (alpha) recursion over windows [0, ws), leaving alpha checkpoints  CK[w] = alpha_{8w}
+//                 warp B: tail + backward (beta) recursion over windows [ws, nw), leaving            CK[w] = beta_{8w+8}
+//       phase 2   warp F: windows ws..nw-1 upwards: rebuild the window's 8 beta vectors in registers from CK[w], then
+//                         8 forward steps with LLR output (fwd_window)
+//                 warp B: windows ws-1..0 downwards: rebuild the window's 8 alpha vectors from CK[w], then 8 backward
+//                         steps with LLR output (bwd_window)
+//     No beta array (98 KB/block in the reference, turbodecoder_gen.c:206) is ever materialised.  beta checkpoints hold
+//     the value BEFORE the every-4th-step normalisation, like the reference's beta[] does (turbodecoder_gen.c:98-110);
+//     alpha checkpoints sit on multiples of 8 and are therefore freshly normalised (turbodecoder_gen.c:186-191).
+//   * Everything is stored k-major / code-block-minor so that one trellis step of a warp is one contiguous row:
+//       int16 inputs  S, P0, P1 : uint4 [tile][(K+4)/4][32 lanes]  4 consecutive steps of a lane's block pair per 16 B
+//       int8 inputs   S8,P08,P18: uint4 [tile][K/8+1][32 lanes]    8 consecutive steps x 2 blocks per 16 B
+//                   (used for a tile when every channel LLR of its 64 blocks fits int8: half the bytes per sweep;
+//                    fmt[tile] says which set is valid; rows past K hold the three tail steps; S2T = encoder 2's
+//                    systematic tail, always int16)
 //       E         : u32   [tile][K][32 lanes]         the one extrinsic array, natural bit order, updated in place
-//       CK        : uint4 [tile][K/8][2][32 lanes]    un-normalised backward metrics every 8th step (scratch)
+//       CK        : uint4 [tile][K/8][2][32 lanes]    checkpoints (scratch), alpha below the split, beta above
 //       HB        : u16   [tile][K/8][32 lanes]       hard decisions of the last pass run, 8 per block per entry
-//   * A pass is: backward sweep over the whole block keeping only every 8th metric vector (CK), then a forward
-//     sweep that, per window of 8 steps, rebuilds the 8 backward vectors in registers from its checkpoint and runs
-//     the forward recursion + LLR output.  No beta array (98 KB/block in the reference, turbodecoder_gen.c:206) is
-//     ever materialised.  Checkpoints hold the value BEFORE the every-4th-step normalisation, like the reference's
-//     beta[] does (turbodecoder_gen.c:98-110), so the recomputed vectors are the very same int16 values.
 //   * The two constituent decoders share E in place:
 //       DEC1 (even pass): a-priori = E[j];              x = S[j] + E[j];  E[j]     <- L1[j] - E[j]
 //       DEC2 (odd pass) : x = E[PI(i)] (no a-priori);                      E[PI(i)] <- L2[i] - x
 //     which is turbodecoder_iter.h:104-128 with app1/app2/ext1 folded into one array: ext1 - app1 interleaved is
 //     DEC2's systematic input, and ext2 de-interleaved minus that same value is DEC1's next a-priori.
 //   * The CRC the caller's loop checks after every pass (sch.c:437-452) is accumulated on the fly as a syndrome:
-//     sum over decided-one positions j of x^(K-1-j) mod g(x); zero <=> srsran_crc_checksum_byte()==0.  This works
-//     in DEC2's permuted visiting order too, so no per-pass de-interleave of decisions is needed.
+//     sum over decided-one positions j of x^(K-1-j) mod g(x); zero <=> srsran_crc_checksum_byte()==0.  It is a XOR,
+//     so it works in DEC2's permuted visiting order and in either sweep direction.
 #pragma once
 #include "packed16.h"
 
 namespace b200 {
 
-constexpr int      TDEC_TILE_CB = 64;  // code blocks per warp tile
+constexpr int      TDEC_TILE_CB = 64;  // code blocks per tile
 constexpr int      TDEC_WIN     = 8;   // checkpoint spacing / register window
 constexpr uint32_t NEG_INF2     = 0xD8F0D8F0u; // -10000 in both halves (turbodecoder_gen.c:37)
 
@@ -59,10 +67,15 @@ struct alignas(8) CrcPow {
 struct TdecView {
   int K;      // code block length (one of the 188 LTE sizes, multiple of 8)
   int ntiles; // tiles of 64 blocks
+  int ws;     // split window: 1 <= ws <= K/8-1 (see tdec_split)
   u4*             S;
   u4*             P0;
   u4*             P1;
-  u4*             S2T; // [tile][32] : x,y,z = systematic tail of encoder 2 (app2[K..K+2])
+  u4*             S8;
+  u4*             P08;
+  u4*             P18;
+  uint32_t*       fmt;  // [ntiles] 0: the int8 arrays hold the tile, 1: the int16 arrays do
+  u4*             S2T;  // [tile][32] : x,y,z = systematic tail of encoder 2 (app2[K..K+2])
   uint32_t*       E;
   u4*             CK;
   uint16_t*       HB;
@@ -75,9 +88,24 @@ struct TdecView {
   int             max_pass;
 };
 
+// Split of the trellis between the two warps.  Per step warp F spends ~15 instructions below the split and ~56 above,
+// warp B ~62 below (its alpha rebuild cannot share the branch sums with the LLR) and ~15 above: equal at ws ~ 0.47 nw.
+B200_HD int tdec_split(int K, int percent)
+{
+  const int nw = K / 8;
+  int       ws = (nw * percent + 50) / 100;
+  if (ws < 1) ws = 1;
+  if (ws > nw - 1) ws = nw - 1;
+  return ws;
+}
+
 B200_HD size_t vec_row(const TdecView& v, int tile, int k4, int lane)
 {
   return ((size_t)tile * (size_t)((v.K + 4) / 4) + (size_t)k4) * 32 + (size_t)lane;
+}
+B200_HD size_t row8(const TdecView& v, int tile, int w, int lane)
+{
+  return ((size_t)tile * (size_t)(v.K / 8 + 1) + (size_t)w) * 32 + (size_t)lane;
 }
 B200_HD size_t e_idx(const TdecView& v, int tile, int k, int lane)
 {
@@ -90,6 +118,45 @@ B200_HD size_t ck_idx(const TdecView& v, int tile, int w, int half, int lane)
 B200_HD size_t hb_idx(const TdecView& v, int tile, int w, int lane)
 {
   return ((size_t)tile * (size_t)(v.K / 8) + (size_t)w) * 32 + (size_t)lane;
+}
+
+B200_HD uint32_t u4_get(const u4& q, int i)
+{
+  return i == 0 ? q.x : (i == 1 ? q.y : (i == 2 ? q.z : q.w));
+}
+
+// two int8 (bytes 0,1 or 2,3 of word) sign-extended into an int16x2
+B200_HD uint32_t sext8x2(uint32_t word, int odd)
+{
+#if defined(__CUDA_ARCH__)
+  uint32_t r;
+  if (odd) {
+    asm("prmt.b32 %0, %1, 0, 0xB3A2;" : "=r"(r) : "r"(word));
+  } else {
+    asm("prmt.b32 %0, %1, 0, 0x9180;" : "=r"(r) : "r"(word));
+  }
+  return r;
+#else
+  const int8_t lo = (int8_t)(uint8_t)(word >> (odd ? 16 : 0)), hi = (int8_t)(uint8_t)(word >> (odd ? 24 : 8));
+  return pack2((int16_t)lo, (int16_t)hi);
+#endif
+}
+
+// value of step t (0..7) of a window out of its raw words: int16 format = two uint4 (4 steps each), int8 = one uint4
+template <bool IN8>
+B200_HD uint32_t win_val(const u4 q[2], int t)
+{
+  if (IN8) {
+    return sext8x2(u4_get(q[0], t >> 1), t & 1);
+  }
+  return u4_get(q[t >> 2], t & 3);
+}
+
+// PI(8w+t) out of the packed table words
+B200_HD uint32_t win_pi(const u4& q, int t)
+{
+  const uint32_t word = u4_get(q, t >> 1);
+  return (t & 1) ? (word >> 16) : (word & 0xFFFFu);
 }
 
 // One backward step (turbodecoder_gen.c:71-103 without the store): B <- beta_k from beta_{k+1}
@@ -107,6 +174,23 @@ B200_HD void beta_step(uint32_t B[8], uint32_t x, uint32_t y, uint32_t xy)
   B[0] = n0; B[1] = n1; B[2] = n2; B[3] = n3; B[4] = n4; B[5] = n5; B[6] = n6; B[7] = n7;
 }
 
+// One forward step without output (turbodecoder_gen.c:139-184, the state update only): A <- alpha_{k+1} from alpha_k.
+// Same sixteen branch sums as alpha_step below, folded into add+max pairs (max is commutative, so the result is the
+// same int16 value).
+B200_HD void alpha_update(uint32_t A[8], uint32_t x, uint32_t y, uint32_t xy)
+{
+  uint32_t t1 = add2(A[3], y), t2 = add2(A[4], y), t5 = add2(A[2], y), t6 = add2(A[5], y);
+  uint32_t n0 = addmax2(A[1], xy, A[0]);
+  uint32_t n1 = addmax2(A[2], x, t1);
+  uint32_t n2 = addmax2(A[5], x, t2);
+  uint32_t n3 = addmax2(A[6], xy, A[7]);
+  uint32_t n4 = addmax2(A[0], xy, A[1]);
+  uint32_t n5 = addmax2(A[3], x, t5);
+  uint32_t n6 = addmax2(A[4], x, t6);
+  uint32_t n7 = addmax2(A[7], xy, A[6]);
+  A[0] = n0; A[1] = n1; A[2] = n2; A[3] = n3; A[4] = n4; A[5] = n5; A[6] = n6; A[7] = n7;
+}
+
 // subtract state 0 from every state (turbodecoder_gen.c:105-110,186-191)
 B200_HD void normalise(uint32_t M[8])
 {
@@ -116,9 +200,10 @@ B200_HD void normalise(uint32_t M[8])
   M[0] = 0;
 }
 
-// One forward step (turbodecoder_gen.c:139-184): returns L = max over 1-branches - max over 0-branches and
-// advances A.  b = beta_k for the step's own k.
-B200_HD uint32_t alpha_step(uint32_t A[8], const uint32_t b[8], uint32_t x, uint32_t y, uint32_t xy)
+// LLR of one step (turbodecoder_gen.c:139-184): L = max over 1-branches - max over 0-branches of
+// alpha_k[s] + gamma + beta_{k+1}[s'].  b = the stored (un-normalised) beta_{k+1}.  UPDATE also advances A.
+template <bool UPDATE>
+B200_HD uint32_t llr_step(uint32_t A[8], const uint32_t b[8], uint32_t x, uint32_t y, uint32_t xy)
 {
   uint32_t m0 = A[0], m1 = add2(A[3], y), m2 = add2(A[4], y), m3 = A[7];
   uint32_t m4 = A[1], m5 = add2(A[2], y), m6 = add2(A[5], y), m7 = A[6];
@@ -145,253 +230,152 @@ B200_HD uint32_t alpha_step(uint32_t A[8], const uint32_t b[8], uint32_t x, uint
   uint32_t zero_side = max2(z0, z1);
   uint32_t one_side  = max2(o0, o1);
 
-  A[0] = max2(m0, n0); A[1] = max2(m1, n1); A[2] = max2(m2, n2); A[3] = max2(m3, n3);
-  A[4] = max2(m4, n4); A[5] = max2(m5, n5); A[6] = max2(m6, n6); A[7] = max2(m7, n7);
-
+  if (UPDATE) {
+    A[0] = max2(m0, n0); A[1] = max2(m1, n1); A[2] = max2(m2, n2); A[3] = max2(m3, n3);
+    A[4] = max2(m4, n4); A[5] = max2(m5, n5); A[6] = max2(m6, n6); A[7] = max2(m7, n7);
+  }
   return sub2(one_side, zero_side);
 }
 
-// Per-lane base pointers of one tile: every access below is base + small 32-bit offset, so the address math per
-// window is a couple of integer ops instead of 64-bit index products.
-struct LanePtrs {
-  const u4* S;   // lane's uint4 in row 0 of the tile; row r at S[r * 32]
-  const u4* P;   // parity stream of the running constituent decoder
-  uint32_t* E;   // lane's word in E row 0; row k at E[k * 32]
-  u4*       CK;  // window w, half h at CK[(2 * w + h) * 32]
-  uint16_t* HB;  // window w at HB[w * 32]
-  const uint16_t* qpp;
+// ---- one window of 8 trellis steps in registers ---------------------------------------------------------------
+struct WinRegs {
+  uint32_t xs[8]; // systematic (+ a-priori) input of the constituent decoder
+  uint32_t ys[8]; // its parity input
+  uint32_t es[8]; // what is subtracted from the LLR to form the new extrinsic: DEC1 the a-priori, DEC2 xs itself
 };
 
-template <bool DEC2>
-B200_HD LanePtrs lane_ptrs(const TdecView& v, int tile, int lane)
+// s, p: raw words of the window (s unused for DEC2), e: the eight E words (DEC1: E[8w+t], DEC2: E[PI(8w+t)])
+template <bool DEC2, bool FIRST, bool IN8>
+B200_HD void win_unpack(WinRegs& r, const u4 s[2], const u4 p[2], const uint32_t e[8])
 {
-  LanePtrs p;
-  p.S   = v.S + vec_row(v, tile, 0, lane);
-  p.P   = (DEC2 ? v.P1 : v.P0) + vec_row(v, tile, 0, lane);
-  p.E   = v.E + e_idx(v, tile, 0, lane);
-  p.CK  = v.CK + ck_idx(v, tile, 0, 0, lane);
-  p.HB  = v.HB + hb_idx(v, tile, 0, lane);
-  p.qpp = v.qpp_fwd;
-  return p;
-}
-
-// Inputs of one window of 8 trellis steps for one lane
-template <bool DEC2>
-struct WinIn {
-  u4       s[2]; // DEC1 only: systematic
-  u4       p[2]; // parity of this constituent decoder
-  uint32_t e[8]; // DEC1: E[j] (a-priori), DEC2: E[PI(i)] (systematic input)
-  u4       q;    // DEC2 only: the eight interleaver entries PI(8w..8w+7), two per word
-};
-
-B200_HD uint32_t u4_get(const u4& q, int i)
-{
-  return i == 0 ? q.x : (i == 1 ? q.y : (i == 2 ? q.z : q.w));
-}
-
-// PI(8w+t) out of the packed table words
-B200_HD uint32_t win_pi(const u4& q, int t)
-{
-  const uint32_t word = u4_get(q, t >> 1);
-  return (t & 1) ? (word >> 16) : (word & 0xFFFFu);
-}
-
-template <bool DEC2, bool FIRST>
-B200_HD void load_window(WinIn<DEC2>& in, const LanePtrs& p, uint32_t w)
-{
-  in.p[0] = p.P[(2u * w) * 32u];
-  in.p[1] = p.P[(2u * w + 1u) * 32u];
-  if (!DEC2) {
-    in.s[0] = p.S[(2u * w) * 32u];
-    in.s[1] = p.S[(2u * w + 1u) * 32u];
-    if (FIRST) {
 #pragma unroll
-      for (int t = 0; t < 8; t++) in.e[t] = 0;
+  for (int t = 0; t < 8; t++) {
+    r.ys[t] = win_val<IN8>(p, t);
+    if (DEC2) {
+      r.es[t] = e[t];
+      r.xs[t] = e[t];
+    } else if (FIRST) {
+      r.es[t] = 0;
+      r.xs[t] = win_val<IN8>(s, t);
     } else {
-#pragma unroll
-      for (int t = 0; t < 8; t++) in.e[t] = p.E[(8u * w + (uint32_t)t) * 32u];
-    }
-  } else {
-    // eight warp-uniform interleaver entries: one 16-byte load
-    in.q = *reinterpret_cast<const u4*>(p.qpp + 8u * w);
-#pragma unroll
-    for (int t = 0; t < 8; t++) in.e[t] = p.E[win_pi(in.q, t) * 32u];
-  }
-}
-
-// x (systematic + a-priori), y (parity) of step t inside the window
-template <bool DEC2>
-B200_HD void win_xy(const WinIn<DEC2>& in, int t, uint32_t& x, uint32_t& y)
-{
-  y = u4_get(in.p[t >> 2], t & 3);
-  if (DEC2) {
-    x = in.e[t];
-  } else {
-    x = add2(u4_get(in.s[t >> 2], t & 3), in.e[t]);
-  }
-}
-
-B200_HD void store_ck(const LanePtrs& p, uint32_t w, const uint32_t B[8])
-{
-  u4 c0 = {B[0], B[1], B[2], B[3]}, c1 = {B[4], B[5], B[6], B[7]};
-  p.CK[(2u * w) * 32u]      = c0;
-  p.CK[(2u * w + 1u) * 32u] = c1;
-}
-
-// ---- backward sweep: leaves CK[w] = un-normalised beta_{8(w+1)} for every window ------------------------------
-// PF windows are kept in flight in registers; a buffer is refilled (for window w-PF) right after window w consumed
-// it, so a load has PF-1 windows of arithmetic to land.
-template <bool DEC2, bool FIRST, int PF>
-B200_HD void beta_sweep_lane(const TdecView& v, int tile, int lane)
-{
-  const int      K  = v.K;
-  const int      nw = K / 8;
-  const LanePtrs p  = lane_ptrs<DEC2>(v, tile, lane);
-  uint32_t       B[8];
-  B[0] = 0;
-#pragma unroll
-  for (int i = 1; i < 8; i++) B[i] = NEG_INF2;
-
-  WinIn<DEC2> buf[PF];
-#pragma unroll
-  for (int u = 0; u < PF; u++) {
-    if (nw - 1 - u >= 0) load_window<DEC2, FIRST>(buf[u], p, (uint32_t)(nw - 1 - u));
-  }
-
-  // three tail steps k = K+2, K+1, K: no a-priori, no normalisation (turbodecoder_gen.c:73-75,105)
-  {
-    u4 pt = p.P[(uint32_t)(K / 4) * 32u];
-    u4 st = DEC2 ? v.S2T[(size_t)tile * 32 + lane] : p.S[(uint32_t)(K / 4) * 32u];
-#pragma unroll
-    for (int t = 2; t >= 0; t--) {
-      uint32_t x = u4_get(st, t), y = u4_get(pt, t);
-      beta_step(B, x, y, add2(x, y));
-    }
-  }
-  store_ck(p, (uint32_t)(nw - 1), B);
-
-  for (int wb = nw - 1; wb >= 0; wb -= PF) {
-#pragma unroll
-    for (int u = 0; u < PF; u++) {
-      const int w = wb - u;
-      if (w >= 0) {
-#pragma unroll
-        for (int t = 7; t >= 0; t--) {
-          uint32_t x, y;
-          win_xy<DEC2>(buf[u], t, x, y);
-          beta_step(B, x, y, add2(x, y));
-          if (t == 0 && w > 0) store_ck(p, (uint32_t)(w - 1), B);
-          if ((t & 3) == 0) normalise(B); // k = 8w+t, always < K here
-        }
-        if (w - PF >= 0) load_window<DEC2, FIRST>(buf[u], p, (uint32_t)(w - PF));
-      }
+      r.es[t] = e[t];
+      r.xs[t] = add2(win_val<IN8>(s, t), e[t]);
     }
   }
 }
 
-// ---- forward sweep ------------------------------------------------------------------------------------------------
 struct LaneResult {
   uint32_t crc_lo16x2; // syndrome bits 0..15 of both blocks
   uint32_t crc_hi8x2;  // syndrome bits 16..23 of both blocks
 };
 
-// One window: rebuild its 8 backward vectors from checkpoint (c0,c1), then 8 forward steps with LLR output.
-template <bool DEC2>
-B200_HD void alpha_window(const TdecView&    v,
-                          const LanePtrs&    p,
-                          uint32_t           w,
-                          const WinIn<DEC2>& cur,
-                          const u4&          c0,
-                          const u4&          c1,
-                          const CrcPow*      cw, // the 8 syndrome weights of this window's steps, or nullptr
-                          uint32_t           A[8],
-                          LaneResult&        res,
-                          bool               act_lo,
-                          bool               act_hi)
-{
-  const uint32_t K = (uint32_t)v.K;
-  uint32_t       xs[8], ys[8];
-#pragma unroll
-  for (int t = 0; t < 8; t++) win_xy<DEC2>(cur, t, xs[t], ys[t]);
+struct WinOut {
+  uint32_t enew[8]; // new extrinsic of each step (turbodecoder_iter.h:108,118-127)
+  uint32_t bits;    // decisions (turbodecoder_gen.c:266: LLR > 0 -> 1): bit 7-t = step t, low block in bits 0..7, high in 16..23
+};
 
+B200_HD void win_emit(WinOut& o, LaneResult& res, const CrcPow* cw, int t, uint32_t L, uint32_t e)
+{
+  o.enew[t]          = sub2(L, e);
+  const uint32_t one = pos2(L);
+  o.bits |= one << (7 - t);
+  if (cw) {
+    const CrcPow   c    = cw[t];
+    const uint32_t mask = one * 0xFFFFu;
+    res.crc_lo16x2 ^= (c.lo16x2 & mask);
+    res.crc_hi8x2 ^= (c.hi8x2 & mask);
+  }
+}
+
+// Warp F, phase 2.  A = alpha_{8w} on entry, alpha_{8w+8} on exit.  ck = beta_{8w+8} un-normalised; norm_ck = (8w+8 < K):
+// the recursion continues from the normalised value except at the very end of the block (turbodecoder_gen.c:105).
+B200_HD void fwd_window(uint32_t A[8], const uint32_t ck[8], bool norm_ck, const WinRegs& r, const CrcPow* cw, LaneResult& res, WinOut& o)
+{
   // bw[t] is the vector the forward step at position 8w+t needs (beta_{8w+t+1})
   uint32_t bw[8][8];
-  uint32_t B[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+  uint32_t B[8];
 #pragma unroll
-  for (int i = 0; i < 8; i++) bw[7][i] = B[i];
-  if (8u * w + 8u < K) normalise(B); // beta_{8w+8} sits on a multiple of 4; the last one (k==K) is not normalised
+  for (int i = 0; i < 8; i++) B[i] = bw[7][i] = ck[i];
+  if (norm_ck) normalise(B);
 #pragma unroll
   for (int t = 7; t >= 1; t--) {
-    beta_step(B, xs[t], ys[t], add2(xs[t], ys[t]));
+    beta_step(B, r.xs[t], r.ys[t], add2(r.xs[t], r.ys[t]));
 #pragma unroll
     for (int i = 0; i < 8; i++) bw[t - 1][i] = B[i];
     if (t == 4) normalise(B);
   }
-
-  uint32_t bits = 0; // two 8-bit shift registers: bits 0..7 low block, 16..23 high block
+  o.bits = 0;
 #pragma unroll
   for (int t = 0; t < 8; t++) {
-    uint32_t L = alpha_step(A, bw[t], xs[t], ys[t], add2(xs[t], ys[t]));
+    const uint32_t L = llr_step<true>(A, bw[t], r.xs[t], r.ys[t], add2(r.xs[t], r.ys[t]));
     if ((t & 3) == 3) normalise(A); // forward index k = 8w+t+1 (turbodecoder_gen.c:186)
-    const uint32_t pos = DEC2 ? win_pi(cur.q, t) : 8u * w + (uint32_t)t;
-    // extrinsic hand-over, in place (turbodecoder_iter.h:108,118-127)
-    p.E[pos * 32u] = sub2(L, cur.e[t]);
-    uint32_t one   = pos2(L); // turbodecoder_gen.c:266: LLR > 0 -> 1
-    bits           = (bits << 1) | one;
-    if (cw) {
-      const CrcPow   c    = cw[t];
-      const uint32_t mask = one * 0xFFFFu;
-      res.crc_lo16x2 ^= (c.lo16x2 & mask);
-      res.crc_hi8x2 ^= (c.hi8x2 & mask);
-    }
-  }
-  // hard decisions of this window: low byte = low block, high byte = high block, MSB = first step
-  const uint16_t hb = (uint16_t)((bits & 0xFFu) | ((bits >> 8) & 0xFF00u));
-  if (act_lo && act_hi) {
-    p.HB[w * 32u] = hb;
-  } else {
-    const uint16_t old = p.HB[w * 32u];
-    const uint16_t m   = (uint16_t)((act_lo ? 0x00FFu : 0u) | (act_hi ? 0xFF00u : 0u));
-    p.HB[w * 32u]      = (uint16_t)((hb & m) | (old & ~m));
+    win_emit(o, res, cw, t, L, r.es[t]);
   }
 }
 
-template <bool DEC2, bool FIRST>
-B200_HD LaneResult alpha_sweep_lane(const TdecView& v, int tile, int lane, bool act_lo, bool act_hi)
+// Warp B, phase 2.  U = beta_{8w+8} un-normalised on entry (8w+8 < K always: this warp works below the split),
+// beta_{8w} un-normalised on exit.  ack = alpha_{8w}.
+B200_HD void bwd_window(uint32_t U[8], const uint32_t ack[8], const WinRegs& r, const CrcPow* cw, LaneResult& res, WinOut& o)
 {
-  const uint32_t nw = (uint32_t)v.K / 8u;
-  const LanePtrs p  = lane_ptrs<DEC2>(v, tile, lane);
-  const CrcPow*  cbase = DEC2 ? v.crc_perm : v.crc_nat;
-  uint32_t       A[8];
-  LaneResult     res = {0u, 0u};
-  A[0]               = 0;
+  // aw[t] = alpha_{8w+t}, the vector the LLR of step 8w+t needs
+  uint32_t aw[8][8];
+  uint32_t A[8];
 #pragma unroll
-  for (int i = 1; i < 8; i++) A[i] = NEG_INF2;
-
-  // two register buffers, windows alternate between them (no copies); the other buffer's loads are issued before
-  // the current window's ~450 instructions of arithmetic
-  WinIn<DEC2> inA, inB;
-  u4          ckA0, ckA1, ckB0, ckB1;
-  load_window<DEC2, FIRST>(inA, p, 0u);
-  ckA0 = p.CK[0];
-  ckA1 = p.CK[32];
-  for (uint32_t w = 0; w < nw; w += 2) {
-    if (w + 1 < nw) {
-      load_window<DEC2, FIRST>(inB, p, w + 1);
-      ckB0 = p.CK[(2u * (w + 1)) * 32u];
-      ckB1 = p.CK[(2u * (w + 1) + 1u) * 32u];
-    }
-    alpha_window<DEC2>(v, p, w, inA, ckA0, ckA1, cbase ? cbase + 8u * w : nullptr, A, res, act_lo, act_hi);
-    if (w + 1 < nw) {
-      if (w + 2 < nw) {
-        load_window<DEC2, FIRST>(inA, p, w + 2);
-        ckA0 = p.CK[(2u * (w + 2)) * 32u];
-        ckA1 = p.CK[(2u * (w + 2) + 1u) * 32u];
-      }
-      alpha_window<DEC2>(v, p, w + 1, inB, ckB0, ckB1, cbase ? cbase + 8u * (w + 1) : nullptr, A, res, act_lo, act_hi);
-    }
+  for (int i = 0; i < 8; i++) A[i] = aw[0][i] = ack[i];
+#pragma unroll
+  for (int t = 0; t < 7; t++) {
+    alpha_update(A, r.xs[t], r.ys[t], add2(r.xs[t], r.ys[t]));
+    if (t == 3) normalise(A);
+#pragma unroll
+    for (int i = 0; i < 8; i++) aw[t + 1][i] = A[i];
   }
-  return res;
+  o.bits = 0;
+#pragma unroll
+  for (int t = 7; t >= 0; t--) {
+    const uint32_t xy = add2(r.xs[t], r.ys[t]);
+    const uint32_t L  = llr_step<false>(aw[t], U, r.xs[t], r.ys[t], xy);
+    if ((t & 3) == 3) normalise(U); // U is beta_{8w+t+1}: a multiple of 4 (and < K)
+    beta_step(U, r.xs[t], r.ys[t], xy);
+    win_emit(o, res, cw, t, L, r.es[t]);
+  }
+}
+
+// Warp F, phase 1: 8 forward steps, no output
+B200_HD void alpha_window(uint32_t A[8], const WinRegs& r)
+{
+#pragma unroll
+  for (int t = 0; t < 8; t++) {
+    alpha_update(A, r.xs[t], r.ys[t], add2(r.xs[t], r.ys[t]));
+    if ((t & 3) == 3) normalise(A);
+  }
+}
+
+// Warp B, phase 1: 8 backward steps.  On exit B = beta_{8w} un-normalised (the caller stores it as CK[w-1] and then
+// normalises, or hands it to phase 2 as is when w is the split window).
+B200_HD void beta_window(uint32_t B[8], const WinRegs& r)
+{
+#pragma unroll
+  for (int t = 7; t >= 0; t--) {
+    beta_step(B, r.xs[t], r.ys[t], add2(r.xs[t], r.ys[t]));
+    if (t == 4) normalise(B); // k = 8w+4
+  }
+}
+
+// hard decisions of a window: low byte = low block, high byte = high block, MSB = first step
+B200_HD uint16_t hb_word(uint32_t bits)
+{
+  return (uint16_t)((bits & 0xFFu) | ((bits >> 8) & 0xFF00u));
+}
+B200_HD void hb_store(uint16_t* dst, uint32_t bits, bool act_lo, bool act_hi)
+{
+  const uint16_t hb = hb_word(bits);
+  if (act_lo && act_hi) {
+    *dst = hb;
+  } else { // a block that already stopped keeps its decisions
+    const uint16_t old = *dst;
+    const uint16_t m   = (uint16_t)((act_lo ? 0x00FFu : 0u) | (act_hi ? 0xFF00u : 0u));
+    *dst               = (uint16_t)((hb & m) | (old & ~m));
+  }
 }
 
 // ---- end of a pass: CRC verdict, pass counters, stop flag (sch.c:431-452) ---------------------------------------
@@ -427,10 +411,60 @@ B200_HD void finish_pass(const TdecView&   v,
   }
 }
 
-// ---- one full pass for one lane (two code blocks), direct-from-global variant ------------------------------------
-// Used by the CPU emulation (and kept as the reference structure of the pass); the GPU kernel in tdec_kernels.cu runs
-// the same steps but feeds the windows through a TMA-filled shared-memory ring.
-template <bool DEC2, bool FIRST, int PF>
+// ---- one full pass for one lane (two code blocks) straight from global memory --------------------------------------
+// The CPU emulation (tests/emu) runs this; it is also the readable statement of the schedule.  The GPU kernel in
+// tdec_kernels.cu runs the same window functions, two warps at a time, fed through shared-memory rings.
+template <bool DEC2, bool FIRST, bool IN8>
+B200_HD void load_window_direct(const TdecView& v, int tile, int lane, int w, WinRegs& r, uint32_t pos[8])
+{
+  u4       s[2] = {}, p[2] = {};
+  uint32_t e[8] = {};
+  if (IN8) {
+    p[0] = (DEC2 ? v.P18 : v.P08)[row8(v, tile, w, lane)];
+    if (!DEC2) s[0] = v.S8[row8(v, tile, w, lane)];
+  } else {
+    const u4* P = DEC2 ? v.P1 : v.P0;
+    p[0]        = P[vec_row(v, tile, 2 * w, lane)];
+    p[1]        = P[vec_row(v, tile, 2 * w + 1, lane)];
+    if (!DEC2) {
+      s[0] = v.S[vec_row(v, tile, 2 * w, lane)];
+      s[1] = v.S[vec_row(v, tile, 2 * w + 1, lane)];
+    }
+  }
+  for (int t = 0; t < 8; t++) {
+    pos[t] = DEC2 ? (uint32_t)v.qpp_fwd[8 * w + t] : (uint32_t)(8 * w + t);
+    if (!FIRST) e[t] = v.E[e_idx(v, tile, (int)pos[t], lane)];
+  }
+  win_unpack<DEC2, FIRST, IN8>(r, s, p, e);
+}
+
+B200_HD void ck_load(const TdecView& v, int tile, int lane, int w, uint32_t c[8])
+{
+  const u4 c0 = v.CK[ck_idx(v, tile, w, 0, lane)], c1 = v.CK[ck_idx(v, tile, w, 1, lane)];
+  c[0] = c0.x; c[1] = c0.y; c[2] = c0.z; c[3] = c0.w; c[4] = c1.x; c[5] = c1.y; c[6] = c1.z; c[7] = c1.w;
+}
+B200_HD void ck_store(const TdecView& v, int tile, int lane, int w, const uint32_t c[8])
+{
+  v.CK[ck_idx(v, tile, w, 0, lane)] = u4{c[0], c[1], c[2], c[3]};
+  v.CK[ck_idx(v, tile, w, 1, lane)] = u4{c[4], c[5], c[6], c[7]};
+}
+
+// the three tail steps k = K+2, K+1, K: no a-priori, no normalisation (turbodecoder_gen.c:73-75,105)
+template <bool IN8>
+B200_HD void beta_tail(uint32_t B[8], const u4& st, const u4& pt)
+{
+  B[0] = 0;
+#pragma unroll
+  for (int i = 1; i < 8; i++) B[i] = NEG_INF2;
+#pragma unroll
+  for (int t = 2; t >= 0; t--) {
+    const u4       sq[2] = {st, st}, pq[2] = {pt, pt};
+    const uint32_t x = win_val<IN8>(sq, t), y = win_val<IN8>(pq, t);
+    beta_step(B, x, y, add2(x, y));
+  }
+}
+
+template <bool DEC2, bool FIRST, bool IN8>
 B200_HD void siso_pass_lane(const TdecView& v, int tile, int lane, int pass_idx)
 {
   CbStatus* st     = v.status + ((size_t)tile * TDEC_TILE_CB + 2 * (size_t)lane);
@@ -440,9 +474,74 @@ B200_HD void siso_pass_lane(const TdecView& v, int tile, int lane, int pass_idx)
   if (!act_lo && !act_hi) {
     return;
   }
-  beta_sweep_lane<DEC2, FIRST, PF>(v, tile, lane);
-  LaneResult r = alpha_sweep_lane<DEC2, FIRST>(v, tile, lane, act_lo, act_hi);
-  finish_pass(v, st, s_lo, s_hi, act_lo, act_hi, r, pass_idx);
+  const int     K = v.K, nw = K / 8, ws = v.ws;
+  const CrcPow* cbase = DEC2 ? v.crc_perm : v.crc_nat;
+  WinRegs       r;
+  uint32_t      pos[8];
+
+  // phase 1, warp F
+  uint32_t A[8];
+  A[0] = 0;
+  for (int i = 1; i < 8; i++) A[i] = NEG_INF2;
+  for (int w = 0; w < ws; w++) {
+    ck_store(v, tile, lane, w, A);
+    load_window_direct<DEC2, FIRST, IN8>(v, tile, lane, w, r, pos);
+    alpha_window(A, r);
+  }
+  // phase 1, warp B
+  uint32_t B[8];
+  {
+    // encoder 2's systematic tail is always int16 (S2T); widen an int8 parity tail to match by using IN8 on both
+    u4 pt, stl;
+    if (IN8) {
+      pt  = (DEC2 ? v.P18 : v.P08)[row8(v, tile, nw, lane)];
+      stl = v.S8[row8(v, tile, nw, lane)];
+    } else {
+      pt  = (DEC2 ? v.P1 : v.P0)[vec_row(v, tile, K / 4, lane)];
+      stl = v.S[vec_row(v, tile, K / 4, lane)];
+    }
+    if (DEC2) {
+      const u4 s2 = v.S2T[(size_t)tile * 32 + lane];
+      B[0]        = 0;
+      for (int i = 1; i < 8; i++) B[i] = NEG_INF2;
+      for (int t = 2; t >= 0; t--) {
+        const u4       pq[2] = {pt, pt};
+        const uint32_t x = u4_get(s2, t), y = win_val<IN8>(pq, t);
+        beta_step(B, x, y, add2(x, y));
+      }
+    } else {
+      beta_tail<IN8>(B, stl, pt);
+    }
+  }
+  ck_store(v, tile, lane, nw - 1, B);
+  for (int w = nw - 1; w >= ws; w--) {
+    load_window_direct<DEC2, FIRST, IN8>(v, tile, lane, w, r, pos);
+    beta_window(B, r);
+    if (w > ws) {
+      ck_store(v, tile, lane, w - 1, B);
+      normalise(B);
+    }
+  }
+  // phase 2, warp F
+  LaneResult res = {0u, 0u};
+  WinOut     o;
+  uint32_t   c[8];
+  for (int w = ws; w < nw; w++) {
+    load_window_direct<DEC2, FIRST, IN8>(v, tile, lane, w, r, pos);
+    ck_load(v, tile, lane, w, c);
+    fwd_window(A, c, 8 * w + 8 < K, r, cbase ? cbase + 8 * w : nullptr, res, o);
+    for (int t = 0; t < 8; t++) v.E[e_idx(v, tile, (int)pos[t], lane)] = o.enew[t];
+    hb_store(&v.HB[hb_idx(v, tile, w, lane)], o.bits, act_lo, act_hi);
+  }
+  // phase 2, warp B
+  for (int w = ws - 1; w >= 0; w--) {
+    load_window_direct<DEC2, FIRST, IN8>(v, tile, lane, w, r, pos);
+    ck_load(v, tile, lane, w, c);
+    bwd_window(B, c, r, cbase ? cbase + 8 * w : nullptr, res, o);
+    for (int t = 0; t < 8; t++) v.E[e_idx(v, tile, (int)pos[t], lane)] = o.enew[t];
+    hb_store(&v.HB[hb_idx(v, tile, w, lane)], o.bits, act_lo, act_hi);
+  }
+  finish_pass(v, st, s_lo, s_hi, act_lo, act_hi, res, pass_idx);
 }
 
 } // namespace b200

@@ -1,5 +1,7 @@
 // Host side of the batched turbo decoder: workspace carving, pass scheduling, host<->device pipelining and the
 // extern "C" entries declared in include/srslte_b200.h.
+#include <stdlib.h>
+
 #include <atomic>
 #include <new>
 
@@ -19,12 +21,26 @@ size_t TdecEngine::workspace_bytes(int K, uint32_t ncb)
   const size_t vrows  = ntiles * (size_t)((K + 4) / 4) * 32 * sizeof(u4);
   size_t       total  = 0;
   total += 3 * (vrows + 256);                                      // S, P0, P1
+  total += 3 * (ntiles * (size_t)(K / 8 + 1) * 32 * sizeof(u4) + 256); // S8, P08, P18
+  total += ntiles * sizeof(uint32_t) + 256;                        // fmt
   total += ntiles * 32 * sizeof(u4) + 256;                         // S2T
   total += ntiles * (size_t)K * 32 * sizeof(uint32_t) + 256;       // E
   total += ntiles * (size_t)(K / 8) * 2 * 32 * sizeof(u4) + 256;   // CK
   total += ntiles * (size_t)(K / 8) * 32 * sizeof(uint16_t) + 256; // HB
   total += ntiles * TDEC_TILE_CB * sizeof(CbStatus) + 256;         // status
   return total;
+}
+
+// share of the trellis windows below the split (tdec_core.h: tdec_split); SRSLTE_B200_TDEC_SPLIT is a tuning knob
+static int split_percent()
+{
+  static int pct = -1;
+  if (pct < 0) {
+    const char* e = getenv("SRSLTE_B200_TDEC_SPLIT");
+    pct           = e ? atoi(e) : 47;
+    if (pct < 1 || pct > 99) pct = 47;
+  }
+  return pct;
 }
 
 int TdecEngine::carve(DeviceArena& arena, int K, uint32_t ncb, TdecView& v) const
@@ -36,12 +52,18 @@ int TdecEngine::carve(DeviceArena& arena, int K, uint32_t ncb, TdecView& v) cons
   v.S                 = (u4*)arena.take(vrows);
   v.P0                = (u4*)arena.take(vrows);
   v.P1                = (u4*)arena.take(vrows);
+  const size_t rows8  = ntiles * (size_t)(K / 8 + 1) * 32 * sizeof(u4);
+  v.S8                = (u4*)arena.take(rows8);
+  v.P08               = (u4*)arena.take(rows8);
+  v.P18               = (u4*)arena.take(rows8);
+  v.fmt               = (uint32_t*)arena.take(ntiles * sizeof(uint32_t));
+  v.ws                = tdec_split(K, split_percent());
   v.S2T               = (u4*)arena.take(ntiles * 32 * sizeof(u4));
   v.E                 = (uint32_t*)arena.take(ntiles * (size_t)K * 32 * sizeof(uint32_t));
   v.CK                = (u4*)arena.take(ntiles * (size_t)(K / 8) * 2 * 32 * sizeof(u4));
   v.HB                = (uint16_t*)arena.take(ntiles * (size_t)(K / 8) * 32 * sizeof(uint16_t));
   v.status            = (CbStatus*)arena.take(ntiles * TDEC_TILE_CB * sizeof(CbStatus));
-  if (!v.S || !v.P0 || !v.P1 || !v.S2T || !v.E || !v.CK || !v.HB || !v.status) {
+  if (!v.S || !v.P0 || !v.P1 || !v.S8 || !v.P08 || !v.P18 || !v.fmt || !v.S2T || !v.E || !v.CK || !v.HB || !v.status) {
     B200_LOG_ERROR("decoder workspace too small");
     return B200_ERROR;
   }
@@ -159,12 +181,12 @@ int TdecEngine::run_device(DeviceArena&   ws,
   prof_begin(0, stream);
   launch_load_natural(v, llr_dev, llr_offsets_dev, llr_offsets_dev ? offsets_aligned8 : ((reinterpret_cast<uintptr_t>(llr_dev) & 7u) == 0), ncb, stream);
   prof_end(stream);
-  g_kernel_launches++;
+  g_kernel_launches += 2;
   for (uint32_t p = 0; p < max_passes; p++) {
     prof_begin(1, stream);
     launch_siso_pass(v, (int)p, stream);
     prof_end(stream);
-    g_kernel_launches++;
+    g_kernel_launches += 2;
   }
   prof_begin(2, stream);
   launch_decide(v, ctx->qpp_rev(cb_idx), out_dev, crc_ok_dev, npass_dev, nullptr, ncb, stream);
