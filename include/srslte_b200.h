@@ -89,6 +89,9 @@ SRSRAN_B200_API int srsran_b200_tdec_run(srsran_b200_tdec_t* h,
  */
 SRSRAN_B200_API void srsran_b200_tdec_profile_reset(srsran_b200_tdec_t* h, int enable);
 SRSRAN_B200_API int  srsran_b200_tdec_profile_get(srsran_b200_tdec_t* h, double* ms_by_class, uint64_t* launches_by_class);
+/* Resident CTAs (tiles of 64 code blocks) per SM of the SISO pass kernel on the current device, as the CUDA occupancy
+ * calculator reports it; -1 on error.  Diagnostic: a 65,536-block batch is one wave when this is >= 7 on 148 SMs. */
+SRSRAN_B200_API int  srsran_b200_tdec_resident_tiles_per_sm(void);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Shared-channel receive processing: batched rate de-matching and the transport-block decode loop.

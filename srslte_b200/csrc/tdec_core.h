@@ -210,11 +210,14 @@ B200_HD uint32_t llr_step(uint32_t A[8], const uint32_t b[8], uint32_t x, uint32
   uint32_t n0 = add2(A[1], xy), n1 = add2(A[2], x), n2 = add2(A[5], x), n3 = add2(A[6], xy);
   uint32_t n4 = add2(A[0], xy), n5 = add2(A[3], x), n6 = add2(A[4], x), n7 = add2(A[7], xy);
 
-  // two half-chains per side keep the dependency depth at 5 instead of 8
-  uint32_t z0 = add2(m0, b[0]);
-  uint32_t z1 = add2(m4, b[4]);
-  uint32_t o0 = add2(n0, b[0]);
-  uint32_t o1 = add2(n4, b[4]);
+  // two half-chains per side keep the dependency depth at 5 instead of 8.  The packed add and the packed add+max issue
+  // on different half-rate pipes; warp F (UPDATE) is add-heavy, so its four chain heads are written as max(a+b, -32768),
+  // which is the same value on the other pipe.
+  constexpr uint32_t MIN2 = 0x80008000u;
+  uint32_t z0 = UPDATE ? addmax2(m0, b[0], MIN2) : add2(m0, b[0]);
+  uint32_t z1 = UPDATE ? addmax2(m4, b[4], MIN2) : add2(m4, b[4]);
+  uint32_t o0 = UPDATE ? addmax2(n0, b[0], MIN2) : add2(n0, b[0]);
+  uint32_t o1 = UPDATE ? addmax2(n4, b[4], MIN2) : add2(n4, b[4]);
   z0 = addmax2(m1, b[1], z0);
   z1 = addmax2(m5, b[5], z1);
   o0 = addmax2(n1, b[1], o0);

@@ -51,7 +51,8 @@ struct TdecEngine {
                  uint8_t*       npass_dev,
                  cudaStream_t   stream,
                  const uint64_t* llr_offsets_dev = nullptr, // optional: block cb's vector starts at llr_dev + offsets[cb]
-                 bool            offsets_aligned8 = false);
+                 bool            offsets_aligned8 = false,
+                 bool            reset_ws = true);
 
   int run(const int16_t* llr,
           uint32_t       ncb,

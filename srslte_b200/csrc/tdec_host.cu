@@ -2,8 +2,10 @@
 // extern "C" entries declared in include/srslte_b200.h.
 #include <stdlib.h>
 
+#include <algorithm>
 #include <atomic>
 #include <new>
+#include <utility>
 
 #include "../../include/srslte_b200.h"
 #include "b200_runtime.h"
@@ -81,6 +83,7 @@ int TdecEngine::init(int device, uint32_t max_cb_hint)
   for (int i = 0; i < 2; i++) {
     B200_CUDA_TRY(cudaStreamCreateWithFlags(&pipe_stream[i], cudaStreamNonBlocking));
   }
+
   if (max_cb_hint) {
     if (arena.reserve(workspace_bytes(MAX_CB_LEN, max_cb_hint)) != B200_SUCCESS) {
       return B200_ERROR;
@@ -129,6 +132,8 @@ void TdecEngine::prof_reset(bool enable)
   profiling = enable;
 }
 
+// Per class: the time during which at least one span of that class was open (spans of concurrent streams overlap, so
+// their plain sum would count that time twice) and the number of spans.
 int TdecEngine::prof_get(double* ms_by_class, uint64_t* launches_by_class)
 {
   for (int i = 0; i < 3; i++) {
@@ -136,12 +141,33 @@ int TdecEngine::prof_get(double* ms_by_class, uint64_t* launches_by_class)
     launches_by_class[i] = 0;
   }
   B200_CUDA_TRY(cudaDeviceSynchronize());
+  if (spans.empty()) return B200_SUCCESS;
+  std::vector<std::pair<double, double>> iv[3];
   for (auto& s : spans) {
-    float ms = 0;
-    if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) {
-      ms_by_class[s.cls] += ms;
-      launches_by_class[s.cls]++;
+    float t0 = 0, t1 = 0;
+    // event times relative to the first span's start (negative when a concurrent stream started earlier)
+    if (cudaEventElapsedTime(&t0, spans[0].a, s.a) != cudaSuccess) {
+      float r = 0;
+      if (cudaEventElapsedTime(&r, s.a, spans[0].a) != cudaSuccess) continue;
+      t0 = -r;
     }
+    if (cudaEventElapsedTime(&t1, s.a, s.b) != cudaSuccess) continue;
+    iv[s.cls].push_back({(double)t0, (double)t0 + (double)t1});
+    launches_by_class[s.cls]++;
+  }
+  for (int c = 0; c < 3; c++) {
+    std::sort(iv[c].begin(), iv[c].end());
+    double cur_a = 0, cur_b = -1e300;
+    for (auto& x : iv[c]) {
+      if (x.first > cur_b) {
+        if (cur_b > -1e299) ms_by_class[c] += cur_b - cur_a;
+        cur_a = x.first;
+        cur_b = x.second;
+      } else if (x.second > cur_b) {
+        cur_b = x.second;
+      }
+    }
+    if (cur_b > -1e299) ms_by_class[c] += cur_b - cur_a;
   }
   return B200_SUCCESS;
 }
@@ -160,10 +186,11 @@ int TdecEngine::run_device(DeviceArena&   ws,
                            uint8_t*       npass_dev,
                            cudaStream_t   stream,
                            const uint64_t* llr_offsets_dev,
-                           bool            offsets_aligned8)
+                           bool            offsets_aligned8,
+                           bool            reset_ws)
 {
   TdecView v;
-  ws.reset();
+  if (reset_ws) ws.reset();
   if (carve(ws, K, ncb, v) != B200_SUCCESS) {
     return B200_ERROR;
   }
@@ -186,7 +213,7 @@ int TdecEngine::run_device(DeviceArena&   ws,
     prof_begin(1, stream);
     launch_siso_pass(v, (int)p, stream);
     prof_end(stream);
-    g_kernel_launches += 2;
+    g_kernel_launches++;
   }
   prof_begin(2, stream);
   launch_decide(v, ctx->qpp_rev(cb_idx), out_dev, crc_ok_dev, npass_dev, nullptr, ncb, stream);
@@ -334,6 +361,11 @@ int srsran_b200_tdec_run(srsran_b200_tdec_t* h,
     return B200_ERROR_INVALID_INPUTS;
   }
   return h->eng.run(llr, ncb, K, max_passes, crc_kind, early_stop, out, crc_ok, npass, flags, (cudaStream_t)stream);
+}
+
+int srsran_b200_tdec_resident_tiles_per_sm(void)
+{
+  return siso_resident_tiles_per_sm();
 }
 
 void srsran_b200_tdec_profile_reset(srsran_b200_tdec_t* h, int enable)

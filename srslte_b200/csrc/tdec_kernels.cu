@@ -8,6 +8,8 @@
 #include <cuda_runtime.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "tdec_core.h"
 #include "tdec_kernels.h"
 
@@ -62,98 +64,118 @@ __device__ __forceinline__ void cp_wait()
   asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
+// Every global access below is (tile base, uniform across the CTA) + (32-bit byte offset): the bases can live in
+// uniform registers and the per-window address arithmetic is 32-bit.
 template <bool DEC2, bool FIRST, bool IN8>
 struct WarpRing {
   using L = ring::Lay<DEC2, IN8>;
-  uint8_t*        gen;  // generic pointer to stage 0
-  uint32_t        base; // shared-space address of stage 0
-  int             lane;
-  const u4*       gS;   // lane's uint4 in row 0 of the tile
-  const u4*       gP;
-  const uint8_t*  gE;   // tile base of E (bytes)
-  const u4*       gCK;  // lane's uint4 of checkpoint 0, half 0
-  const uint8_t*  gCRC; // syndrome weights in this decoder's visiting order, or nullptr
-  const uint16_t* qpp;
-  uint32_t        slot = 0;
+  static constexpr uint32_t RING_END = L::NST * L::BYTES;
+  uint8_t*       gen;  // generic pointer to stage 0
+  uint32_t       base; // shared-space address of stage 0
+  uint32_t       l16, l4;
+  const uint8_t* tS;   // tile bases (bytes)
+  const uint8_t* tP;
+  uint8_t*       tE;
+  uint8_t*       tCK;
+  uint8_t*       tHB;
+  const uint8_t* gCRC; // syndrome weights in this decoder's visiting order, or nullptr
+  uint32_t       fill = 0, drain = 0; // byte offsets of the next stage to fill / to consume
 
-  __device__ WarpRing(const TdecView& v, uint8_t* smem, int tile, int lane_) : lane(lane_)
+  __device__ WarpRing(const TdecView& v, uint8_t* smem, int tile, int lane)
   {
     gen  = smem;
     base = smem_u32(smem);
+    l16  = (uint32_t)lane * 16u;
+    l4   = (uint32_t)lane * 4u;
     if (IN8) {
-      gS = v.S8 + row8(v, tile, 0, lane);
-      gP = (DEC2 ? v.P18 : v.P08) + row8(v, tile, 0, lane);
+      tS = reinterpret_cast<const uint8_t*>(v.S8 + row8(v, tile, 0, 0));
+      tP = reinterpret_cast<const uint8_t*>((DEC2 ? v.P18 : v.P08) + row8(v, tile, 0, 0));
     } else {
-      gS = v.S + vec_row(v, tile, 0, lane);
-      gP = (DEC2 ? v.P1 : v.P0) + vec_row(v, tile, 0, lane);
+      tS = reinterpret_cast<const uint8_t*>(v.S + vec_row(v, tile, 0, 0));
+      tP = reinterpret_cast<const uint8_t*>((DEC2 ? v.P1 : v.P0) + vec_row(v, tile, 0, 0));
     }
-    gE   = reinterpret_cast<const uint8_t*>(v.E + e_idx(v, tile, 0, 0));
-    gCK  = v.CK + ck_idx(v, tile, 0, 0, lane);
+    tE   = reinterpret_cast<uint8_t*>(v.E + e_idx(v, tile, 0, 0));
+    tCK  = reinterpret_cast<uint8_t*>(v.CK + ck_idx(v, tile, 0, 0, 0));
+    tHB  = reinterpret_cast<uint8_t*>(v.HB + hb_idx(v, tile, 0, 0));
     gCRC = reinterpret_cast<const uint8_t*>(DEC2 ? v.crc_perm : v.crc_nat);
-    qpp  = v.qpp_fwd;
   }
 
-  // Enqueue the copies of window w into the next stage (one cp.async group).  PH2 adds the checkpoint, the CRC weights
-  // and (DEC2) the interleaver entries q = PI(8w..8w+7), which the caller fetched one issue ahead.
+  __device__ __forceinline__ void restart() { fill = drain = 0; }
+
+  // Enqueue the copies of window w into the next stage (the caller commits the cp.async group).  PH2 adds the
+  // checkpoint, the CRC weights and (DEC2) the interleaver entries q = PI(8w..8w+7), fetched one issue ahead.
   template <bool PH2>
   __device__ __forceinline__ void issue(uint32_t w, const u4& q)
   {
-    const uint32_t st = base + (slot % L::NST) * L::BYTES;
-    const uint32_t l16 = (uint32_t)lane * 16u;
-    if (IN8) {
-      cp16(st + L::OFF_P + l16, gP + (size_t)w * 32u);
-      if (!DEC2) cp16(st + L::OFF_S + l16, gS + (size_t)w * 32u);
-    } else {
-      cp16(st + L::OFF_P + l16, gP + (size_t)(2u * w) * 32u);
-      cp16(st + L::OFF_P + 512u + l16, gP + (size_t)(2u * w + 1u) * 32u);
-      if (!DEC2) {
-        cp16(st + L::OFF_S + l16, gS + (size_t)(2u * w) * 32u);
-        cp16(st + L::OFF_S + 512u + l16, gS + (size_t)(2u * w + 1u) * 32u);
-      }
+    const uint32_t     st = base + fill;
+    constexpr uint32_t WB = IN8 ? 512u : 1024u; // bytes of S / P per window
+    cp16(st + L::OFF_P + l16, tP + (w * WB + l16));
+    if (!IN8) cp16(st + L::OFF_P + 512u + l16, tP + (w * WB + 512u + l16));
+    if (!DEC2) {
+      cp16(st + L::OFF_S + l16, tS + (w * WB + l16));
+      if (!IN8) cp16(st + L::OFF_S + 512u + l16, tS + (w * WB + 512u + l16));
     }
     if (!FIRST) {
       if (!DEC2) { // eight consecutive 128-byte rows = 1 KB
-        cp16(st + L::OFF_E + l16, gE + (size_t)w * 1024u + l16);
-        cp16(st + L::OFF_E + 512u + l16, gE + (size_t)w * 1024u + 512u + l16);
+        cp16(st + L::OFF_E + l16, tE + (w * 1024u + l16));
+        cp16(st + L::OFF_E + 512u + l16, tE + (w * 1024u + 512u + l16));
       } else {
 #pragma unroll
-        for (int t = 0; t < 8; t++) {
-          cp4(st + L::OFF_E + (uint32_t)t * 128u + (uint32_t)lane * 4u, gE + (size_t)win_pi(q, t) * 128u + (uint32_t)lane * 4u);
-        }
+        for (int t = 0; t < 8; t++) cp4(st + L::OFF_E + (uint32_t)t * 128u + l4, tE + (win_pi(q, t) * 128u + l4));
       }
     }
     if (PH2) {
-      cp16(st + L::OFF_CK + l16, gCK + (size_t)(2u * w) * 32u);
-      cp16(st + L::OFF_CK + 512u + l16, gCK + (size_t)(2u * w + 1u) * 32u);
-      if (gCRC != nullptr && lane < 4) cp16(st + L::OFF_CRC + l16, gCRC + (size_t)w * 64u + l16);
-      if (DEC2 && lane == 0) *reinterpret_cast<u4*>(gen + (slot % L::NST) * L::BYTES + L::OFF_QPP) = q;
+      cp16(st + L::OFF_CK + l16, tCK + (w * 1024u + l16));
+      cp16(st + L::OFF_CK + 512u + l16, tCK + (w * 1024u + 512u + l16));
+      if (gCRC != nullptr && l16 < 64u) cp16(st + L::OFF_CRC + l16, gCRC + (w * 64u + l16));
+      if (DEC2 && l16 == 0u) *reinterpret_cast<u4*>(gen + fill + L::OFF_QPP) = q;
     }
-    slot++;
+    fill = (fill + L::BYTES == RING_END) ? 0u : fill + L::BYTES;
   }
 
-  __device__ __forceinline__ const uint8_t* stage(uint32_t i) const { return gen + (i % L::NST) * L::BYTES; }
+  // stage holding the oldest window; call after cp_wait + __syncwarp
+  __device__ __forceinline__ const uint8_t* next_stage()
+  {
+    const uint8_t* st = gen + drain;
+    drain             = (drain + L::BYTES == RING_END) ? 0u : drain + L::BYTES;
+    return st;
+  }
 
   __device__ __forceinline__ void read(WinRegs& r, const uint8_t* st) const
   {
     u4       s[2] = {}, p[2] = {};
     uint32_t e[8] = {};
-    p[0] = *reinterpret_cast<const u4*>(st + L::OFF_P + lane * 16);
-    if (!IN8) p[1] = *reinterpret_cast<const u4*>(st + L::OFF_P + 512 + lane * 16);
+    p[0] = *reinterpret_cast<const u4*>(st + L::OFF_P + l16);
+    if (!IN8) p[1] = *reinterpret_cast<const u4*>(st + L::OFF_P + 512 + l16);
     if (!DEC2) {
-      s[0] = *reinterpret_cast<const u4*>(st + L::OFF_S + lane * 16);
-      if (!IN8) s[1] = *reinterpret_cast<const u4*>(st + L::OFF_S + 512 + lane * 16);
+      s[0] = *reinterpret_cast<const u4*>(st + L::OFF_S + l16);
+      if (!IN8) s[1] = *reinterpret_cast<const u4*>(st + L::OFF_S + 512 + l16);
     }
     if (!FIRST) {
 #pragma unroll
-      for (int t = 0; t < 8; t++) e[t] = *reinterpret_cast<const uint32_t*>(st + L::OFF_E + t * 128 + lane * 4);
+      for (int t = 0; t < 8; t++) e[t] = *reinterpret_cast<const uint32_t*>(st + L::OFF_E + t * 128 + l4);
     }
     win_unpack<DEC2, FIRST, IN8>(r, s, p, e);
   }
   __device__ __forceinline__ void read_ck(uint32_t c[8], const uint8_t* st) const
   {
-    const u4 c0 = *reinterpret_cast<const u4*>(st + L::OFF_CK + lane * 16);
-    const u4 c1 = *reinterpret_cast<const u4*>(st + L::OFF_CK + 512 + lane * 16);
+    const u4 c0 = *reinterpret_cast<const u4*>(st + L::OFF_CK + l16);
+    const u4 c1 = *reinterpret_cast<const u4*>(st + L::OFF_CK + 512 + l16);
     c[0] = c0.x; c[1] = c0.y; c[2] = c0.z; c[3] = c0.w; c[4] = c1.x; c[5] = c1.y; c[6] = c1.z; c[7] = c1.w;
+  }
+  __device__ __forceinline__ void store_ck(uint32_t w, const uint32_t c[8]) const
+  {
+    *reinterpret_cast<u4*>(tCK + (w * 1024u + l16))        = u4{c[0], c[1], c[2], c[3]};
+    *reinterpret_cast<u4*>(tCK + (w * 1024u + 512u + l16)) = u4{c[4], c[5], c[6], c[7]};
+  }
+  // new extrinsics + hard decisions of window w; q = its interleaver entries (DEC2)
+  __device__ __forceinline__ void store_out(uint32_t w, const u4& q, const WinOut& o, bool act_lo, bool act_hi) const
+  {
+#pragma unroll
+    for (int t = 0; t < 8; t++) {
+      *reinterpret_cast<uint32_t*>(tE + ((DEC2 ? win_pi(q, t) : 8u * w + (uint32_t)t) * 128u + l4)) = o.enew[t];
+    }
+    hb_store(reinterpret_cast<uint16_t*>(tHB + (w * 64u + (l4 >> 1))), o.bits, act_lo, act_hi);
   }
 };
 
@@ -164,14 +186,11 @@ __device__ __forceinline__ u4 ldg_q(const uint16_t* qpp, uint32_t w)
 }
 
 template <bool DEC2, bool FIRST, bool IN8>
-__global__ void __maxnreg__(144) tdec_siso_pass_kernel(TdecView v, int pass_idx)
+__device__ __forceinline__ void siso_pass_tile(const TdecView& v, int pass_idx, uint8_t* smem, LaneResult* xres)
 {
-  extern __shared__ __align__(128) uint8_t smem[];
-  __shared__ LaneResult xres[32];
   const int tile = blockIdx.x;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  if (tile >= v.ntiles || v.fmt[tile] != (IN8 ? 0 : 1)) return;
   // whole tile finished (early stop): nothing to do.  Both warps read the same flags, so the exit is CTA-uniform.
   CbStatus*  stp  = v.status + ((size_t)tile * TDEC_TILE_CB + 2 * (size_t)lane);
   CbStatus   s_lo = stp[0], s_hi = stp[1];
@@ -179,72 +198,60 @@ __global__ void __maxnreg__(144) tdec_siso_pass_kernel(TdecView v, int pass_idx)
   if (__ballot_sync(0xFFFFFFFFu, act_lo || act_hi) == 0u) return;
 
   using RG = WarpRing<DEC2, FIRST, IN8>;
-  constexpr int NST = RG::L::NST;
-  const int      K  = v.K;
-  const uint32_t nw = (uint32_t)K / 8u, ws = (uint32_t)v.ws;
+  constexpr int  NST = RG::L::NST;
+  const uint32_t K   = (uint32_t)v.K;
+  const uint32_t nw  = K / 8u, ws = (uint32_t)v.ws;
   RG             rg(v, smem + warp * ring::RING_BYTES, tile, lane);
-  u4* const       ckw = v.CK + ck_idx(v, tile, 0, 0, lane);  // checkpoint w, half h at ckw[(2w+h)*32]
-  uint32_t* const ew  = v.E + e_idx(v, tile, 0, lane);       // row k at ew[k*32]
-  uint16_t* const hbw = v.HB + hb_idx(v, tile, 0, lane);     // window w at hbw[w*32]
-  const CrcPow*   have_crc = DEC2 ? v.crc_perm : v.crc_nat;
+  const bool     have_crc = (DEC2 ? v.crc_perm : v.crc_nat) != nullptr;
 
   WinRegs    r;
   LaneResult res = {0u, 0u};
   uint32_t   M[8]; // warp F: alpha, warp B: beta (un-normalised at window boundaries)
   u4         qn = {};
 
-  if (warp == 0) {
-    // ================= warp F =================
-    // ---- phase 1: forward recursion over windows [0, ws), alpha checkpoints ----
-    uint32_t nxt = 0;
-    if (DEC2) qn = ldg_q(v.qpp_fwd, 0);
-#pragma unroll 1
-    for (int i = 0; i < NST; i++) {
-      if (nxt < ws) {
+  // the windows a warp visits in a phase: first, first+dir, ..., last (dir = +1 or -1)
+  auto run_phase = [&](auto ph2_tag, uint32_t first, uint32_t count, int dir, auto&& body) {
+    constexpr bool PH2 = decltype(ph2_tag)::value;
+    rg.restart();
+    uint32_t nxt = first, left = count;
+    if (DEC2) qn = ldg_q(v.qpp_fwd, first);
+    auto issue_next = [&]() {
+      if (left > 0) {
         const u4 q = qn;
-        if (DEC2 && nxt + 1 < ws) qn = ldg_q(v.qpp_fwd, nxt + 1);
-        rg.template issue<false>(nxt, q);
-        nxt++;
+        if (DEC2 && left > 1) qn = ldg_q(v.qpp_fwd, nxt + dir);
+        rg.template issue<PH2>(nxt, q);
+        nxt += dir;
+        left--;
       }
       cp_commit();
+    };
+#pragma unroll 1
+    for (int i = 0; i < NST; i++) issue_next();
+    uint32_t w = first;
+#pragma unroll 1
+    for (uint32_t n = 0; n < count; n++, w += dir) {
+      cp_wait<NST - 1>();
+      __syncwarp();
+      body(w, rg.next_stage());
+      __syncwarp(); // every lane has consumed the stage before it is refilled
+      issue_next();
     }
+  };
+
+  if (warp == 0) {
+    // warp F, phase 1: forward recursion over windows [0, ws), alpha checkpoints
     M[0] = 0;
 #pragma unroll
     for (int i = 1; i < 8; i++) M[i] = NEG_INF2;
-#pragma unroll 1
-    for (uint32_t w = 0; w < ws; w++) {
-      cp_wait<NST - 1>();
-      __syncwarp();
-      rg.read(r, rg.stage(w));
-      ckw[(2u * w) * 32u]      = u4{M[0], M[1], M[2], M[3]};
-      ckw[(2u * w + 1u) * 32u] = u4{M[4], M[5], M[6], M[7]};
+    run_phase(std::false_type{}, 0u, ws, +1, [&](uint32_t w, const uint8_t* st) {
+      rg.read(r, st);
+      rg.store_ck(w, M);
       alpha_window(M, r);
-      __syncwarp(); // every lane has consumed the stage before it is refilled
-      if (nxt < ws) {
-        const u4 q = qn;
-        if (DEC2 && nxt + 1 < ws) qn = ldg_q(v.qpp_fwd, nxt + 1);
-        rg.template issue<false>(nxt, q);
-        nxt++;
-      }
-      cp_commit();
-    }
+    });
   } else {
-    // ================= warp B =================
-    // ---- phase 1: tail + backward recursion over windows [ws, nw), beta checkpoints ----
-    uint32_t nxt = nw; // windows are issued nw-1, nw-2, ..., ws
-    if (DEC2) qn = ldg_q(v.qpp_fwd, nw - 1);
-#pragma unroll 1
-    for (int i = 0; i < NST; i++) {
-      if (nxt > ws) {
-        nxt--;
-        const u4 q = qn;
-        if (DEC2 && nxt > ws) qn = ldg_q(v.qpp_fwd, nxt - 1);
-        rg.template issue<false>(nxt, q);
-      }
-      cp_commit();
-    }
+    // warp B, phase 1: tail + backward recursion over windows [ws, nw), beta checkpoints
     {
-      const u4 pt = IN8 ? rg.gP[(size_t)nw * 32u] : rg.gP[(size_t)(K / 4) * 32u];
+      const u4 pt = *reinterpret_cast<const u4*>(rg.tP + (nw * (IN8 ? 512u : 1024u) + rg.l16));
       M[0]        = 0;
 #pragma unroll
       for (int i = 1; i < 8; i++) M[i] = NEG_INF2;
@@ -257,34 +264,19 @@ __global__ void __maxnreg__(144) tdec_siso_pass_kernel(TdecView v, int pass_idx)
           beta_step(M, x, y, add2(x, y));
         }
       } else {
-        const u4 stl = IN8 ? rg.gS[(size_t)nw * 32u] : rg.gS[(size_t)(K / 4) * 32u];
+        const u4 stl = *reinterpret_cast<const u4*>(rg.tS + (nw * (IN8 ? 512u : 1024u) + rg.l16));
         beta_tail<IN8>(M, stl, pt);
       }
     }
-    ckw[(2u * (nw - 1)) * 32u]      = u4{M[0], M[1], M[2], M[3]};
-    ckw[(2u * (nw - 1) + 1u) * 32u] = u4{M[4], M[5], M[6], M[7]};
-    uint32_t i = 0;
-#pragma unroll 1
-    for (uint32_t w = nw - 1;; w--, i++) {
-      cp_wait<NST - 1>();
-      __syncwarp();
-      rg.read(r, rg.stage(i));
+    rg.store_ck(nw - 1, M);
+    run_phase(std::false_type{}, nw - 1, nw - ws, -1, [&](uint32_t w, const uint8_t* st) {
+      rg.read(r, st);
       beta_window(M, r);
       if (w > ws) {
-        ckw[(2u * (w - 1)) * 32u]      = u4{M[0], M[1], M[2], M[3]};
-        ckw[(2u * (w - 1) + 1u) * 32u] = u4{M[4], M[5], M[6], M[7]};
+        rg.store_ck(w - 1, M);
         normalise(M);
       }
-      __syncwarp();
-      if (nxt > ws) {
-        nxt--;
-        const u4 q = qn;
-        if (DEC2 && nxt > ws) qn = ldg_q(v.qpp_fwd, nxt - 1);
-        rg.template issue<false>(nxt, q);
-      }
-      cp_commit();
-      if (w == ws) break;
-    }
+    });
   }
 
   // the checkpoints were written by the other warp
@@ -294,81 +286,25 @@ __global__ void __maxnreg__(144) tdec_siso_pass_kernel(TdecView v, int pass_idx)
   WinOut   o;
   uint32_t c[8];
   if (warp == 0) {
-    // ---- phase 2: windows ws..nw-1 upwards ----
-    rg.slot      = 0;
-    uint32_t nxt = ws;
-    if (DEC2) qn = ldg_q(v.qpp_fwd, ws);
-#pragma unroll 1
-    for (int i = 0; i < NST; i++) {
-      if (nxt < nw) {
-        const u4 q = qn;
-        if (DEC2 && nxt + 1 < nw) qn = ldg_q(v.qpp_fwd, nxt + 1);
-        rg.template issue<true>(nxt, q);
-        nxt++;
-      }
-      cp_commit();
-    }
-#pragma unroll 1
-    for (uint32_t w = ws; w < nw; w++) {
-      cp_wait<NST - 1>();
-      __syncwarp();
-      const uint8_t* st = rg.stage(w - ws);
+    // warp F, phase 2: windows ws..nw-1 upwards
+    run_phase(std::true_type{}, ws, nw - ws, +1, [&](uint32_t w, const uint8_t* st) {
       rg.read(r, st);
       rg.read_ck(c, st);
       u4 q = {};
       if (DEC2) q = *reinterpret_cast<const u4*>(st + RG::L::OFF_QPP);
-      fwd_window(M, c, 8u * w + 8u < (uint32_t)K, r, have_crc ? reinterpret_cast<const CrcPow*>(st + RG::L::OFF_CRC) : nullptr, res, o);
-#pragma unroll
-      for (int t = 0; t < 8; t++) ew[(DEC2 ? win_pi(q, t) : 8u * w + (uint32_t)t) * 32u] = o.enew[t];
-      hb_store(&hbw[w * 32u], o.bits, act_lo, act_hi);
-      __syncwarp();
-      if (nxt < nw) {
-        const u4 qi = qn;
-        if (DEC2 && nxt + 1 < nw) qn = ldg_q(v.qpp_fwd, nxt + 1);
-        rg.template issue<true>(nxt, qi);
-        nxt++;
-      }
-      cp_commit();
-    }
+      fwd_window(M, c, 8u * w + 8u < K, r, have_crc ? reinterpret_cast<const CrcPow*>(st + RG::L::OFF_CRC) : nullptr, res, o);
+      rg.store_out(w, q, o, act_lo, act_hi);
+    });
   } else {
-    // ---- phase 2: windows ws-1..0 downwards ----
-    rg.slot      = 0;
-    uint32_t nxt = ws;
-    if (DEC2) qn = ldg_q(v.qpp_fwd, ws - 1);
-#pragma unroll 1
-    for (int i = 0; i < NST; i++) {
-      if (nxt > 0) {
-        nxt--;
-        const u4 q = qn;
-        if (DEC2 && nxt > 0) qn = ldg_q(v.qpp_fwd, nxt - 1);
-        rg.template issue<true>(nxt, q);
-      }
-      cp_commit();
-    }
-    uint32_t i = 0;
-#pragma unroll 1
-    for (uint32_t w = ws - 1;; w--, i++) {
-      cp_wait<NST - 1>();
-      __syncwarp();
-      const uint8_t* st = rg.stage(i);
+    // warp B, phase 2: windows ws-1..0 downwards
+    run_phase(std::true_type{}, ws - 1, ws, -1, [&](uint32_t w, const uint8_t* st) {
       rg.read(r, st);
       rg.read_ck(c, st);
       u4 q = {};
       if (DEC2) q = *reinterpret_cast<const u4*>(st + RG::L::OFF_QPP);
       bwd_window(M, c, r, have_crc ? reinterpret_cast<const CrcPow*>(st + RG::L::OFF_CRC) : nullptr, res, o);
-#pragma unroll
-      for (int t = 0; t < 8; t++) ew[(DEC2 ? win_pi(q, t) : 8u * w + (uint32_t)t) * 32u] = o.enew[t];
-      hb_store(&hbw[w * 32u], o.bits, act_lo, act_hi);
-      __syncwarp();
-      if (nxt > 0) {
-        nxt--;
-        const u4 qi = qn;
-        if (DEC2 && nxt > 0) qn = ldg_q(v.qpp_fwd, nxt - 1);
-        rg.template issue<true>(nxt, qi);
-      }
-      cp_commit();
-      if (w == 0) break;
-    }
+      rg.store_out(w, q, o, act_lo, act_hi);
+    });
     xres[lane] = res;
   }
   __syncthreads();
@@ -379,34 +315,61 @@ __global__ void __maxnreg__(144) tdec_siso_pass_kernel(TdecView v, int pass_idx)
   }
 }
 
-template <bool IN8>
-static void launch_siso_pass_fmt(const TdecView& v, int pass_idx, cudaStream_t stream)
+// One launch per pass; a CTA takes the int8 or the int16 code path according to its tile's format (which tiles are
+// which is only known on the device, after the load kernels ran).
+template <bool DEC2, bool FIRST>
+__global__ void __maxnreg__(128) tdec_siso_pass_kernel(TdecView v, int pass_idx)
 {
-  const size_t smem = 2 * ring::RING_BYTES;
-  dim3         grid((unsigned)v.ntiles), block(64);
-  static bool  attr_done = false;
-  if (!attr_done) {
-    cudaFuncSetAttribute(tdec_siso_pass_kernel<false, true, IN8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(tdec_siso_pass_kernel<true, false, IN8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(tdec_siso_pass_kernel<false, false, IN8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    attr_done = true;
-  }
-  if (pass_idx == 0) {
-    tdec_siso_pass_kernel<false, true, IN8><<<grid, block, smem, stream>>>(v, pass_idx);
-  } else if (pass_idx & 1) {
-    tdec_siso_pass_kernel<true, false, IN8><<<grid, block, smem, stream>>>(v, pass_idx);
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ LaneResult xres[32];
+  if ((int)blockIdx.x >= v.ntiles) return;
+  if (v.fmt[blockIdx.x] == 0u) {
+    siso_pass_tile<DEC2, FIRST, true>(v, pass_idx, smem, xres);
   } else {
-    tdec_siso_pass_kernel<false, false, IN8><<<grid, block, smem, stream>>>(v, pass_idx);
+    siso_pass_tile<DEC2, FIRST, false>(v, pass_idx, smem, xres);
   }
 }
 
-// Two launches per pass: the tiles held in the int8 format and those held in int16 (a CTA whose tile is in the other
-// format exits at once; which tiles are which is only known on the device, after the load kernel ran).
+static void siso_set_attributes()
+{
+  const size_t smem = 2 * ring::RING_BYTES;
+  static bool  attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(tdec_siso_pass_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(tdec_siso_pass_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(tdec_siso_pass_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // 7 CTAs per SM (one wave for the 1024 tiles of a 65,536-block batch) need the full shared-memory carve-out
+    cudaFuncSetAttribute(tdec_siso_pass_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(tdec_siso_pass_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(tdec_siso_pass_kernel<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    attr_done = true;
+  }
+}
+
+int siso_resident_tiles_per_sm()
+{
+  siso_set_attributes();
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, tdec_siso_pass_kernel<false, false>, 64, 2 * ring::RING_BYTES) != cudaSuccess) {
+    return -1;
+  }
+  return n;
+}
+
 void launch_siso_pass(const TdecView& v, int pass_idx, cudaStream_t stream)
 {
-  launch_siso_pass_fmt<true>(v, pass_idx, stream);
-  launch_siso_pass_fmt<false>(v, pass_idx, stream);
+  const size_t smem = 2 * ring::RING_BYTES;
+  dim3         grid((unsigned)v.ntiles), block(64);
+  siso_set_attributes();
+  if (pass_idx == 0) {
+    tdec_siso_pass_kernel<false, true><<<grid, block, smem, stream>>>(v, pass_idx);
+  } else if (pass_idx & 1) {
+    tdec_siso_pass_kernel<true, false><<<grid, block, smem, stream>>>(v, pass_idx);
+  } else {
+    tdec_siso_pass_kernel<false, false><<<grid, block, smem, stream>>>(v, pass_idx);
+  }
 }
+
 
 // ---------------------------------------------------------------------------------------------------------------
 // natural -> tiled.  Block = (tile, chunk of 32 trellis rows).  Phase 1 stages the 64 blocks' 96 contiguous int16
@@ -415,8 +378,16 @@ void launch_siso_pass(const TdecView& v, int pass_idx, cudaStream_t stream)
 //   tdec_load8_kernel   always runs: writes the int8 arrays (8 rows x 2 blocks per uint4) and raises fmt[tile] when a
 //                       value of the tile does not fit int8; also arms the per-block state.
 //   tdec_load16_kernel  runs after it and fills the int16 arrays (4 rows x 2 blocks per uint4) of the raised tiles only.
-constexpr int LOAD_ROWS = 32;
-constexpr int LOAD_PITCH = 3 * LOAD_ROWS + 4; // int16 per staged block, +4 keeps 8-byte alignment and skews banks
+constexpr int LOAD_ROWS = 64; // trellis rows per CTA: 384 contiguous bytes of each block's natural vector
+constexpr size_t LOAD_SMEM = (size_t)3 * LOAD_ROWS * (TDEC_TILE_CB + 2) * sizeof(int16_t);
+constexpr int LOAD_PITCH = TDEC_TILE_CB + 2;  // staging buffer sm[value index o = 3*row+stream][block]: the two blocks of a
+                                              // lane are one aligned 32-bit word, consecutive lanes consecutive banks
+// int16 index of (value o, block c).  Block pairs are XOR-swizzled with bits 5..6 of o so that the staging stores of a
+// warp (fixed block, o = 4*lane + i) fall into 32 different banks as well.
+__device__ __forceinline__ int load_sm_idx(int o, int c)
+{
+  return o * LOAD_PITCH + 2 * ((c >> 1) ^ ((o >> 5) & 3)) + (c & 1);
+}
 
 __device__ __forceinline__ bool fits8(int16_t a)
 {
@@ -431,24 +402,51 @@ __device__ __forceinline__ bool load_stage_chunk(int16_t* sm, const TdecView& v,
                                                  const uint64_t* __restrict__ offsets, uint32_t ncb, int tile, int k0, int rows)
 {
   const size_t nllr = 3 * (size_t)v.K + 12;
-  const int    nvec = rows * 3 / 4; // 8-byte vectors per block in this chunk
-  bool         bad  = false;
-  for (int idx = threadIdx.x; idx < TDEC_TILE_CB * nvec; idx += blockDim.x) {
-    const int      c  = idx / nvec, q = idx % nvec;
-    const uint32_t cb = (uint32_t)tile * TDEC_TILE_CB + c;
-    uint2          val = make_uint2(0u, 0u);
-    if (cb < ncb) {
-      const int16_t* src = llr + (offsets ? offsets[cb] : cb * nllr) + 3 * (size_t)k0 + 4 * (size_t)q;
-      if (ALIGNED8) {
-        val = __ldcs(reinterpret_cast<const uint2*>(src));
-      } else {
-        val.x = (uint32_t)(uint16_t)src[0] | ((uint32_t)(uint16_t)src[1] << 16);
-        val.y = (uint32_t)(uint16_t)src[2] | ((uint32_t)(uint16_t)src[3] << 16);
+  const int    nvec = rows * 3 / 4; // 8-byte vectors per block in this chunk (<= 48)
+  // warp w stages blocks w, w+8, ...; lane q takes the q-th 8-byte piece of the block's chunk (no divisions).  Two
+  // blocks per round keep 6 independent 8-byte loads per thread in flight.
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  uint32_t  acc  = 0; // OR of (value + 128) high bytes: non-zero <=> some value does not fit int8
+  constexpr int NB = 2;
+  for (int c0 = wid; c0 < TDEC_TILE_CB; c0 += NB * nwarp) {
+    constexpr int NH = (LOAD_ROWS * 3 / 4 + 31) / 32; // 8-byte pieces per lane and block
+    uint2 val[NB][NH];
+#pragma unroll
+    for (int u = 0; u < NB; u++) {
+      const int      c  = c0 + u * nwarp;
+      const uint32_t cb = (uint32_t)tile * TDEC_TILE_CB + c;
+#pragma unroll
+      for (int h = 0; h < NH; h++) {
+        const int q = lane + 32 * h;
+        val[u][h]   = make_uint2(0u, 0u);
+        if (c < TDEC_TILE_CB && cb < ncb && q < nvec) {
+          const int16_t* src = llr + (offsets ? offsets[cb] : cb * nllr) + 3 * (size_t)k0 + 4 * (size_t)q;
+          if (ALIGNED8) {
+            val[u][h] = __ldcs(reinterpret_cast<const uint2*>(src));
+          } else {
+            val[u][h].x = (uint32_t)(uint16_t)src[0] | ((uint32_t)(uint16_t)src[1] << 16);
+            val[u][h].y = (uint32_t)(uint16_t)src[2] | ((uint32_t)(uint16_t)src[3] << 16);
+          }
+        }
       }
     }
-    bad |= !fits8(lo16(val.x)) || !fits8(hi16(val.x)) || !fits8(lo16(val.y)) || !fits8(hi16(val.y));
-    *reinterpret_cast<uint2*>(&sm[c * LOAD_PITCH + 4 * q]) = val;
+#pragma unroll
+    for (int u = 0; u < NB; u++) {
+      const int c = c0 + u * nwarp;
+#pragma unroll
+      for (int h = 0; h < NH; h++) {
+        const int q = lane + 32 * h;
+        if (c < TDEC_TILE_CB && q < nvec) {
+          acc |= (add2(val[u][h].x, 0x00800080u) | add2(val[u][h].y, 0x00800080u)) & 0xFF00FF00u;
+          sm[load_sm_idx(4 * q + 0, c)] = lo16(val[u][h].x);
+          sm[load_sm_idx(4 * q + 1, c)] = hi16(val[u][h].x);
+          sm[load_sm_idx(4 * q + 2, c)] = lo16(val[u][h].y);
+          sm[load_sm_idx(4 * q + 3, c)] = hi16(val[u][h].y);
+        }
+      }
+    }
   }
+  const bool bad = acc != 0u;
   return __syncthreads_or(bad) == 0;
 }
 
@@ -456,7 +454,7 @@ template <bool ALIGNED8>
 __global__ void __launch_bounds__(256)
     tdec_load8_kernel(TdecView v, const int16_t* __restrict__ llr, const uint64_t* __restrict__ offsets, uint32_t ncb)
 {
-  __shared__ __align__(16) int16_t sm[TDEC_TILE_CB * LOAD_PITCH];
+  extern __shared__ __align__(16) int16_t sm[];
   const int    tile  = blockIdx.y;
   const int    chunk = blockIdx.x;
   const int    K     = v.K;
@@ -468,23 +466,22 @@ __global__ void __launch_bounds__(256)
     const int  rows = min(LOAD_ROWS, K - k0); // multiple of 8
     const bool ok   = load_stage_chunk<ALIGNED8>(sm, v, llr, offsets, ncb, tile, k0, rows);
     if (!ok && tid == 0) atomicOr(v.fmt + tile, 1u);
-    // (window, stream, lane) -> one uint4 of 8 rows x 2 blocks
-    for (int idx = tid; idx < (rows / 8) * 3 * 32; idx += 256) {
-      const int lane = idx & 31, s = (idx >> 5) % 3, w8 = idx / 96;
+    // (window, stream, lane) -> one uint4 of 8 rows x 2 blocks; warp = window of the chunk
+    const int lane = tid & 31;
+    for (int w8 = tid >> 5; w8 < rows / 8; w8 += 8) {
+#pragma unroll
+    for (int s = 0; s < 3; s++) {
       uint32_t  w[4];
 #pragma unroll
       for (int q = 0; q < 4; q++) {
-        uint32_t word = 0;
-#pragma unroll
-        for (int j = 0; j < 2; j++) {
-          const int      o  = 3 * (8 * w8 + 2 * q + j) + s;
-          const uint32_t lo = (uint8_t)sm[(2 * lane) * LOAD_PITCH + o], hi = (uint8_t)sm[(2 * lane + 1) * LOAD_PITCH + o];
-          word |= (lo | (hi << 8)) << (16 * j);
-        }
-        w[q] = word;
+        // rows 2q, 2q+1 of the window: (block 2*lane, block 2*lane+1) as int16 pairs -> their low bytes
+        const uint32_t p0 = *reinterpret_cast<const uint32_t*>(&sm[load_sm_idx(3 * (8 * w8 + 2 * q) + s, 2 * lane)]);
+        const uint32_t p1 = *reinterpret_cast<const uint32_t*>(&sm[load_sm_idx(3 * (8 * w8 + 2 * q + 1) + s, 2 * lane)]);
+        w[q]              = __byte_perm(p0, p1, 0x6420);
       }
       u4* dst = s == 0 ? v.S8 : (s == 1 ? v.P08 : v.P18);
       dst[row8(v, tile, k0 / 8 + w8, lane)] = u4{w[0], w[1], w[2], w[3]};
+    }
     }
   } else {
     // the chunk past the payload carries the 12 tail values: row K/8 of S8/P08/P18 and S2T
@@ -529,14 +526,17 @@ template <bool ALIGNED8>
 __global__ void __launch_bounds__(256)
     tdec_load16_kernel(TdecView v, const int16_t* __restrict__ llr, const uint64_t* __restrict__ offsets, uint32_t ncb)
 {
-  __shared__ __align__(16) int16_t sm[TDEC_TILE_CB * LOAD_PITCH];
-  const int    tile  = blockIdx.y;
-  const int    chunk = blockIdx.x;
-  const int    K     = v.K;
-  const int    k0    = chunk * LOAD_ROWS;
-  const size_t nllr  = 3 * (size_t)K + 12;
-  const int    tid   = threadIdx.x;
-  if (v.fmt[tile] == 0u) return; // the tile lives in the int8 arrays
+  extern __shared__ __align__(16) int16_t sm[];
+  const int    K      = v.K;
+  const size_t nllr   = 3 * (size_t)K + 12;
+  const int    tid    = threadIdx.x;
+  const int    chunks = (K + LOAD_ROWS - 1) / LOAD_ROWS + 1;
+  // few CTAs walking all (tile, chunk) items: in the common case no tile is raised and this costs microseconds
+  for (int item = blockIdx.x; item < v.ntiles * chunks; item += gridDim.x) {
+  const int tile = item / chunks, chunk = item % chunks;
+  const int k0   = chunk * LOAD_ROWS;
+  if (v.fmt[tile] == 0u) continue; // the tile lives in the int8 arrays
+  __syncthreads();                 // the previous item's readers of sm are done
 
   if (k0 < K) {
     const int rows = min(LOAD_ROWS, K - k0); // multiple of 8
@@ -548,8 +548,7 @@ __global__ void __launch_bounds__(256)
       for (int t = 0; t < 4; t++) {
 #pragma unroll
         for (int s = 0; s < 3; s++) {
-          const int o = 3 * (4 * r4 + t) + s;
-          w[s][t]     = pack2(sm[(2 * lane) * LOAD_PITCH + o], sm[(2 * lane + 1) * LOAD_PITCH + o]);
+          w[s][t] = *reinterpret_cast<const uint32_t*>(&sm[load_sm_idx(3 * (4 * r4 + t) + s, 2 * lane)]);
         }
       }
       const size_t row = vec_row(v, tile, k0 / 4 + r4, lane);
@@ -576,6 +575,7 @@ __global__ void __launch_bounds__(256)
     v.P0[row]        = u4{w[1][0], w[1][1], w[1][2], w[1][3]};
     v.P1[row]        = u4{w[2][0], w[2][1], w[2][2], w[2][3]};
   }
+  }
 }
 
 void launch_load_natural(const TdecView& v,
@@ -587,19 +587,32 @@ void launch_load_natural(const TdecView& v,
 {
   const int chunks = (v.K + LOAD_ROWS - 1) / LOAD_ROWS + 1; // +1: the tail chunk
   dim3      grid((unsigned)chunks, (unsigned)v.ntiles), block(256);
+  const long items = (long)chunks * v.ntiles;
+  dim3       grid16((unsigned)(items < 148 * 8 ? items : 148 * 8));
+  static bool attr_done = false;
+  if (!attr_done) { // 8 CTAs of 25 KB per SM
+    cudaFuncSetAttribute(tdec_load8_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(tdec_load8_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(tdec_load8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LOAD_SMEM);
+    cudaFuncSetAttribute(tdec_load8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LOAD_SMEM);
+    cudaFuncSetAttribute(tdec_load16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LOAD_SMEM);
+    cudaFuncSetAttribute(tdec_load16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LOAD_SMEM);
+    attr_done = true;
+  }
   cudaMemsetAsync(v.fmt, 0, (size_t)v.ntiles * sizeof(uint32_t), stream);
   if (aligned8) {
-    tdec_load8_kernel<true><<<grid, block, 0, stream>>>(v, llr_dev, offsets_dev, ncb);
-    tdec_load16_kernel<true><<<grid, block, 0, stream>>>(v, llr_dev, offsets_dev, ncb);
+    tdec_load8_kernel<true><<<grid, block, LOAD_SMEM, stream>>>(v, llr_dev, offsets_dev, ncb);
+    tdec_load16_kernel<true><<<grid16, block, LOAD_SMEM, stream>>>(v, llr_dev, offsets_dev, ncb);
   } else {
-    tdec_load8_kernel<false><<<grid, block, 0, stream>>>(v, llr_dev, offsets_dev, ncb);
-    tdec_load16_kernel<false><<<grid, block, 0, stream>>>(v, llr_dev, offsets_dev, ncb);
+    tdec_load8_kernel<false><<<grid, block, LOAD_SMEM, stream>>>(v, llr_dev, offsets_dev, ncb);
+    tdec_load16_kernel<false><<<grid16, block, LOAD_SMEM, stream>>>(v, llr_dev, offsets_dev, ncb);
   }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// HB -> bytes.  Block = (tile, 32 output bytes per code block); decisions are transposed through shared memory so
-// that both the HB reads (64 B rows) and the byte writes (32 B runs per block) are contiguous.
+// HB -> bytes.  One CTA per tile: the tile's decisions (K/8 x 64 bytes) are staged in shared memory, so the gather
+// through the inverse interleaver that a block ending on a DEC2 pass needs (eight 1-bit lookups per output byte)
+// never leaves the SM; the 64 x K/8 output bytes are assembled in shared memory too and leave as one contiguous run.
 __global__ void __launch_bounds__(256) tdec_decide_kernel(TdecView v,
                                                           const uint16_t* __restrict__ qpp_rev,
                                                           uint8_t* __restrict__ out,
@@ -608,29 +621,61 @@ __global__ void __launch_bounds__(256) tdec_decide_kernel(TdecView v,
                                                           uint8_t* __restrict__ npass_run,
                                                           uint32_t ncb)
 {
-  __shared__ uint8_t sm[TDEC_TILE_CB][33];
-  const int tile = blockIdx.y;
-  const int jb0  = blockIdx.x * 32;
-  const int nb   = v.K / 8;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  extern __shared__ __align__(16) uint8_t dsm[];
+  const int      tile  = blockIdx.x;
+  const int      nb    = v.K / 8; // bytes per block = windows per block
+  const int      pitch = nb + 4;
+  uint16_t*      hb    = reinterpret_cast<uint16_t*>(dsm);           // [nb][32]
+  uint8_t*       so    = dsm + (((size_t)nb * 64 + 15) / 16) * 16;   // [64][pitch]
+  const int      tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const uint4*   src = reinterpret_cast<const uint4*>(v.HB + hb_idx(v, tile, 0, 0));
+  for (int i = tid; i < nb * 4; i += 256) reinterpret_cast<uint4*>(hb)[i] = src[i];
+  __syncthreads();
 
-  for (int j = wid; j < 32; j += 8) {
-    const int jb = jb0 + j;
-    if (jb < nb) {
-      sm[2 * lane][j]     = decide_byte(v, qpp_rev, tile * TDEC_TILE_CB + 2 * lane, jb);
-      sm[2 * lane + 1][j] = decide_byte(v, qpp_rev, tile * TDEC_TILE_CB + 2 * lane + 1, jb);
+  // a warp takes 4 output bytes (32 decisions) at a time for all 64 blocks; lane = block within a half tile
+  for (int j0 = wid * 4; j0 < nb; j0 += 32) {
+    const int      nj  = min(4, nb - j0);
+    const uint32_t rev = (8 * j0 + lane < v.K) ? qpp_rev[8 * j0 + lane] : 0u; // visiting index of bit 8*j0+lane
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int      c    = 32 * h + lane; // block within the tile
+      const CbStatus st   = v.status[(size_t)tile * TDEC_TILE_CB + c];
+      const bool     perm = st.npass_run > 0 && ((st.npass_run - 1) & 1); // last pass was DEC2: HB is in its visiting order
+      const int      sh   = (c & 1) ? 8 : 0;
+      for (int j = 0; j < nj; j++) {
+        uint32_t byte;
+        if (!__any_sync(0xFFFFFFFFu, perm)) {
+          byte = (hb[(j0 + j) * 32 + (c >> 1)] >> sh) & 0xFFu;
+        } else {
+          byte = 0;
+#pragma unroll
+          for (int t = 0; t < 8; t++) {
+            const uint32_t i   = __shfl_sync(0xFFFFFFFFu, rev, 8 * j + t);
+            const uint32_t w   = hb[(i >> 3) * 32 + (c >> 1)] >> sh;
+            byte               = (byte << 1) | ((w >> (7 - (i & 7))) & 1u);
+          }
+          if (!perm) byte = (hb[(j0 + j) * 32 + (c >> 1)] >> sh) & 0xFFu;
+        }
+        so[c * pitch + j0 + j] = (uint8_t)byte;
+      }
     }
   }
   __syncthreads();
-  for (int c = wid; c < TDEC_TILE_CB; c += 8) {
-    const uint32_t cb = (uint32_t)tile * TDEC_TILE_CB + c;
-    const int      jb = jb0 + lane;
-    if (cb < ncb && jb < nb) {
-      out[(size_t)cb * nb + jb] = sm[c][lane];
+  const size_t   first = (size_t)tile * TDEC_TILE_CB;
+  const uint32_t nblk  = first < ncb ? (uint32_t)min((size_t)TDEC_TILE_CB, (size_t)ncb - first) : 0u;
+  uint8_t*       dst   = out + first * nb;
+  if ((nb & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+    const int q = nb / 16;
+    for (uint32_t i = tid; i < nblk * q; i += 256) {
+      const uint32_t c = i / q, k = i % q;
+      const uint32_t* p = reinterpret_cast<const uint32_t*>(so + c * pitch + 16 * k);
+      reinterpret_cast<uint4*>(dst + (size_t)c * nb)[k] = make_uint4(p[0], p[1], p[2], p[3]);
     }
+  } else {
+    for (uint32_t i = tid; i < nblk * nb; i += 256) dst[i] = so[(i / nb) * pitch + (i % nb)];
   }
-  if (blockIdx.x == 0 && threadIdx.x < TDEC_TILE_CB) {
-    const uint32_t cb = (uint32_t)tile * TDEC_TILE_CB + threadIdx.x;
+  if (tid < TDEC_TILE_CB) {
+    const uint32_t cb = (uint32_t)first + tid;
     if (cb < ncb) {
       const CbStatus s = v.status[cb];
       if (crc_ok) crc_ok[cb] = s.crc_ok;
@@ -650,8 +695,14 @@ void launch_decide(const TdecView& v,
                    uint32_t        ncb,
                    cudaStream_t    stream)
 {
-  dim3 grid((unsigned)((v.K / 8 + 31) / 32), (unsigned)v.ntiles), block(256);
-  tdec_decide_kernel<<<grid, block, 0, stream>>>(v, qpp_rev_dev, out_dev, crc_ok_dev, npass_dev, npass_run_dev, ncb);
+  const int    nb   = v.K / 8;
+  const size_t smem = (((size_t)nb * 64 + 15) / 16) * 16 + (size_t)TDEC_TILE_CB * (nb + 4);
+  static bool  attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(tdec_decide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    attr_done = true;
+  }
+  tdec_decide_kernel<<<(unsigned)v.ntiles, 256, smem, stream>>>(v, qpp_rev_dev, out_dev, crc_ok_dev, npass_dev, npass_run_dev, ncb);
 }
 
 } // namespace b200

@@ -14,6 +14,7 @@ void launch_load_natural(const TdecView& v,
                          uint32_t        ncb,
                          cudaStream_t    stream);
 void launch_siso_pass(const TdecView& v, int pass_idx, cudaStream_t stream);
+int  siso_resident_tiles_per_sm();
 void launch_decide(const TdecView& v,
                    const uint16_t* qpp_rev_dev,
                    uint8_t*        out_dev,

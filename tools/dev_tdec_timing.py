@@ -20,6 +20,8 @@ def main():
     torch.cuda.synchronize()
     print(f"synth {ncb} x K={K}: {time.time()-t0:.2f} s")
     dec = TurboDecoderBatch(0, ncb)
+    from srslte_b200 import _lib
+    print("resident tiles per SM:", _lib.lib().srsran_b200_tdec_resident_tiles_per_sm())
     out = torch.empty((ncb, K // 8), dtype=torch.uint8, device="cuda")
     ok = torch.empty(ncb, dtype=torch.uint8, device="cuda")
     npass = torch.empty(ncb, dtype=torch.uint8, device="cuda")
