@@ -165,6 +165,7 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as dist
 
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: the contract is ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -256,9 +257,10 @@ def run_ours(args):
     e2e_match = bool((h_out.to(dev) == out).all().item()) if False else None  # (out now holds the early-stop decode)
 
     # ---- roofline of the dominant kernel (tdec_siso_pass_kernel) -----------------------------------------------
-    # Algorithmic bytes per SISO launch and code block (DESIGN.md section 4): one read of the pass's inputs and one
+    # Algorithmic bytes per SISO launch and code block (DESIGN.md section 2.3): one read of the pass's inputs and one
     # write of the extrinsics, int16:  DEC1 (even pass): S, E, P0 in + E out = 8K bytes (6K on pass 0, no a-priori yet);
-    # DEC2 (odd pass): E, P1 in + E out = 6K bytes.  Averaged over the 8 launches of a step.
+    # DEC2 (odd pass): E, P1 in + E out = 6K bytes.  Averaged over the 8 launches of a step.  (The kernel's actual DRAM
+    # traffic -- "traffic", from ncu -- is higher by construction: checkpoint + recompute reads the inputs twice.)
     alg_per_cb = (6 * K + 4 * 6 * K + 3 * 8 * K) / 8.0
     siso_ms = prof["siso_ms"] / max(1, prof["siso_launches"])
     peaks = measured_peaks()
@@ -294,10 +296,14 @@ def run_ours(args):
             sub = llr[:n].cpu().numpy()
             api.decode_batch(sub[:cores], K, MAX_PASSES, "B", 0, False, nthreads=cores,
                              impl=loader.TDEC_AUTO if have_ref else loader.TDEC_GENERIC)
-            _, _, _, sec = api.decode_batch(sub, K, MAX_PASSES, "B", 0, False, nthreads=cores,
-                                            impl=loader.TDEC_AUTO if have_ref else loader.TDEC_GENERIC)
-            cpu = {"value": n * K / sec / 1e9, "unit": UNIT, "cores": cores, "kind": "reference" if have_ref else "port",
-                   "sample": f"first {n} code blocks of the same batch, {MAX_PASSES} passes each, no early stop, {sec:.1f} s, "
+            sec, reps = 0.0, 0
+            while sec * cores < 16.0 and reps < 8:  # about 16-20 core-seconds of CPU work in total
+                _, _, _, s1 = api.decode_batch(sub, K, MAX_PASSES, "B", 0, False, nthreads=cores,
+                                               impl=loader.TDEC_AUTO if have_ref else loader.TDEC_GENERIC)
+                sec += s1
+                reps += 1
+            cpu = {"value": reps * n * K / sec / 1e9, "unit": UNIT, "cores": cores, "kind": "reference" if have_ref else "port",
+                   "sample": f"first {n} code blocks of the same batch x {reps} repetitions, {MAX_PASSES} passes each, no early stop, {sec:.1f} s wall on {cores} threads, "
                              + ("srsran_tdec AUTO (AVX2 window decoder)" if have_ref else "scalar generic port")}
         except Exception as ex:  # the baseline is informative; never fail the bench on it
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {ex}"}

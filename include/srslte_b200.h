@@ -223,6 +223,28 @@ SRSRAN_B200_API int srsran_b200_demod_soft_demodulate_s(int         device,
                                                         uint32_t    flags,
                                                         void*       stream);
 
+/*
+ * PUSCH glue between srsran_b200_ofdm_rx_sf_batch and srsran_b200_sch_decode_batch (device buffers only, flags must carry
+ * SRSRAN_B200_FLAG_DEVICE_PTRS): per subframe, the OFDM symbols whose bit is set in sym_mask (bit l = symbol l; clear
+ * the DMRS symbols 3 and 10 of a normal-CP PUSCH subframe: 0x3BF7) are soft-demapped in order as one
+ * srsran_demod_soft_demodulate_s(modulation, d, q, nof_re_total) call (lib/src/phy/phch/pusch.c:449) and every soft
+ * bit is then shifted right arithmetically by llr_shift bits (0 = the reference's scale; 4 brings 64QAM's 700x scale
+ * into the overflow-free envelope of the generic int16 decoder).  Channel estimation, equalisation, transform
+ * de-precoding, descrambling and UL-SCH de-interleaving are NOT part of this entry (identity channel pipeline).
+ * grid: nsf x nof_symbols x nof_re cf_t;  llr: nsf x popcount(sym_mask) x nof_re x {2,4,6} int16.
+ */
+SRSRAN_B200_API int srsran_b200_pusch_demap_batch(int         device,
+                                                  int         modulation,
+                                                  const void* grid,
+                                                  int16_t*    llr,
+                                                  uint32_t    nsf,
+                                                  uint32_t    nof_symbols,
+                                                  uint32_t    nof_re,
+                                                  uint32_t    sym_mask,
+                                                  uint32_t    llr_shift,
+                                                  uint32_t    flags,
+                                                  void*       stream);
+
 /* ---------------------------------------------------------------------------------------------------------------
  * Synthetic workload (bench / tests only, never on the decode path): fills llr_dev[ncb][3K+12] (device memory) with
  * the quantised channel output of randomly drawn, CRC24B-terminated, turbo-encoded blocks:

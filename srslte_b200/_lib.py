@@ -74,6 +74,7 @@ EXPORTED_SYMBOLS = [
     "srsran_b200_tdec_profile_reset",
     "srsran_b200_tdec_profile_get",
     "srsran_b200_tdec_resident_tiles_per_sm",
+    "srsran_b200_pusch_demap_batch",
     "srsran_b200_synth_llr",
     "srsran_b200_sch_init",
     "srsran_b200_sch_free",

@@ -37,19 +37,14 @@ __device__ __forceinline__ int trunc16(float f)
   return (int)wrap16(__float2int_rz(f));
 }
 
-__global__ void demod_s_kernel(int mod, const float2* __restrict__ sym, int16_t* __restrict__ llr, uint32_t n, uint32_t group,
-                               float qpsk_scale)
+// One symbol -> its bps soft bits (returned in o[0..bps)).  body: the symbol falls into the SIMD body of its reference
+// call (rounding) rather than the scalar tail (truncation); for QPSK fpos0 = float position of s.x inside the call and
+// fbody = 16 * (nfloats / 16).
+__device__ __forceinline__ void demod_one(int mod, float2 s, bool body, uint32_t fpos0, uint32_t fbody, float qpsk_scale, int16_t o[6])
 {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const uint32_t g0   = (i / group) * group;               // first symbol of this reference call
-  const uint32_t glen = min(group, n - g0);                // its length
-  const uint32_t pos  = i - g0;
-  const float2   s    = sym[i];
   if (mod == 3) {
-    const bool body = pos < 4u * (glen / 4u);
-    const int  t1 = 432, t2 = 216; // (int16)(4*700/sqrtf(42)), (int16)(2*700/sqrtf(42))
-    int        yr, yi, ar, ai;
+    const int t1 = 432, t2 = 216; // (int16)(4*700/sqrtf(42)), (int16)(2*700/sqrtf(42))
+    int       yr, yi, ar, ai;
     if (body) {
       yr = sat16i(__float2int_rn(s.x * -700.0f));
       yi = sat16i(__float2int_rn(s.y * -700.0f));
@@ -62,16 +57,13 @@ __global__ void demod_s_kernel(int mod, const float2* __restrict__ sym, int16_t*
       ar = (int)wrap16(abs16w(pr) - t1);
       ai = (int)wrap16(abs16w(pi) - t1);
     }
-    int16_t* o = llr + 6 * (size_t)i;
-    o[0]       = (int16_t)yr;
-    o[1]       = (int16_t)yi;
-    o[2]       = (int16_t)ar;
-    o[3]       = (int16_t)ai;
-    o[4]       = wrap16(abs16w(ar) - t2);
-    o[5]       = wrap16(abs16w(ai) - t2);
+    o[0] = (int16_t)yr;
+    o[1] = (int16_t)yi;
+    o[2] = (int16_t)ar;
+    o[3] = (int16_t)ai;
+    o[4] = wrap16(abs16w(ar) - t2);
+    o[5] = wrap16(abs16w(ai) - t2);
   } else if (mod == 2) {
-    const bool body = pos < 4u * (glen / 4u);
-    int16_t*   o    = llr + 4 * (size_t)i;
     if (body) {
       const int yr = sat16i(__float2int_rn(s.x * -400.0f)), yi = sat16i(__float2int_rn(s.y * -400.0f));
       o[0]         = (int16_t)yr;
@@ -87,16 +79,54 @@ __global__ void demod_s_kernel(int mod, const float2* __restrict__ sym, int16_t*
       o[3]           = (int16_t)trunc16((float)abs(pi) - th);
     }
   } else { // QPSK
-    const uint32_t nf   = 2u * glen;
-    const uint32_t body = 16u * (nf / 16u);
-    int16_t*       o    = llr + 2 * (size_t)i;
-    const float    v[2] = {s.x * qpsk_scale, s.y * qpsk_scale};
+    const float v[2] = {s.x * qpsk_scale, s.y * qpsk_scale};
 #pragma unroll
     for (int c = 0; c < 2; c++) {
-      const uint32_t fpos = 2u * pos + c;
-      o[c] = fpos < body ? (int16_t)sat16i(__float2int_rz(v[c])) : (int16_t)trunc16(v[c]);
+      o[c] = fpos0 + c < fbody ? (int16_t)sat16i(__float2int_rz(v[c])) : (int16_t)trunc16(v[c]);
     }
   }
+}
+
+__global__ void demod_s_kernel(int mod, const float2* __restrict__ sym, int16_t* __restrict__ llr, uint32_t n, uint32_t group,
+                               float qpsk_scale)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t g0   = (i / group) * group;               // first symbol of this reference call
+  const uint32_t glen = min(group, n - g0);                // its length
+  const uint32_t pos  = i - g0;
+  const int      bps  = 2 * mod;
+  int16_t        o[6];
+  demod_one(mod, sym[i], pos < 4u * (glen / 4u), 2u * pos, 16u * (2u * glen / 16u), qpsk_scale, o);
+  for (int b = 0; b < bps; b++) llr[(size_t)bps * i + b] = o[b];
+}
+
+// PUSCH glue for the identity-channel pipeline (BASELINE config 4): the data-carrying OFDM symbols of each subframe's
+// resource grid are demapped as ONE reference call per subframe (pusch.c:449: srsran_demod_soft_demodulate_s over
+// grant.nof_re symbols), then every soft bit is shifted right arithmetically by `shift` bits to bring the reference's
+// 700x / 400x / 141x fixed-point scale into the generic int16 decoder's overflow-free envelope.
+__global__ void pusch_demap_kernel(int mod, const float2* __restrict__ grid, int16_t* __restrict__ llr, uint32_t nsf, uint32_t nof_symbols,
+                                   uint32_t nof_re, uint32_t sym_mask, uint32_t n_data_sym, int shift, float qpsk_scale)
+{
+  const uint32_t per_sf = n_data_sym * nof_re;
+  const uint64_t i      = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (uint64_t)nsf * per_sf) return;
+  const uint32_t sf  = (uint32_t)(i / per_sf);
+  const uint32_t pos = (uint32_t)(i - (uint64_t)sf * per_sf); // symbol index inside the subframe's reference call
+  const uint32_t d   = pos / nof_re, re = pos - d * nof_re;   // d-th data symbol
+  // d-th set bit of sym_mask
+  uint32_t l = 0, seen = 0;
+  for (; l < nof_symbols; l++) {
+    if ((sym_mask >> l) & 1u) {
+      if (seen == d) break;
+      seen++;
+    }
+  }
+  const float2 s   = grid[((size_t)sf * nof_symbols + l) * nof_re + re];
+  const int    bps = 2 * mod;
+  int16_t      o[6];
+  demod_one(mod, s, pos < 4u * (per_sf / 4u), 2u * pos, 16u * (2u * per_sf / 16u), qpsk_scale, o);
+  for (int b = 0; b < bps; b++) llr[(size_t)bps * i + b] = (int16_t)(o[b] >> shift);
 }
 
 } // namespace b200
@@ -142,6 +172,43 @@ extern "C" SRSRAN_B200_API int srsran_b200_demod_soft_demodulate_s(int         d
   B200_CUDA_TRY(cudaMemcpy(llr, d_llr, (size_t)nsymbols * bps * sizeof(int16_t), cudaMemcpyDeviceToHost));
   B200_CUDA_TRY(cudaFree(d_sym));
   B200_CUDA_TRY(cudaFree(d_llr));
+  B200_CUDA_TRY(cudaGetLastError());
+  return B200_SUCCESS;
+}
+
+extern "C" SRSRAN_B200_API int srsran_b200_pusch_demap_batch(int         device,
+                                                            int         modulation,
+                                                            const void* grid,
+                                                            int16_t*    llr,
+                                                            uint32_t    nsf,
+                                                            uint32_t    nof_symbols,
+                                                            uint32_t    nof_re,
+                                                            uint32_t    sym_mask,
+                                                            uint32_t    llr_shift,
+                                                            uint32_t    flags,
+                                                            void*       stream)
+{
+  if (modulation < 1 || modulation > 3) {
+    B200_LOG_ERROR("Invalid modulation %d", modulation);
+    return B200_ERROR;
+  }
+  if (!grid || !llr || nof_symbols == 0 || nof_symbols > 14 || nof_re == 0 || llr_shift > 15) return B200_ERROR_INVALID_INPUTS;
+  if (!(flags & SRSRAN_B200_FLAG_DEVICE_PTRS)) {
+    B200_LOG_ERROR("srsran_b200_pusch_demap_batch works on device buffers (it sits between two device-side stages)");
+    return B200_ERROR_INVALID_INPUTS;
+  }
+  sym_mask &= (1u << nof_symbols) - 1u;
+  const uint32_t nd = (uint32_t)__builtin_popcount(sym_mask);
+  if (nsf == 0 || nd == 0) return B200_SUCCESS;
+  DeviceContext* ctx = device_context(device);
+  if (!ctx) return B200_ERROR;
+  B200_CUDA_TRY(cudaSetDevice(device));
+  const uint64_t n    = (uint64_t)nsf * nd * nof_re;
+  const float    qs   = (float)(-100.0 * M_SQRT2);
+  const unsigned nblk = (unsigned)((n + 255) / 256);
+  pusch_demap_kernel<<<nblk, 256, 0, (cudaStream_t)stream>>>(modulation, (const float2*)grid, llr, nsf, nof_symbols, nof_re, sym_mask,
+                                                           nd, (int)llr_shift, qs);
+  g_kernel_launches++;
   B200_CUDA_TRY(cudaGetLastError());
   return B200_SUCCESS;
 }

@@ -1,0 +1,73 @@
+"""The numpy transmit chain used to synthesise PUSCH subframes (srslte_b200/synth_pusch.py, bench/tests only) against the
+oracle's encoder, rate matcher and CRC, and against the oracle's OFDM receiver (loop-back)."""
+import numpy as np
+
+from srslte_b200 import synth_pusch as sp
+
+
+def test_crc_and_qpp(port):
+    rng = np.random.default_rng(1)
+    bits = rng.integers(0, 2, (3, 6120)).astype(np.uint8)
+    for poly, kind in ((sp.CRC24A, "A"), (sp.CRC24B, "B")):
+        par = sp.crc24(bits, poly)
+        for r in range(3):
+            want = port.crc24(kind, np.packbits(bits[r]), 6120)
+            assert sum(int(b) << (23 - i) for i, b in enumerate(par[r])) == want
+    for K in (40, 1024, 5824, 6144):
+        fwd, _ = port.interleaver(K)
+        assert (sp.qpp_interleaver(K) == fwd).all()
+
+
+def test_turbo_encoder_and_rate_matching(port):
+    rng = np.random.default_rng(2)
+    for K in (40, 504, 5824):
+        bits = rng.integers(0, 2, (2, K)).astype(np.uint8)
+        d = sp.turbo_encode(bits, sp.qpp_interleaver(K))
+        for r in range(2):
+            cw = port.tcod_encode(bits[r])  # natural order [3k+j], k = 0..K+3
+            assert (d[r].T.reshape(-1) == cw).all(), K
+            for rv in range(4):
+                for E in (int(0.4 * 3 * K), 3 * K + 12, int(1.7 * 3 * K)):
+                    assert (sp.rate_match(d[r:r + 1], E, rv)[0] == port.rm_tx(cw, K, E, rv)).all(), (K, rv, E)
+
+
+def test_transport_block_matches_helper_chain(port):
+    """Same segmentation / E split as the oracle-built chain of tests/helpers.make_tb (sch.c:240-350 restated)."""
+    tbs, Qm, G = 75376, 6, 86400
+    assert sp.segment(tbs) == (13, 5824)
+    f, payload = sp.make_transport_blocks(tbs, Qm, G, 0, sp.qpp_interleaver(5824), 1, seed=3)
+    s = port.cbsegm(tbs)
+    tb = np.unpackbits(payload[0])[:tbs + 24]
+    C, K = s["C"], s["K1"]
+    Gp = G // Qm
+    gamma = Gp % C
+    tx = []
+    for c in range(C):
+        bits = tb[c * (K - 24):(c + 1) * (K - 24)]
+        r = port.crc24("B", np.packbits(bits), K - 24)
+        bits = np.concatenate([bits, np.array([(r >> (23 - i)) & 1 for i in range(24)], np.uint8)])
+        n_e = Qm * (Gp // C) if c <= C - gamma - 1 else Qm * -(-Gp // C)
+        tx.append(port.rm_tx(port.tcod_encode(bits), K, n_e, 0))
+    assert (np.concatenate(tx) == f[0]).all()
+    assert port.crc24("A", payload[0], tbs + 24) == 0
+
+
+def test_ofdm_loopback_through_oracle_receiver(port):
+    """ofdm_modulate is the inverse of the eNB uplink receive configuration (shift -0.5, window offset 0.5, no normalisation)."""
+    rng = np.random.default_rng(4)
+    for prb, N in ((6, 128), (100, 2048)):
+        R = 12 * prb
+        grid = (rng.normal(size=(2, 14, R)) + 1j * rng.normal(size=(2, 14, R))).astype(np.complex64)
+        x = sp.ofdm_modulate(grid, N)
+        got, _ = port.ofdm_rx(x.reshape(-1), prb, False, N, -0.5, 0.5, False, False)
+        assert np.linalg.norm(got - grid) / np.linalg.norm(grid) < 1e-4
+
+
+def test_soft_bits_have_the_right_sign(port):
+    """64QAM/16QAM/QPSK mapper vs the reference's soft demapper convention (LLR > 0 <=> bit 1)."""
+    rng = np.random.default_rng(5)
+    for mod, Qm in ((1, 2), (2, 4), (3, 6)):
+        bits = rng.integers(0, 2, 240 * Qm).astype(np.uint8)
+        sym = sp._qam(bits, Qm).astype(np.complex64)
+        llr = port.demod_s(mod, sym)
+        assert ((llr > 0).astype(np.uint8) == bits).all(), mod
