@@ -105,28 +105,35 @@ __global__ void demod_s_kernel(int mod, const float2* __restrict__ sym, int16_t*
 // resource grid are demapped as ONE reference call per subframe (pusch.c:449: srsran_demod_soft_demodulate_s over
 // grant.nof_re symbols), then every soft bit is shifted right arithmetically by `shift` bits to bring the reference's
 // 700x / 400x / 141x fixed-point scale into the generic int16 decoder's overflow-free envelope.
-__global__ void pusch_demap_kernel(int mod, const float2* __restrict__ grid, int16_t* __restrict__ llr, uint32_t nsf, uint32_t nof_symbols,
-                                   uint32_t nof_re, uint32_t sym_mask, uint32_t n_data_sym, int shift, float qpsk_scale)
+struct DataSymbols {
+  uint8_t l[16]; // OFDM symbol index of the d-th data-carrying symbol
+};
+
+// One block per subframe walks its data symbols (no index divisions); the 2*mod soft bits of an element leave as
+// 32-bit words.
+__global__ void __launch_bounds__(256) pusch_demap_kernel(int mod, const float2* __restrict__ grid, int16_t* __restrict__ llr,
+                                                          uint32_t nof_symbols, uint32_t nof_re, DataSymbols ds, uint32_t n_data_sym,
+                                                          int shift, float qpsk_scale)
 {
+  const uint32_t sf     = blockIdx.x;
   const uint32_t per_sf = n_data_sym * nof_re;
-  const uint64_t i      = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (uint64_t)nsf * per_sf) return;
-  const uint32_t sf  = (uint32_t)(i / per_sf);
-  const uint32_t pos = (uint32_t)(i - (uint64_t)sf * per_sf); // symbol index inside the subframe's reference call
-  const uint32_t d   = pos / nof_re, re = pos - d * nof_re;   // d-th data symbol
-  // d-th set bit of sym_mask
-  uint32_t l = 0, seen = 0;
-  for (; l < nof_symbols; l++) {
-    if ((sym_mask >> l) & 1u) {
-      if (seen == d) break;
-      seen++;
+  const uint32_t body = 4u * (per_sf / 4u), fbody = 16u * (2u * per_sf / 16u);
+  for (uint32_t d = 0; d < n_data_sym; d++) {
+    const float2* src = grid + ((size_t)sf * nof_symbols + ds.l[d]) * nof_re;
+    uint32_t*     dst = reinterpret_cast<uint32_t*>(llr + ((size_t)sf * per_sf + (size_t)d * nof_re) * (size_t)(2 * mod));
+    for (uint32_t re = threadIdx.x; re < nof_re; re += blockDim.x) {
+      const uint32_t pos = d * nof_re + re; // symbol index inside the subframe's reference call
+      int16_t        o[6];
+      demod_one(mod, __ldcs(&src[re]), pos < body, 2u * pos, fbody, qpsk_scale, o);
+#pragma unroll
+      for (int w = 0; w < 3; w++) {
+        if (w < mod) {
+          const uint32_t lo = (uint16_t)(int16_t)(o[2 * w] >> shift), hi = (uint16_t)(int16_t)(o[2 * w + 1] >> shift);
+          dst[(size_t)re * mod + w] = lo | (hi << 16);
+        }
+      }
     }
   }
-  const float2 s   = grid[((size_t)sf * nof_symbols + l) * nof_re + re];
-  const int    bps = 2 * mod;
-  int16_t      o[6];
-  demod_one(mod, s, pos < 4u * (per_sf / 4u), 2u * pos, 16u * (2u * per_sf / 16u), qpsk_scale, o);
-  for (int b = 0; b < bps; b++) llr[(size_t)bps * i + b] = (int16_t)(o[b] >> shift);
 }
 
 } // namespace b200
@@ -203,11 +210,13 @@ extern "C" SRSRAN_B200_API int srsran_b200_pusch_demap_batch(int         device,
   DeviceContext* ctx = device_context(device);
   if (!ctx) return B200_ERROR;
   B200_CUDA_TRY(cudaSetDevice(device));
-  const uint64_t n    = (uint64_t)nsf * nd * nof_re;
-  const float    qs   = (float)(-100.0 * M_SQRT2);
-  const unsigned nblk = (unsigned)((n + 255) / 256);
-  pusch_demap_kernel<<<nblk, 256, 0, (cudaStream_t)stream>>>(modulation, (const float2*)grid, llr, nsf, nof_symbols, nof_re, sym_mask,
-                                                           nd, (int)llr_shift, qs);
+  const float qs = (float)(-100.0 * M_SQRT2);
+  DataSymbols ds = {};
+  for (uint32_t l = 0, d = 0; l < nof_symbols; l++) {
+    if ((sym_mask >> l) & 1u) ds.l[d++] = (uint8_t)l;
+  }
+  pusch_demap_kernel<<<nsf, 256, 0, (cudaStream_t)stream>>>(modulation, (const float2*)grid, llr, nof_symbols, nof_re, ds, nd,
+                                                          (int)llr_shift, qs);
   g_kernel_launches++;
   B200_CUDA_TRY(cudaGetLastError());
   return B200_SUCCESS;

@@ -250,9 +250,137 @@ __global__ void __launch_bounds__(OFDM_THREADS) ofdm_rx_kernel(OfdmPlanDev p, co
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Specialised kernel for the power-of-two LTE sizes (N = 128 .. 2048): everything that the generic kernel above
+// derives at run time (pass sequence, strides, index divisions) is a compile-time constant, N/16 threads hold 16 points
+// each in registers through every pass, and the passes exchange IN PLACE through one padded shared buffer (all loads of
+// a pass, barrier, all stores), which halves the shared memory per symbol and doubles the resident warps.
+template <int N, int RADIX, int NS, bool FIRST, bool LAST>
+__device__ __forceinline__ void pass_ct(const OfdmPlanDev& p, const float2* __restrict__ gin, float2* buf, float2* __restrict__ gout, int t,
+                                        bool active)
+{
+  constexpr int TPS = N / 16, T = N / RADIX, ITER = 16 / RADIX;
+  float2        u[ITER][RADIX];
+  if (active) {
+#pragma unroll
+    for (int it = 0; it < ITER; it++) {
+      const int j = t + it * TPS;
+#pragma unroll
+      for (int q = 0; q < RADIX; q++) {
+        const int idx = j + q * T;
+        if (FIRST) {
+          float2 v = __ldcs(&gin[idx]);
+          if (p.shift) v = cmul(v, p.shift[idx]);
+          u[it][q] = v;
+        } else {
+          u[it][q] = buf[pad_idx(idx)];
+        }
+      }
+    }
+  }
+  if (!FIRST) __syncthreads(); // in place: everybody has read its points before anybody overwrites them
+  if (active) {
+#pragma unroll
+    for (int it = 0; it < ITER; it++) {
+      const int j = t + it * TPS;
+      const int k = j % NS;
+      if (NS > 1) {
+        constexpr int step = N / (NS * RADIX);
+#pragma unroll
+        for (int q = 1; q < RADIX; q++) u[it][q] = cmul(u[it][q], p.W[q * k * step]);
+      }
+      dft_small<RADIX>(u[it]);
+      const int j0 = (j / NS) * NS * RADIX + k;
+#pragma unroll
+      for (int q = 0; q < RADIX; q++) {
+        const int o = j0 + q * NS;
+        if (LAST) {
+          const int re = bin_to_re(o, N, p.R, p.dc);
+          if (re >= 0) {
+            float2 v = u[it][q];
+            if (p.ramp) v = cmul(v, p.ramp[re]);
+            __stcs(&gout[re], v);
+          }
+        } else {
+          buf[pad_idx(o)] = u[it][q];
+        }
+      }
+    }
+  }
+  if (!LAST) __syncthreads();
+}
+
+template <int N, int R0, int R1, int R2>
+__global__ void __launch_bounds__(OFDM_THREADS, 6) ofdm_rx_kernel_ct(OfdmPlanDev p, const float2* __restrict__ in, float2* __restrict__ out,
+                                                                  uint32_t nsf)
+{
+  extern __shared__ __align__(16) float2 smem[];
+  constexpr int  TPS  = N / 16;
+  constexpr int  SPB  = OFDM_THREADS / TPS;
+  constexpr int  PADN = N + (N >> 4) + 1;
+  const int      g    = threadIdx.x / TPS;
+  const int      t    = threadIdx.x % TPS;
+  float2*        buf  = smem + (size_t)g * PADN;
+  const uint32_t nsymtot = nsf * (uint32_t)p.nsym;
+  const int      half    = p.nsym / 2;
+  for (uint32_t base = blockIdx.x * SPB; base < nsymtot; base += gridDim.x * SPB) {
+    const uint32_t sidx   = base + g;
+    const bool     active = sidx < nsymtot;
+    const uint32_t sf = active ? sidx / p.nsym : 0, l = active ? sidx % p.nsym : 0;
+    const int      slot = (int)l / half, ls = (int)l % half;
+    const float2*  gin  = in + (size_t)sf * p.sf_sz + (size_t)slot * p.slot_sz + p.cp1 + (size_t)ls * (N + p.cp2) - p.noff;
+    float2*        gout = out + (size_t)sidx * p.R;
+    pass_ct<N, R0, 1, true, false>(p, gin, buf, gout, t, active);
+    if (R2 > 1) {
+      pass_ct<N, R1, R0, false, false>(p, gin, buf, gout, t, active);
+      pass_ct<N, (R2 > 1 ? R2 : 2), R0 * R1, false, true>(p, gin, buf, gout, t, active);
+    } else {
+      pass_ct<N, R1, R0, false, true>(p, gin, buf, gout, t, active);
+    }
+    __syncthreads(); // the last pass's reads of buf are done before the next symbol's first pass overwrites it
+  }
+}
+
+template <int N, int R0, int R1, int R2>
+static int launch_ct(const OfdmPlanDev& p, const float2* in_dev, float2* out_dev, uint32_t nsf, int sm_count, cudaStream_t stream)
+{
+  constexpr int    SPB  = OFDM_THREADS / (N / 16);
+  constexpr size_t smem = (size_t)SPB * (N + (N >> 4) + 1) * sizeof(float2);
+  static bool      attr_done = false;
+  if (!attr_done) {
+    B200_CUDA_TRY(cudaFuncSetAttribute(ofdm_rx_kernel_ct<N, R0, R1, R2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200_CUDA_TRY(cudaFuncSetAttribute(ofdm_rx_kernel_ct<N, R0, R1, R2>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                       cudaSharedmemCarveoutMaxShared));
+    attr_done = true;
+  }
+  const uint32_t nsymtot = nsf * (uint32_t)p.nsym;
+  uint32_t       blocks  = (nsymtot + SPB - 1) / SPB;
+  const uint32_t cap     = (uint32_t)sm_count * 12u; // persistent: the resident blocks loop over the symbols
+  if (blocks > cap) blocks = cap;
+  ofdm_rx_kernel_ct<N, R0, R1, R2><<<blocks, OFDM_THREADS, smem, stream>>>(p, in_dev, out_dev, nsf);
+  B200_CUDA_TRY(cudaGetLastError());
+  return B200_SUCCESS;
+}
+
 int launch_ofdm_rx(const OfdmPlanDev& p, const float2* in_dev, float2* out_dev, uint32_t nsf, int sm_count, cudaStream_t stream)
 {
   if (nsf == 0) return B200_SUCCESS;
+  if (!p.generic && !p.inverse) {
+    switch (p.N) {
+      case 2048:
+        return launch_ct<2048, 16, 16, 8>(p, in_dev, out_dev, nsf, sm_count, stream);
+      case 1024:
+        return launch_ct<1024, 16, 16, 4>(p, in_dev, out_dev, nsf, sm_count, stream);
+      case 512:
+        return launch_ct<512, 16, 8, 4>(p, in_dev, out_dev, nsf, sm_count, stream);
+      case 256:
+        return launch_ct<256, 16, 16, 1>(p, in_dev, out_dev, nsf, sm_count, stream);
+      case 128:
+        return launch_ct<128, 16, 8, 1>(p, in_dev, out_dev, nsf, sm_count, stream);
+      default:
+        break; // 384 / 768 / 1536 / forced sizes: the generic kernel
+    }
+  }
   const int      spb     = OFDM_THREADS / p.tps;
   const size_t   smem    = (size_t)spb * 2 * (p.N + (p.N >> 4) + 1) * sizeof(float2);
   const uint32_t nsymtot = p.generic ? nsf : nsf * (uint32_t)p.nsym;

@@ -42,8 +42,36 @@ __global__ void __launch_bounds__(RM_THREADS) rm_rx_gather_kernel(const int16_t*
     const uint32_t len = (d.E > base) ? min(N, d.E - base) : 0u;
     __syncthreads();
     // stage this wrap's received values; 'in' is only 2-byte aligned in general (rp offsets of sch.c:399-405)
-    for (uint32_t i = threadIdx.x; i < len; i += RM_THREADS) stage[i] = in[base + i];
+    if ((reinterpret_cast<uintptr_t>(in + base) & 3u) == 0) {
+      const uint32_t* in2 = reinterpret_cast<const uint32_t*>(in + base);
+      uint32_t*       st2 = reinterpret_cast<uint32_t*>(stage);
+      for (uint32_t i = threadIdx.x; i < len / 2; i += RM_THREADS) st2[i] = __ldcs(&in2[i]);
+      if ((len & 1u) && threadIdx.x == 0) stage[len - 1] = in[base + len - 1];
+    } else {
+      for (uint32_t i = threadIdx.x; i < len; i += RM_THREADS) stage[i] = in[base + i];
+    }
     __syncthreads();
+    // two outputs per thread and step: n_out = 3K+12 is even and every soft buffer starts on a 4-byte boundary when its
+    // offset is even (the decode loop's 18600-value slots are), so pairs move as aligned 32-bit words
+    if (((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(inv)) & 3u) == 0) {
+      const uint32_t* inv2 = reinterpret_cast<const uint32_t*>(inv);
+      uint32_t*       out2 = reinterpret_cast<uint32_t*>(out);
+      for (uint32_t o2 = threadIdx.x; o2 < N / 2; o2 += RM_THREADS) {
+        const uint32_t ii = inv2[o2];
+        const uint32_t ia = ii & 0xFFFFu, ib = ii >> 16;
+        uint32_t       w  = 0;
+        if (base == 0) {
+          if (!fresh) w = out2[o2];
+        } else {
+          if (ia >= len && ib >= len) continue;
+          w = out2[o2];
+        }
+        int a = (int)(int16_t)(w & 0xFFFFu), b2 = (int)(int16_t)(w >> 16);
+        if (ia < len) a += (int)stage[ia];
+        if (ib < len) b2 += (int)stage[ib];
+        out2[o2] = ((uint32_t)a & 0xFFFFu) | ((uint32_t)b2 << 16);
+      }
+    } else {
     for (uint32_t o = threadIdx.x; o < N; o += RM_THREADS) {
       const uint32_t i0 = inv[o];
       int            acc;
@@ -55,6 +83,7 @@ __global__ void __launch_bounds__(RM_THREADS) rm_rx_gather_kernel(const int16_t*
       }
       if (i0 < len) acc += (int)stage[i0];
       out[o] = (int16_t)(uint16_t)(unsigned)acc;
+    }
     }
     if (len < N) break;
   }

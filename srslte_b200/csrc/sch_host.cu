@@ -44,8 +44,24 @@ struct TbCrcJob {
   uint32_t pad;
 };
 
-__global__ void sch_tb_crc_kernel(const uint8_t* __restrict__ data, const TbCrcJob* __restrict__ jobs, uint32_t n,
-                                  uint8_t* __restrict__ ok)
+// a(x) * b(x) mod g(x) over GF(2), 24-bit operands
+__device__ __forceinline__ uint32_t crc24_mulmod(uint32_t a, uint32_t b)
+{
+  uint32_t r = 0;
+#pragma unroll 1
+  for (int i = 23; i >= 0; i--) {
+    r = (r & 0x800000u) ? ((r << 1) ^ CRC24A_POLY) : (r << 1);
+    if ((b >> i) & 1u) r ^= a;
+  }
+  return r & 0xFFFFFFu;
+}
+
+// Transport block CRC24A (sch.c:543-559), one warp per transport block.  The block's bytes are cut into 32 chunks of L
+// bytes aligned to the END of the block (the first chunks may be short or empty, which is harmless with a zero initial
+// value); lane i computes the plain CRC of chunk i and the results are combined by linearity:
+//   crc(block) = sum_i crc(chunk_i) * x^(8 L (31 - i))  mod g.
+__global__ void __launch_bounds__(128) sch_tb_crc_kernel(const uint8_t* __restrict__ data, const TbCrcJob* __restrict__ jobs,
+                                                         uint32_t n, uint8_t* __restrict__ ok)
 {
   __shared__ uint32_t table[256];
   for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) {
@@ -56,16 +72,33 @@ __global__ void sch_tb_crc_kernel(const uint8_t* __restrict__ data, const TbCrcJ
     table[i] = r & 0xFFFFFFu;
   }
   __syncthreads();
-  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t t    = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (t >= n) return;
-  const TbCrcJob  j = jobs[t];
-  const uint8_t*  p = data + j.data_off;
-  uint32_t        crc = 0;
-  for (uint32_t i = 0; i < j.tbs / 8; i++) {
+  const TbCrcJob j      = jobs[t];
+  const uint8_t* p      = data + j.data_off;
+  const int      nbytes = (int)(j.tbs / 8);
+  const int      L      = (nbytes + 31) / 32;
+  const int      end    = nbytes - (31 - (int)lane) * L; // one past this lane's last byte
+  uint32_t       crc    = 0;
+  for (int i = max(end - L, 0); i < end; i++) {
     crc = ((crc << 8) ^ table[((crc >> 16) ^ p[i]) & 0xFFu]) & 0xFFFFFFu;
   }
-  const uint32_t rx = ((uint32_t)p[j.tbs / 8] << 16) | ((uint32_t)p[j.tbs / 8 + 1] << 8) | (uint32_t)p[j.tbs / 8 + 2];
-  ok[t]             = (crc == rx && crc != 0) ? 1 : 0; // sch.c:553: parity must match AND be non-zero
+  // x^(8L) mod g by L table steps from 1, then this lane's multiplier (x^(8L))^(31-lane) by square and multiply
+  uint32_t pw = 1;
+  for (int i = 0; i < L; i++) pw = ((pw << 8) ^ table[(pw >> 16) & 0xFFu]) & 0xFFFFFFu;
+  uint32_t mult = 1, sq = pw;
+  for (uint32_t e = 31u - lane; e; e >>= 1) {
+    if (e & 1u) mult = crc24_mulmod(mult, sq);
+    sq = crc24_mulmod(sq, sq);
+  }
+  uint32_t part = crc24_mulmod(crc, mult);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) part ^= __shfl_xor_sync(0xFFFFFFFFu, part, o);
+  if (lane == 0) {
+    const uint32_t rx = ((uint32_t)p[nbytes] << 16) | ((uint32_t)p[nbytes + 1] << 8) | (uint32_t)p[nbytes + 2];
+    ok[t]             = (part == rx && part != 0) ? 1 : 0; // sch.c:553: parity must match AND be non-zero
+  }
 }
 
 struct SchEngine {
@@ -346,7 +379,7 @@ int SchEngine::decode_batch(const int16_t* e_bits, uint64_t e_len, int16_t* soft
   if (upload(meta, crc_jobs, &d_cj, st) != B200_SUCCESS) return B200_ERROR;
   uint8_t* d_tbok = (uint8_t*)meta.take(n_tb);
   if (!d_tbok) return B200_ERROR;
-  sch_tb_crc_kernel<<<(n_tb + 63) / 64, 64, 0, st>>>(d_data, d_cj, n_tb, d_tbok);
+  sch_tb_crc_kernel<<<(n_tb + 3) / 4, 128, 0, st>>>(d_data, d_cj, n_tb, d_tbok);
   g_kernel_launches++;
   std::vector<uint8_t> h_tbok(n_tb, 0);
   B200_CUDA_TRY(cudaMemcpyAsync(h_tbok.data(), d_tbok, n_tb, cudaMemcpyDeviceToHost, st));

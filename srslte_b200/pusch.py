@@ -16,6 +16,12 @@ from . import _lib
 from .ofdm import OfdmRx
 from .sch import SOFTBUFFER_SIZE, SchDecoder, Tb
 
+# numpy image of srsran_b200_tb_t (include/srslte_b200.h)
+TB_DTYPE = np.dtype([("tbs", "<u4"), ("Qm", "<u4"), ("rv", "<u4"), ("nof_e_bits", "<u4"), ("e_offset", "<u8"), ("soft_offset", "<u8"),
+                     ("data_offset", "<u8"), ("new_data", "<u4"), ("cb_crc_mask", "<u4"), ("result", "<i4"), ("nof_cb", "<u4"),
+                     ("avg_iterations", "<f4")], align=True)
+assert TB_DTYPE.itemsize == C.sizeof(Tb)
+
 DATA_SYMBOL_MASK = 0x3FFF & ~((1 << 3) | (1 << 10))  # normal CP: symbols 3 and 10 carry the DMRS
 
 
@@ -52,7 +58,13 @@ class PuschRx:
         self.llr = t.empty((nsf, self.G), dtype=t.int16, device=self.dev)
         self.soft = t.zeros((nsf, 13 * SOFTBUFFER_SIZE), dtype=t.int16, device=self.dev)  # up to 13 code blocks per TB here
         self.data = t.zeros((nsf, self.data_stride), dtype=t.uint8, device=self.dev)
-        self.tbs_arr = (Tb * nsf)()
+        # transport block descriptors (srsran_b200_tb_t), filled once; only the in/out fields are reset per call
+        self.tb_np = np.zeros(nsf, TB_DTYPE)
+        i = np.arange(nsf, dtype=np.uint64)
+        self.tb_np["tbs"], self.tb_np["Qm"], self.tb_np["nof_e_bits"] = self.tbs, self.Qm, self.G
+        self.tb_np["e_offset"] = i * np.uint64(self.G)
+        self.tb_np["soft_offset"] = i * np.uint64(self.soft.shape[1])
+        self.tb_np["data_offset"] = i * np.uint64(self.data_stride)
         self._cap = nsf
 
     def front_end(self, iq, nsf: int):
@@ -69,22 +81,16 @@ class PuschRx:
     def decode(self, nsf: int, rv: int = 0):
         """Rate de-matching + transport block decode loop of the nsf subframes demapped last (synchronous)."""
         t = self.torch
-        arr = self.tbs_arr
+        d = self.tb_np
         soft_stride = self.soft.shape[1]
-        for i in range(nsf):
-            a = arr[i]
-            a.tbs, a.Qm, a.rv, a.nof_e_bits = self.tbs, self.Qm, rv, self.G
-            a.e_offset, a.soft_offset, a.data_offset = i * self.G, i * soft_stride, i * self.data_stride
-            a.new_data, a.cb_crc_mask = 1, 0
+        d["rv"][:nsf], d["new_data"][:nsf], d["cb_crc_mask"][:nsf] = rv, 1, 0
         t.cuda.current_stream(self.dev).synchronize()  # the decode loop runs on the library's own stream
         rc = self._lib.srsran_b200_sch_decode_batch(self.sch._h, self.llr.data_ptr(), nsf * self.G, self.soft.data_ptr(),
-                                                    nsf * soft_stride, self.data.data_ptr(), nsf * self.data_stride, arr, nsf,
-                                                    _lib.FLAG_DEVICE_PTRS)
+                                                    nsf * soft_stride, self.data.data_ptr(), nsf * self.data_stride,
+                                                    d.ctypes.data, nsf, _lib.FLAG_DEVICE_PTRS)
         if rc != _lib.SUCCESS:
             raise RuntimeError(f"srsran_b200_sch_decode_batch failed ({rc})")
-        ok = np.fromiter((arr[i].result == 0 for i in range(nsf)), bool, nsf)
-        its = np.fromiter((arr[i].avg_iterations for i in range(nsf)), np.float32, nsf)
-        return ok, its
+        return d["result"][:nsf] == 0, d["avg_iterations"][:nsf].copy()
 
     def run(self, iq, nsf: int, rv: int = 0):
         """iq: torch CUDA complex64 (nsf, sf_sz).  Returns (tb_ok (nsf,), avg passes (nsf,)); bytes are in self.data[:, :tbs/8+3]."""
