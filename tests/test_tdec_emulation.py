@@ -71,3 +71,16 @@ def test_emulation_crc24a_and_no_crc(emu, port):
     o1, k1, n1, _ = port.decode_batch(llr, K, 3, None, 0, True)
     o2, k2, nc, nr = run_emu(emu, llr, K, 3, 2, True)
     assert (o1 == o2).all() and not k2.any() and (nr == 3).all()
+
+
+def test_emulation_mixed_int8_and_int16_tiles(emu, port):
+    """Per-tile input format (int8 when every channel LLR of the tile fits, else int16) inside one batch."""
+    K = 512
+    llr, _ = coded_llrs(port, K, 64 * 3 + 5, 0.9, 16, 31, seed=21)
+    llr[:64] = np.clip(llr[:64].astype(np.int32) * 4, -128, 127).astype(np.int16)
+    llr[64:128] = (llr[64:128].astype(np.int32) * 5).astype(np.int16)
+    llr[130, 3 * K + 1] = 128
+    llr[190, 3 * K + 6] = 3000  # encoder 2's systematic tail is kept in int16 regardless
+    o1, k1, n1, _ = port.decode_batch(llr, K, 5, "B", 0, True)
+    o2, k2, nc, nr = run_emu(emu, llr, K, 5, 0, True)
+    assert (o1 == o2).all() and (k1 == k2).all() and (n1 == npass_of(k2, nc, nr)).all()

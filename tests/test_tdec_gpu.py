@@ -120,3 +120,19 @@ def test_device_pointer_path_and_full_size_properties(dec, port):
     assert (k1 == ok[idx].cpu().numpy()).all() and (n1 == npass[idx].cpu().numpy()).all()
     o1, _, _, _ = port.decode_batch(sub, K, 8, "B", 0, False, nthreads=8)
     assert (o1 == out8[idx].cpu().numpy()).all()
+
+
+def test_mixed_int8_and_int16_tiles_in_one_batch(dec, port):
+    """The decoder keeps a tile's channel LLRs as int8 when all 64 blocks fit and as int16 otherwise (fmt per tile): one
+    batch with both kinds of tiles, values sitting exactly on the int8 boundary, and a tile that leaves int8 only through
+    a tail value must decode bit-exactly like the oracle either way."""
+    K = 1024
+    llr, _ = coded_llrs(port, K, 64 * 4 + 7, 0.9, 16, 31, seed=21)
+    llr[:64] = np.clip(llr[:64].astype(np.int32) * 4, -128, 127).astype(np.int16)       # tile 0: int8, touching both ends
+    llr[64:128] = (llr[64:128].astype(np.int32) * 5).astype(np.int16)                   # tile 1: up to +-155 -> int16
+    llr[130, 3 * K + 1] = 128                                                            # tile 2: one parity tail value
+    llr[200, 3 * K + 6] = 3000                                                           # tile 3: encoder-2 systematic tail only
+    for early in (True, False):
+        o1, k1, n1, _ = port.decode_batch(llr, K, 6, "B", 0, early, nthreads=8)
+        o2, k2, n2 = dec.decode(llr, K, 6, "B", early)
+        assert (o1 == o2).all() and (k1 == k2).all() and (n1 == n2).all(), early
