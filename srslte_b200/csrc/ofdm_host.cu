@@ -136,6 +136,7 @@ struct OfdmEngine {
     plan.W     = dW;
     plan.shift = nullptr;
     plan.ramp  = nullptr;
+    plan.norm  = c.normalize ? 1.0f / sqrtf((float)N) : 1.0f;
     if (shift) {
       // ofdm.c:347-355: shift[t] = cexpf(I 2 pi (t - cplen) f / N); inside the FFT window t - cplen = n - noff for every symbol
       std::vector<float2> S(N);

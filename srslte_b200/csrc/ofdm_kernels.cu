@@ -262,15 +262,25 @@ __device__ __forceinline__ void pass_ct(const OfdmPlanDev& p, const float2* __re
   constexpr int TPS = N / 16, T = N / RADIX, ITER = 16 / RADIX;
   float2        u[ITER][RADIX];
   if (active) {
+    // Table values reach the multipliers through ONE load per butterfly plus a recurrence (the tables are bigger than
+    // what is left of L1 beside the shared-memory carve-out, so every table load is an L2 round trip):
+    // shift[j + q*T] = shift[j] * c^q with c = shift[noff + T] (the table is a pure phasor, 1 at index noff).
+    float2 c1 = make_float2(1.f, 0.f);
+    if (FIRST && p.shift) c1 = p.shift[p.noff + T];
 #pragma unroll
     for (int it = 0; it < ITER; it++) {
       const int j = t + it * TPS;
+      float2    sh = make_float2(1.f, 0.f);
+      if (FIRST && p.shift) sh = p.shift[j];
 #pragma unroll
       for (int q = 0; q < RADIX; q++) {
         const int idx = j + q * T;
-        if (FIRST) {
-          float2 v = __ldcs(&gin[idx]);
-          if (p.shift) v = cmul(v, p.shift[idx]);
+        if (FIRST) { // gin = this symbol's window, already staged in shared memory (natural order)
+          float2 v = gin[idx];
+          if (p.shift) {
+            v  = cmul(v, sh);
+            sh = cmul(sh, c1);
+          }
           u[it][q] = v;
         } else {
           u[it][q] = buf[pad_idx(idx)];
@@ -284,13 +294,26 @@ __device__ __forceinline__ void pass_ct(const OfdmPlanDev& p, const float2* __re
     for (int it = 0; it < ITER; it++) {
       const int j = t + it * TPS;
       const int k = j % NS;
-      if (NS > 1) {
+      if (NS > 1) { // twiddles W^(q k step) = w1^q
         constexpr int step = N / (NS * RADIX);
+        const float2  w1   = p.W[k * step];
+        float2        w    = w1;
 #pragma unroll
-        for (int q = 1; q < RADIX; q++) u[it][q] = cmul(u[it][q], p.W[q * k * step]);
+        for (int q = 1; q < RADIX; q++) {
+          u[it][q] = cmul(u[it][q], w);
+          if (q + 1 < RADIX) w = cmul(w, w1);
+        }
       }
       dft_small<RADIX>(u[it]);
       const int j0 = (j / NS) * NS * RADIX + k;
+      // window-offset phase ramp x normalisation of bin o = j0 + q NS:  norm * exp(+2 pi i noff o / N) = rb * d^q with
+      // rb = norm * conj(W[noff j0 mod N]) and d = conj(W[noff NS mod N]): two table loads per butterfly, not RADIX
+      float2 rb = make_float2(1.f, 0.f), d1 = rb;
+      if (LAST && p.ramp) {
+        const float2 a = p.W[(p.noff * j0) % N], b = p.W[(p.noff * NS) % N];
+        rb             = make_float2(a.x * p.norm, -a.y * p.norm);
+        d1             = make_float2(b.x, -b.y);
+      }
 #pragma unroll
       for (int q = 0; q < RADIX; q++) {
         const int o = j0 + q * NS;
@@ -298,9 +321,10 @@ __device__ __forceinline__ void pass_ct(const OfdmPlanDev& p, const float2* __re
           const int re = bin_to_re(o, N, p.R, p.dc);
           if (re >= 0) {
             float2 v = u[it][q];
-            if (p.ramp) v = cmul(v, p.ramp[re]);
+            if (p.ramp) v = cmul(v, rb);
             __stcs(&gout[re], v);
           }
+          if (p.ramp) rb = cmul(rb, d1);
         } else {
           buf[pad_idx(o)] = u[it][q];
         }
@@ -310,9 +334,18 @@ __device__ __forceinline__ void pass_ct(const OfdmPlanDev& p, const float2* __re
   if (!LAST) __syncthreads();
 }
 
+__device__ __forceinline__ void cp_async8(float2* dst_smem, const float2* src)
+{
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)),
+               "l"(__cvta_generic_to_global(src))
+               : "memory");
+}
+
+// Persistent blocks; the window of the NEXT symbol is fetched with cp.async into a staging buffer while the current
+// symbol's passes run, so the global-memory latency is off the critical path.
 template <int N, int R0, int R1, int R2>
 __global__ void __launch_bounds__(OFDM_THREADS, 6) ofdm_rx_kernel_ct(OfdmPlanDev p, const float2* __restrict__ in, float2* __restrict__ out,
-                                                                  uint32_t nsf)
+                                                                     uint32_t nsf)
 {
   extern __shared__ __align__(16) float2 smem[];
   constexpr int  TPS  = N / 16;
@@ -320,22 +353,37 @@ __global__ void __launch_bounds__(OFDM_THREADS, 6) ofdm_rx_kernel_ct(OfdmPlanDev
   constexpr int  PADN = N + (N >> 4) + 1;
   const int      g    = threadIdx.x / TPS;
   const int      t    = threadIdx.x % TPS;
-  float2*        buf  = smem + (size_t)g * PADN;
+  float2*        buf   = smem + (size_t)g * (PADN + N);
+  float2*        stage = buf + PADN;
   const uint32_t nsymtot = nsf * (uint32_t)p.nsym;
   const int      half    = p.nsym / 2;
+  auto window = [&](uint32_t sidx) {
+    const uint32_t sf = sidx / p.nsym, l = sidx % p.nsym;
+    const int      slot = (int)l / half, ls = (int)l % half;
+    return in + (size_t)sf * p.sf_sz + (size_t)slot * p.slot_sz + p.cp1 + (size_t)ls * (N + p.cp2) - p.noff;
+  };
+  auto prefetch = [&](uint32_t sidx) {
+    if (sidx < nsymtot) {
+      const float2* gin = window(sidx);
+#pragma unroll
+      for (int q = 0; q < 16; q++) cp_async8(stage + t + q * TPS, gin + t + q * TPS);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  prefetch(blockIdx.x * SPB + g);
   for (uint32_t base = blockIdx.x * SPB; base < nsymtot; base += gridDim.x * SPB) {
     const uint32_t sidx   = base + g;
     const bool     active = sidx < nsymtot;
-    const uint32_t sf = active ? sidx / p.nsym : 0, l = active ? sidx % p.nsym : 0;
-    const int      slot = (int)l / half, ls = (int)l % half;
-    const float2*  gin  = in + (size_t)sf * p.sf_sz + (size_t)slot * p.slot_sz + p.cp1 + (size_t)ls * (N + p.cp2) - p.noff;
-    float2*        gout = out + (size_t)sidx * p.R;
-    pass_ct<N, R0, 1, true, false>(p, gin, buf, gout, t, active);
+    float2*        gout   = out + (size_t)sidx * p.R;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads(); // the staged window is complete and visible to the whole group
+    pass_ct<N, R0, 1, true, false>(p, stage, buf, gout, t, active);
+    prefetch(sidx + gridDim.x * SPB); // the barrier that ended the first pass: every thread has read its staged points
     if (R2 > 1) {
-      pass_ct<N, R1, R0, false, false>(p, gin, buf, gout, t, active);
-      pass_ct<N, (R2 > 1 ? R2 : 2), R0 * R1, false, true>(p, gin, buf, gout, t, active);
+      pass_ct<N, R1, R0, false, false>(p, stage, buf, gout, t, active);
+      pass_ct<N, (R2 > 1 ? R2 : 2), R0 * R1, false, true>(p, stage, buf, gout, t, active);
     } else {
-      pass_ct<N, R1, R0, false, true>(p, gin, buf, gout, t, active);
+      pass_ct<N, R1, R0, false, true>(p, stage, buf, gout, t, active);
     }
     __syncthreads(); // the last pass's reads of buf are done before the next symbol's first pass overwrites it
   }
@@ -345,7 +393,7 @@ template <int N, int R0, int R1, int R2>
 static int launch_ct(const OfdmPlanDev& p, const float2* in_dev, float2* out_dev, uint32_t nsf, int sm_count, cudaStream_t stream)
 {
   constexpr int    SPB  = OFDM_THREADS / (N / 16);
-  constexpr size_t smem = (size_t)SPB * (N + (N >> 4) + 1) * sizeof(float2);
+  constexpr size_t smem = (size_t)SPB * (2 * N + (N >> 4) + 1) * sizeof(float2); // work buffer + staged next window
   static bool      attr_done = false;
   if (!attr_done) {
     B200_CUDA_TRY(cudaFuncSetAttribute(ofdm_rx_kernel_ct<N, R0, R1, R2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -27,6 +27,7 @@ struct OfdmPlanDev {
   int idist;
   int odist;
   int inverse; // 1: e^{+2 pi i kn/N} (conjugate in, conjugate out)
+  float norm;  // 1/sqrt(N) when normalising, else 1 (already folded into ramp[]; the specialised kernel rebuilds the ramp)
   const float2* W;     // exp(-2 pi i m / N), m < N
   const float2* shift; // N entries: half-subcarrier rotation inside the FFT window, or nullptr
   const float2* ramp;  // R entries: window-offset phase fix x normalisation per output element, or nullptr
