@@ -339,7 +339,7 @@ def run_ours(args):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-PUSCH_SF_PER_GPU = 2048   # (cell, subframe) pairs per GPU and step: 26,624 code blocks K=5824
+PUSCH_SF_PER_GPU = 4096   # (cell, subframe) pairs per GPU and step: 53,248 code blocks K=5824 = 832 tiles, one wave
 PUSCH_SNR_DB = 23.0
 
 
