@@ -378,16 +378,9 @@ void launch_siso_pass(const TdecView& v, int pass_idx, cudaStream_t stream)
 //   tdec_load8_kernel   always runs: writes the int8 arrays (8 rows x 2 blocks per uint4) and raises fmt[tile] when a
 //                       value of the tile does not fit int8; also arms the per-block state.
 //   tdec_load16_kernel  runs after it and fills the int16 arrays (4 rows x 2 blocks per uint4) of the raised tiles only.
-constexpr int LOAD_ROWS = 64; // trellis rows per CTA: 384 contiguous bytes of each block's natural vector
-constexpr size_t LOAD_SMEM = (size_t)3 * LOAD_ROWS * (TDEC_TILE_CB + 2) * sizeof(int16_t);
-constexpr int LOAD_PITCH = TDEC_TILE_CB + 2;  // staging buffer sm[value index o = 3*row+stream][block]: the two blocks of a
-                                              // lane are one aligned 32-bit word, consecutive lanes consecutive banks
-// int16 index of (value o, block c).  Block pairs are XOR-swizzled with bits 5..6 of o so that the staging stores of a
-// warp (fixed block, o = 4*lane + i) fall into 32 different banks as well.
-__device__ __forceinline__ int load_sm_idx(int o, int c)
-{
-  return o * LOAD_PITCH + 2 * ((c >> 1) ^ ((o >> 5) & 3)) + (c & 1);
-}
+constexpr int    LOAD_ROWS = 64;                 // trellis rows per CTA: 384 contiguous bytes of each block's natural vector
+constexpr int    RAW_PITCH = LOAD_ROWS * 6 + 8;  // staging buffer: block c's chunk as loaded, at byte c * RAW_PITCH
+constexpr size_t LOAD_SMEM = (size_t)TDEC_TILE_CB * RAW_PITCH;
 
 __device__ __forceinline__ bool fits8(int16_t a)
 {
@@ -398,7 +391,7 @@ __device__ __forceinline__ bool fits8(int16_t a)
 // the vectors are contiguous, block cb at cb*(3K+12).  ALIGNED8: every vector starts on an 8-byte boundary.
 // Returns (to all threads) whether every staged value fits int8.
 template <bool ALIGNED8>
-__device__ __forceinline__ bool load_stage_chunk(int16_t* sm, const TdecView& v, const int16_t* __restrict__ llr,
+__device__ __forceinline__ bool load_stage_chunk(uint8_t* sm, const TdecView& v, const int16_t* __restrict__ llr,
                                                  const uint64_t* __restrict__ offsets, uint32_t ncb, int tile, int k0, int rows)
 {
   const size_t nllr = 3 * (size_t)v.K + 12;
@@ -406,7 +399,7 @@ __device__ __forceinline__ bool load_stage_chunk(int16_t* sm, const TdecView& v,
   // warp w stages blocks w, w+8, ...; lane q takes the q-th 8-byte piece of the block's chunk (no divisions).  Two
   // blocks per round keep 6 independent 8-byte loads per thread in flight.
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-  uint32_t  acc  = 0; // OR of (value + 128) high bytes: non-zero <=> some value does not fit int8
+  uint32_t  acc  = 0; // v ^ (v << 1) has bits 15..8 clear <=> bits 15..7 of v are equal <=> v fits int8 (per half)
   constexpr int NB = 2;
   for (int c0 = wid; c0 < TDEC_TILE_CB; c0 += NB * nwarp) {
     constexpr int NH = (LOAD_ROWS * 3 / 4 + 31) / 32; // 8-byte pieces per lane and block
@@ -437,16 +430,13 @@ __device__ __forceinline__ bool load_stage_chunk(int16_t* sm, const TdecView& v,
       for (int h = 0; h < NH; h++) {
         const int q = lane + 32 * h;
         if (c < TDEC_TILE_CB && q < nvec) {
-          acc |= (add2(val[u][h].x, 0x00800080u) | add2(val[u][h].y, 0x00800080u)) & 0xFF00FF00u;
-          sm[load_sm_idx(4 * q + 0, c)] = lo16(val[u][h].x);
-          sm[load_sm_idx(4 * q + 1, c)] = hi16(val[u][h].x);
-          sm[load_sm_idx(4 * q + 2, c)] = lo16(val[u][h].y);
-          sm[load_sm_idx(4 * q + 3, c)] = hi16(val[u][h].y);
+          acc |= (val[u][h].x ^ (val[u][h].x << 1)) | (val[u][h].y ^ (val[u][h].y << 1));
+          *reinterpret_cast<uint2*>(sm + c * RAW_PITCH + 8 * q) = val[u][h];
         }
       }
     }
   }
-  const bool bad = acc != 0u;
+  const bool bad = (acc & 0xFF00FF00u) != 0u;
   return __syncthreads_or(bad) == 0;
 }
 
@@ -454,7 +444,7 @@ template <bool ALIGNED8>
 __global__ void __launch_bounds__(256)
     tdec_load8_kernel(TdecView v, const int16_t* __restrict__ llr, const uint64_t* __restrict__ offsets, uint32_t ncb)
 {
-  extern __shared__ __align__(16) int16_t sm[];
+  extern __shared__ __align__(16) uint8_t sm[];
   const int    tile  = blockIdx.y;
   const int    chunk = blockIdx.x;
   const int    K     = v.K;
@@ -466,22 +456,31 @@ __global__ void __launch_bounds__(256)
     const int  rows = min(LOAD_ROWS, K - k0); // multiple of 8
     const bool ok   = load_stage_chunk<ALIGNED8>(sm, v, llr, offsets, ncb, tile, k0, rows);
     if (!ok && tid == 0) atomicOr(v.fmt + tile, 1u);
-    // (window, stream, lane) -> one uint4 of 8 rows x 2 blocks; warp = window of the chunk
+    // warp = window of the chunk; a lane reads the 48 bytes of its two blocks, pairs and packs them with byte permutes
+    // and writes its 16 bytes of each int8 tile row
     const int lane = tid & 31;
     for (int w8 = tid >> 5; w8 < rows / 8; w8 += 8) {
+      uint32_t a[12], b[12];
 #pragma unroll
-    for (int s = 0; s < 3; s++) {
-      uint32_t  w[4];
-#pragma unroll
-      for (int q = 0; q < 4; q++) {
-        // rows 2q, 2q+1 of the window: (block 2*lane, block 2*lane+1) as int16 pairs -> their low bytes
-        const uint32_t p0 = *reinterpret_cast<const uint32_t*>(&sm[load_sm_idx(3 * (8 * w8 + 2 * q) + s, 2 * lane)]);
-        const uint32_t p1 = *reinterpret_cast<const uint32_t*>(&sm[load_sm_idx(3 * (8 * w8 + 2 * q + 1) + s, 2 * lane)]);
-        w[q]              = __byte_perm(p0, p1, 0x6420);
+      for (int j = 0; j < 6; j++) {
+        const uint2 x = *reinterpret_cast<const uint2*>(sm + (2 * lane) * RAW_PITCH + w8 * 48 + 8 * j);
+        const uint2 y = *reinterpret_cast<const uint2*>(sm + (2 * lane + 1) * RAW_PITCH + w8 * 48 + 8 * j);
+        a[2 * j] = x.x; a[2 * j + 1] = x.y; b[2 * j] = y.x; b[2 * j + 1] = y.y;
       }
-      u4* dst = s == 0 ? v.S8 : (s == 1 ? v.P08 : v.P18);
-      dst[row8(v, tile, k0 / 8 + w8, lane)] = u4{w[0], w[1], w[2], w[3]};
-    }
+#pragma unroll
+      for (int s = 0; s < 3; s++) {
+        uint32_t w[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          // rows 2q, 2q+1 of stream s: value index i = 3*row + s inside the window's 24 values of a block
+          const int      i0 = 3 * (2 * q) + s, i1 = 3 * (2 * q + 1) + s;
+          const uint32_t p0 = __byte_perm(a[i0 >> 1], b[i0 >> 1], (i0 & 1) ? 0x7632 : 0x5410); // (a, b) as an int16 pair
+          const uint32_t p1 = __byte_perm(a[i1 >> 1], b[i1 >> 1], (i1 & 1) ? 0x7632 : 0x5410);
+          w[q]              = __byte_perm(p0, p1, 0x6420);                                     // their low bytes
+        }
+        u4* dst = s == 0 ? v.S8 : (s == 1 ? v.P08 : v.P18);
+        dst[row8(v, tile, k0 / 8 + w8, lane)] = u4{w[0], w[1], w[2], w[3]};
+      }
     }
   } else {
     // the chunk past the payload carries the 12 tail values: row K/8 of S8/P08/P18 and S2T
@@ -526,7 +525,7 @@ template <bool ALIGNED8>
 __global__ void __launch_bounds__(256)
     tdec_load16_kernel(TdecView v, const int16_t* __restrict__ llr, const uint64_t* __restrict__ offsets, uint32_t ncb)
 {
-  extern __shared__ __align__(16) int16_t sm[];
+  extern __shared__ __align__(16) uint8_t sm[];
   const int    K      = v.K;
   const size_t nllr   = 3 * (size_t)K + 12;
   const int    tid    = threadIdx.x;
@@ -548,7 +547,9 @@ __global__ void __launch_bounds__(256)
       for (int t = 0; t < 4; t++) {
 #pragma unroll
         for (int s = 0; s < 3; s++) {
-          w[s][t] = *reinterpret_cast<const uint32_t*>(&sm[load_sm_idx(3 * (4 * r4 + t) + s, 2 * lane)]);
+          const int o = 3 * (4 * r4 + t) + s;
+          w[s][t]     = pack2(reinterpret_cast<const int16_t*>(sm + (2 * lane) * RAW_PITCH)[o],
+                              reinterpret_cast<const int16_t*>(sm + (2 * lane + 1) * RAW_PITCH)[o]);
         }
       }
       const size_t row = vec_row(v, tile, k0 / 4 + r4, lane);
