@@ -246,6 +246,70 @@ SRSRAN_B200_API int srsran_b200_pusch_demap_batch(int         device,
                                                   void*       stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * PUSCH receive chain between the OFDM demodulator and the rate de-matcher, for a batch of subframes that share one
+ * allocation: what srsran_chest_ul_estimate_pusch (lib/src/phy/ch_estimation/chest_ul.c:370) and the front half of
+ * srsran_pusch_decode (lib/src/phy/phch/pusch.c:392-443) + ulsch_deinterleave (sch.c:993, called from
+ * srsran_ulsch_decode sch.c:1150) do per subframe:
+ *   DMRS least-squares estimate, 3-tap smoothing, noise / SNR / CFO  ->  MMSE equaliser (srsran_predecoding_single)
+ *   ->  transform de-precoding (srsran_dft_precoding, backward DFT of 12*L_prb points / sqrt(N))  ->  int16 soft
+ *   demapping  ->  descrambling (srsran_sequence_pusch_apply_s)  ->  UL-SCH de-interleaving.
+ * Scope: one receive antenna; no RI / ACK / CQI multiplexed into the PUSCH; no intra-subframe hopping; L_prb >= 3 and
+ * 12*L_prb = 2^a 3^b 5^c (srsran_dft_precoding_valid_prb).  All data pointers are DEVICE memory (flags must carry
+ * SRSRAN_B200_FLAG_DEVICE_PTRS), the per-subframe parameter arrays (rnti, tti, n_dmrs) are HOST memory; every call is
+ * enqueued on `stream` and returns without synchronising.
+ */
+typedef struct srsran_b200_pusch srsran_b200_pusch_t; /* opaque; one per host thread */
+
+typedef struct {
+  uint32_t cell_id;             /* physical cell identity: scrambling seed (sequences.c:120) and DMRS sequences */
+  uint32_t cell_nof_prb;        /* the resource grid holds 12*cell_nof_prb elements per OFDM symbol */
+  int      cp_ext;              /* 0: normal CP (14 symbols, DMRS in symbols 3 and 10), 1: extended (12; 2 and 8) */
+  uint32_t L_prb;               /* allocation width in PRB (srsran_pusch_grant_t.L_prb) */
+  uint32_t n_prb;               /* first allocated PRB, the same in both slots (grant.n_prb[0] == n_prb[1]) */
+  int      modulation;          /* srsran_mod_t: 1 QPSK, 2 16QAM, 3 64QAM */
+  uint32_t llr_shift;           /* arithmetic right shift applied to every soft bit after the demapper (0 = reference scale) */
+  uint32_t dmrs_cyclic_shift;   /* srsran_refsignal_dmrs_pusch_cfg_t (refsignal_ul.h:46-51) */
+  uint32_t dmrs_delta_ss;
+  int      group_hopping_en;
+  int      sequence_hopping_en;
+} srsran_b200_pusch_cfg_t;
+
+SRSRAN_B200_API int  srsran_b200_pusch_init(srsran_b200_pusch_t** q, int device, const srsran_b200_pusch_cfg_t* cfg);
+SRSRAN_B200_API void srsran_b200_pusch_free(srsran_b200_pusch_t* q);
+/* nof_re = data symbols * 12 * L_prb (grant.nof_re), nof_bits = nof_re * Qm (grant.tb.nof_bits) */
+SRSRAN_B200_API int srsran_b200_pusch_geometry(const srsran_b200_pusch_t* q, uint32_t* nof_re, uint32_t* nof_bits,
+                                               uint32_t* nof_data_symbols);
+
+/* srsran_refsignal_dmrs_pusch_gen (refsignal_ul.c:337): the known DMRS of subframe index sf_idx (0..9) for the DCI's cyclic
+ * shift n_dmrs (0..7), r = 2 slots x 12*L_prb cf_t written to HOST memory (the object pre-generates all 80 like
+ * srsran_refsignal_dmrs_pusch_pregen). */
+SRSRAN_B200_API int srsran_b200_refsignal_dmrs_pusch_gen(const srsran_b200_pusch_t* q, uint32_t sf_idx, uint32_t n_dmrs, void* r);
+
+/* srsran_chest_ul_estimate_pusch for nsf subframes.  grid: nsf x nof_symbols x 12*cell_nof_prb cf_t (output of
+ * srsran_b200_ofdm_rx_sf_batch); tti[nsf], n_dmrs[nsf] (NULL = all zero): host arrays;
+ * ce: nsf x 2 slots x 12*L_prb cf_t -- the reference copies a slot's estimate to every symbol of the slot
+ * (chest_ul.c:246-259), the equaliser below reads it per slot instead;
+ * meas: nsf x 4 floats {noise_estimate, snr (linear), cfo_hz, ta_us = 0} (srsran_chest_ul_res_t). */
+SRSRAN_B200_API int srsran_b200_chest_ul_pusch_batch(srsran_b200_pusch_t* q, const void* grid, uint32_t nsf, const uint32_t* tti,
+                                                     const uint32_t* n_dmrs, void* ce, float* meas, uint32_t flags, void* stream);
+
+/* srsran_predecoding_single (noise_estimate = meas[4*sf], NULL = zero forcing) fused into the first pass of
+ * srsran_dft_precoding.  d: nsf x nof_re cf_t, data-symbol major like pusch.c's q->d. */
+SRSRAN_B200_API int srsran_b200_pusch_equalize_deprecode_batch(srsran_b200_pusch_t* q, const void* grid, const void* ce,
+                                                               const float* meas, void* d, uint32_t nsf, uint32_t flags, void* stream);
+
+/* srsran_demod_soft_demodulate_s (one call per subframe over nof_re symbols), >> llr_shift, srsran_sequence_pusch_apply_s
+ * with nslot = 2*(tti % 10), ulsch_deinterleave.  g: nsf x nof_bits int16, the e_bits of srsran_b200_sch_decode_batch.
+ * rnti[nsf], tti[nsf]: host arrays. */
+SRSRAN_B200_API int srsran_b200_pusch_demod_descramble_batch(srsran_b200_pusch_t* q, const void* d, int16_t* g, uint32_t nsf,
+                                                             const uint32_t* rnti, const uint32_t* tti, uint32_t flags, void* stream);
+
+/* The three stages above back to back on the object's scratch buffers.  meas may be NULL. */
+SRSRAN_B200_API int srsran_b200_pusch_rx_batch(srsran_b200_pusch_t* q, const void* grid, int16_t* g, float* meas, uint32_t nsf,
+                                               const uint32_t* rnti, const uint32_t* tti, const uint32_t* n_dmrs, uint32_t flags,
+                                               void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Synthetic workload (bench / tests only, never on the decode path): fills llr_dev[ncb][3K+12] (device memory) with
  * the quantised channel output of randomly drawn, CRC24B-terminated, turbo-encoded blocks:
  * llr = clip(rint(scale * ((2c-1) + sigma*n)), +-clip), the recipe of turbodecoder_test.c:211-255 plus a clip.

@@ -219,6 +219,110 @@ class _Api:
         assert r == 0
         return o.copy()
 
+    # -- PUSCH chain between OFDM and de-matching ---------------------------------------------
+    def pusch_seq_apply_s(self, x: np.ndarray, rnti: int, nslot: int, cell_id: int) -> np.ndarray:
+        x = _aligned_copy(x, np.int16)
+        out = _aligned(x.size, np.int16)
+        self.f("pusch_seq_apply_s")(_p(x), _p(out), C.c_uint32(rnti), C.c_uint32(nslot), C.c_uint32(cell_id), C.c_uint32(x.size))
+        return out.copy()
+
+    def ulsch_deinterleave(self, q: np.ndarray, Qm: int, nof_symb: int) -> np.ndarray:
+        q = _aligned_copy(q, np.int16)
+        g = _aligned(q.size, np.int16)
+        r = self.f("ulsch_deinterleave")(_p(q), _p(g), C.c_uint32(Qm), C.c_uint32(q.size // Qm), C.c_uint32(nof_symb))
+        assert r == 0
+        return g.copy()
+
+    def dft_precoding(self, x: np.ndarray, nof_prb: int, is_tx: bool) -> np.ndarray:
+        x = _aligned_copy(x, np.complex64)
+        nsym = x.size // (12 * nof_prb)
+        out = _aligned(x.size, np.complex64)
+        r = self.f("dft_precoding")(_p(x), _p(out), C.c_uint32(nof_prb), C.c_uint32(nsym), C.c_int(int(is_tx)))
+        assert r == 0
+        return out.copy()
+
+    def predecoding_single(self, y: np.ndarray, h: np.ndarray, noise: float, scaling: float = 1.0) -> np.ndarray:
+        y = _aligned_copy(y, np.complex64)
+        h = _aligned_copy(h, np.complex64)
+        x = _aligned(y.size, np.complex64)
+        r = self.f("predecoding_single")(_p(y), _p(h), _p(x), C.c_int(y.size), C.c_float(scaling), C.c_float(noise))
+        assert r == y.size
+        return x.copy()
+
+    def dmrs_pusch_gen(self, link: np.ndarray) -> np.ndarray:
+        link = np.ascontiguousarray(link, np.uint32)
+        r = _aligned(2 * 12 * int(link[9]), np.complex64)
+        ret = self.f("dmrs_pusch_gen")(_p(link), _p(r))
+        assert ret == 0, ret
+        return r.copy()
+
+    def chest_ul_pusch(self, link: np.ndarray, grid: np.ndarray, dmrs: np.ndarray | None = None):
+        """Returns (ce grid, [noise_estimate, snr, cfo_hz, ta_us]).  The port takes the known DMRS as an argument."""
+        link = np.ascontiguousarray(link, np.uint32)
+        grid = _aligned_copy(grid, np.complex64)
+        ce = _aligned(grid.size, np.complex64)
+        meas = np.zeros(8, np.float32)
+        if self.which == "port":
+            dmrs = _aligned_copy(dmrs, np.complex64)
+            r = self.lib.orc_chest_ul_pusch(_p(link), _p(grid), _p(dmrs), _p(ce), _p(meas))
+        else:
+            r = self.lib.ref_chest_ul_pusch(_p(link), _p(grid), _p(ce), _p(meas))
+        assert r == 0, r
+        return ce.copy(), meas[:4].copy()
+
+    def pusch_encode(self, link: np.ndarray, data: np.ndarray) -> np.ndarray:
+        """Reference only: srsran_pusch_encode + DMRS into one subframe's resource grid (nsymb*2, 12*nof_prb)."""
+        assert self.which == "ref"
+        link = np.ascontiguousarray(link, np.uint32)
+        nsym = 12 if link[2] else 14
+        data = np.concatenate([np.ascontiguousarray(data, np.uint8), np.zeros(8, np.uint8)])
+        grid = _aligned(nsym * 12 * int(link[1]), np.complex64)
+        r = self.lib.ref_pusch_encode(_p(link), _p(data), _p(grid))
+        assert r == 0, r
+        return grid.reshape(nsym, -1).copy()
+
+    def pusch_decode(self, link: np.ndarray, grid: np.ndarray, identity_ce: bool = False) -> dict:
+        """Reference only: (chest +) srsran_pusch_decode of one subframe, with the object's intermediate buffers."""
+        assert self.which == "ref"
+        link = np.ascontiguousarray(link, np.uint32)
+        Qm = {1: 2, 2: 4, 3: 6}[int(link[11])]
+        nsym = 12 if link[2] else 14
+        nre = (nsym - 2) * 12 * int(link[9])
+        grid = _aligned_copy(grid, np.complex64)
+        data = np.zeros(int(link[12]) // 8 + 16, np.uint8)
+        crc = C.c_int(0)
+        meas = np.zeros(8, np.float32)
+        d = _aligned(nre, np.complex64)
+        q = _aligned(nre * Qm, np.int16)
+        g = _aligned(nre * Qm, np.int16)
+        ce = _aligned(grid.size, np.complex64)
+        r = self.lib.ref_pusch_decode(_p(link), _p(grid), C.c_int(int(identity_ce)), _p(data), C.byref(crc), _p(meas), _p(d), _p(q),
+                                      _p(g), _p(ce))
+        return dict(ret=int(r), crc=bool(crc.value), data=data[: int(link[12]) // 8].copy(), noise=float(meas[0]), snr=float(meas[1]),
+                    cfo_hz=float(meas[2]), avg_iter=float(meas[4]), d=d.copy(), q=q.copy(), g=g.copy(), ce=ce.reshape(nsym, -1).copy())
+
+
+def pusch_link(cell_id=1, nof_prb=100, cp_ext=0, cyclic_shift=0, delta_ss=0, group_hopping=0, sequence_hopping=0, rnti=62, tti=0,
+               L_prb=100, n_prb=0, mod=3, tbs=75376, rv=0, n_dmrs=0, max_iter=8) -> np.ndarray:
+    """The uint32 parameter block shared by ref_harness.c and oracle_port.c (mod: 1 QPSK, 2 16QAM, 3 64QAM)."""
+    return np.array([cell_id, nof_prb, cp_ext, cyclic_shift, delta_ss, group_hopping, sequence_hopping, rnti, tti, L_prb, n_prb, mod,
+                     tbs, rv, n_dmrs, max_iter], np.uint32)
+
+
+def _aligned(n: int, dtype, align: int = 64) -> np.ndarray:
+    """Zeroed 1-D array whose data pointer is `align`-byte aligned (the reference's AVX kernels use aligned loads)."""
+    item = np.dtype(dtype).itemsize
+    raw = np.zeros(n * item + align, np.uint8)
+    off = (-raw.ctypes.data) % align
+    return raw[off:off + n * item].view(dtype)
+
+
+def _aligned_copy(a: np.ndarray, dtype) -> np.ndarray:
+    a = np.asarray(a, dtype).reshape(-1)
+    out = _aligned(a.size, dtype)
+    out[:] = a
+    return out
+
 
 def api(which: str = "port") -> _Api:
     return _Api(which)

@@ -884,3 +884,219 @@ int orc_decode_tb(const int16_t* e_bits,
   uint32_t par_tx = ((uint32_t)data[tbs / 8] << 16) | ((uint32_t)data[tbs / 8 + 1] << 8) | data[tbs / 8 + 2];
   return (par_rx == par_tx && par_rx) ? 0 : -1; /* sch.c:553 */
 }
+
+/* ================================================================================================================
+ * PUSCH receive chain between the OFDM demodulator and the rate de-matcher
+ * ================================================================================================================ */
+
+/* ---- pseudo-random (Gold) sequence, TS 36.211 7.2 as used by sequence.c:33-120,494-548 --------------------------------
+ * c(n) = x1(n+1600) ^ x2(n+1600), x1(n+31) = x1(n+3)^x1(n), x2(n+31) = x2(n+3)^x2(n+2)^x2(n+1)^x2(n),
+ * x1(0)=1, x2 = c_init.  Plain bit-serial form. */
+static void orc_gold(uint32_t c_init, uint8_t* c, uint32_t len)
+{
+  uint32_t x1 = 1, x2 = c_init;
+  for (uint32_t n = 0; n < 1600 + len; n++) {
+    if (n >= 1600) c[n - 1600] = (uint8_t)((x1 ^ x2) & 1u);
+    uint32_t f1 = ((x1 >> 3) ^ x1) & 1u;
+    uint32_t f2 = ((x2 >> 3) ^ (x2 >> 2) ^ (x2 >> 1) ^ x2) & 1u;
+    x1          = (x1 >> 1) | (f1 << 30);
+    x2          = (x2 >> 1) | (f2 << 30);
+  }
+}
+
+int orc_gold_bits(uint32_t c_init, uint8_t* c, uint32_t len)
+{
+  orc_gold(c_init, c, len);
+  return 0;
+}
+
+/* sequences.c:120-147 + sequence.c:494-548: out[i] = c[i] ? -in[i] : in[i], int16 wrap (-(-32768) stays -32768) */
+void orc_pusch_seq_apply_s(const int16_t* in, int16_t* out, uint32_t rnti, uint32_t nslot, uint32_t cell_id, uint32_t len)
+{
+  uint8_t* c = malloc(len ? len : 1);
+  orc_gold(((rnti & 0xFFFFu) << 14) + ((nslot / 2) << 9) + cell_id, c, len);
+  for (uint32_t i = 0; i < len; i++) out[i] = c[i] ? w16(-(int)in[i]) : in[i];
+  free(c);
+}
+
+/* sch.c:660-681,993-1020 without RI bits: q is symbol(column)-major as the demodulator leaves it, g row-major:
+ * g[(j*cols + i)*Qm + k] = q[(i*rows + j)*Qm + k], rows = H'/N_pusch_symbs, cols = N_pusch_symbs */
+int orc_ulsch_deinterleave(const int16_t* q_bits, int16_t* g_bits, uint32_t Qm, uint32_t H_prime_total, uint32_t N_pusch_symbs)
+{
+  const uint32_t rows = H_prime_total / N_pusch_symbs, cols = N_pusch_symbs;
+  uint32_t       idx = 0;
+  for (uint32_t j = 0; j < rows; j++)
+    for (uint32_t i = 0; i < cols; i++)
+      for (uint32_t k = 0; k < Qm; k++) g_bits[idx++] = q_bits[j * Qm + i * rows * Qm + k];
+  return 0;
+}
+
+/* dft_precoding.c:39-64,114-126 over dft_fftw.c (norm => 1/sqrt(N), dft_fftw.c:343-350): nof_symbols transforms of
+ * 12*nof_prb points, forward (tx) e^{-j} or backward (rx) e^{+j}, scaled by 1/sqrt(N).  float64 arithmetic. */
+int orc_dft_precoding(const float complex* in, float complex* out, uint32_t nof_prb, uint32_t nof_symbols, int is_tx)
+{
+  const uint32_t  N = 12 * nof_prb;
+  double complex* w = malloc(sizeof(double complex) * N);
+  const double    sgn = is_tx ? -1.0 : 1.0, sc = 1.0 / sqrt((double)N);
+  for (uint32_t m = 0; m < N; m++) w[m] = cexp(I * sgn * 2.0 * M_PI * (double)m / (double)N);
+  for (uint32_t s = 0; s < nof_symbols; s++) {
+    for (uint32_t k = 0; k < N; k++) {
+      double complex acc = 0;
+      for (uint32_t n = 0; n < N; n++) acc += (double complex)in[s * N + n] * w[(uint32_t)(((uint64_t)k * n) % N)];
+      out[s * N + k] = (float complex)(acc * sc);
+    }
+  }
+  free(w);
+  return 0;
+}
+
+/* precoding.c:182-305,357: x = y conj(h) / ((|h|^2 + noise) * scaling), one receive antenna.  The reference's SIMD body
+ * only adds the noise term when noise_estimate > 0 (precoding.c:235) */
+int orc_predecoding_single(const float complex* y, const float complex* h, float complex* x, int n, float scaling, float noise)
+{
+  for (int i = 0; i < n; i++) {
+    float hr = crealf(h[i]), hi = cimagf(h[i]), yr = crealf(y[i]), yi = cimagf(y[i]);
+    float hh = hr * hr + hi * hi;
+    if (noise > 0) hh += noise;
+    float re = yr * hr + yi * hi, im = yi * hr - yr * hi;
+    x[i]     = ((re / hh) * (1.0f / scaling)) + I * ((im / hh) * (1.0f / scaling));
+  }
+  return n;
+}
+
+/* Link parameters shared with oracle/ref_harness.c (all uint32):
+ *  0 cell_id  1 cell nof_prb  2 cp_ext  3 dmrs cyclic_shift  4 delta_ss  5 group_hopping  6 sequence_hopping
+ *  7 rnti  8 tti  9 L_prb  10 n_prb  11 mod  12 tbs  13 rv  14 n_dmrs  15 max_nof_iterations */
+enum { OP_CELL_ID, OP_NOF_PRB, OP_CP_EXT, OP_CSHIFT, OP_DELTA_SS, OP_GH, OP_SH, OP_RNTI, OP_TTI, OP_L_PRB, OP_N_PRB, OP_MOD,
+       OP_TBS, OP_RV, OP_N_DMRS, OP_MAX_ITER };
+
+static uint32_t orc_prime_lower_than(uint32_t n) /* primes.c: largest prime < n */
+{
+  for (uint32_t p = n - 1; p >= 2; p--) {
+    int ok = 1;
+    for (uint32_t d = 2; d * d <= p; d++)
+      if (p % d == 0) {
+        ok = 0;
+        break;
+      }
+    if (ok) return p;
+  }
+  return 0;
+}
+
+/* refsignal_ul.c:95-181,227-249,337-357 + zc_sequence.c:205-235,273-300 + phy_common.c:471-489.
+ * PUSCH DMRS of one subframe, r[2][12*L_prb] (slot-major).  Only M_sc >= 36 (L_prb >= 3): the 1- and 2-PRB base
+ * sequences are table look-ups of TS 36.211 5.5.1.2 and are not restated. */
+int orc_dmrs_pusch_gen(const uint32_t* p, float complex* r)
+{
+  static const uint32_t n_dmrs_1[8] = {0, 2, 3, 4, 6, 8, 9, 10}, n_dmrs_2[8] = {0, 6, 3, 4, 2, 8, 10, 9}; /* 36.211 5.5.2.1.1 */
+  const uint32_t cell_id = p[OP_CELL_ID], L = p[OP_L_PRB], sf_idx = p[OP_TTI] % 10, dss = p[OP_DELTA_SS];
+  const uint32_t nsymb = p[OP_CP_EXT] ? 6 : 7, M = 12 * L;
+  if (L < 3 || p[OP_CSHIFT] > 7 || p[OP_N_DMRS] > 7 || dss > 29) return -1;
+  uint8_t        c[8 * 7 * 20];
+  const uint32_t c_init = ((cell_id / 30) << 5) + (((cell_id % 30) + dss) % 30);
+  orc_gold(c_init, c, 8 * nsymb * 20);
+  uint8_t cg[160];
+  orc_gold(cell_id / 30, cg, 160);
+  const uint32_t Nzc = orc_prime_lower_than(M);
+  for (uint32_t ns = 2 * sf_idx; ns < 2 * sf_idx + 2; ns++) {
+    uint32_t n_prs = 0, f_gh = 0;
+    for (int i = 0; i < 8; i++) n_prs += (uint32_t)c[8 * nsymb * ns + i] << i;
+    if (p[OP_GH])
+      for (int i = 0; i < 8; i++) f_gh += (uint32_t)cg[8 * ns + i] << i;
+    const uint32_t n_cs  = (n_dmrs_1[p[OP_CSHIFT]] + n_dmrs_2[p[OP_N_DMRS]] + n_prs) % 12;
+    const float    alpha = (float)(2 * M_PI * (n_cs) / 12);
+    const uint32_t u     = (f_gh + (cell_id % 30) + dss) % 30;
+    uint32_t       v     = 0;
+    if (L >= 6 && p[OP_SH]) v = c[ns]; /* same generator, first 20 bits (refsignal_ul.c:121-126) */
+    /* zc_sequence.c:205-218 */
+    const float n_sz  = (float)Nzc;
+    float       q_hat = n_sz * (u + 1) / 31, qf;
+    if ((((uint32_t)(2 * q_hat)) % 2) == 0) qf = q_hat + 0.5 + v;
+    else qf = q_hat + 0.5 - v;
+    const float q = (float)(uint32_t)qf;
+    for (uint32_t i = 0; i < M; i++) {
+      const float m   = (float)(i % Nzc);
+      const float arg = (float)(-M_PI * q * m * (m + 1) / n_sz); /* double expression rounded into a float (cf_t) */
+      /* the reference is built with -mfma and GCC contracts arg + alpha*i into one fused multiply-add (oracle/Makefile
+       * uses the reference's own ISA flags); restated explicitly so that this file does not depend on its own flags */
+      r[(ns % 2) * M + i] = cexpf(I * fmaf(alpha, (float)i, arg));
+    }
+  }
+  return 0;
+}
+
+/* srsran_conv_same_cf, extrapolating variant (convolution.c:181-218), real filter of odd length M <= 7 */
+static void orc_conv_same(const float complex* in, const float* f, float complex* out, uint32_t N, uint32_t M)
+{
+  float complex first[16], last[16];
+  for (uint32_t i = 0; i < M + M / 2; i++) {
+    if (i < M / 2) first[i] = (2 + M / 2 - i) * in[1] - (1 + M / 2 - i) * in[0];
+    else first[i] = in[i - M / 2];
+  }
+  for (uint32_t i = 0; i < M + M / 2; i++) {
+    if (i >= M - 1) last[i] = (2 + i - M / 2) * in[N - 1] - (1 + i - M / 2) * in[N - 2];
+    else last[i] = in[N - M + i + 1];
+  }
+  uint32_t i = 0, j = 0;
+  for (; i < M / 2; i++) {
+    float complex a = 0;
+    for (uint32_t t = 0; t < M; t++) a += first[i + t] * f[t];
+    out[i] = a;
+  }
+  for (; i < N - M / 2; i++) {
+    float complex a = 0;
+    for (uint32_t t = 0; t < M; t++) a += in[i - M / 2 + t] * f[t];
+    out[i] = a;
+  }
+  for (; i < N; i++, j++) {
+    float complex a = 0;
+    for (uint32_t t = 0; t < M; t++) a += last[j + t] * f[t];
+    out[i] = a;
+  }
+}
+
+/* chest_ul.c:225-357,370-400 with the object defaults of chest_ul.c:82-83 (3-tap filter, w = 0.3333), no linear
+ * interpolation (the estimate of a slot's DMRS symbol is copied to its other symbols), no TA measurement.
+ * grid/ce: 2*nsymb symbols of 12*nof_prb; dmrs: the known sequence [2][12*L_prb]; meas = {noise_estimate, snr, cfo_hz, 0} */
+int orc_chest_ul_pusch(const uint32_t* p, const float complex* grid, const float complex* dmrs, float complex* ce, float* meas)
+{
+  const uint32_t nsymb = p[OP_CP_EXT] ? 6 : 7, R = 12 * p[OP_NOF_PRB], M = 12 * p[OP_L_PRB], off = 12 * p[OP_N_PRB];
+  const float    w = 0.3333f;
+  const float    f[3] = {w, 1 - 2 * w, w};
+  float complex* ls   = malloc(sizeof(float complex) * 2 * M);
+  float          noise = 0, rxpow = 0;
+  for (uint32_t s = 0; s < 2; s++) {
+    const uint32_t l = (s + 1) * nsymb - 4;
+    for (uint32_t i = 0; i < M; i++) {
+      const float complex y = grid[l * R + off + i];
+      ls[s * M + i]         = y * conjf(dmrs[s * M + i]);
+      rxpow += crealf(y) * crealf(y) + cimagf(y) * cimagf(y);
+    }
+  }
+  double complex dot = 0;
+  for (uint32_t i = 0; i < M; i++) dot += (double complex)ls[i] * conj((double complex)ls[M + i]);
+  meas[2] = (float)(carg(dot) / (2.0 * M_PI * 0.0005));
+  for (uint32_t s = 0; s < 2; s++) {
+    const uint32_t l = (s + 1) * nsymb - 4;
+    orc_conv_same(&ls[s * M], f, &ce[l * R + off], M, 3);
+    float pw = 0;
+    for (uint32_t i = 0; i < M; i++) {
+      const float complex d = ce[l * R + off + i] - ls[s * M + i];
+      pw += crealf(d) * crealf(d) + cimagf(d) * cimagf(d);
+    }
+    noise += pw / (float)M;
+    for (uint32_t k = 0; k < nsymb; k++) {
+      const uint32_t dst = s * nsymb + k;
+      if (dst != l) memcpy(&ce[dst * R + off], &ce[l * R + off], sizeof(float complex) * M);
+    }
+  }
+  noise /= 2;
+  const float a = 7.419 * w * w + 0.1117 * w - 0.005387; /* chest_ul.c:216-219 */
+  noise         = noise / (a * 0.8);
+  meas[0]       = noise;
+  meas[1]       = (rxpow / (float)(2 * M)) / noise;
+  meas[3]       = 0;
+  free(ls);
+  return 0;
+}

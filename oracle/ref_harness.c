@@ -426,3 +426,234 @@ int ref_demod_s(int mod, const cf_t* symbols, short* llr, int nsymbols)
 {
   return srsran_demod_soft_demodulate_s((srsran_mod_t)mod, symbols, llr, nsymbols);
 }
+
+/* ---- PUSCH receive chain beyond OFDM: DMRS, channel estimation, equaliser, transform de-precoding,
+ *      descrambling, UL-SCH de-interleave ------------------------------------------------ */
+#include "srsran/phy/ch_estimation/chest_ul.h"
+#include "srsran/phy/ch_estimation/refsignal_ul.h"
+#include "srsran/phy/dft/dft_precoding.h"
+#include "srsran/phy/mimo/precoding.h"
+#include "srsran/phy/phch/pusch.h"
+#include "srsran/phy/phch/ra.h"
+#include "srsran/phy/common/sequence.h"
+
+/* sequences.c:139 */
+void ref_pusch_seq_apply_s(const int16_t* in, int16_t* out, uint32_t rnti, uint32_t nslot, uint32_t cell_id, uint32_t len)
+{
+  srsran_sequence_pusch_apply_s(in, out, (uint16_t)rnti, nslot, cell_id, len);
+}
+
+/* sch.c:993 (not declared in a header), no RI bits */
+void ulsch_deinterleave(int16_t*          q_bits,
+                        uint32_t          Qm,
+                        uint32_t          H_prime_total,
+                        uint32_t          N_pusch_symbs,
+                        int16_t*          g_bits,
+                        srsran_uci_bit_t* ri_bits,
+                        uint32_t          nof_ri_bits,
+                        uint8_t*          ri_present,
+                        uint32_t*         inteleaver_lut);
+
+int ref_ulsch_deinterleave(int16_t* q_bits, int16_t* g_bits, uint32_t Qm, uint32_t H_prime_total, uint32_t N_pusch_symbs)
+{
+  uint32_t  n   = H_prime_total * Qm;
+  uint8_t*  tmp = calloc(n, 1);
+  uint32_t* lut = calloc(n, sizeof(uint32_t));
+  if (!tmp || !lut) return -1;
+  ulsch_deinterleave(q_bits, Qm, H_prime_total, N_pusch_symbs, g_bits, NULL, 0, tmp, lut);
+  free(tmp);
+  free(lut);
+  return 0;
+}
+
+/* dft_precoding.c:114; is_tx selects the forward plan (precoding) or the backward one (receiver) */
+int ref_dft_precoding(cf_t* in, cf_t* out, uint32_t nof_prb, uint32_t nof_symbols, int is_tx)
+{
+  srsran_dft_precoding_t q;
+  if (srsran_dft_precoding_init(&q, nof_prb, is_tx != 0)) return -1;
+  int r = srsran_dft_precoding(&q, in, out, nof_prb, nof_symbols);
+  srsran_dft_precoding_free(&q);
+  return r;
+}
+
+/* precoding.c:357 */
+int ref_predecoding_single(cf_t* y, cf_t* h, cf_t* x, int nof_symbols, float scaling, float noise_estimate)
+{
+  return srsran_predecoding_single(y, h, x, NULL, nof_symbols, scaling, noise_estimate);
+}
+
+/* Link parameters, all uint32:
+ *  0 cell_id  1 cell nof_prb  2 cp_ext  3 dmrs cyclic_shift  4 delta_ss  5 group_hopping  6 sequence_hopping
+ *  7 rnti  8 tti  9 L_prb  10 n_prb  11 mod (srsran_mod_t)  12 tbs  13 rv  14 n_dmrs (cyclic shift for DMRS, 0..7)
+ *  15 max_nof_iterations */
+enum { P_CELL_ID, P_NOF_PRB, P_CP_EXT, P_CSHIFT, P_DELTA_SS, P_GH, P_SH, P_RNTI, P_TTI, P_L_PRB, P_N_PRB, P_MOD, P_TBS, P_RV,
+       P_N_DMRS, P_MAX_ITER, P_COUNT };
+
+static srsran_cell_t link_cell(const uint32_t* p)
+{
+  srsran_cell_t cell;
+  memset(&cell, 0, sizeof(cell));
+  cell.nof_prb         = p[P_NOF_PRB];
+  cell.nof_ports       = 1;
+  cell.id              = p[P_CELL_ID];
+  cell.cp              = p[P_CP_EXT] ? SRSRAN_CP_EXT : SRSRAN_CP_NORM;
+  cell.phich_length    = SRSRAN_PHICH_NORM;
+  cell.phich_resources = SRSRAN_PHICH_R_1;
+  cell.frame_type      = SRSRAN_FDD;
+  return cell;
+}
+
+static void link_cfg(const uint32_t* p, srsran_cell_t* cell, srsran_pusch_cfg_t* cfg, srsran_ul_sf_cfg_t* sf,
+                     srsran_refsignal_dmrs_pusch_cfg_t* dmrs)
+{
+  memset(cfg, 0, sizeof(*cfg));
+  memset(sf, 0, sizeof(*sf));
+  memset(dmrs, 0, sizeof(*dmrs));
+  sf->tti                   = p[P_TTI];
+  dmrs->cyclic_shift        = p[P_CSHIFT];
+  dmrs->delta_ss            = p[P_DELTA_SS];
+  dmrs->group_hopping_en    = p[P_GH] != 0;
+  dmrs->sequence_hopping_en = p[P_SH] != 0;
+  cfg->rnti                 = (uint16_t)p[P_RNTI];
+  cfg->grant.L_prb          = p[P_L_PRB];
+  cfg->grant.n_prb[0] = cfg->grant.n_prb[1] = p[P_N_PRB];
+  cfg->grant.n_prb_tilde[0] = cfg->grant.n_prb_tilde[1] = p[P_N_PRB];
+  cfg->grant.tb.mod   = (srsran_mod_t)p[P_MOD];
+  cfg->grant.tb.tbs   = (int)p[P_TBS];
+  cfg->grant.tb.rv    = (int)p[P_RV];
+  cfg->grant.n_dmrs   = p[P_N_DMRS];
+  srsran_ra_ul_compute_nof_re(&cfg->grant, cell->cp, 0); /* ra_ul.c:230 */
+  cfg->max_nof_iterations = p[P_MAX_ITER];
+  cfg->enable_64qam       = true;
+}
+
+/* refsignal_ul.c:337: r[2 * 12 * L_prb], slot-major */
+int ref_dmrs_pusch_gen(const uint32_t* p, cf_t* r)
+{
+  srsran_cell_t                     cell = link_cell(p);
+  srsran_pusch_cfg_t                cfg;
+  srsran_ul_sf_cfg_t                sf;
+  srsran_refsignal_dmrs_pusch_cfg_t dmrs;
+  srsran_refsignal_ul_t             q;
+  link_cfg(p, &cell, &cfg, &sf, &dmrs);
+  memset(&q, 0, sizeof(q));
+  if (srsran_refsignal_ul_set_cell(&q, cell)) return -1;
+  return srsran_refsignal_dmrs_pusch_gen(&q, &dmrs, p[P_L_PRB], p[P_TTI] % 10, p[P_N_DMRS], r);
+}
+
+/* chest_ul.c:370: grid = 2*nsymb*12*nof_prb RE of one subframe; ce_out same size; meas = {noise_estimate, snr, cfo_hz, ta_us} */
+int ref_chest_ul_pusch(const uint32_t* p, cf_t* grid, cf_t* ce_out, float* meas)
+{
+  srsran_cell_t                     cell = link_cell(p);
+  srsran_pusch_cfg_t                cfg;
+  srsran_ul_sf_cfg_t                sf;
+  srsran_refsignal_dmrs_pusch_cfg_t dmrs;
+  srsran_chest_ul_t                 q;
+  srsran_chest_ul_res_t             res;
+  link_cfg(p, &cell, &cfg, &sf, &dmrs);
+  if (srsran_chest_ul_init(&q, cell.nof_prb)) return -1;
+  if (srsran_chest_ul_set_cell(&q, cell)) return -2;
+  srsran_chest_ul_pregen(&q, &dmrs, NULL);
+  if (srsran_chest_ul_res_init(&res, cell.nof_prb)) return -3;
+  memset(res.ce, 0, sizeof(cf_t) * res.nof_re);
+  int r = srsran_chest_ul_estimate_pusch(&q, &sf, &cfg, grid, &res);
+  memcpy(ce_out, res.ce, sizeof(cf_t) * 2 * SRSRAN_CP_NSYMB(cell.cp) * 12 * cell.nof_prb);
+  meas[0] = res.noise_estimate;
+  meas[1] = res.snr;
+  meas[2] = res.cfo_hz;
+  meas[3] = res.ta_us;
+  srsran_chest_ul_res_free(&res);
+  srsran_chest_ul_free(&q);
+  return r;
+}
+
+/* Transmit side, to synthesise test input: srsran_pusch_encode (pusch.c) + DMRS (refsignal_ul.c:192) into a zeroed grid */
+int ref_pusch_encode(const uint32_t* p, uint8_t* data, cf_t* grid)
+{
+  srsran_cell_t                     cell = link_cell(p);
+  srsran_pusch_cfg_t                cfg;
+  srsran_ul_sf_cfg_t                sf;
+  srsran_refsignal_dmrs_pusch_cfg_t dmrs;
+  srsran_pusch_t                    tx;
+  srsran_softbuffer_tx_t            sb;
+  srsran_refsignal_ul_t             rs;
+  link_cfg(p, &cell, &cfg, &sf, &dmrs);
+  ensure_tables();
+  if (srsran_pusch_init_ue(&tx, cell.nof_prb)) return -1;
+  if (srsran_pusch_set_cell(&tx, cell)) return -2;
+  if (srsran_softbuffer_tx_init(&sb, cell.nof_prb)) return -3;
+  srsran_softbuffer_tx_reset(&sb);
+  cfg.softbuffers.tx = &sb;
+  srsran_pusch_data_t pdata;
+  memset(&pdata, 0, sizeof(pdata));
+  pdata.ptr = data;
+  uint32_t nre = 2 * SRSRAN_CP_NSYMB(cell.cp) * 12 * cell.nof_prb;
+  memset(grid, 0, sizeof(cf_t) * nre);
+  int r = srsran_pusch_encode(&tx, &sf, &cfg, &pdata, grid);
+  if (r == 0) {
+    cf_t* rp = srsran_vec_cf_malloc(2 * 12 * p[P_L_PRB]);
+    memset(&rs, 0, sizeof(rs));
+    if (srsran_refsignal_ul_set_cell(&rs, cell)) r = -4;
+    else if (srsran_refsignal_dmrs_pusch_gen(&rs, &dmrs, p[P_L_PRB], p[P_TTI] % 10, p[P_N_DMRS], rp)) r = -5;
+    else srsran_refsignal_dmrs_pusch_put(&rs, &cfg, rp, grid);
+    free(rp);
+  }
+  srsran_softbuffer_tx_free(&sb);
+  srsran_pusch_free(&tx);
+  return r;
+}
+
+/* Receive side: chest (unless use_identity_ce) + srsran_pusch_decode (pusch.c:358).  Besides the payload it hands out the
+ * object's intermediate buffers: d = de-precoded symbols (nof_re), q = descrambled soft bits, g = de-interleaved soft bits
+ * (nof_bits each), so a pipeline can be compared stage by stage. */
+int ref_pusch_decode(const uint32_t* p, cf_t* grid, int use_identity_ce, uint8_t* data, int* crc_ok, float* meas, cf_t* d_out,
+                     int16_t* q_out, int16_t* g_out, cf_t* ce_out)
+{
+  srsran_cell_t                     cell = link_cell(p);
+  srsran_pusch_cfg_t                cfg;
+  srsran_ul_sf_cfg_t                sf;
+  srsran_refsignal_dmrs_pusch_cfg_t dmrs;
+  srsran_pusch_t                    rx;
+  srsran_softbuffer_rx_t            sb;
+  srsran_chest_ul_t                 chest;
+  srsran_chest_ul_res_t             res;
+  link_cfg(p, &cell, &cfg, &sf, &dmrs);
+  ensure_tables();
+  if (srsran_pusch_init_enb(&rx, cell.nof_prb)) return -1;
+  if (srsran_pusch_set_cell(&rx, cell)) return -2;
+  if (srsran_softbuffer_rx_init(&sb, cell.nof_prb)) return -3;
+  srsran_softbuffer_rx_reset(&sb);
+  cfg.softbuffers.rx = &sb;
+  if (srsran_chest_ul_res_init(&res, cell.nof_prb)) return -4;
+  if (use_identity_ce) {
+    srsran_chest_ul_res_set_identity(&res);
+    res.noise_estimate = 0;
+  } else {
+    if (srsran_chest_ul_init(&chest, cell.nof_prb)) return -5;
+    if (srsran_chest_ul_set_cell(&chest, cell)) return -6;
+    srsran_chest_ul_pregen(&chest, &dmrs, NULL);
+    memset(res.ce, 0, sizeof(cf_t) * res.nof_re);
+    if (srsran_chest_ul_estimate_pusch(&chest, &sf, &cfg, grid, &res)) return -7;
+    srsran_chest_ul_free(&chest);
+  }
+  if (meas) {
+    meas[0] = res.noise_estimate;
+    meas[1] = res.snr;
+    meas[2] = res.cfo_hz;
+    meas[3] = res.ta_us;
+  }
+  if (ce_out) memcpy(ce_out, res.ce, sizeof(cf_t) * 2 * SRSRAN_CP_NSYMB(cell.cp) * 12 * cell.nof_prb);
+  srsran_pusch_res_t out;
+  memset(&out, 0, sizeof(out));
+  out.data = data;
+  int r    = srsran_pusch_decode(&rx, &sf, &cfg, &res, grid, &out);
+  if (crc_ok) *crc_ok = out.crc ? 1 : 0;
+  if (meas) meas[4] = out.avg_iterations_block;
+  if (d_out) memcpy(d_out, rx.d, sizeof(cf_t) * cfg.grant.nof_re);
+  if (q_out) memcpy(q_out, rx.q, sizeof(int16_t) * cfg.grant.tb.nof_bits);
+  if (g_out) memcpy(g_out, rx.g, sizeof(int16_t) * cfg.grant.tb.nof_bits);
+  srsran_chest_ul_res_free(&res);
+  srsran_softbuffer_rx_free(&sb);
+  srsran_pusch_free(&rx);
+  return r;
+}

@@ -19,6 +19,7 @@ SOURCES = [
     "ofdm_kernels.cu",
     "ofdm_host.cu",
     "demod_kernels.cu",
+    "pusch_kernels.cu",
     "srsran_compat.cu",
     "synth.cu",
 ]

@@ -77,24 +77,11 @@ struct OfdmEngine {
       }
     }
     // factor N into the register radices the kernel has
-    std::vector<int> radix;
-    int              rem = N;
-    for (int r : {16, 8, 4, 2, 3}) {
-      while (rem % r == 0 && rem > 1 && (int)radix.size() < OFDM_MAX_PASSES) {
-        radix.push_back(r);
-        rem /= r;
-      }
-    }
-    if (rem != 1 || 12 * (int)c.nof_prb > N || c.nof_prb == 0 || N < 16) {
-      B200_LOG_ERROR("unsupported OFDM size: symbol_sz=%d nof_prb=%u (sizes 2^a 3^b, nof_re <= symbol_sz)", N, c.nof_prb);
+    int       radix[OFDM_MAX_PASSES];
+    const int npass = N >= 16 ? fft_factorise(N, radix) : 0;
+    if (npass == 0 || 12 * (int)c.nof_prb > N || c.nof_prb == 0) {
+      B200_LOG_ERROR("unsupported OFDM size: symbol_sz=%d nof_prb=%u (sizes 2^a 3^b 5^c, nof_re <= symbol_sz)", N, c.nof_prb);
       return B200_ERROR;
-    }
-    if (radix.size() == 1) { // a single pass would have to be first and last at once: split it
-      int r = radix[0];
-      radix.clear();
-      if (r == 16) radix = {4, 4};
-      else if (r == 8) radix = {4, 2};
-      else radix = {2, 2};
     }
     cfg          = c;
     const bool ext = c.cp_ext != 0;
@@ -105,8 +92,8 @@ struct OfdmEngine {
     plan.cp2     = ext ? cp_len(512, N) : cp_len(144, N);
     plan.sf_sz   = 15 * N;
     plan.slot_sz = 15 * N / 2;
-    plan.npass   = (int)radix.size();
-    for (int i = 0; i < OFDM_MAX_PASSES; i++) plan.radix[i] = i < plan.npass ? radix[i] : 1;
+    plan.npass   = npass;
+    for (int i = 0; i < OFDM_MAX_PASSES; i++) plan.radix[i] = radix[i];
     int tps = N / 16;
     if (tps < 8) tps = 8;
     if (tps > OFDM_THREADS) tps = OFDM_THREADS;

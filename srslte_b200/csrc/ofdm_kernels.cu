@@ -66,6 +66,24 @@ __device__ __forceinline__ void dft_small<3>(float2* u)
 }
 
 template <>
+__device__ __forceinline__ void dft_small<5>(float2* u)
+{
+  // Winograd-style radix 5 (transform de-precoding sizes 12 L with L = 2^a 3^b 5^c, dft_precoding.c:88-95)
+  const float c1 = 0.30901699437494742410f, c2 = -0.80901699437494742410f; // cos(2 pi/5), cos(4 pi/5)
+  const float s1 = 0.95105651629515357212f, s2 = 0.58778525229247312917f;  // sin(2 pi/5), sin(4 pi/5)
+  const float2 t1 = cadd(u[1], u[4]), t2 = cadd(u[2], u[3]), t3 = csub(u[1], u[4]), t4 = csub(u[2], u[3]);
+  const float2 a1 = make_float2(u[0].x + c1 * t1.x + c2 * t2.x, u[0].y + c1 * t1.y + c2 * t2.y);
+  const float2 a2 = make_float2(u[0].x + c2 * t1.x + c1 * t2.x, u[0].y + c2 * t1.y + c1 * t2.y);
+  const float2 b1 = make_float2(s1 * t3.x + s2 * t4.x, s1 * t3.y + s2 * t4.y);
+  const float2 b2 = make_float2(s2 * t3.x - s1 * t4.x, s2 * t3.y - s1 * t4.y);
+  u[0]            = make_float2(u[0].x + t1.x + t2.x, u[0].y + t1.y + t2.y);
+  u[1]            = cadd(a1, mul_mi(b1)); // a1 - i b1
+  u[4]            = csub(a1, mul_mi(b1));
+  u[2]            = cadd(a2, mul_mi(b2));
+  u[3]            = csub(a2, mul_mi(b2));
+}
+
+template <>
 __device__ __forceinline__ void dft_small<4>(float2* u)
 {
   float2 a = cadd(u[0], u[2]), b = csub(u[0], u[2]);
@@ -151,7 +169,9 @@ __device__ __forceinline__ void fft_pass(const OfdmPlanDev& p,
                                          float2*           sout,          // shared destination (all but last pass)
                                          float2* __restrict__ gout,       // symbol's output row (last pass)
                                          int               t,
-                                         int               tps)
+                                         int               tps,
+                                         const float2* __restrict__ eq_h = nullptr, // PUSCH mode: the slot's channel estimates
+                                         float             eq_n0 = 0.f)
 {
   const int N = p.N, T = N / RADIX;
   for (int j = t; j < T; j += tps) {
@@ -162,6 +182,12 @@ __device__ __forceinline__ void fft_pass(const OfdmPlanDev& p,
       if (first) {
         float2 v = gin[idx];
         if (p.shift) v = cmul(v, p.shift[idx]);
+        if (eq_h) { // precoding.c:224-262: (y conj(h)) / (|h|^2 [+ noise when noise > 0])
+          const float2 h  = eq_h[idx];
+          float        hh = h.x * h.x + h.y * h.y;
+          if (eq_n0 > 0.f) hh += eq_n0;
+          v = make_float2((v.x * h.x + v.y * h.y) / hh, (v.y * h.x - v.x * h.y) / hh);
+        }
         if (p.inverse) v.y = -v.y;
         u[q] = v;
       } else {
@@ -185,6 +211,7 @@ __device__ __forceinline__ void fft_pass(const OfdmPlanDev& p,
           float2 v = u[q];
           if (p.ramp) v = cmul(v, p.ramp[re]);
           if (p.inverse) v.y = -v.y;
+          if (p.gscale != 0.f) v = make_float2(v.x * p.gscale, v.y * p.gscale);
           gout[re] = v;
         }
       } else {
@@ -218,6 +245,16 @@ __global__ void __launch_bounds__(OFDM_THREADS) ofdm_rx_kernel(OfdmPlanDev p, co
     const float2*  gin  = p.generic ? in + (size_t)sidx * p.idist
                                     : in + (size_t)sf * p.sf_sz + (size_t)slot * p.slot_sz + p.cp1 + (size_t)ls * (p.N + p.cp2) - p.noff;
     float2*        gout = p.generic ? out + (size_t)sidx * p.odist : out + (size_t)sidx * p.R;
+    const float2*  eq_h  = nullptr;
+    float          eq_n0 = 0.f;
+    if (p.generic == 2 && active) {
+      const uint32_t psf = sidx / (uint32_t)p.pusch_nd, d = sidx % (uint32_t)p.pusch_nd;
+      const int      lsym = p.pusch_l[d];
+      gin   = in + ((size_t)psf * p.grid_nsym + lsym) * p.grid_R + p.grid_off;
+      gout  = out + (size_t)sidx * p.N;
+      eq_h  = p.eq_ce + ((size_t)psf * 2 + (lsym >= p.grid_nsym / 2 ? 1 : 0)) * p.N;
+      eq_n0 = p.eq_noise ? p.eq_noise[(size_t)psf * p.eq_noise_stride] : 0.f;
+    }
     int            Ns   = 1;
     float2 *       src = bufA, *dst = bufB;
     for (int ps = 0; ps < p.npass; ps++) {
@@ -225,19 +262,22 @@ __global__ void __launch_bounds__(OFDM_THREADS) ofdm_rx_kernel(OfdmPlanDev p, co
       if (active) {
         switch (p.radix[ps]) {
           case 16:
-            fft_pass<16>(p, Ns, first, last, gin, src, dst, gout, t, tps);
+            fft_pass<16>(p, Ns, first, last, gin, src, dst, gout, t, tps, eq_h, eq_n0);
             break;
           case 8:
-            fft_pass<8>(p, Ns, first, last, gin, src, dst, gout, t, tps);
+            fft_pass<8>(p, Ns, first, last, gin, src, dst, gout, t, tps, eq_h, eq_n0);
             break;
           case 4:
-            fft_pass<4>(p, Ns, first, last, gin, src, dst, gout, t, tps);
+            fft_pass<4>(p, Ns, first, last, gin, src, dst, gout, t, tps, eq_h, eq_n0);
             break;
           case 3:
-            fft_pass<3>(p, Ns, first, last, gin, src, dst, gout, t, tps);
+            fft_pass<3>(p, Ns, first, last, gin, src, dst, gout, t, tps, eq_h, eq_n0);
+            break;
+          case 5:
+            fft_pass<5>(p, Ns, first, last, gin, src, dst, gout, t, tps, eq_h, eq_n0);
             break;
           default:
-            fft_pass<2>(p, Ns, first, last, gin, src, dst, gout, t, tps);
+            fft_pass<2>(p, Ns, first, last, gin, src, dst, gout, t, tps, eq_h, eq_n0);
             break;
         }
       }

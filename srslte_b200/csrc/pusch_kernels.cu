@@ -1,0 +1,561 @@
+// PUSCH receive chain between the OFDM demodulator and the rate de-matcher, for a batch of subframes:
+//
+//   DMRS known sequence        srsran_refsignal_dmrs_pusch_gen       lib/src/phy/ch_estimation/refsignal_ul.c:95-181,227-249,337-357
+//                              srsran_zc_sequence_generate_lte       lib/src/phy/common/zc_sequence.c:205-235,273-300
+//   channel estimation         srsran_chest_ul_estimate_pusch        lib/src/phy/ch_estimation/chest_ul.c:197-357,370-400
+//                              srsran_conv_same_cf (3-tap smoothing) lib/src/phy/utils/convolution.c:181-218
+//   equaliser                  srsran_predecoding_single             lib/src/phy/mimo/precoding.c:182-305,357  } one kernel: the FFT core of
+//   transform de-precoding     srsran_dft_precoding                  lib/src/phy/dft/dft_precoding.c:114-126   } ofdm_kernels.cu in PUSCH mode
+//   soft demapping             srsran_demod_soft_demodulate_s        lib/src/phy/modem/demod_soft.c:871          }
+//   descrambling               srsran_sequence_pusch_apply_s         lib/src/phy/phch/sequences.c:120-147        } one kernel
+//   UL-SCH de-interleaving     ulsch_deinterleave                    lib/src/phy/phch/sch.c:660-681,993-1020     }
+//
+// in the order lib/src/phy/phch/pusch.c:392-456 (srsran_pusch_decode) and sch.c:1121-1190 (srsran_ulsch_decode) call them.
+// Scope: one receive antenna, no uplink control information multiplexed into the PUSCH (no RI / ACK / CQI bits), no
+// intra-subframe hopping (the reference's estimator refuses it too, chest_ul.c:276), allocations of >= 3 PRB (the 1- and
+// 2-PRB DMRS base sequences are table look-ups of TS 36.211 5.5.1.2 that are not carried here).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "../../include/srslte_b200.h"
+#include "b200_runtime.h"
+#include "demod_core.h"
+#include "ofdm_kernels.h"
+#include "tdec_engine.h"
+
+namespace b200 {
+
+struct PuschSfParam {
+  uint32_t c_init;   // scrambling seed of the subframe: (rnti << 14) + (sf_idx << 9) + cell_id  (sequences.c:120-123)
+  uint32_t dmrs_idx; // n_dmrs * 10 + sf_idx: row of the DMRS table
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// Channel estimation: one block per subframe.  LS estimates of the two DMRS symbols (received x conj(known)), 3-tap
+// smoothing with the reference's extrapolated edges, noise from the difference between smoothed and raw estimates,
+// received pilot power and the slot-to-slot phase (CFO).  Output: the two slots' estimates [nsf][2][M] (the reference
+// copies them to every symbol of the slot, chest_ul.c:246-259: the equaliser reads them per slot instead) and
+// meas[nsf][4] = {noise_estimate, snr, cfo_hz, ta_us = 0}.
+__global__ void __launch_bounds__(256) pusch_chest_kernel(const float2* __restrict__ grid, const float2* __restrict__ dmrs_tab,
+                                                          const PuschSfParam* __restrict__ prm, float2* __restrict__ ce,
+                                                          float* __restrict__ meas, int nsym, int R, int off, int M, float w, float noise_cal)
+{
+  extern __shared__ __align__(16) float2 ls[]; // [2][M]
+  __shared__ float red[4][8];
+  const uint32_t sf   = blockIdx.x;
+  const float2*  known = dmrs_tab + (size_t)prm[sf].dmrs_idx * 2 * M;
+  const int      half = nsym / 2;
+  float          rxpow = 0.f, dre = 0.f, dim = 0.f, npow = 0.f;
+  for (int s = 0; s < 2; s++) {
+    const float2* y = grid + ((size_t)sf * nsym + (size_t)((s + 1) * half - 4)) * R + off; // SRSRAN_REFSIGNAL_UL_L (refsignal_ul.h:43)
+    for (int i = threadIdx.x; i < M; i += blockDim.x) {
+      const float2 v = y[i], r = known[s * M + i];
+      ls[s * M + i]  = make_float2(v.x * r.x + v.y * r.y, v.y * r.x - v.x * r.y); // srsran_vec_prod_conj_ccc
+      rxpow += v.x * v.x + v.y * v.y;
+    }
+  }
+  __syncthreads();
+  const float f0 = w, f1 = 1.f - 2.f * w;
+  for (int s = 0; s < 2; s++) {
+    const float2* in = ls + s * M;
+    for (int i = threadIdx.x; i < M; i += blockDim.x) {
+      // convolution.c:187-204: samples beyond the edges are 3 in[1] - 2 in[0] and 3 in[M-1] - 2 in[M-2]
+      const float2 c = in[i];
+      float2       a, b;
+      if (i > 0) a = in[i - 1];
+      else a = make_float2(3.f * in[1].x - 2.f * in[0].x, 3.f * in[1].y - 2.f * in[0].y);
+      if (i < M - 1) b = in[i + 1];
+      else b = make_float2(3.f * in[M - 1].x - 2.f * in[M - 2].x, 3.f * in[M - 1].y - 2.f * in[M - 2].y);
+      const float2 o = make_float2(a.x * f0 + c.x * f1 + b.x * f0, a.y * f0 + c.y * f1 + b.y * f0);
+      ce[((size_t)sf * 2 + s) * M + i] = o;
+      const float ex = o.x - c.x, ey = o.y - c.y;
+      npow += ex * ex + ey * ey;
+      if (s == 0) { // CFO: sum ls0 conj(ls1) (chest_ul.c:252-255)
+        const float2 o1 = in[M + i];
+        dre += c.x * o1.x + c.y * o1.y;
+        dim += c.y * o1.x - c.x * o1.y;
+      }
+    }
+  }
+  float v[4] = {npow, rxpow, dre, dim};
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xFFFFFFFFu, v[k], o);
+    if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5] = v[k];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k = 0; k < 4; k++)
+      for (int q = 0; q < (int)(blockDim.x >> 5); q++) t[k] += red[k][q];
+    // chest_ul.c:197-222: mean over the slots of the per-slot average power, calibrated for the 3-tap filter
+    const float noise = (t[0] / (float)M) / 2.f / noise_cal;
+    const bool  ok    = isfinite(noise) && fabsf(noise) >= 1.17549435e-38f; // isnormal()
+    meas[4 * sf + 0]  = noise;
+    meas[4 * sf + 1]  = ok ? (t[1] / (float)(2 * M)) / noise : nanf("");
+    meas[4 * sf + 2]  = atan2f(t[3], t[2]) / (2.0f * 3.14159265358979323846f * 0.0005f);
+    meas[4 * sf + 3]  = 0.f;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Scrambling sequences: one warp per subframe.  c(n) = x1(n+1600) ^ x2(n+1600) (TS 36.211 7.2; sequence.c:33-120).
+// x1 does not depend on the seed: its words come from a table.  x2 is linear in the 31 seed bits, so lane l starts at its
+// own chunk of the sequence from the XOR of per-seed-bit jump states, then steps 16 bits at a time (all taps of the
+// recurrence x2(n+31) = x2(n+3)^x2(n+2)^x2(n+1)^x2(n) lie inside the 31-bit state for 16 new bits).
+__global__ void __launch_bounds__(256) pusch_gold_kernel(const PuschSfParam* __restrict__ prm, const uint32_t* __restrict__ x1w,
+                                                         const uint32_t* __restrict__ jump, uint32_t* __restrict__ seq, uint32_t nsf,
+                                                         uint32_t nwords, uint32_t wpl)
+{
+  const uint32_t sf = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (sf >= nsf) return;
+  const uint32_t seed = prm[sf].c_init;
+  uint32_t       s    = 0;
+#pragma unroll
+  for (int b = 0; b < 31; b++) s ^= ((seed >> b) & 1u) ? jump[lane * 31 + b] : 0u;
+  const uint32_t w0 = lane * wpl, w1 = min(w0 + wpl, nwords);
+  for (uint32_t w = w0; w < w1; w++) {
+    uint32_t out = s & 0xFFFFu;
+    uint32_t f   = (s ^ (s >> 1) ^ (s >> 2) ^ (s >> 3)) & 0xFFFFu;
+    s            = (s >> 16) | (f << 15);
+    out |= (s & 0xFFFFu) << 16;
+    f = (s ^ (s >> 1) ^ (s >> 2) ^ (s >> 3)) & 0xFFFFu;
+    s = (s >> 16) | (f << 15);
+    seq[(size_t)sf * nwords + w] = out ^ x1w[w];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Soft demapping + arithmetic shift + descrambling + UL-SCH de-interleaving.  The demapper sees the subframe's nd*M
+// de-precoded symbols as ONE reference call (pusch.c:421: vector body / scalar tail split over grant.nof_re); soft bit
+// n = (i*M + j)*Qm + k of data symbol i, subcarrier j changes sign when c(n) = 1 (int16 wrap, sequence.c:521-532) and lands
+// at g[(j*nd + i)*Qm + k] (sch.c:660-681 with rows = M, cols = nd, no RI bits).  A block stages a tile of 64 subcarriers x nd
+// symbols in shared memory (coalesced row reads), then walks it in output order so the stores are contiguous.
+constexpr int DEMOD_TJ = 64;
+__global__ void __launch_bounds__(256) pusch_demod_descramble_kernel(int mod, const float2* __restrict__ d, const uint32_t* __restrict__ seq,
+                                                                     int16_t* __restrict__ g, uint32_t M, uint32_t nd, uint32_t nwords,
+                                                                     int shift, float qpsk_scale)
+{
+  __shared__ float2 tile[12][DEMOD_TJ];
+  const uint32_t sf = blockIdx.y, j0 = blockIdx.x * DEMOD_TJ;
+  const uint32_t per_sf = nd * M;
+  const float2*  src    = d + (size_t)sf * per_sf;
+  for (uint32_t idx = threadIdx.x; idx < nd * DEMOD_TJ; idx += blockDim.x) {
+    const uint32_t i = idx / DEMOD_TJ, jl = idx % DEMOD_TJ;
+    if (j0 + jl < M) tile[i][jl] = __ldcs(&src[(size_t)i * M + j0 + jl]);
+  }
+  __syncthreads();
+  const uint32_t  body = 4u * (per_sf / 4u), fbody = 16u * (2u * per_sf / 16u);
+  const int       Qm   = 2 * mod;
+  const uint32_t* sq   = seq + (size_t)sf * nwords;
+  uint32_t*       dst  = reinterpret_cast<uint32_t*>(g + (size_t)sf * per_sf * Qm);
+  for (uint32_t idx = threadIdx.x; idx < nd * DEMOD_TJ; idx += blockDim.x) {
+    const uint32_t jl = idx / nd, i = idx % nd, j = j0 + jl;
+    if (j >= M) break;
+    const uint32_t pos = i * M + j;
+    int16_t        o[6];
+    demod_one(mod, tile[i][jl], pos < body, 2u * pos, fbody, qpsk_scale, o);
+    const uint32_t n = pos * (uint32_t)Qm, wd = n >> 5, sh = n & 31u;
+    uint32_t       bits = sq[wd] >> sh;
+    if (sh + (uint32_t)Qm > 32u) bits |= sq[wd + 1] << (32u - sh);
+    const size_t ow = ((size_t)j * nd + i) * (size_t)mod;
+#pragma unroll
+    for (int w = 0; w < 3; w++) {
+      if (w < mod) {
+        int lo = (int)o[2 * w] >> shift, hi = (int)o[2 * w + 1] >> shift;
+        if ((bits >> (2 * w)) & 1u) lo = -lo;
+        if ((bits >> (2 * w + 1)) & 1u) hi = -hi;
+        dst[ow + w] = (uint32_t)(uint16_t)(int16_t)lo | ((uint32_t)(uint16_t)(int16_t)hi << 16);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+
+// TS 36.211 7.2 generator, bit-serial (init-time tables only)
+struct Gold31 {
+  uint32_t x1 = 1, x2 = 0;
+  explicit Gold31(uint32_t c_init) : x2(c_init) {}
+  static uint32_t step1(uint32_t x) { return (x >> 1) | ((((x >> 3) ^ x) & 1u) << 30); }
+  static uint32_t step2(uint32_t x) { return (x >> 1) | ((((x >> 3) ^ (x >> 2) ^ (x >> 1) ^ x) & 1u) << 30); }
+  void            bits(uint8_t* c, uint32_t len)
+  {
+    for (uint32_t n = 0; n < 1600 + len; n++) {
+      if (n >= 1600) c[n - 1600] = (uint8_t)((x1 ^ x2) & 1u);
+      x1 = step1(x1);
+      x2 = step2(x2);
+    }
+  }
+};
+
+static uint32_t prime_lower_than(uint32_t n)
+{
+  for (uint32_t p = n - 1; p >= 2; p--) {
+    bool ok = true;
+    for (uint32_t d = 2; d * d <= p; d++) {
+      if (p % d == 0) {
+        ok = false;
+        break;
+      }
+    }
+    if (ok) return p;
+  }
+  return 0;
+}
+
+struct PuschRx {
+  DeviceContext*          ctx = nullptr;
+  srsran_b200_pusch_cfg_t cfg{};
+  int                     nsym = 14, nd = 12, M = 0, R = 0, Qm = 0;
+  uint32_t                nwords = 0, wpl = 0;
+  OfdmPlanDev             plan{};
+  int                     sm_count = 148;
+  float2*                 dW      = nullptr;
+  float2*                 d_dmrs  = nullptr; // [8][10][2][M]
+  uint32_t*               d_x1w   = nullptr;
+  uint32_t*               d_jump  = nullptr;
+  std::vector<float2>     h_dmrs;
+  // per-call scratch, grow-only
+  PuschSfParam* d_prm = nullptr;
+  uint32_t*     d_seq = nullptr;
+  float2*       d_ce  = nullptr;
+  float2*       d_d   = nullptr;
+  float*        d_meas = nullptr;
+  uint32_t      cap_sf = 0;
+  std::vector<PuschSfParam> h_prm;
+
+  ~PuschRx()
+  {
+    if (ctx) cudaSetDevice(ctx->device);
+    for (void* p : {(void*)dW, (void*)d_dmrs, (void*)d_x1w, (void*)d_jump, (void*)d_prm, (void*)d_seq, (void*)d_ce, (void*)d_d, (void*)d_meas}) {
+      if (p) cudaFree(p);
+    }
+  }
+
+  // refsignal_ul.c:337-357 for every (n_dmrs, sf_idx); float arithmetic of zc_sequence.c:205-300 as the x86 build of the
+  // reference evaluates it: the ZC argument is a double expression rounded to float, the cyclic-shift term joins it in one
+  // fused multiply-add, then a single-precision complex exponential.
+  int gen_dmrs()
+  {
+    static const uint32_t n_dmrs_1[8] = {0, 2, 3, 4, 6, 8, 9, 10}, n_dmrs_2[8] = {0, 6, 3, 4, 2, 8, 10, 9}; // TS 36.211 5.5.2.1.1
+    const uint32_t cell_id = cfg.cell_id, L = cfg.L_prb, dss = cfg.dmrs_delta_ss;
+    const uint32_t nsl = (uint32_t)nsym / 2;
+    uint8_t        c[8 * 7 * 20], cg[160];
+    Gold31(((cell_id / 30) << 5) + (((cell_id % 30) + dss) % 30)).bits(c, 8 * nsl * 20); // refsignal_ul.c:95-118
+    Gold31(cell_id / 30).bits(cg, 160);                                                  // phy_common.c:471-489
+    const uint32_t Nzc = prime_lower_than((uint32_t)M);
+    h_dmrs.assign((size_t)80 * 2 * M, make_float2(0.f, 0.f));
+    for (uint32_t nd_ = 0; nd_ < 8; nd_++) {
+      for (uint32_t sf_idx = 0; sf_idx < 10; sf_idx++) {
+        float2* r = h_dmrs.data() + (size_t)(nd_ * 10 + sf_idx) * 2 * M;
+        for (uint32_t ns = 2 * sf_idx; ns < 2 * sf_idx + 2; ns++) {
+          uint32_t n_prs = 0, f_gh = 0;
+          for (int i = 0; i < 8; i++) n_prs += (uint32_t)c[8 * nsl * ns + i] << i;
+          if (cfg.group_hopping_en) {
+            for (int i = 0; i < 8; i++) f_gh += (uint32_t)cg[8 * ns + i] << i;
+          }
+          const uint32_t n_cs  = (n_dmrs_1[cfg.dmrs_cyclic_shift] + n_dmrs_2[nd_] + n_prs) % 12;
+          const float    alpha = (float)(2 * M_PI * (n_cs) / 12); // refsignal_ul.c:172-181
+          const uint32_t u     = (f_gh + (cell_id % 30) + dss) % 30;
+          uint32_t       v     = 0;
+          if (L >= 6 && cfg.sequence_hopping_en) v = c[ns]; // refsignal_ul.c:121-132,242-245
+          const float n_sz  = (float)Nzc;
+          const float q_hat = n_sz * (float)(u + 1) / 31;
+          float       qf;
+          if ((((uint32_t)(2 * q_hat)) % 2) == 0) qf = (float)((double)q_hat + 0.5 + (double)v);
+          else qf = (float)((double)q_hat + 0.5 - (double)v);
+          const float q = (float)(uint32_t)qf;
+          for (int i = 0; i < M; i++) {
+            const float m   = (float)((uint32_t)i % Nzc);
+            const float arg = (float)(-M_PI * (double)q * (double)m * (double)(m + 1) / (double)n_sz);
+            const float a   = fmaf(alpha, (float)i, arg);
+            float       sn, cs;
+            sincosf(a, &sn, &cs);
+            r[(ns % 2) * M + i] = make_float2(cs, sn);
+          }
+        }
+      }
+    }
+    return B200_SUCCESS;
+  }
+
+  int configure(const srsran_b200_pusch_cfg_t& c)
+  {
+    cfg  = c;
+    nsym = c.cp_ext ? 12 : 14;
+    nd   = nsym - 2;
+    M    = 12 * (int)c.L_prb;
+    R    = 12 * (int)c.cell_nof_prb;
+    Qm   = 2 * c.modulation;
+    int       radix[OFDM_MAX_PASSES];
+    const int npass = fft_factorise(M, radix);
+    if (c.modulation < 1 || c.modulation > 3 || c.L_prb < 3 || c.n_prb + c.L_prb > c.cell_nof_prb || c.cell_nof_prb > 110 || npass == 0 ||
+        c.dmrs_cyclic_shift > 7 || c.dmrs_delta_ss > 29 || c.cell_id > 503 || c.llr_shift > 15) {
+      // dft_precoding.c:88-104 accepts exactly the allocations whose 12 L_prb is 2^a 3^b 5^c
+      B200_LOG_ERROR("unsupported PUSCH configuration (L_prb=%u n_prb=%u cell_nof_prb=%u mod=%d)", c.L_prb, c.n_prb, c.cell_nof_prb, c.modulation);
+      return B200_ERROR_INVALID_INPUTS;
+    }
+    B200_CUDA_TRY(cudaSetDevice(ctx->device));
+    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, ctx->device);
+    // transform de-precoding plan: backward DFT of 12 L_prb points scaled by 1/sqrt(N) (dft_precoding.c:46-50)
+    plan         = OfdmPlanDev{};
+    plan.N       = M;
+    plan.R       = M;
+    plan.nsym    = 1;
+    plan.generic = 2;
+    plan.inverse = 1;
+    plan.gscale  = 1.0f / sqrtf((float)M);
+    plan.npass   = npass;
+    for (int i = 0; i < OFDM_MAX_PASSES; i++) plan.radix[i] = radix[i];
+    int tps = M / 16;
+    if (tps < 8) tps = 8;
+    if (tps > OFDM_THREADS) tps = OFDM_THREADS;
+    plan.tps       = tps;
+    plan.pusch_nd  = nd;
+    for (int l = 0, k = 0; l < nsym; l++) {
+      if (l != nsym / 2 - 4 && l != nsym - 4) plan.pusch_l[k++] = (unsigned char)l;
+    }
+    plan.grid_nsym = nsym;
+    plan.grid_R    = R;
+    plan.grid_off  = 12 * (int)c.n_prb;
+    std::vector<float2> W(M);
+    for (int m = 0; m < M; m++) {
+      const double a = -2.0 * M_PI * (double)m / (double)M;
+      W[m]           = make_float2((float)cos(a), (float)sin(a));
+    }
+    B200_CUDA_TRY(cudaMalloc(&dW, M * sizeof(float2)));
+    B200_CUDA_TRY(cudaMemcpy(dW, W.data(), M * sizeof(float2), cudaMemcpyHostToDevice));
+    plan.W = dW;
+    // DMRS table
+    if (gen_dmrs() != B200_SUCCESS) return B200_ERROR;
+    B200_CUDA_TRY(cudaMalloc(&d_dmrs, h_dmrs.size() * sizeof(float2)));
+    B200_CUDA_TRY(cudaMemcpy(d_dmrs, h_dmrs.data(), h_dmrs.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    // scrambling tables: x1 words and the jump states of the 31 seed bits at every lane's chunk start
+    const uint32_t nbits = (uint32_t)(nd * M * Qm);
+    nwords               = (nbits + 31) / 32 + 1; // one spare word: the kernel may look one word ahead
+    wpl                  = (nwords + 31) / 32;
+    std::vector<uint32_t> x1w(nwords, 0u), jump(32 * 31, 0u);
+    {
+      uint32_t x1 = 1;
+      for (uint32_t n = 0; n < 1600; n++) x1 = Gold31::step1(x1);
+      for (uint32_t w = 0; w < nwords; w++) {
+        uint32_t v = 0;
+        for (int b = 0; b < 32; b++) {
+          v |= (x1 & 1u) << b;
+          x1 = Gold31::step1(x1);
+        }
+        x1w[w] = v;
+      }
+      for (int b = 0; b < 31; b++) {
+        uint32_t x2 = 1u << b;
+        for (uint32_t n = 0; n < 1600; n++) x2 = Gold31::step2(x2);
+        for (uint32_t lane = 0; lane < 32; lane++) {
+          jump[lane * 31 + b] = x2;
+          for (uint32_t n = 0; n < 32 * wpl; n++) x2 = Gold31::step2(x2);
+        }
+      }
+    }
+    B200_CUDA_TRY(cudaMalloc(&d_x1w, nwords * sizeof(uint32_t)));
+    B200_CUDA_TRY(cudaMemcpy(d_x1w, x1w.data(), nwords * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    B200_CUDA_TRY(cudaMalloc(&d_jump, jump.size() * sizeof(uint32_t)));
+    B200_CUDA_TRY(cudaMemcpy(d_jump, jump.data(), jump.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    return B200_SUCCESS;
+  }
+
+  int reserve(uint32_t nsf)
+  {
+    if (nsf <= cap_sf) return B200_SUCCESS;
+    for (void* p : {(void*)d_prm, (void*)d_seq, (void*)d_ce, (void*)d_d, (void*)d_meas}) {
+      if (p) cudaFree(p);
+    }
+    d_prm = nullptr; d_seq = nullptr; d_ce = nullptr; d_d = nullptr; d_meas = nullptr;
+    cap_sf = 0;
+    B200_CUDA_TRY(cudaMalloc(&d_prm, (size_t)nsf * sizeof(PuschSfParam)));
+    B200_CUDA_TRY(cudaMalloc(&d_seq, (size_t)nsf * nwords * sizeof(uint32_t)));
+    B200_CUDA_TRY(cudaMalloc(&d_ce, (size_t)nsf * 2 * M * sizeof(float2)));
+    B200_CUDA_TRY(cudaMalloc(&d_d, (size_t)nsf * nd * M * sizeof(float2)));
+    B200_CUDA_TRY(cudaMalloc(&d_meas, (size_t)nsf * 4 * sizeof(float)));
+    cap_sf = nsf;
+    return B200_SUCCESS;
+  }
+
+  // per-subframe parameters -> device (the copy is stream ordered; the host vector is staged by the runtime)
+  int upload_params(uint32_t nsf, const uint32_t* rnti, const uint32_t* tti, const uint32_t* n_dmrs, cudaStream_t st)
+  {
+    h_prm.resize(nsf);
+    for (uint32_t i = 0; i < nsf; i++) {
+      const uint32_t sf_idx = tti ? tti[i] % 10 : 0, nd_ = n_dmrs ? n_dmrs[i] : 0, r = rnti ? rnti[i] : 0;
+      if (nd_ > 7) {
+        B200_LOG_ERROR("n_dmrs %u out of range (refsignal_ul.c:327)", nd_);
+        return B200_ERROR_INVALID_INPUTS;
+      }
+      h_prm[i].c_init   = ((r & 0xFFFFu) << 14) + (sf_idx << 9) + cfg.cell_id;
+      h_prm[i].dmrs_idx = nd_ * 10 + sf_idx;
+    }
+    B200_CUDA_TRY(cudaMemcpyAsync(d_prm, h_prm.data(), (size_t)nsf * sizeof(PuschSfParam), cudaMemcpyHostToDevice, st));
+    return B200_SUCCESS;
+  }
+
+  int chest(const float2* grid, float2* ce, float* meas, uint32_t nsf, cudaStream_t st)
+  {
+    const float  w   = 0.3333f;                                                         // chest_ul.c:82-83
+    const float  cal = (float)((7.419 * w * w + 0.1117 * w - 0.005387) * 0.8);           // chest_ul.c:216-219
+    const size_t sm  = (size_t)2 * M * sizeof(float2);
+    static size_t attr = 0;
+    if (sm > 48 * 1024 && sm > attr) {
+      B200_CUDA_TRY(cudaFuncSetAttribute(pusch_chest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+      attr = sm;
+    }
+    pusch_chest_kernel<<<nsf, 256, sm, st>>>(grid, d_dmrs, d_prm, ce, meas, nsym, R, plan.grid_off, M, w, cal);
+    g_kernel_launches++;
+    B200_CUDA_TRY(cudaGetLastError());
+    return B200_SUCCESS;
+  }
+
+  int equalize_deprecode(const float2* grid, const float2* ce, const float* meas, float2* d, uint32_t nsf, cudaStream_t st)
+  {
+    OfdmPlanDev p     = plan;
+    p.eq_ce           = ce;
+    p.eq_noise        = meas;
+    p.eq_noise_stride = 4;
+    if (launch_ofdm_rx(p, grid, d, nsf * (uint32_t)nd, sm_count, st) != B200_SUCCESS) return B200_ERROR;
+    g_kernel_launches++;
+    return B200_SUCCESS;
+  }
+
+  int demod(const float2* d, int16_t* g, uint32_t nsf, cudaStream_t st)
+  {
+    pusch_gold_kernel<<<(nsf + 7) / 8, 256, 0, st>>>(d_prm, d_x1w, d_jump, d_seq, nsf, nwords, wpl);
+    g_kernel_launches++;
+    B200_CUDA_TRY(cudaGetLastError());
+    dim3 grid((unsigned)((M + DEMOD_TJ - 1) / DEMOD_TJ), nsf);
+    pusch_demod_descramble_kernel<<<grid, 256, 0, st>>>(cfg.modulation, d, d_seq, g, (uint32_t)M, (uint32_t)nd, nwords, (int)cfg.llr_shift,
+                                                       (float)(-100.0 * M_SQRT2));
+    g_kernel_launches++;
+    B200_CUDA_TRY(cudaGetLastError());
+    return B200_SUCCESS;
+  }
+};
+
+} // namespace b200
+
+using namespace b200;
+
+struct srsran_b200_pusch {
+  PuschRx rx;
+};
+
+extern "C" SRSRAN_B200_API int srsran_b200_pusch_init(srsran_b200_pusch_t** q, int device, const srsran_b200_pusch_cfg_t* cfg)
+{
+  if (!q || !cfg) return B200_ERROR_INVALID_INPUTS;
+  *q                 = nullptr;
+  DeviceContext* ctx = device_context(device);
+  if (!ctx) return B200_ERROR;
+  srsran_b200_pusch_t* h = new (std::nothrow) srsran_b200_pusch_t();
+  if (!h) return B200_ERROR;
+  h->rx.ctx = ctx;
+  const int rc = h->rx.configure(*cfg);
+  if (rc != B200_SUCCESS) {
+    delete h;
+    return rc;
+  }
+  *q = h;
+  return B200_SUCCESS;
+}
+
+extern "C" SRSRAN_B200_API void srsran_b200_pusch_free(srsran_b200_pusch_t* q)
+{
+  delete q;
+}
+
+extern "C" SRSRAN_B200_API int srsran_b200_pusch_geometry(const srsran_b200_pusch_t* q, uint32_t* nof_re, uint32_t* nof_bits,
+                                                         uint32_t* nof_data_symbols)
+{
+  if (!q) return B200_ERROR_INVALID_INPUTS;
+  if (nof_re) *nof_re = (uint32_t)(q->rx.nd * q->rx.M);
+  if (nof_bits) *nof_bits = (uint32_t)(q->rx.nd * q->rx.M * q->rx.Qm);
+  if (nof_data_symbols) *nof_data_symbols = (uint32_t)q->rx.nd;
+  return B200_SUCCESS;
+}
+
+extern "C" SRSRAN_B200_API int srsran_b200_refsignal_dmrs_pusch_gen(const srsran_b200_pusch_t* q, uint32_t sf_idx, uint32_t n_dmrs, void* r)
+{
+  if (!q || !r || sf_idx > 9 || n_dmrs > 7) return B200_ERROR_INVALID_INPUTS;
+  const size_t n = (size_t)2 * q->rx.M;
+  memcpy(r, q->rx.h_dmrs.data() + (size_t)(n_dmrs * 10 + sf_idx) * n, n * sizeof(float2));
+  return B200_SUCCESS;
+}
+
+static int need_device(uint32_t flags, const char* who)
+{
+  if (!(flags & SRSRAN_B200_FLAG_DEVICE_PTRS)) {
+    B200_LOG_ERROR("%s works on device buffers (it sits between two device-side stages)", who);
+    return B200_ERROR_INVALID_INPUTS;
+  }
+  return B200_SUCCESS;
+}
+
+extern "C" SRSRAN_B200_API int srsran_b200_chest_ul_pusch_batch(srsran_b200_pusch_t* q, const void* grid, uint32_t nsf, const uint32_t* tti,
+                                                               const uint32_t* n_dmrs, void* ce, float* meas, uint32_t flags, void* stream)
+{
+  if (!q || !grid || !ce || !meas) return B200_ERROR_INVALID_INPUTS;
+  if (need_device(flags, "srsran_b200_chest_ul_pusch_batch")) return B200_ERROR_INVALID_INPUTS;
+  if (nsf == 0) return B200_SUCCESS;
+  PuschRx& rx = q->rx;
+  B200_CUDA_TRY(cudaSetDevice(rx.ctx->device));
+  if (rx.reserve(nsf) != B200_SUCCESS) return B200_ERROR;
+  int rc = rx.upload_params(nsf, nullptr, tti, n_dmrs, (cudaStream_t)stream);
+  if (rc != B200_SUCCESS) return rc;
+  return rx.chest((const float2*)grid, (float2*)ce, meas, nsf, (cudaStream_t)stream);
+}
+
+extern "C" SRSRAN_B200_API int srsran_b200_pusch_equalize_deprecode_batch(srsran_b200_pusch_t* q, const void* grid, const void* ce,
+                                                                         const float* meas, void* d, uint32_t nsf, uint32_t flags, void* stream)
+{
+  if (!q || !grid || !ce || !d) return B200_ERROR_INVALID_INPUTS;
+  if (need_device(flags, "srsran_b200_pusch_equalize_deprecode_batch")) return B200_ERROR_INVALID_INPUTS;
+  if (nsf == 0) return B200_SUCCESS;
+  PuschRx& rx = q->rx;
+  B200_CUDA_TRY(cudaSetDevice(rx.ctx->device));
+  return rx.equalize_deprecode((const float2*)grid, (const float2*)ce, meas, (float2*)d, nsf, (cudaStream_t)stream);
+}
+
+extern "C" SRSRAN_B200_API int srsran_b200_pusch_demod_descramble_batch(srsran_b200_pusch_t* q, const void* d, int16_t* g, uint32_t nsf,
+                                                                       const uint32_t* rnti, const uint32_t* tti, uint32_t flags, void* stream)
+{
+  if (!q || !d || !g) return B200_ERROR_INVALID_INPUTS;
+  if (need_device(flags, "srsran_b200_pusch_demod_descramble_batch")) return B200_ERROR_INVALID_INPUTS;
+  if (nsf == 0) return B200_SUCCESS;
+  PuschRx& rx = q->rx;
+  B200_CUDA_TRY(cudaSetDevice(rx.ctx->device));
+  if (rx.reserve(nsf) != B200_SUCCESS) return B200_ERROR;
+  int rc = rx.upload_params(nsf, rnti, tti, nullptr, (cudaStream_t)stream);
+  if (rc != B200_SUCCESS) return rc;
+  return rx.demod((const float2*)d, g, nsf, (cudaStream_t)stream);
+}
+
+extern "C" SRSRAN_B200_API int srsran_b200_pusch_rx_batch(srsran_b200_pusch_t* q, const void* grid, int16_t* g, float* meas, uint32_t nsf,
+                                                         const uint32_t* rnti, const uint32_t* tti, const uint32_t* n_dmrs, uint32_t flags,
+                                                         void* stream)
+{
+  if (!q || !grid || !g) return B200_ERROR_INVALID_INPUTS;
+  if (need_device(flags, "srsran_b200_pusch_rx_batch")) return B200_ERROR_INVALID_INPUTS;
+  if (nsf == 0) return B200_SUCCESS;
+  PuschRx&     rx = q->rx;
+  cudaStream_t st = (cudaStream_t)stream;
+  B200_CUDA_TRY(cudaSetDevice(rx.ctx->device));
+  if (rx.reserve(nsf) != B200_SUCCESS) return B200_ERROR;
+  int rc = rx.upload_params(nsf, rnti, tti, n_dmrs, st);
+  if (rc != B200_SUCCESS) return rc;
+  float* m = meas ? meas : rx.d_meas;
+  if ((rc = rx.chest((const float2*)grid, rx.d_ce, m, nsf, st)) != B200_SUCCESS) return rc;
+  if ((rc = rx.equalize_deprecode((const float2*)grid, rx.d_ce, m, rx.d_d, nsf, st)) != B200_SUCCESS) return rc;
+  return rx.demod(rx.d_d, g, nsf, st);
+}

@@ -352,7 +352,7 @@ int srsran_tdec_run_all_8bit(srsran_tdec_t*, int8_t*, uint8_t*, uint32_t, uint32
 } // extern "C"
 
 // ===================================================================================================================
-// srsran_dft_plan_t: generic complex DFT of size 2^a 3^b on the OFDM kernel's FFT core
+// srsran_dft_plan_t: generic complex DFT of size 2^a 3^b 5^c on the OFDM kernel's FFT core
 struct CompatDft {
   DeviceContext* ctx = nullptr;
   OfdmPlanDev    plan{};
@@ -378,24 +378,11 @@ static void dft_destroy(CompatDft* d)
 
 static int dft_setup(CompatDft* d, int N, bool forward)
 {
-  std::vector<int> radix;
-  int              rem = N;
-  for (int r : {16, 8, 4, 2, 3}) {
-    while (rem % r == 0 && rem > 1 && (int)radix.size() < OFDM_MAX_PASSES) {
-      radix.push_back(r);
-      rem /= r;
-    }
-  }
-  if (rem != 1 || N < 4) {
-    B200_LOG_ERROR("DFT size %d not supported on the GPU path (2^a 3^b, >= 4)", N);
+  int       radix[OFDM_MAX_PASSES];
+  const int npass = N >= 4 ? fft_factorise(N, radix) : 0;
+  if (npass == 0) {
+    B200_LOG_ERROR("DFT size %d not supported on the GPU path (2^a 3^b 5^c, >= 4)", N);
     return SRSRAN_ERROR;
-  }
-  if (radix.size() == 1) {
-    int r = radix[0];
-    radix.clear();
-    if (r == 16) radix = {4, 4};
-    else if (r == 8) radix = {4, 2};
-    else radix = {2, 2};
   }
   OfdmPlanDev& p = d->plan;
   p              = OfdmPlanDev{};
@@ -404,8 +391,8 @@ static int dft_setup(CompatDft* d, int N, bool forward)
   p.nsym         = 1;
   p.generic      = 1;
   p.inverse      = forward ? 0 : 1;
-  p.npass        = (int)radix.size();
-  for (int i = 0; i < OFDM_MAX_PASSES; i++) p.radix[i] = i < p.npass ? radix[i] : 1;
+  p.npass        = npass;
+  for (int i = 0; i < OFDM_MAX_PASSES; i++) p.radix[i] = radix[i];
   int tps = N / 16;
   if (tps < 8) tps = 8;
   if (tps > OFDM_THREADS) tps = OFDM_THREADS;

@@ -39,8 +39,8 @@ static int split_percent()
   static int pct = -1;
   if (pct < 0) {
     const char* e = getenv("SRSLTE_B200_TDEC_SPLIT");
-    pct           = e ? atoi(e) : 47;
-    if (pct < 1 || pct > 99) pct = 47;
+    pct           = e ? atoi(e) : 48;
+    if (pct < 1 || pct > 99) pct = 48;
   }
   return pct;
 }

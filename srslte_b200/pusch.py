@@ -96,3 +96,115 @@ class PuschRx:
         """iq: torch CUDA complex64 (nsf, sf_sz).  Returns (tb_ok (nsf,), avg passes (nsf,)); bytes are in self.data[:, :tbs/8+3]."""
         self.front_end(iq, nsf)
         return self.decode(nsf, rv)
+
+
+class PuschCfg(C.Structure):
+    """srsran_b200_pusch_cfg_t (include/srslte_b200.h)"""
+    _fields_ = [("cell_id", C.c_uint32), ("cell_nof_prb", C.c_uint32), ("cp_ext", C.c_int), ("L_prb", C.c_uint32), ("n_prb", C.c_uint32),
+                ("modulation", C.c_int), ("llr_shift", C.c_uint32), ("dmrs_cyclic_shift", C.c_uint32), ("dmrs_delta_ss", C.c_uint32),
+                ("group_hopping_en", C.c_int), ("sequence_hopping_en", C.c_int)]
+
+
+class PuschChain:
+    """Mirror of the srsran_b200_pusch_* entries: channel estimation -> equaliser + transform de-precoding -> soft demapping +
+    descrambling + UL-SCH de-interleaving for a batch of subframes sharing one allocation (chest_ul.c:370, pusch.c:392-443,
+    sch.c:993).  All tensors are torch CUDA tensors; rnti / tti / n_dmrs are numpy uint32 arrays (host)."""
+
+    def __init__(self, cell_id=1, cell_nof_prb=100, cp_ext=False, L_prb=100, n_prb=0, mod=3, llr_shift=0, cyclic_shift=0, delta_ss=0,
+                 group_hopping=False, sequence_hopping=False, device=0):
+        import torch
+
+        self.torch = torch
+        self.device = device
+        self.dev = torch.device("cuda", device)
+        self._lib = _lib.lib()
+        self.cfg = PuschCfg(cell_id, cell_nof_prb, int(cp_ext), L_prb, n_prb, mod, llr_shift, cyclic_shift, delta_ss, int(group_hopping),
+                            int(sequence_hopping))
+        self._h = C.c_void_p()
+        rc = self._lib.srsran_b200_pusch_init(C.byref(self._h), device, C.byref(self.cfg))
+        if rc != _lib.SUCCESS:
+            raise RuntimeError(f"srsran_b200_pusch_init failed ({rc})")
+        a, b, c = C.c_uint32(), C.c_uint32(), C.c_uint32()
+        self._lib.srsran_b200_pusch_geometry(self._h, C.byref(a), C.byref(b), C.byref(c))
+        self.nof_re, self.nof_bits, self.nd = a.value, b.value, c.value
+        self.M = 12 * L_prb
+        self.nsym = 12 if cp_ext else 14
+        self.R = 12 * cell_nof_prb
+
+    def close(self):
+        if self._h:
+            self._lib.srsran_b200_pusch_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @staticmethod
+    def _u32(a, n):
+        if a is None:
+            return None, None
+        a = np.ascontiguousarray(np.broadcast_to(np.asarray(a, np.uint32), (n,)))
+        return a, a.ctypes.data
+
+    def _st(self):
+        return self.torch.cuda.current_stream(self.dev).cuda_stream
+
+    def dmrs(self, sf_idx: int, n_dmrs: int = 0) -> np.ndarray:
+        r = np.zeros(2 * self.M, np.complex64)
+        rc = self._lib.srsran_b200_refsignal_dmrs_pusch_gen(self._h, sf_idx, n_dmrs, r.ctypes.data)
+        if rc != _lib.SUCCESS:
+            raise RuntimeError(f"srsran_b200_refsignal_dmrs_pusch_gen failed ({rc})")
+        return r.reshape(2, self.M)
+
+    def chest(self, grid, tti, n_dmrs=None):
+        t = self.torch
+        nsf = grid.shape[0]
+        ce = t.empty((nsf, 2, self.M), dtype=t.complex64, device=self.dev)
+        meas = t.empty((nsf, 4), dtype=t.float32, device=self.dev)
+        k1, p1 = self._u32(tti, nsf)
+        k2, p2 = self._u32(n_dmrs, nsf)
+        rc = self._lib.srsran_b200_chest_ul_pusch_batch(self._h, grid.data_ptr(), nsf, p1, p2, ce.data_ptr(), meas.data_ptr(),
+                                                        _lib.FLAG_DEVICE_PTRS, self._st())
+        if rc != _lib.SUCCESS:
+            raise RuntimeError(f"srsran_b200_chest_ul_pusch_batch failed ({rc})")
+        return ce, meas
+
+    def equalize_deprecode(self, grid, ce, meas):
+        t = self.torch
+        nsf = grid.shape[0]
+        d = t.empty((nsf, self.nof_re), dtype=t.complex64, device=self.dev)
+        rc = self._lib.srsran_b200_pusch_equalize_deprecode_batch(self._h, grid.data_ptr(), ce.data_ptr(),
+                                                                  meas.data_ptr() if meas is not None else None, d.data_ptr(), nsf,
+                                                                  _lib.FLAG_DEVICE_PTRS, self._st())
+        if rc != _lib.SUCCESS:
+            raise RuntimeError(f"srsran_b200_pusch_equalize_deprecode_batch failed ({rc})")
+        return d
+
+    def demod_descramble(self, d, rnti, tti, out=None):
+        t = self.torch
+        nsf = d.shape[0]
+        g = out if out is not None else t.empty((nsf, self.nof_bits), dtype=t.int16, device=self.dev)
+        k1, p1 = self._u32(rnti, nsf)
+        k2, p2 = self._u32(tti, nsf)
+        rc = self._lib.srsran_b200_pusch_demod_descramble_batch(self._h, d.data_ptr(), g.data_ptr(), nsf, p1, p2, _lib.FLAG_DEVICE_PTRS,
+                                                                self._st())
+        if rc != _lib.SUCCESS:
+            raise RuntimeError(f"srsran_b200_pusch_demod_descramble_batch failed ({rc})")
+        return g
+
+    def rx(self, grid, rnti, tti, n_dmrs=None, out=None, meas=None):
+        """grid (nsf, nsym, 12*cell_nof_prb) complex64 -> g (nsf, nof_bits) int16 (+ meas (nsf, 4) if a tensor is passed)."""
+        t = self.torch
+        nsf = grid.shape[0]
+        g = out if out is not None else t.empty((nsf, self.nof_bits), dtype=t.int16, device=self.dev)
+        k1, p1 = self._u32(rnti, nsf)
+        k2, p2 = self._u32(tti, nsf)
+        k3, p3 = self._u32(n_dmrs, nsf)
+        rc = self._lib.srsran_b200_pusch_rx_batch(self._h, grid.data_ptr(), g.data_ptr(), meas.data_ptr() if meas is not None else None,
+                                                  nsf, p1, p2, p3, _lib.FLAG_DEVICE_PTRS, self._st())
+        if rc != _lib.SUCCESS:
+            raise RuntimeError(f"srsran_b200_pusch_rx_batch failed ({rc})")
+        return g

@@ -86,7 +86,7 @@ def test_invalid_configurations():
     with pytest.raises(RuntimeError):
         OfdmRx(111)
     with pytest.raises(RuntimeError):
-        OfdmRx(6, symbol_sz=1000)  # not 2^a 3^b
+        OfdmRx(6, symbol_sz=1001)  # 7 x 11 x 13: not 2^a 3^b 5^c
 
 
 def test_demod_bit_exact(port):

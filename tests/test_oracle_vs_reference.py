@@ -105,3 +105,86 @@ def test_demod(port, ref):
             s = ((rng.normal(size=n) + 1j * rng.normal(size=n)) * 0.8).astype(np.complex64)
             s[:1] = 47.0 - 46.9j
             assert (port.demod_s(mod, s) == ref.demod_s(mod, s)).all()
+
+
+# ---- PUSCH chain between OFDM and de-matching ------------------------------------------------
+def test_pusch_descrambling_and_deinterleave(port, ref):
+    rng = np.random.default_rng(31)
+    x = rng.integers(-32768, 32768, 86400).astype(np.int16)
+    x[:5] = -32768
+    for rnti, ns, cid in ((62, 6, 1), (0xFFFF, 18, 503), (1, 0, 0), (4660, 9, 301)):
+        for n in (86400, 23, 24, 1, 4801):
+            assert (ref.pusch_seq_apply_s(x[:n], rnti, ns, cid) == port.pusch_seq_apply_s(x[:n], rnti, ns, cid)).all()
+    for Qm, nre, nsym in ((6, 14400, 12), (2, 12 * 36, 12), (4, 10 * 12 * 5, 10), (6, 12 * 1200, 12)):
+        q = rng.integers(-3000, 3000, nre * Qm).astype(np.int16)
+        assert (ref.ulsch_deinterleave(q, Qm, nsym) == port.ulsch_deinterleave(q, Qm, nsym)).all()
+
+
+@pytest.mark.parametrize("L", [3, 5, 6, 25, 27, 60, 81, 100])
+def test_dft_precoding(port, ref, L):
+    rng = np.random.default_rng(L)
+    z = (rng.standard_normal(12 * 12 * L) + 1j * rng.standard_normal(12 * 12 * L)).astype(np.complex64)
+    for tx in (False, True):
+        a, b = ref.dft_precoding(z, L, tx), port.dft_precoding(z, L, tx)
+        assert np.linalg.norm(a - b) / np.linalg.norm(a) < 1e-6
+    # the receiver's transform undoes the transmitter's
+    assert np.linalg.norm(ref.dft_precoding(ref.dft_precoding(z, L, True), L, False) - z) / np.linalg.norm(z) < 1e-5
+
+
+def test_predecoding_single(port, ref):
+    rng = np.random.default_rng(32)
+    for n in (14400, 40, 33, 8):  # AVX body (> 32 symbols) and the generic loop (precoding.c:372-377)
+        y = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+        h = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+        for n0 in (0.0, 0.01, 0.5):
+            a, b = ref.predecoding_single(y, h, n0), port.predecoding_single(y, h, n0)
+            assert np.abs(a - b).max() <= 2e-6 * np.abs(a).max()
+
+
+PUSCH_LINKS = [dict(), dict(cell_id=301, tti=7, n_dmrs=3, cyclic_shift=5, delta_ss=11), dict(L_prb=6, group_hopping=1, tti=4, tbs=2216, mod=2),
+               dict(L_prb=50, n_prb=20, sequence_hopping=1, tti=9, cell_id=77, tbs=14112, mod=2), dict(L_prb=3, nof_prb=6, cell_id=9, tbs=392, mod=1),
+               dict(L_prb=5, nof_prb=15, cell_id=42, cp_ext=1, tti=12, tbs=1000, mod=2), dict(L_prb=81, n_prb=3, cell_id=503, delta_ss=29, tti=5, tbs=51024)]
+
+
+@pytest.mark.parametrize("kw", PUSCH_LINKS)
+def test_dmrs_and_chest(port, ref, kw):
+    from oracle import loader
+
+    lk = loader.pusch_link(**kw)
+    a, b = ref.dmrs_pusch_gen(lk), port.dmrs_pusch_gen(lk)
+    assert np.abs(a - b).max() < 1e-6
+    assert np.abs(np.abs(a) - 1).max() < 1e-5
+    rng = np.random.default_rng(int(lk[0]))
+    data = rng.integers(0, 256, int(lk[12]) // 8, dtype=np.uint8)
+    grid = ref.pusch_encode(lk, data)
+    noise = (rng.standard_normal(grid.shape) + 1j * rng.standard_normal(grid.shape)).astype(np.complex64) * np.float32(0.03)
+    rx = (grid * np.complex64(0.8 * np.exp(0.7j)) + noise).astype(np.complex64)
+    ce_r, m_r = ref.chest_ul_pusch(lk, rx)
+    ce_p, m_p = port.chest_ul_pusch(lk, rx, b)
+    assert np.linalg.norm(ce_r - ce_p) / np.linalg.norm(ce_r) < 1e-6
+    assert abs(m_r[0] - m_p[0]) <= 1e-4 * m_r[0] and abs(m_r[1] - m_p[1]) <= 2e-4 * m_r[1]
+    assert abs(m_r[2] - m_p[2]) <= 1e-3 * max(1.0, abs(m_r[2]))
+
+
+def test_reference_pusch_link_closes(ref):
+    """The reference's own transmitter and receiver (the end-to-end oracle of tests/test_pusch_chain_gpu.py) agree with each
+    other, and its receiver's buffers relate the way the port's stage functions say they do."""
+    from oracle import loader
+
+    port = loader.api("port")
+    lk = loader.pusch_link(tti=3, rnti=1234)
+    rng = np.random.default_rng(33)
+    data = rng.integers(0, 256, 75376 // 8, dtype=np.uint8)
+    grid = ref.pusch_encode(lk, data)
+    noise = (rng.standard_normal(grid.shape) + 1j * rng.standard_normal(grid.shape)).astype(np.complex64) * np.float32(0.02)
+    rx = (grid * np.complex64(0.9 * np.exp(-0.4j)) + noise).astype(np.complex64)
+    r = ref.pusch_decode(lk, rx)
+    assert r["ret"] == 0 and r["crc"] and (r["data"] == data).all()
+    data_syms = [l for l in range(14) if l not in (3, 10)]
+    y = np.concatenate([rx[l] for l in data_syms])
+    h = np.concatenate([r["ce"][l] for l in data_syms])
+    d = port.dft_precoding(port.predecoding_single(y, h, r["noise"]), 100, False)
+    assert np.linalg.norm(d - r["d"]) / np.linalg.norm(r["d"]) < 1e-6
+    q = port.pusch_seq_apply_s(port.demod_s(3, r["d"]), 1234, 6, 1)
+    assert (q == r["q"]).all()
+    assert (port.ulsch_deinterleave(q, 6, 12) == r["g"]).all()

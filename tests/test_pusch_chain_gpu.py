@@ -1,0 +1,212 @@
+"""PUSCH receive chain between OFDM and de-matching on the GPU: DMRS, channel estimation, equaliser +
+transform de-precoding, soft demapping + descrambling + UL-SCH de-interleaving, against the oracle stage by stage and, where the
+reference build is available, end to end against srsran_pusch_encode / srsran_chest_ul_estimate_pusch / srsran_pusch_decode.
+-m gpu."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+# float stages: relative L2 error bound (the north star's 1e-4 for FFT-type outputs)
+TOL = 1e-4
+
+
+def rel(a, b):
+    return float(np.linalg.norm(a.astype(np.complex128) - b.astype(np.complex128)) / max(np.linalg.norm(b.astype(np.complex128)), 1e-30))
+
+
+def link_of(loader, ch, rnti=0, tti=0, n_dmrs=0, tbs=0):
+    c = ch.cfg
+    return loader.pusch_link(c.cell_id, c.cell_nof_prb, c.cp_ext, c.dmrs_cyclic_shift, c.dmrs_delta_ss, c.group_hopping_en,
+                             c.sequence_hopping_en, rnti, tti, c.L_prb, c.n_prb, c.modulation, tbs, 0, n_dmrs, 8)
+
+
+CONFIGS = [
+    dict(cell_id=1, cell_nof_prb=100, L_prb=100, n_prb=0, mod=3),
+    dict(cell_id=301, cell_nof_prb=50, L_prb=25, n_prb=10, mod=2, cyclic_shift=5, delta_ss=11),
+    dict(cell_id=77, cell_nof_prb=25, L_prb=6, n_prb=19, mod=1, group_hopping=True),
+    dict(cell_id=503, cell_nof_prb=100, L_prb=81, n_prb=3, mod=3, sequence_hopping=True, delta_ss=29),
+    dict(cell_id=9, cell_nof_prb=6, L_prb=3, n_prb=2, mod=2),
+    dict(cell_id=42, cell_nof_prb=15, L_prb=5, n_prb=0, mod=3, cp_ext=True),
+]
+
+
+@pytest.mark.parametrize("kw", CONFIGS)
+def test_dmrs_table_matches_oracle(port, kw):
+    from oracle import loader
+    from srslte_b200.pusch import PuschChain
+
+    ch = PuschChain(**kw)
+    for sf_idx, n_dmrs in ((0, 0), (3, 1), (7, 5), (9, 7)):
+        want = port.dmrs_pusch_gen(link_of(loader, ch, tti=sf_idx, n_dmrs=n_dmrs))
+        got = ch.dmrs(sf_idx, n_dmrs).reshape(-1)
+        assert np.abs(got - want).max() < 1e-6, (kw, sf_idx, n_dmrs)
+    ch.close()
+
+
+@pytest.mark.parametrize("kw", CONFIGS)
+def test_chest_matches_oracle(port, kw):
+    import torch
+    from oracle import loader
+    from srslte_b200.pusch import PuschChain
+
+    ch = PuschChain(**kw)
+    rng = np.random.default_rng(5)
+    nsf = 5
+    tti = np.array([0, 3, 14, 7, 29], np.uint32)
+    n_dmrs = np.array([0, 2, 7, 1, 4], np.uint32)
+    grid = (rng.standard_normal((nsf, ch.nsym, ch.R)) + 1j * rng.standard_normal((nsf, ch.nsym, ch.R))).astype(np.complex64) * 0.05
+    off = 12 * kw["n_prb"]
+    # a smooth channel over the allocation plus noise on the two DMRS symbols
+    for s in range(nsf):
+        h = (0.7 + 0.2 * s) * np.exp(1j * (0.3 * s + 2 * np.pi * 0.0007 * np.arange(ch.M)))
+        r = ch.dmrs(int(tti[s] % 10), int(n_dmrs[s]))
+        for slot in range(2):
+            l = (slot + 1) * (ch.nsym // 2) - 4
+            grid[s, l, off:off + ch.M] += (r[slot] * h * np.exp(1j * 0.05 * slot)).astype(np.complex64)
+    ce, meas = ch.chest(torch.from_numpy(grid).cuda(), tti, n_dmrs)
+    torch.cuda.synchronize()
+    ce, meas = ce.cpu().numpy(), meas.cpu().numpy()
+    for s in range(nsf):
+        lk = link_of(loader, ch, tti=int(tti[s]), n_dmrs=int(n_dmrs[s]))
+        want_ce, want_meas = port.chest_ul_pusch(lk, grid[s], port.dmrs_pusch_gen(lk))
+        want_ce = want_ce.reshape(ch.nsym, ch.R)
+        for slot in range(2):
+            l = (slot + 1) * (ch.nsym // 2) - 4
+            assert rel(ce[s, slot], want_ce[l, off:off + ch.M]) < 1e-5
+            # the reference copies the slot's estimate to every symbol of the slot (chest_ul.c:246-259)
+            assert (want_ce[slot * (ch.nsym // 2), off:off + ch.M] == want_ce[l, off:off + ch.M]).all()
+        assert abs(meas[s, 0] - want_meas[0]) <= 2e-4 * abs(want_meas[0])
+        assert abs(meas[s, 1] - want_meas[1]) <= 4e-4 * abs(want_meas[1])
+        assert abs(meas[s, 2] - want_meas[2]) <= 1e-3 * max(abs(want_meas[2]), 1.0)
+    ch.close()
+
+
+@pytest.mark.parametrize("kw", CONFIGS)
+def test_equalize_deprecode_matches_oracle(port, kw):
+    import torch
+    from srslte_b200.pusch import PuschChain
+
+    ch = PuschChain(**kw)
+    rng = np.random.default_rng(6)
+    nsf = 3
+    grid = (rng.standard_normal((nsf, ch.nsym, ch.R)) + 1j * rng.standard_normal((nsf, ch.nsym, ch.R))).astype(np.complex64)
+    ce = (rng.standard_normal((nsf, 2, ch.M)) + 1j * rng.standard_normal((nsf, 2, ch.M))).astype(np.complex64)
+    meas = np.zeros((nsf, 4), np.float32)
+    meas[:, 0] = [0.0, 0.01, 0.3]
+    d = ch.equalize_deprecode(torch.from_numpy(grid).cuda(), torch.from_numpy(ce).cuda(), torch.from_numpy(meas).cuda())
+    torch.cuda.synchronize()
+    d = d.cpu().numpy()
+    off = 12 * kw["n_prb"]
+    half = ch.nsym // 2
+    data_syms = [l for l in range(ch.nsym) if l not in (half - 4, ch.nsym - 4)]
+    for s in range(nsf):
+        y = np.concatenate([grid[s, l, off:off + ch.M] for l in data_syms])
+        h = np.concatenate([ce[s, l // half] for l in data_syms])
+        z = port.predecoding_single(y, h, float(meas[s, 0]))
+        want = port.dft_precoding(z, kw["L_prb"], False)
+        assert rel(d[s], want) < TOL, (kw, s, rel(d[s], want))
+    ch.close()
+
+
+@pytest.mark.parametrize("kw", CONFIGS)
+@pytest.mark.parametrize("shift", [0, 4])
+def test_demod_descramble_deinterleave_is_bit_exact(port, kw, shift):
+    import torch
+    from srslte_b200.pusch import PuschChain
+
+    ch = PuschChain(llr_shift=shift, **kw)
+    rng = np.random.default_rng(7)
+    nsf = 4
+    rnti = np.array([62, 0xFFFF, 1, 0x1234], np.uint32)
+    tti = np.array([0, 9, 13, 5], np.uint32)
+    d = (rng.standard_normal((nsf, ch.nof_re)) + 1j * rng.standard_normal((nsf, ch.nof_re))).astype(np.complex64)
+    d[0, :7] *= 100.0  # saturating values
+    g = ch.demod_descramble(torch.from_numpy(d).cuda(), rnti, tti)
+    torch.cuda.synchronize()
+    g = g.cpu().numpy()
+    Qm = 2 * kw["mod"]
+    for s in range(nsf):
+        q = port.demod_s(kw["mod"], d[s]) >> shift
+        q = port.pusch_seq_apply_s(q, int(rnti[s]), 2 * int(tti[s] % 10), kw["cell_id"])
+        want = port.ulsch_deinterleave(q, Qm, ch.nd)
+        assert (g[s] == want).all(), (kw, shift, s, int((g[s] != want).sum()))
+    ch.close()
+
+
+def test_unsupported_configurations_fail_cleanly():
+    from srslte_b200.pusch import PuschChain
+
+    for kw in (dict(L_prb=7, cell_nof_prb=25), dict(L_prb=2, cell_nof_prb=6), dict(L_prb=50, n_prb=60), dict(mod=4)):
+        with pytest.raises(RuntimeError):
+            PuschChain(**kw)
+
+
+@pytest.mark.parametrize("kw,tbs", [(dict(cell_id=1, cell_nof_prb=100, L_prb=100, n_prb=0, mod=3), 75376),
+                                    (dict(cell_id=150, cell_nof_prb=50, L_prb=24, n_prb=13, mod=2, cyclic_shift=3), 9912),
+                                    (dict(cell_id=7, cell_nof_prb=25, L_prb=10, n_prb=5, mod=1), 1544)])
+def test_chain_against_the_reference_link(ref, port, kw, tbs):
+    """Reference transmitter (srsran_pusch_encode + DMRS) -> flat fading + AWGN -> GPU chain, compared with the buffers of the
+    reference receiver (chest + srsran_pusch_decode) and decoded down to the transport block."""
+    import torch
+    from oracle import loader
+    from srslte_b200.pusch import PuschChain
+    from srslte_b200.sch import SOFTBUFFER_SIZE, SchDecoder
+
+    ch0 = PuschChain(llr_shift=0, **kw)
+    nsf = 3
+    rng = np.random.default_rng(8)
+    rnti = np.array([62, 4097, 65000], np.uint32)
+    tti = np.array([3, 18, 4], np.uint32)
+    n_dmrs = np.array([0, 6, 3], np.uint32)
+    grids, datas, refs = [], [], []
+    for s in range(nsf):
+        lk = link_of(loader, ch0, rnti=int(rnti[s]), tti=int(tti[s]), n_dmrs=int(n_dmrs[s]), tbs=tbs)
+        data = rng.integers(0, 256, tbs // 8, dtype=np.uint8)
+        tx = ref.pusch_encode(lk, data)
+        h = np.complex64((0.6 + 0.3 * s) * np.exp(1j * (0.4 + s)))
+        noise = (rng.standard_normal(tx.shape) + 1j * rng.standard_normal(tx.shape)).astype(np.complex64) * np.float32(0.012)
+        rxg = (tx * h + noise).astype(np.complex64)
+        grids.append(rxg)
+        datas.append(data)
+        refs.append(ref.pusch_decode(lk, rxg))
+        assert refs[-1]["crc"] and (refs[-1]["data"] == data).all()
+    grid = torch.from_numpy(np.stack(grids)).cuda()
+    # stage by stage against the reference receiver's own buffers
+    ce, meas = ch0.chest(grid, tti, n_dmrs)
+    d = ch0.equalize_deprecode(grid, ce, meas)
+    g0 = ch0.demod_descramble(d, rnti, tti)
+    torch.cuda.synchronize()
+    off, half = 12 * kw["n_prb"], ch0.nsym // 2
+    for s in range(nsf):
+        r = refs[s]
+        for slot in range(2):
+            assert rel(ce[s, slot].cpu().numpy(), r["ce"][(slot + 1) * half - 4, off:off + ch0.M]) < 1e-5
+        assert abs(float(meas[s, 0]) - r["noise"]) <= 2e-4 * r["noise"]
+        assert rel(d[s].cpu().numpy(), r["d"]) < TOL
+        # soft bits: the float path differs in the last bits, so a value next to a rounding boundary may move by one step
+        diff = np.abs(g0[s].cpu().numpy().astype(np.int32) - r["g"].astype(np.int32))
+        assert diff.max() <= 1 and (diff != 0).mean() < 2e-3, (diff.max(), (diff != 0).mean())
+    # the one-call entry gives the same soft bits as the three stages
+    g1 = ch0.rx(grid, rnti, tti, n_dmrs)
+    torch.cuda.synchronize()
+    assert torch.equal(g0, g1)
+    ch0.close()
+    # ... and the transport blocks decode (soft bits scaled into the generic decoder's envelope)
+    ch4 = PuschChain(llr_shift=4 if kw["mod"] == 3 else 3 if kw["mod"] == 2 else 1, **kw)
+    g = ch4.rx(grid, rnti, tti, n_dmrs)
+    torch.cuda.synchronize()
+    sch = SchDecoder(0, 8)
+    seg = port.cbsegm(tbs)
+    stride = (tbs // 8 + 3 + 768 + 15) // 16 * 16
+    soft = np.zeros((nsf, seg["C"] * SOFTBUFFER_SIZE), np.int16)
+    out = np.zeros((nsf, stride), np.uint8)
+    rc, res = sch.decode(g.cpu().numpy().reshape(-1), soft.reshape(-1), out.reshape(-1),
+                         [dict(tbs=tbs, Qm=2 * kw["mod"], rv=0, nof_e_bits=ch4.nof_bits, e_offset=s * ch4.nof_bits,
+                               soft_offset=s * soft.shape[1], data_offset=s * stride) for s in range(nsf)])
+    assert rc == 0
+    for s in range(nsf):
+        assert res[s]["result"] == 0, s
+        assert (out[s, :tbs // 8] == datas[s]).all()
+    sch.close()
+    ch4.close()

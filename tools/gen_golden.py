@@ -100,6 +100,27 @@ def main():
         of[f"{name}_sym"] = s
         of[f"{name}_llr"] = R.demod_s(mod, s)
     np.savez_compressed(os.path.join(OUT, "ofdm_demod.npz"), **of)
+
+    # ---- PUSCH chain between OFDM and de-matching: DMRS, chest, equaliser, transform de-precoding, descrambling, de-interleave
+    pc = {}
+    links = [loader.pusch_link(cell_id=301, nof_prb=25, L_prb=12, n_prb=7, mod=2, tbs=4584, tti=7, n_dmrs=3, cyclic_shift=5, delta_ss=11, rnti=4660),
+             loader.pusch_link(cell_id=9, nof_prb=6, L_prb=3, n_prb=2, mod=1, tbs=392, tti=12, rnti=62),
+             loader.pusch_link(cell_id=77, nof_prb=15, L_prb=10, n_prb=0, mod=3, tbs=5160, tti=5, group_hopping=1, rnti=65535)]
+    for i, lk in enumerate(links):
+        data = rng.integers(0, 256, int(lk[12]) // 8, dtype=np.uint8)
+        tx = R.pusch_encode(lk, data)
+        noise = (rng.normal(size=tx.shape) + 1j * rng.normal(size=tx.shape)).astype(np.complex64) * np.float32(0.02)
+        rx = (tx * np.complex64(0.8 * np.exp(0.7j)) + noise).astype(np.complex64)
+        res = R.pusch_decode(lk, rx)
+        assert res["crc"] and (res["data"] == data).all()
+        pc[f"link{i}"] = lk
+        pc[f"data{i}"] = data
+        pc[f"rx{i}"] = rx
+        pc[f"dmrs{i}"] = R.dmrs_pusch_gen(lk)
+        for k in ("d", "q", "g", "ce"):
+            pc[f"{k}{i}"] = res[k]
+        pc[f"meas{i}"] = np.array([res["noise"], res["snr"], res["cfo_hz"]], np.float32)
+    np.savez_compressed(os.path.join(OUT, "pusch_chain.npz"), **pc)
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 
