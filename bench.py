@@ -309,6 +309,12 @@ def run_ours(args):
             pusch = pusch_leg(args, torch, dev, local, rank, world, barrier, max_over_ranks, sum_over_ranks, peaks)
         except Exception as ex:  # secondary metric: report the failure, keep the headline
             pusch = {"error": repr(ex)}
+    pusch_full = None
+    if not args.no_pusch:
+        try:
+            pusch_full = pusch_full_leg(args, torch, dev, local, rank, world, barrier, max_over_ranks, sum_over_ranks, peaks)
+        except Exception as ex:  # noqa: BLE001
+            pusch_full = {"error": repr(ex)}
 
     if rank != 0:
         if dist is not None:
@@ -332,6 +338,7 @@ def run_ours(args):
         "checks": {"crc_ok_fraction_fixed8": frac_ok_fixed, "crc_ok_blocks_equal_transmitted_bits": ber_ok},
         "kernel_ms": prof,
         "pusch": pusch,
+        "pusch_full": pusch_full,
     }
     print(json.dumps(line), flush=True)
     if dist is not None:
@@ -413,6 +420,111 @@ def pusch_leg(args, torch, dev, local, rank, world, barrier, max_over_ranks, sum
                           "demap_frac_of_hbm_peak": demap_bytes / (fe_demap * 1e-3) / 1e9 / peaks["hbm_gbs"]},
             "config": "configs[3] pipeline batched as configs[4]: 100 PRB, N=2048, normal CP, f=-0.5, window offset 0.5, 64QAM, "
                       "TBS 75376 -> 13 x K=5824, rv 0, identity channel, 8 distinct subframes tiled, soft bits >> 4"}
+
+
+def pusch_full_leg(args, torch, dev, local, rank, world, barrier, max_over_ranks, sum_over_ranks, peaks):
+    """The same 20 MHz subframe through the COMPLETE receive chain (SURVEY 8f ranks 1-3 added to config 4): transmit side with
+    channel interleaver, scrambling, transform precoding and DMRS; per-subframe flat fading + timing offset + AWGN; receive side
+    OFDM rx -> channel estimation -> MMSE equaliser + transform de-precoding -> soft demap + descrambling + UL-SCH de-interleave
+    -> rate de-matching -> turbo decoding with CRC early stop."""
+    import numpy as np
+
+    from srslte_b200 import synth_pusch as sp
+    from srslte_b200.pusch import PuschRxFull
+
+    nsf, tbs, nd, cell_id = PUSCH_SF_PER_GPU, 75376, 8, 1 + rank
+    rx = PuschRxFull(cell_id, 100, tbs, 3, llr_shift=4, max_noi=MAX_PASSES, device=local, symbol_sz=2048)
+    rnti8 = np.arange(nd, dtype=np.uint32) * 97 + 62
+    tti8 = np.arange(nd, dtype=np.uint32) * 3 + rank
+    iq8, payload8, G = sp.make_subframes_full(cell_id, 100, 2048, tbs, 6, 0, sp.qpp_interleaver(5824), nd, rnti8, tti8,
+                                              lambda sf: rx.chain.dmrs(sf, 0), PUSCH_SNR_DB, seed=0x77 + rank)
+    rnti, tti = np.tile(rnti8, nsf // nd), np.tile(tti8, nsf // nd)
+    h_iq = torch.from_numpy(np.ascontiguousarray(np.tile(iq8, (nsf // nd, 1)))).pin_memory()
+    x = h_iq.to(dev)
+    nbytes = tbs // 8 + 3
+    h_data = torch.empty((nsf, rx.data_stride), dtype=torch.uint8).pin_memory()
+    steps, warm = max(3, min(args.steps, 10)), 2
+    ok, its = None, None
+    for _ in range(warm):
+        ok, its = rx.run(x, nsf, rnti, tti)
+    good = bool(ok.all()) and bool((rx.data[:nd, :nbytes].cpu().numpy() == payload8).all())
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        rx.run(x, nsf, rnti, tti)
+    torch.cuda.synchronize()
+    ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / steps
+    # the new front-end kernels alone (CUDA events on the launching stream)
+    ch = rx.chain
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    t_chest = t_eq = t_demod = 0.0
+    grid = rx.grid[:nsf]
+    for _ in range(steps):
+        e[0].record()
+        ce, meas = ch.chest(grid, tti)
+        e[1].record()
+        d = ch.equalize_deprecode(grid, ce, meas)
+        e[2].record()
+        ch.demod_descramble(d, rnti, tti, out=rx.llr)
+        e[3].record()
+        torch.cuda.synchronize()
+        t_chest += e[0].elapsed_time(e[1]) / steps
+        t_eq += e[1].elapsed_time(e[2]) / steps
+        t_demod += e[2].elapsed_time(e[3]) / steps
+
+    def step_e2e():
+        x.copy_(h_iq, non_blocking=True)
+        rx.run(x, nsf, rnti, tti)
+        h_data.copy_(rx.data[:nsf], non_blocking=True)
+        torch.cuda.synchronize()
+
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step_e2e()
+    ms_e2e = max_over_ranks((time.perf_counter() - t0) * 1e3) / steps
+    mean_its = sum_over_ranks(float(its.mean())) / world
+    snr_est = float(rx.meas[:nd, 1].log10().mean().item() * 10.0)
+    # CPU baseline: the reference's own receiver after the OFDM demodulator (FFTW is not available to build its srsran_ofdm)
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        try:
+            from oracle import loader
+
+            if loader.have_ref():
+                R = loader.api("ref")
+                cores = os.cpu_count() or 1
+                grids8 = rx.grid[:nd].cpu().numpy()
+                n_cpu = 16 * cores
+                lk = loader.pusch_link(cell_id=cell_id, rnti=int(rnti8[0]), tti=int(tti8[0]), tbs=tbs, max_iter=MAX_PASSES)
+                okc, sec = R.pusch_rx_bench(lk, np.ascontiguousarray(np.tile(grids8[:1], (n_cpu, 1, 1))), cores)
+                cpu = {"value": n_cpu / sec, "unit": "subframes/s", "cores": cores, "kind": "reference",
+                       "sample": f"{n_cpu} copies of one subframe's resource grid (demodulated on the GPU: the reference's OFDM needs FFTW, "
+                                 f"absent here): srsran_chest_ul_estimate_pusch + srsran_pusch_decode per subframe, one object set per thread, "
+                                 f"all crc ok = {bool(okc.all())}"}
+        except Exception as ex:  # noqa: BLE001
+            cpu = {"error": repr(ex)}
+    rx.close()
+    M = 1200
+    chest_bytes = nsf * (2 * M * 8 * 2 + 2 * M * 8)          # two DMRS symbols + known sequence in, two slot estimates out
+    eq_bytes = nsf * (12 * M * 8 + 2 * M * 8 + 12 * M * 8)   # data symbols + estimates in, de-precoded symbols out
+    demod_bytes = nsf * 12 * M * (8 + 12 + 6 / 8.0 * 2)      # symbols in, soft bits out, scrambling bits written + read
+    gbs = lambda b, t: b / (t * 1e-3) / 1e9
+    return {"metric": "pusch_full_chain_subframes_per_s_20mhz_64qam_tbs75376", "value": world * nsf / (ms * 1e-3), "unit": "subframes/s",
+            "ms_per_step": ms, "subframes_per_gpu_per_step": nsf, "info_gbit_per_s": world * nsf * tbs / (ms * 1e-3) / 1e9,
+            "mean_passes": mean_its, "snr_db": PUSCH_SNR_DB, "estimated_snr_db": snr_est, "all_tb_crc_ok_and_bytes_equal_payload": good,
+            "e2e": {"value": world * nsf / (ms_e2e * 1e-3), "unit": "subframes/s", "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": int(nsf * 15 * 2048 * 8), "d2h_bytes_per_step": int(nsf * h_data.shape[1])},
+            "front_end": {"chest_ms": t_chest, "chest_gbs": gbs(chest_bytes, t_chest), "chest_frac_of_hbm_peak": gbs(chest_bytes, t_chest) / peaks["hbm_gbs"],
+                          "equalize_deprecode_ms": t_eq, "equalize_deprecode_gbs": gbs(eq_bytes, t_eq),
+                          "equalize_deprecode_frac_of_hbm_peak": gbs(eq_bytes, t_eq) / peaks["hbm_gbs"],
+                          "demod_descramble_deinterleave_ms": t_demod, "demod_descramble_deinterleave_gbs": gbs(demod_bytes, t_demod),
+                          "demod_descramble_deinterleave_frac_of_hbm_peak": gbs(demod_bytes, t_demod) / peaks["hbm_gbs"]},
+            "cpu_baseline": cpu,
+            "config": "configs[3]/[4] with the complete chain: 100 PRB, N=2048, normal CP, f=-0.5, window offset 0.5, 64QAM, TBS 75376 -> "
+                      "13 x K=5824, rv 0, DMRS + channel interleaver + scrambling + transform precoding, flat fading with timing offset per "
+                      "subframe, 8 distinct subframes tiled, soft bits >> 4"}
 
 
 def main():

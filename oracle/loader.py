@@ -301,6 +301,19 @@ class _Api:
         return dict(ret=int(r), crc=bool(crc.value), data=data[: int(link[12]) // 8].copy(), noise=float(meas[0]), snr=float(meas[1]),
                     cfo_hz=float(meas[2]), avg_iter=float(meas[4]), d=d.copy(), q=q.copy(), g=g.copy(), ce=ce.reshape(nsym, -1).copy())
 
+    def pusch_rx_bench(self, link: np.ndarray, grids: np.ndarray, nthreads: int):
+        """Reference only: chest + srsran_pusch_decode over grids (nsf, nsym, 12 nof_prb) on nthreads workers.
+        Returns (crc verdicts (nsf,), seconds of the decode loops)."""
+        assert self.which == "ref"
+        link = np.ascontiguousarray(link, np.uint32)
+        nsf = grids.shape[0]
+        g = _aligned_copy(grids, np.complex64)
+        ok = np.zeros(nsf, np.uint8)
+        sec = C.c_double(0)
+        r = self.lib.ref_pusch_rx_bench(_p(link), _p(g), C.c_uint32(nsf), C.c_int(nthreads), _p(ok), C.byref(sec))
+        assert r == 0, r
+        return ok, sec.value
+
 
 def pusch_link(cell_id=1, nof_prb=100, cp_ext=0, cyclic_shift=0, delta_ss=0, group_hopping=0, sequence_hopping=0, rnti=62, tti=0,
                L_prb=100, n_prb=0, mod=3, tbs=75376, rv=0, n_dmrs=0, max_iter=8) -> np.ndarray:

@@ -657,3 +657,94 @@ int ref_pusch_decode(const uint32_t* p, cf_t* grid, int use_identity_ce, uint8_t
   srsran_pusch_free(&rx);
   return r;
 }
+
+/* CPU baseline of the PUSCH receive chain after the OFDM demodulator (FFTW is not available here): nthreads workers, each
+ * with its own srsran_chest_ul_t / srsran_pusch_t / soft buffer like one cc_worker, run chest + srsran_pusch_decode over
+ * their share of nsf subframes (all the same link parameters, grids[nsf][2*nsymb*12*nof_prb]).  Object set-up is outside the
+ * timed region.  ok_out[nsf] = CRC verdicts. */
+typedef struct {
+  const uint32_t* p;
+  cf_t*           grids;
+  uint32_t        first, count;
+  uint8_t*        ok;
+  int             err;
+  pthread_barrier_t* bar;
+} pusch_job_t;
+
+static void* pusch_job_run(void* arg)
+{
+  pusch_job_t*                      j    = (pusch_job_t*)arg;
+  srsran_cell_t                     cell = link_cell(j->p);
+  srsran_pusch_cfg_t                cfg;
+  srsran_ul_sf_cfg_t                sf;
+  srsran_refsignal_dmrs_pusch_cfg_t dmrs;
+  srsran_pusch_t                    rx;
+  srsran_softbuffer_rx_t            sb;
+  srsran_chest_ul_t                 chest;
+  srsran_chest_ul_res_t             res;
+  link_cfg(j->p, &cell, &cfg, &sf, &dmrs);
+  uint32_t nre  = 2 * SRSRAN_CP_NSYMB(cell.cp) * 12 * cell.nof_prb;
+  uint8_t* data = calloc(cfg.grant.tb.tbs / 8 + 64, 1);
+  j->err        = 0;
+  if (srsran_pusch_init_enb(&rx, cell.nof_prb) || srsran_pusch_set_cell(&rx, cell) || srsran_softbuffer_rx_init(&sb, cell.nof_prb) ||
+      srsran_chest_ul_init(&chest, cell.nof_prb) || srsran_chest_ul_set_cell(&chest, cell) || srsran_chest_ul_res_init(&res, cell.nof_prb)) {
+    j->err = -1;
+  } else {
+    srsran_chest_ul_pregen(&chest, &dmrs, NULL);
+  }
+  pthread_barrier_wait(j->bar); /* start of the timed region */
+  if (!j->err) {
+    for (uint32_t s = j->first; s < j->first + j->count; s++) {
+      srsran_softbuffer_rx_reset(&sb);
+      cfg.softbuffers.rx = &sb;
+      srsran_pusch_res_t out;
+      memset(&out, 0, sizeof(out));
+      out.data = data;
+      if (srsran_chest_ul_estimate_pusch(&chest, &sf, &cfg, &j->grids[(size_t)s * nre], &res) ||
+          srsran_pusch_decode(&rx, &sf, &cfg, &res, &j->grids[(size_t)s * nre], &out)) {
+        j->err = -2;
+        break;
+      }
+      j->ok[s] = out.crc ? 1 : 0;
+    }
+  }
+  pthread_barrier_wait(j->bar); /* end of the timed region */
+  free(data);
+  return NULL;
+}
+
+int ref_pusch_rx_bench(const uint32_t* p, cf_t* grids, uint32_t nsf, int nthreads, uint8_t* ok_out, double* seconds)
+{
+  if (nthreads < 1) nthreads = 1;
+  ensure_tables();
+  pthread_t*        th   = calloc(nthreads, sizeof(pthread_t));
+  pusch_job_t*      jobs = calloc(nthreads, sizeof(pusch_job_t));
+  pthread_barrier_t bar;
+  pthread_barrier_init(&bar, NULL, nthreads + 1);
+  uint32_t per = (nsf + nthreads - 1) / nthreads;
+  for (int t = 0; t < nthreads; t++) {
+    uint32_t first = (uint32_t)t * per;
+    jobs[t].p      = p;
+    jobs[t].grids  = grids;
+    jobs[t].first  = first < nsf ? first : nsf;
+    jobs[t].count  = first < nsf ? (first + per <= nsf ? per : nsf - first) : 0;
+    jobs[t].ok     = ok_out;
+    jobs[t].bar    = &bar;
+    pthread_create(&th[t], NULL, pusch_job_run, &jobs[t]);
+  }
+  struct timespec t0, t1;
+  pthread_barrier_wait(&bar);
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  pthread_barrier_wait(&bar);
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  int err = 0;
+  for (int t = 0; t < nthreads; t++) {
+    pthread_join(th[t], NULL);
+    if (jobs[t].err) err = jobs[t].err;
+  }
+  if (seconds) *seconds = (double)(t1.tv_sec - t0.tv_sec) + 1e-9 * (double)(t1.tv_nsec - t0.tv_nsec);
+  pthread_barrier_destroy(&bar);
+  free(th);
+  free(jobs);
+  return err;
+}

@@ -16,6 +16,7 @@
 // Unlike the reference the caller's input buffer is NOT modified (ofdm.c:455-457 multiplies the shift in place, which
 // makes its srsran_ofdm_rx_sf non-idempotent).
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 #include "b200_runtime.h"
 #include "ofdm_kernels.h"
@@ -450,9 +451,209 @@ static int launch_ct(const OfdmPlanDev& p, const float2* in_dev, float2* out_dev
   return B200_SUCCESS;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Compile-time specialised batched DFT for the generic / PUSCH de-precoding modes (sizes 12 L_prb with factors 3 and 5):
+// radices, strides and index divisions are constants, the twiddles of a butterfly come from ONE table load plus a
+// recurrence, a thread keeps all its points of a pass in registers (<= 16) so the passes exchange in place through one
+// padded shared buffer, several symbols share a block so that no thread idles, and the inputs of a block's NEXT symbols
+// (samples and, in PUSCH mode, channel estimates) are fetched with cp.async into a staging buffer while the current ones
+// are transformed.
+template <int N, int RADIX, int NS, int TPS, bool FIRST, bool LAST>
+__device__ __forceinline__ void dft_pass_ct(const OfdmPlanDev& p, const float2* gin, const float2* eq_h, float eq_n0, float2* buf,
+                                            float2* __restrict__ gout, int t, bool active)
+{
+  constexpr int T = N / RADIX, ITER = (T + TPS - 1) / TPS;
+  static_assert(ITER * RADIX <= 16, "a thread holds at most 16 points");
+  float2 u[ITER][RADIX];
+  if (active) {
+#pragma unroll
+    for (int it = 0; it < ITER; it++) {
+      const int j = t + it * TPS;
+      if (ITER * TPS == T || j < T) {
+#pragma unroll
+        for (int q = 0; q < RADIX; q++) {
+          const int idx = j + q * T;
+          if (FIRST) {
+            float2 v = gin[idx];
+            if (eq_h) { // precoding.c:224-262: (y conj(h)) / (|h|^2 [+ noise when noise > 0]); one rounded reciprocal
+              const float2 h  = eq_h[idx];
+              float        hh = h.x * h.x + h.y * h.y;
+              if (eq_n0 > 0.f) hh += eq_n0;
+              const float r = __frcp_rn(hh);
+              v = make_float2((v.x * h.x + v.y * h.y) * r, (v.y * h.x - v.x * h.y) * r);
+            }
+            if (p.inverse) v.y = -v.y;
+            u[it][q] = v;
+          } else {
+            u[it][q] = buf[pad_idx(idx)];
+          }
+        }
+      }
+    }
+  }
+  if (!FIRST) __syncthreads(); // in place: everybody has read its points before anybody overwrites them
+  if (active) {
+#pragma unroll
+    for (int it = 0; it < ITER; it++) {
+      const int j = t + it * TPS;
+      if (ITER * TPS == T || j < T) {
+        const int k = j % NS;
+        if (NS > 1) {
+          constexpr int step = N / (NS * RADIX);
+          const float2  w1   = p.W[k * step];
+          float2        w    = w1;
+#pragma unroll
+          for (int q = 1; q < RADIX; q++) {
+            u[it][q] = cmul(u[it][q], w);
+            if (q + 1 < RADIX) w = cmul(w, w1);
+          }
+        }
+        dft_small<RADIX>(u[it]);
+        const int j0 = (j / NS) * NS * RADIX + k;
+#pragma unroll
+        for (int q = 0; q < RADIX; q++) {
+          const int o = j0 + q * NS;
+          if (LAST) {
+            float2 v = u[it][q];
+            if (p.inverse) v.y = -v.y;
+            if (p.gscale != 0.f) v = make_float2(v.x * p.gscale, v.y * p.gscale);
+            __stcs(&gout[o], v);
+          } else {
+            buf[pad_idx(o)] = u[it][q];
+          }
+        }
+      }
+    }
+  }
+  if (!LAST) __syncthreads();
+}
+
+constexpr int dft_ct_tps(int N, int r0, int r1, int r2, int r3)
+{
+  int tps = 1;
+  const int r[4] = {r0, r1, r2, r3};
+  for (int i = 0; i < 4; i++) {
+    if (r[i] > 1) {
+      const int T = N / r[i], per = 16 / r[i], need = (T + per - 1) / per;
+      if (need > tps) tps = need;
+    }
+  }
+  return tps;
+}
+
+template <int N, int R0, int R1, int R2, int R3>
+struct DftCt {
+  static constexpr int TPS  = dft_ct_tps(N, R0, R1, R2, R3);
+  static constexpr int SPB  = (256 / TPS) > 0 ? (256 / TPS) : 1;
+  static constexpr int PADN = N + (N >> 4) + 1;
+};
+
+template <int N, int R0, int R1, int R2, int R3>
+__global__ void __launch_bounds__(256, 2) dft_batch_kernel_ct(OfdmPlanDev p, const float2* __restrict__ in, float2* __restrict__ out, uint32_t ntot)
+{
+  using C = DftCt<N, R0, R1, R2, R3>;
+  extern __shared__ __align__(16) float2 smem[];
+  const int  graw  = threadIdx.x / C::TPS;
+  const bool spare = graw >= C::SPB; // threads beyond the last full group only keep the barriers company
+  const int  g     = spare ? 0 : graw;
+  const int  t     = threadIdx.x % C::TPS;
+  const bool eq    = p.generic == 2;
+  float2*    buf   = smem + (size_t)g * (C::PADN + 2 * N);
+  float2*    sy    = buf + C::PADN; // staged samples of the next symbol, natural order
+  float2*    sh    = sy + N;        // staged channel estimates (PUSCH mode)
+  auto source = [&](uint32_t sidx, const float2*& y, const float2*& h) {
+    if (eq) {
+      const uint32_t psf = sidx / (uint32_t)p.pusch_nd, d = sidx % (uint32_t)p.pusch_nd;
+      const int      lsym = p.pusch_l[d];
+      y = in + ((size_t)psf * p.grid_nsym + lsym) * p.grid_R + p.grid_off;
+      h = p.eq_ce + ((size_t)psf * 2 + (lsym >= p.grid_nsym / 2 ? 1 : 0)) * N;
+    } else {
+      y = in + (size_t)sidx * p.idist;
+      h = nullptr;
+    }
+  };
+  auto prefetch = [&](uint32_t sidx) {
+    if (!spare && sidx < ntot) {
+      const float2 *y, *h;
+      source(sidx, y, h);
+      for (int i = t; i < N; i += C::TPS) {
+        cp_async8(sy + i, y + i);
+        if (eq) cp_async8(sh + i, h + i);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  prefetch(blockIdx.x * C::SPB + g);
+  for (uint32_t base = blockIdx.x * C::SPB; base < ntot; base += gridDim.x * C::SPB) {
+    const uint32_t sidx   = base + g;
+    const bool     active = !spare && sidx < ntot;
+    float2*        gout   = eq ? out + (size_t)sidx * N : out + (size_t)sidx * p.odist;
+    float          eq_n0  = 0.f;
+    if (eq && active && p.eq_noise) eq_n0 = p.eq_noise[(size_t)(sidx / (uint32_t)p.pusch_nd) * p.eq_noise_stride];
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads(); // the staged inputs are complete and visible to the whole group
+    dft_pass_ct<N, R0, 1, C::TPS, true, false>(p, sy, eq ? sh : nullptr, eq_n0, buf, gout, t, active);
+    prefetch(sidx + gridDim.x * C::SPB); // the barrier that ended the first pass: every thread has read its staged points
+    if (R2 > 1) {
+      dft_pass_ct<N, R1, R0, C::TPS, false, false>(p, sy, sh, eq_n0, buf, gout, t, active);
+      if (R3 > 1) {
+        dft_pass_ct<N, (R2 > 1 ? R2 : 2), R0 * R1, C::TPS, false, false>(p, sy, sh, eq_n0, buf, gout, t, active);
+        dft_pass_ct<N, (R3 > 1 ? R3 : 2), R0 * R1 * (R2 > 1 ? R2 : 1), C::TPS, false, true>(p, sy, sh, eq_n0, buf, gout, t, active);
+      } else {
+        dft_pass_ct<N, (R2 > 1 ? R2 : 2), R0 * R1, C::TPS, false, true>(p, sy, sh, eq_n0, buf, gout, t, active);
+      }
+    } else {
+      dft_pass_ct<N, R1, R0, C::TPS, false, true>(p, sy, sh, eq_n0, buf, gout, t, active);
+    }
+  }
+}
+
+template <int N, int R0, int R1, int R2, int R3>
+static int launch_dft_ct(const OfdmPlanDev& p, const float2* in_dev, float2* out_dev, uint32_t ntot, int sm_count, cudaStream_t stream)
+{
+  using C = DftCt<N, R0, R1, R2, R3>;
+  constexpr size_t smem = (size_t)C::SPB * (C::PADN + 2 * N) * sizeof(float2); // work buffer + staged next inputs per symbol
+  static bool      attr_done = false;
+  if (!attr_done) {
+    B200_CUDA_TRY(cudaFuncSetAttribute(dft_batch_kernel_ct<N, R0, R1, R2, R3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200_CUDA_TRY(cudaFuncSetAttribute(dft_batch_kernel_ct<N, R0, R1, R2, R3>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                       cudaSharedmemCarveoutMaxShared));
+    attr_done = true;
+  }
+  uint32_t       blocks = (ntot + C::SPB - 1) / C::SPB;
+  const uint32_t cap    = (uint32_t)sm_count * 8u;
+  if (blocks > cap) blocks = cap;
+  dft_batch_kernel_ct<N, R0, R1, R2, R3><<<blocks, 256, smem, stream>>>(p, in_dev, out_dev, ntot);
+  B200_CUDA_TRY(cudaGetLastError());
+  return B200_SUCCESS;
+}
+
+// the radix sequence must be the one fft_factorise() produces (the plan carries it; checked by the caller below)
+static bool plan_is(const OfdmPlanDev& p, int r0, int r1, int r2, int r3)
+{
+  const int r[4] = {r0, r1, r2, r3};
+  int       n    = 0;
+  for (int i = 0; i < 4; i++) {
+    if (r[i] > 1) {
+      if (p.radix[i] != r[i]) return false;
+      n++;
+    }
+  }
+  return p.npass == n;
+}
+
 int launch_ofdm_rx(const OfdmPlanDev& p, const float2* in_dev, float2* out_dev, uint32_t nsf, int sm_count, cudaStream_t stream)
 {
   if (nsf == 0) return B200_SUCCESS;
+  if (p.generic && !p.shift && !p.ramp && getenv("SRSLTE_B200_DFT_GENERIC") == nullptr) {
+    // allocation sizes of the wide LTE carriers: 100 / 75 / 50 / 25 / 15 / 6 PRB
+    if (p.N == 1200 && plan_is(p, 16, 3, 5, 5)) return launch_dft_ct<1200, 16, 3, 5, 5>(p, in_dev, out_dev, nsf, sm_count, stream);
+    if (p.N == 600 && plan_is(p, 8, 3, 5, 5)) return launch_dft_ct<600, 8, 3, 5, 5>(p, in_dev, out_dev, nsf, sm_count, stream);
+    if (p.N == 300 && plan_is(p, 4, 3, 5, 5)) return launch_dft_ct<300, 4, 3, 5, 5>(p, in_dev, out_dev, nsf, sm_count, stream);
+    if (p.N == 180 && plan_is(p, 4, 3, 3, 5)) return launch_dft_ct<180, 4, 3, 3, 5>(p, in_dev, out_dev, nsf, sm_count, stream);
+    if (p.N == 72 && plan_is(p, 8, 3, 3, 1)) return launch_dft_ct<72, 8, 3, 3, 1>(p, in_dev, out_dev, nsf, sm_count, stream);
+  }
   if (!p.generic && !p.inverse) {
     switch (p.N) {
       case 2048:

@@ -208,3 +208,38 @@ class PuschChain:
         if rc != _lib.SUCCESS:
             raise RuntimeError(f"srsran_b200_pusch_rx_batch failed ({rc})")
         return g
+
+
+class PuschRxFull(PuschRx):
+    """Complete PUSCH receive pipeline on device buffers, one full-band allocation per (cell, subframe):
+
+        srsran_b200_ofdm_rx_sf_batch -> srsran_b200_pusch_rx_batch (channel estimation, equaliser, transform de-precoding,
+        soft demapping, descrambling, UL-SCH de-interleaving) -> srsran_b200_sch_decode_batch
+
+    i.e. enb_ul.c:151-154 (srsran_enb_ul_fft) + enb_ul.c:262-290 (get_pusch: srsran_chest_ul_estimate_pusch, srsran_pusch_decode)
+    for a batch of subframes of one cell."""
+
+    def __init__(self, cell_id: int = 1, nof_prb: int = 100, tbs: int = 75376, mod: int = 3, llr_shift: int = 4, max_noi: int = 8,
+                 device: int = 0, symbol_sz: int = 0, cyclic_shift: int = 0, delta_ss: int = 0):
+        super().__init__(nof_prb, tbs, mod, llr_shift, max_noi, device, symbol_sz)
+        self.chain = PuschChain(cell_id, nof_prb, False, nof_prb, 0, mod, llr_shift, cyclic_shift, delta_ss, False, False, device)
+        assert self.chain.nof_bits == self.G
+        self.meas = None
+
+    def close(self):
+        self.chain.close()
+        super().close()
+
+    def front_end(self, iq, nsf: int, rnti=None, tti=None, n_dmrs=None):
+        t = self.torch
+        self._reserve(nsf)
+        if self.meas is None or self.meas.shape[0] < nsf:
+            self.meas = t.empty((nsf, 4), dtype=t.float32, device=self.dev)
+        st = t.cuda.current_stream(self.dev).cuda_stream
+        self.ofdm.rx_sf_device(iq, self.grid, nsf, st)
+        self.chain.rx(self.grid[:nsf], rnti if rnti is not None else 0, tti if tti is not None else 0, n_dmrs, out=self.llr,
+                      meas=self.meas)
+
+    def run(self, iq, nsf: int, rnti=None, tti=None, n_dmrs=None, rv: int = 0):
+        self.front_end(iq, nsf, rnti, tti, n_dmrs)
+        return self.decode(nsf, rv)

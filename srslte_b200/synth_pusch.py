@@ -205,3 +205,65 @@ def make_subframes(nof_prb: int, N: int, tbs: int, Qm: int, rv: int, qpp: np.nda
     sigma_t = sigma_f / np.sqrt(N)
     iq += (rng.normal(size=iq.shape) + 1j * rng.normal(size=iq.shape)) * (sigma_t / np.sqrt(2.0))
     return iq.astype(np.complex64), payload, G
+
+
+# ---- full PUSCH transmitter (36.212 5.2.2.7-8, 36.211 5.3.1-5.3.4, 5.5.2.1) -------------------------------------------
+def gold_bits(c_init: np.ndarray, nbits: int) -> np.ndarray:
+    """36.211 7.2 pseudo-random sequence c(0..nbits-1) for every seed in c_init -> (n, nbits) uint8."""
+    c_init = np.atleast_1d(np.asarray(c_init, np.uint32))
+    n = c_init.size
+    x1 = np.zeros((n, 1600 + nbits + 31), np.uint8)
+    x2 = np.zeros_like(x1)
+    x1[:, 0] = 1
+    x2[:, :31] = (c_init[:, None] >> np.arange(31)[None, :]) & 1
+    # the recurrences reach back 28..31 samples, so 28 new samples can be produced per vector step
+    step = 28
+    for p in range(31, x1.shape[1], step):
+        e = min(p + step, x1.shape[1])
+        w = e - p
+        x1[:, p:e] = x1[:, p - 28:p - 28 + w] ^ x1[:, p - 31:p - 31 + w]
+        x2[:, p:e] = x2[:, p - 28:p - 28 + w] ^ x2[:, p - 29:p - 29 + w] ^ x2[:, p - 30:p - 30 + w] ^ x2[:, p - 31:p - 31 + w]
+    return x1[:, 1600:1600 + nbits] ^ x2[:, 1600:1600 + nbits]
+
+
+def make_pusch_grids(cell_id: int, cell_nof_prb: int, L_prb: int, n_prb: int, tbs: int, Qm: int, rv: int, qpp: np.ndarray, n: int,
+                     rnti: np.ndarray, tti: np.ndarray, dmrs, seed: int):
+    """n PUSCH subframes as resource grids (n, 14, 12 cell_nof_prb) complex128 before the channel: transport block coding,
+    channel interleaver (no control information), scrambling, modulation, transform precoding, mapping, DMRS.
+    dmrs(sf_idx) -> (2, 12 L_prb) known reference symbols.  Returns (grid, payload bytes incl. TB CRC)."""
+    M, R = 12 * L_prb, 12 * cell_nof_prb
+    G = 12 * M * Qm
+    f, payload = make_transport_blocks(tbs, Qm, G, rv, qpp, n, seed)
+    # 36.212 5.2.2.8: the matrix is written row by row (rows = M, columns = 12 symbols, Qm bits per entry), read column by column
+    q = f.reshape(n, M, 12, Qm).transpose(0, 2, 1, 3).reshape(n, G)
+    c = gold_bits((np.asarray(rnti, np.uint32) << 14) + ((np.asarray(tti, np.uint32) % 10) << 9) + np.uint32(cell_id), G)
+    d = _qam(q ^ c, Qm).reshape(n, 12, M)
+    z = np.fft.fft(d, axis=2) / np.sqrt(M)               # 36.211 5.3.3 transform precoding
+    grid = np.zeros((n, 14, R), np.complex128)
+    data_syms = [l for l in range(14) if l not in (3, 10)]
+    grid[:, data_syms, 12 * n_prb:12 * n_prb + M] = z
+    for s in range(n):
+        r = dmrs(int(tti[s] % 10))
+        grid[s, 3, 12 * n_prb:12 * n_prb + M] = r[0]
+        grid[s, 10, 12 * n_prb:12 * n_prb + M] = r[1]
+    return grid, payload
+
+
+def make_subframes_full(cell_id: int, nof_prb: int, N: int, tbs: int, Qm: int, rv: int, qpp: np.ndarray, n: int, rnti, tti, dmrs,
+                        snr_db: float, seed: int, fading: bool = True):
+    """Time-domain PUSCH subframes through a per-subframe flat complex gain with a small timing offset (linear phase over the
+    subcarriers) plus AWGN whose level follows the gain, so that every subframe is received at snr_db.
+    Returns (iq (n, 15N) complex64, payload bytes (n, tbs/8+3), G)."""
+    grid, payload = make_pusch_grids(cell_id, nof_prb, nof_prb, 0, tbs, Qm, rv, qpp, n, rnti, tti, dmrs, seed)
+    rng = np.random.default_rng(seed + 1)
+    R = 12 * nof_prb
+    gain = np.ones(n, np.complex128)
+    if fading:
+        gain = (0.7 + 0.6 * rng.random(n)) * np.exp(2j * np.pi * rng.random(n))
+        slope = 2 * np.pi * (rng.random(n) - 0.5) * 2e-3   # radians per subcarrier: a timing offset of up to +-2 samples at N=2048
+        h = gain[:, None] * np.exp(1j * slope[:, None] * (np.arange(R)[None, :] - R / 2))
+        grid = grid * h[:, None, :]
+    iq = ofdm_modulate(grid, N).astype(np.complex128)
+    sigma_t = 10 ** (-snr_db / 20.0) / np.sqrt(N)
+    iq += (rng.normal(size=iq.shape) + 1j * rng.normal(size=iq.shape)) * (sigma_t / np.sqrt(2.0)) * np.abs(gain)[:, None]
+    return iq.astype(np.complex64), payload, 12 * R * Qm

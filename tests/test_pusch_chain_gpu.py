@@ -210,3 +210,29 @@ def test_chain_against_the_reference_link(ref, port, kw, tbs):
         assert (out[s, :tbs // 8] == datas[s]).all()
     sch.close()
     ch4.close()
+
+
+def test_full_pipeline_from_time_samples(port):
+    """bench.py's full-chain leg in small: numpy transmitter (checked against srsran_pusch_encode in tests/test_pusch_synth.py) ->
+    fading + timing offset + AWGN -> OFDM rx -> chain -> de-matching -> turbo decoding; payload bytes and the SNR estimate."""
+    import torch
+    from srslte_b200 import synth_pusch as sp
+    from srslte_b200.pusch import PuschRxFull
+
+    tbs, nsf = 75376, 4
+    rx = PuschRxFull(17, 100, tbs, 3, llr_shift=4, max_noi=8, symbol_sz=2048)
+    rnti = np.array([62, 159, 4000, 65535], np.uint32)
+    tti = np.array([0, 13, 26, 9], np.uint32)
+    iq, payload, G = sp.make_subframes_full(17, 100, 2048, tbs, 6, 0, sp.qpp_interleaver(5824), nsf, rnti, tti,
+                                            lambda sf: rx.chain.dmrs(sf, 0), 23.0, seed=3)
+    ok, its = rx.run(torch.from_numpy(iq).cuda(), nsf, rnti, tti)
+    torch.cuda.synchronize()
+    assert ok.all()
+    assert (rx.data[:nsf, :tbs // 8 + 3].cpu().numpy() == payload).all()
+    meas = rx.meas[:nsf].cpu().numpy()
+    snr_db = 10 * np.log10(meas[:, 1])
+    assert (np.abs(snr_db - 23.0) < 1.5).all(), snr_db
+    # wrong RNTI: the scrambling sequence differs and nothing decodes
+    ok2, _ = rx.run(torch.from_numpy(iq).cuda(), nsf, rnti + 1, tti)
+    assert not ok2.any()
+    rx.close()

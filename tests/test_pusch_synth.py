@@ -71,3 +71,21 @@ def test_soft_bits_have_the_right_sign(port):
         sym = sp._qam(bits, Qm).astype(np.complex64)
         llr = port.demod_s(mod, sym)
         assert ((llr > 0).astype(np.uint8) == bits).all(), mod
+
+
+def test_full_pusch_transmitter_matches_the_reference(ref):
+    """The numpy transmitter used by bench.py's full-chain leg produces the resource grid of srsran_pusch_encode + DMRS."""
+    from oracle import loader
+    from srslte_b200 import synth_pusch as sp
+
+    for kw, tbs, K in ((dict(cell_id=1, nof_prb=100, L_prb=100, n_prb=0, mod=3), 75376, 5824),
+                       (dict(cell_id=150, nof_prb=50, L_prb=24, n_prb=13, mod=2, cyclic_shift=3), 9912, 4992)):
+        rnti = np.array([62, 40000], np.uint32)
+        tti = np.array([3, 18], np.uint32)
+        links = [loader.pusch_link(rnti=int(r), tti=int(t), tbs=tbs, **kw) for r, t in zip(rnti, tti)]
+        dm = {int(t % 10): ref.dmrs_pusch_gen(lk).reshape(2, -1) for t, lk in zip(tti, links)}
+        grid, payload = sp.make_pusch_grids(kw["cell_id"], kw["nof_prb"], kw["L_prb"], kw["n_prb"], tbs, 2 * kw["mod"], 0,
+                                            sp.qpp_interleaver(K), 2, rnti, tti, lambda sf: dm[sf], seed=5)
+        for s in range(2):
+            want = ref.pusch_encode(links[s], payload[s, :tbs // 8])
+            assert np.linalg.norm(grid[s] - want) / np.linalg.norm(want) < 1e-5
