@@ -209,6 +209,25 @@ SRSRAN_B200_API void srsran_dft_run_c(srsran_dft_plan_t* plan, const cf_t* in, c
 SRSRAN_B200_API void srsran_dft_run_c_zerocopy(srsran_dft_plan_t* plan, const cf_t* in, cf_t* out); /* :331 */
 SRSRAN_B200_API void srsran_dft_run_guru_c(srsran_dft_plan_t* plan);                         /* dft_fftw.c:356 */
 
+/* ---- SC-FDMA transform (de-)precoding: lib/include/srsran/phy/dft/dft_precoding.h ----------------------------------------- */
+#ifndef SRSRAN_MAX_PRB
+#define SRSRAN_MAX_PRB 110 /* phy_common.h */
+#endif
+typedef struct { /* dft_precoding.h:39-44 */
+  uint32_t          max_prb;
+  srsran_dft_plan_t dft_plan[SRSRAN_MAX_PRB + 1];
+} srsran_dft_precoding_t;
+
+SRSRAN_B200_API int      srsran_dft_precoding_init(srsran_dft_precoding_t* q, uint32_t max_prb, bool is_tx); /* dft_precoding.c:39 */
+SRSRAN_B200_API int      srsran_dft_precoding_init_tx(srsran_dft_precoding_t* q, uint32_t max_prb);
+SRSRAN_B200_API int      srsran_dft_precoding_init_rx(srsran_dft_precoding_t* q, uint32_t max_prb);
+SRSRAN_B200_API void     srsran_dft_precoding_free(srsran_dft_precoding_t* q);
+SRSRAN_B200_API bool     srsran_dft_precoding_valid_prb(uint32_t nof_prb);     /* 12*nof_prb = 2^a 3^b 5^c, dft_precoding.c:88-104 */
+SRSRAN_B200_API uint32_t srsran_dft_precoding_get_valid_prb(uint32_t nof_prb);
+/* nof_symbols transforms of 12*nof_prb points in ONE kernel launch (the reference loops srsran_dft_run_c, :120-123) */
+SRSRAN_B200_API int
+srsran_dft_precoding(srsran_dft_precoding_t* q, cf_t* input, cf_t* output, uint32_t nof_prb, uint32_t nof_symbols);
+
 /* ---- OFDM receive: lib/include/srsran/phy/dft/ofdm.h ------------------------------------------------------------------------ */
 #ifndef SRSRAN_OFDM_H
 #ifndef SRSRAN_PHY_COMMON_H

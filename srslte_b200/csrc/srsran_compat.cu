@@ -572,6 +572,69 @@ void srsran_dft_run_guru_c(srsran_dft_plan_t* plan)
   dft_exec(d, d->gin, d->gout, d->how_many, d->idist, d->odist);
 }
 
+
+// ---- srsran_dft_precoding_t (dft_precoding.c:39-126) over the plans above -------------------------------------------------
+bool srsran_dft_precoding_valid_prb(uint32_t nof_prb)
+{
+  if (nof_prb == 0 || nof_prb > 100) return nof_prb == 0; // the reference's table marks 0 valid and stops at 100 (:88-104)
+  uint32_t n = nof_prb;
+  for (uint32_t f : {2u, 3u, 5u}) {
+    while (n % f == 0) n /= f;
+  }
+  return n == 1;
+}
+
+uint32_t srsran_dft_precoding_get_valid_prb(uint32_t nof_prb)
+{
+  while (!srsran_dft_precoding_valid_prb(nof_prb)) nof_prb--;
+  return nof_prb;
+}
+
+void srsran_dft_precoding_free(srsran_dft_precoding_t* q)
+{
+  if (!q) return;
+  for (uint32_t i = 1; i <= q->max_prb && i <= SRSRAN_MAX_PRB; i++) {
+    if (q->dft_plan[i].p) srsran_dft_plan_free(&q->dft_plan[i]);
+  }
+  memset(q, 0, sizeof(*q));
+}
+
+int srsran_dft_precoding_init(srsran_dft_precoding_t* q, uint32_t max_prb, bool is_tx)
+{
+  if (!q || max_prb > SRSRAN_MAX_PRB) return SRSRAN_ERROR_INVALID_INPUTS;
+  memset(q, 0, sizeof(*q));
+  q->max_prb = max_prb;
+  for (uint32_t i = 1; i <= max_prb; i++) {
+    if (!srsran_dft_precoding_valid_prb(i)) continue;
+    if (srsran_dft_plan_c(&q->dft_plan[i], (int)(12 * i), is_tx ? SRSRAN_DFT_FORWARD : SRSRAN_DFT_BACKWARD)) {
+      B200_LOG_ERROR("Error: Creating DFT plan %u", i); // dft_precoding.c:51
+      srsran_dft_precoding_free(q);
+      return SRSRAN_ERROR;
+    }
+    srsran_dft_plan_set_norm(&q->dft_plan[i], true);
+  }
+  return SRSRAN_SUCCESS;
+}
+
+int srsran_dft_precoding_init_rx(srsran_dft_precoding_t* q, uint32_t max_prb) { return srsran_dft_precoding_init(q, max_prb, false); }
+int srsran_dft_precoding_init_tx(srsran_dft_precoding_t* q, uint32_t max_prb) { return srsran_dft_precoding_init(q, max_prb, true); }
+
+int srsran_dft_precoding(srsran_dft_precoding_t* q, cf_t* input, cf_t* output, uint32_t nof_prb, uint32_t nof_symbols)
+{
+  if (!q || !input || !output) return SRSRAN_ERROR_INVALID_INPUTS;
+  if (!srsran_dft_precoding_valid_prb(nof_prb) || nof_prb == 0 || nof_prb > q->max_prb || !q->dft_plan[nof_prb].p) {
+    B200_LOG_ERROR("Error invalid number of PRB (%u)", nof_prb); // dft_precoding.c:117
+    return SRSRAN_ERROR;
+  }
+  if (nof_symbols == 0) return SRSRAN_SUCCESS;
+  CompatDft* d = (CompatDft*)q->dft_plan[nof_prb].p;
+  const int  N = 12 * (int)nof_prb;
+  d->plan.gscale = 1.0f / sqrtf((float)N); // srsran_dft_plan_set_norm(true), applied by the kernel's last pass
+  const int rc   = dft_exec(d, input, output, (int)nof_symbols, N, N);
+  d->plan.gscale = 0.f;
+  return rc;
+}
+
 } // extern "C"
 
 // ===================================================================================================================

@@ -277,9 +277,12 @@ struct WinOut {
   uint32_t bits;    // decisions (turbodecoder_gen.c:266: LLR > 0 -> 1): bit 7-t = step t, low block in bits 0..7, high in 16..23
 };
 
-B200_HD void win_emit(WinOut& o, LaneResult& res, const CrcPow* cw, int t, uint32_t L, uint32_t e)
+// sink(t, e_new) receives the new extrinsic of step t: the GPU kernel stores it straight away (the value dies at once
+// instead of occupying a register until the end of the window), the plain overload below keeps it in o.enew[]
+template <class Sink>
+B200_HD void win_emit(WinOut& o, LaneResult& res, const CrcPow* cw, int t, uint32_t L, uint32_t e, Sink&& sink)
 {
-  o.enew[t]          = sub2(L, e);
+  sink(t, sub2(L, e));
   const uint32_t one = pos2(L);
   o.bits |= one << (7 - t);
   if (cw) {
@@ -289,10 +292,20 @@ B200_HD void win_emit(WinOut& o, LaneResult& res, const CrcPow* cw, int t, uint3
     res.crc_hi8x2 ^= (c.hi8x2 & mask);
   }
 }
+struct KeepInWinOut {
+  WinOut& o;
+  B200_HD void operator()(int t, uint32_t e) const { o.enew[t] = e; }
+};
+B200_HD void win_emit(WinOut& o, LaneResult& res, const CrcPow* cw, int t, uint32_t L, uint32_t e)
+{
+  win_emit(o, res, cw, t, L, e, KeepInWinOut{o});
+}
 
 // Warp F, phase 2.  A = alpha_{8w} on entry, alpha_{8w+8} on exit.  ck = beta_{8w+8} un-normalised; norm_ck = (8w+8 < K):
 // the recursion continues from the normalised value except at the very end of the block (turbodecoder_gen.c:105).
-B200_HD void fwd_window(uint32_t A[8], const uint32_t ck[8], bool norm_ck, const WinRegs& r, const CrcPow* cw, LaneResult& res, WinOut& o)
+template <class Sink>
+B200_HD void fwd_window(uint32_t A[8], const uint32_t ck[8], bool norm_ck, const WinRegs& r, const CrcPow* cw, LaneResult& res, WinOut& o,
+                        Sink&& sink)
 {
   // bw[t] is the vector the forward step at position 8w+t needs (beta_{8w+t+1})
   uint32_t bw[8][8];
@@ -312,13 +325,18 @@ B200_HD void fwd_window(uint32_t A[8], const uint32_t ck[8], bool norm_ck, const
   for (int t = 0; t < 8; t++) {
     const uint32_t L = llr_step<true>(A, bw[t], r.xs[t], r.ys[t], add2(r.xs[t], r.ys[t]));
     if ((t & 3) == 3) normalise(A); // forward index k = 8w+t+1 (turbodecoder_gen.c:186)
-    win_emit(o, res, cw, t, L, r.es[t]);
+    win_emit(o, res, cw, t, L, r.es[t], sink);
   }
+}
+B200_HD void fwd_window(uint32_t A[8], const uint32_t ck[8], bool norm_ck, const WinRegs& r, const CrcPow* cw, LaneResult& res, WinOut& o)
+{
+  fwd_window(A, ck, norm_ck, r, cw, res, o, KeepInWinOut{o});
 }
 
 // Warp B, phase 2.  U = beta_{8w+8} un-normalised on entry (8w+8 < K always: this warp works below the split),
 // beta_{8w} un-normalised on exit.  ack = alpha_{8w}.
-B200_HD void bwd_window(uint32_t U[8], const uint32_t ack[8], const WinRegs& r, const CrcPow* cw, LaneResult& res, WinOut& o)
+template <class Sink>
+B200_HD void bwd_window(uint32_t U[8], const uint32_t ack[8], const WinRegs& r, const CrcPow* cw, LaneResult& res, WinOut& o, Sink&& sink)
 {
   // aw[t] = alpha_{8w+t}, the vector the LLR of step 8w+t needs
   uint32_t aw[8][8];
@@ -339,8 +357,12 @@ B200_HD void bwd_window(uint32_t U[8], const uint32_t ack[8], const WinRegs& r, 
     const uint32_t L  = llr_step<false>(aw[t], U, r.xs[t], r.ys[t], xy);
     if ((t & 3) == 3) normalise(U); // U is beta_{8w+t+1}: a multiple of 4 (and < K)
     beta_step(U, r.xs[t], r.ys[t], xy);
-    win_emit(o, res, cw, t, L, r.es[t]);
+    win_emit(o, res, cw, t, L, r.es[t], sink);
   }
+}
+B200_HD void bwd_window(uint32_t U[8], const uint32_t ack[8], const WinRegs& r, const CrcPow* cw, LaneResult& res, WinOut& o)
+{
+  bwd_window(U, ack, r, cw, res, o, KeepInWinOut{o});
 }
 
 // ---- software-pipelined forms of the two phase-2 windows ----------------------------------------------------------
@@ -467,10 +489,10 @@ B200_HD void hb_store(uint16_t* dst, uint32_t bits, bool act_lo, bool act_hi)
   const uint16_t hb = hb_word(bits);
   if (act_lo && act_hi) {
     *dst = hb;
-  } else { // a block that already stopped keeps its decisions
-    const uint16_t old = *dst;
-    const uint16_t m   = (uint16_t)((act_lo ? 0x00FFu : 0u) | (act_hi ? 0xFF00u : 0u));
-    *dst               = (uint16_t)((hb & m) | (old & ~m));
+  } else { // a block that already stopped keeps its decisions: byte stores, nothing is read back
+    uint8_t* b = reinterpret_cast<uint8_t*>(dst); // little endian: byte 0 = low block
+    if (act_lo) b[0] = (uint8_t)(hb & 0xFFu);
+    if (act_hi) b[1] = (uint8_t)(hb >> 8);
   }
 }
 

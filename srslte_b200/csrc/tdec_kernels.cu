@@ -168,14 +168,15 @@ struct WarpRing {
     *reinterpret_cast<u4*>(tCK + (w * 1024u + l16))        = u4{c[0], c[1], c[2], c[3]};
     *reinterpret_cast<u4*>(tCK + (w * 1024u + 512u + l16)) = u4{c[4], c[5], c[6], c[7]};
   }
-  // new extrinsics + hard decisions of window w; q = its interleaver entries (DEC2)
-  __device__ __forceinline__ void store_out(uint32_t w, const u4& q, const WinOut& o, bool act_lo, bool act_hi) const
+  // where the new extrinsic of step t of window w goes; q = the window's interleaver entries (DEC2)
+  __device__ __forceinline__ uint32_t* e_out(uint32_t w, const u4& q, int t) const
   {
-#pragma unroll
-    for (int t = 0; t < 8; t++) {
-      *reinterpret_cast<uint32_t*>(tE + ((DEC2 ? win_pi(q, t) : 8u * w + (uint32_t)t) * 128u + l4)) = o.enew[t];
-    }
-    hb_store(reinterpret_cast<uint16_t*>(tHB + (w * 64u + (l4 >> 1))), o.bits, act_lo, act_hi);
+    return reinterpret_cast<uint32_t*>(tE + ((DEC2 ? win_pi(q, t) : 8u * w + (uint32_t)t) * 128u + l4));
+  }
+  // hard decisions of window w
+  __device__ __forceinline__ void store_hb(uint32_t w, uint32_t bits, bool act_lo, bool act_hi) const
+  {
+    hb_store(reinterpret_cast<uint16_t*>(tHB + (w * 64u + (l4 >> 1))), bits, act_lo, act_hi);
   }
 };
 
@@ -193,8 +194,7 @@ __device__ __forceinline__ void siso_pass_tile(const TdecView& v, int pass_idx, 
   const int warp = threadIdx.x >> 5;
   // whole tile finished (early stop): nothing to do.  Both warps read the same flags, so the exit is CTA-uniform.
   CbStatus*  stp  = v.status + ((size_t)tile * TDEC_TILE_CB + 2 * (size_t)lane);
-  CbStatus   s_lo = stp[0], s_hi = stp[1];
-  const bool act_lo = s_lo.active != 0, act_hi = s_hi.active != 0;
+  const bool act_lo = stp[0].active != 0, act_hi = stp[1].active != 0; // the records themselves are re-read at the end of the pass
   if (__ballot_sync(0xFFFFFFFFu, act_lo || act_hi) == 0u) return;
 
   using RG = WarpRing<DEC2, FIRST, IN8>;
@@ -292,8 +292,9 @@ __device__ __forceinline__ void siso_pass_tile(const TdecView& v, int pass_idx, 
       rg.read_ck(c, st);
       u4 q = {};
       if (DEC2) q = *reinterpret_cast<const u4*>(st + RG::L::OFF_QPP);
-      fwd_window(M, c, 8u * w + 8u < K, r, have_crc ? reinterpret_cast<const CrcPow*>(st + RG::L::OFF_CRC) : nullptr, res, o);
-      rg.store_out(w, q, o, act_lo, act_hi);
+      fwd_window(M, c, 8u * w + 8u < K, r, have_crc ? reinterpret_cast<const CrcPow*>(st + RG::L::OFF_CRC) : nullptr, res, o,
+                 [&](int t, uint32_t e) { *rg.e_out(w, q, t) = e; });
+      rg.store_hb(w, o.bits, act_lo, act_hi);
     });
   } else {
     // warp B, phase 2: windows ws-1..0 downwards
@@ -302,8 +303,9 @@ __device__ __forceinline__ void siso_pass_tile(const TdecView& v, int pass_idx, 
       rg.read_ck(c, st);
       u4 q = {};
       if (DEC2) q = *reinterpret_cast<const u4*>(st + RG::L::OFF_QPP);
-      bwd_window(M, c, r, have_crc ? reinterpret_cast<const CrcPow*>(st + RG::L::OFF_CRC) : nullptr, res, o);
-      rg.store_out(w, q, o, act_lo, act_hi);
+      bwd_window(M, c, r, have_crc ? reinterpret_cast<const CrcPow*>(st + RG::L::OFF_CRC) : nullptr, res, o,
+                 [&](int t, uint32_t e) { *rg.e_out(w, q, t) = e; });
+      rg.store_hb(w, o.bits, act_lo, act_hi);
     });
     xres[lane] = res;
   }
@@ -311,7 +313,7 @@ __device__ __forceinline__ void siso_pass_tile(const TdecView& v, int pass_idx, 
   if (warp == 0) {
     res.crc_lo16x2 ^= xres[lane].crc_lo16x2;
     res.crc_hi8x2 ^= xres[lane].crc_hi8x2;
-    finish_pass(v, stp, s_lo, s_hi, act_lo, act_hi, res, pass_idx);
+    finish_pass(v, stp, stp[0], stp[1], act_lo, act_hi, res, pass_idx);
   }
 }
 

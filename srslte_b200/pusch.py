@@ -159,11 +159,11 @@ class PuschChain:
             raise RuntimeError(f"srsran_b200_refsignal_dmrs_pusch_gen failed ({rc})")
         return r.reshape(2, self.M)
 
-    def chest(self, grid, tti, n_dmrs=None):
+    def chest(self, grid, tti, n_dmrs=None, out=None):
         t = self.torch
         nsf = grid.shape[0]
-        ce = t.empty((nsf, 2, self.M), dtype=t.complex64, device=self.dev)
-        meas = t.empty((nsf, 4), dtype=t.float32, device=self.dev)
+        ce, meas = out if out is not None else (t.empty((nsf, 2, self.M), dtype=t.complex64, device=self.dev),
+                                                t.empty((nsf, 4), dtype=t.float32, device=self.dev))
         k1, p1 = self._u32(tti, nsf)
         k2, p2 = self._u32(n_dmrs, nsf)
         rc = self._lib.srsran_b200_chest_ul_pusch_batch(self._h, grid.data_ptr(), nsf, p1, p2, ce.data_ptr(), meas.data_ptr(),
@@ -172,10 +172,10 @@ class PuschChain:
             raise RuntimeError(f"srsran_b200_chest_ul_pusch_batch failed ({rc})")
         return ce, meas
 
-    def equalize_deprecode(self, grid, ce, meas):
+    def equalize_deprecode(self, grid, ce, meas, out=None):
         t = self.torch
         nsf = grid.shape[0]
-        d = t.empty((nsf, self.nof_re), dtype=t.complex64, device=self.dev)
+        d = out if out is not None else t.empty((nsf, self.nof_re), dtype=t.complex64, device=self.dev)
         rc = self._lib.srsran_b200_pusch_equalize_deprecode_batch(self._h, grid.data_ptr(), ce.data_ptr(),
                                                                   meas.data_ptr() if meas is not None else None, d.data_ptr(), nsf,
                                                                   _lib.FLAG_DEVICE_PTRS, self._st())

@@ -19,6 +19,7 @@ int      orc_ofdm_rx(uint32_t nof_prb, int cp_ext, uint32_t symbol_sz, float fre
                      int keep_dc, const cf_t* in, cf_t* out, uint32_t nsf);
 uint32_t orc_crc24(int kind, const uint8_t* bytes, int nbits);
 int      orc_cbsegm(uint32_t tbs, uint32_t* out);
+int      orc_dft_precoding(const float _Complex* in, float _Complex* out, uint32_t nof_prb, uint32_t nof_symbols, int is_tx);
 
 static int fails = 0;
 #define CHECK(c, ...)                                                                                                  \
@@ -149,6 +150,37 @@ static void test_dft(int N, int backward)
   free(out);
 }
 
+static void test_dft_precoding(uint32_t nof_prb)
+{
+  srsran_dft_precoding_t tx, rx;
+  const int              N = 12 * (int)nof_prb, nsym = 12;
+  cf_t*                  in  = malloc(sizeof(cf_t) * N * nsym);
+  cf_t*                  mid = malloc(sizeof(cf_t) * N * nsym);
+  cf_t*                  out = malloc(sizeof(cf_t) * N * nsym);
+  for (int i = 0; i < N * nsym; i++) in[i] = gauss() + I * gauss();
+  CHECK(srsran_dft_precoding_init_tx(&tx, nof_prb) == 0 && srsran_dft_precoding_init_rx(&rx, nof_prb) == 0, "dft_precoding init");
+  CHECK(srsran_dft_precoding(&tx, in, mid, nof_prb, nsym) == 0, "dft_precoding tx");
+  CHECK(srsran_dft_precoding(&rx, mid, out, nof_prb, nsym) == 0, "dft_precoding rx");
+  /* forward transform against the oracle's restatement, and the round trip */
+  float _Complex* want = malloc(sizeof(float _Complex) * N * nsym);
+  orc_dft_precoding((const float _Complex*)in, want, nof_prb, nsym, 1);
+  double num = 0, den = 0, num2 = 0;
+  for (int i = 0; i < N * nsym; i++) {
+    num += pow(cabsf(mid[i] - want[i]), 2);
+    den += pow(cabsf(want[i]), 2);
+    num2 += pow(cabsf(out[i] - in[i]), 2);
+  }
+  CHECK(sqrt(num / den) < 1e-4 && sqrt(num2 / den) < 1e-4, "dft_precoding prb=%u rel err %g round trip %g", nof_prb, sqrt(num / den),
+        sqrt(num2 / den));
+  CHECK(srsran_dft_precoding(&rx, mid, out, 7, nsym) != 0, "dft_precoding must refuse 7 PRB");
+  srsran_dft_precoding_free(&tx);
+  srsran_dft_precoding_free(&rx);
+  free(in);
+  free(mid);
+  free(out);
+  free(want);
+}
+
 int main(void)
 {
   srand(1234);
@@ -188,6 +220,14 @@ int main(void)
   test_dft(128, 0);
   test_dft(1536, 1);
   test_dft(2048, 0);
+  test_dft(1200, 1);
+  test_dft(60, 0);
+  CHECK(srsran_dft_precoding_valid_prb(100) && srsran_dft_precoding_valid_prb(81) && !srsran_dft_precoding_valid_prb(7) &&
+            !srsran_dft_precoding_valid_prb(101) && srsran_dft_precoding_get_valid_prb(99) == 96,
+        "valid prb");
+  test_dft_precoding(6);
+  test_dft_precoding(25);
+  test_dft_precoding(100);
   printf(fails ? "compat_test: %d FAILURES\n" : "compat_test: all checks passed\n", fails);
   return fails ? 1 : 0;
 }
