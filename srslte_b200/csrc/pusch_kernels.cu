@@ -137,10 +137,13 @@ __global__ void __launch_bounds__(256) pusch_gold_kernel(const PuschSfParam* __r
 // at g[(j*nd + i)*Qm + k] (sch.c:660-681 with rows = M, cols = nd, no RI bits).  A block stages a tile of 64 subcarriers x nd
 // symbols in shared memory (coalesced row reads), then walks it in output order so the stores are contiguous.
 constexpr int DEMOD_TJ = 64;
-__global__ void __launch_bounds__(256) pusch_demod_descramble_kernel(int mod, const float2* __restrict__ d, const uint32_t* __restrict__ seq,
-                                                                     int16_t* __restrict__ g, uint32_t M, uint32_t nd, uint32_t nwords,
-                                                                     int shift, float qpsk_scale)
+template <int MOD, int ND> // srsran_mod_t 1..3; data symbols per subframe 12 (normal CP) or 10 (extended): constants, so no run-time divisions
+__global__ void __launch_bounds__(256) pusch_demod_descramble_kernel(const float2* __restrict__ d, const uint32_t* __restrict__ seq,
+                                                                     int16_t* __restrict__ g, uint32_t M, uint32_t nwords, int shift,
+                                                                     float qpsk_scale)
 {
+  constexpr int      mod = MOD;
+  constexpr uint32_t nd  = ND;
   __shared__ float2 tile[12][DEMOD_TJ];
   const uint32_t sf = blockIdx.y, j0 = blockIdx.x * DEMOD_TJ;
   const uint32_t per_sf = nd * M;
@@ -151,7 +154,7 @@ __global__ void __launch_bounds__(256) pusch_demod_descramble_kernel(int mod, co
   }
   __syncthreads();
   const uint32_t  body = 4u * (per_sf / 4u), fbody = 16u * (2u * per_sf / 16u);
-  const int       Qm   = 2 * mod;
+  constexpr int   Qm   = 2 * MOD;
   const uint32_t* sq   = seq + (size_t)sf * nwords;
   uint32_t*       dst  = reinterpret_cast<uint32_t*>(g + (size_t)sf * per_sf * Qm);
   for (uint32_t idx = threadIdx.x; idx < nd * DEMOD_TJ; idx += blockDim.x) {
@@ -436,8 +439,19 @@ struct PuschRx {
     g_kernel_launches++;
     B200_CUDA_TRY(cudaGetLastError());
     dim3 grid((unsigned)((M + DEMOD_TJ - 1) / DEMOD_TJ), nsf);
-    pusch_demod_descramble_kernel<<<grid, 256, 0, st>>>(cfg.modulation, d, d_seq, g, (uint32_t)M, (uint32_t)nd, nwords, (int)cfg.llr_shift,
-                                                       (float)(-100.0 * M_SQRT2));
+    const float qs = (float)(-100.0 * M_SQRT2);
+    const int   sh = (int)cfg.llr_shift;
+#define B200_DEMOD(MOD, ND) pusch_demod_descramble_kernel<MOD, ND><<<grid, 256, 0, st>>>(d, d_seq, g, (uint32_t)M, nwords, sh, qs)
+    if (nd == 12) {
+      if (cfg.modulation == 1) B200_DEMOD(1, 12);
+      else if (cfg.modulation == 2) B200_DEMOD(2, 12);
+      else B200_DEMOD(3, 12);
+    } else {
+      if (cfg.modulation == 1) B200_DEMOD(1, 10);
+      else if (cfg.modulation == 2) B200_DEMOD(2, 10);
+      else B200_DEMOD(3, 10);
+    }
+#undef B200_DEMOD
     g_kernel_launches++;
     B200_CUDA_TRY(cudaGetLastError());
     return B200_SUCCESS;
