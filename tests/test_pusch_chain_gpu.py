@@ -144,7 +144,9 @@ def test_unsupported_configurations_fail_cleanly():
 
 @pytest.mark.parametrize("kw,tbs", [(dict(cell_id=1, cell_nof_prb=100, L_prb=100, n_prb=0, mod=3), 75376),
                                     (dict(cell_id=150, cell_nof_prb=50, L_prb=24, n_prb=13, mod=2, cyclic_shift=3), 9912),
-                                    (dict(cell_id=7, cell_nof_prb=25, L_prb=10, n_prb=5, mod=1), 1544)])
+                                    (dict(cell_id=7, cell_nof_prb=25, L_prb=10, n_prb=5, mod=1), 1544),
+                                    (dict(cell_id=42, cell_nof_prb=15, L_prb=15, n_prb=0, mod=2, cp_ext=True, delta_ss=7), 4584),
+                                    (dict(cell_id=333, cell_nof_prb=75, L_prb=72, n_prb=2, mod=3, group_hopping=True), 46888)])
 def test_chain_against_the_reference_link(ref, port, kw, tbs):
     """Reference transmitter (srsran_pusch_encode + DMRS) -> flat fading + AWGN -> GPU chain, compared with the buffers of the
     reference receiver (chest + srsran_pusch_decode) and decoded down to the transport block."""
