@@ -365,99 +365,6 @@ B200_HD void bwd_window(uint32_t U[8], const uint32_t ack[8], const WinRegs& r, 
   bwd_window(U, ack, r, cw, res, o, KeepInWinOut{o});
 }
 
-// ---- software-pipelined forms of the two phase-2 windows ----------------------------------------------------------
-// A lone warp issues only ~0.3 instructions per clock through fwd_window / bwd_window: the packed add / add+max have a
-// long dependent-issue latency and every step hangs on the previous one.  The rebuild of the NEXT window's eight vectors
-// is independent of the LLR steps of the CURRENT window, so the two are interleaved step by step: twice the independent
-// work in flight per warp, same operations, same int16 values.  Vectors die (current window, step t) as fast as they are
-// born (next window, step 7-t), so the register footprint stays at about one window's worth.
-
-// rebuild only: bw[t] = beta_{8w+t+1} from ck = beta_{8w+8}
-B200_HD void rebuild_beta(uint32_t bw[8][8], const uint32_t ck[8], bool norm_ck, const WinRegs& r)
-{
-  uint32_t B[8];
-#pragma unroll
-  for (int i = 0; i < 8; i++) B[i] = bw[7][i] = ck[i];
-  if (norm_ck) normalise(B);
-#pragma unroll
-  for (int t = 7; t >= 1; t--) {
-    beta_step(B, r.xs[t], r.ys[t], add2(r.xs[t], r.ys[t]));
-#pragma unroll
-    for (int i = 0; i < 8; i++) bw[t - 1][i] = B[i];
-    if (t == 4) normalise(B);
-  }
-}
-
-// LLR steps of the current window (vectors bw, inputs r) + rebuild of the next window's vectors bn from ckn / rn
-template <bool HAVE_NEXT>
-B200_HD void fwd_window_pipe(uint32_t A[8], const uint32_t bw[8][8], const WinRegs& r, const CrcPow* cw, LaneResult& res, WinOut& o,
-                             uint32_t bn[8][8], const uint32_t ckn[8], bool norm_ckn, const WinRegs& rn)
-{
-  uint32_t B[8];
-  if (HAVE_NEXT) {
-#pragma unroll
-    for (int i = 0; i < 8; i++) B[i] = bn[7][i] = ckn[i];
-    if (norm_ckn) normalise(B);
-  }
-  o.bits = 0;
-#pragma unroll
-  for (int t = 0; t < 8; t++) {
-    const uint32_t L = llr_step<true>(A, const_cast<uint32_t*>(bw[t]), r.xs[t], r.ys[t], add2(r.xs[t], r.ys[t]));
-    if ((t & 3) == 3) normalise(A);
-    win_emit(o, res, cw, t, L, r.es[t]);
-    if (HAVE_NEXT && t < 7) {
-      const int tt = 7 - t;
-      beta_step(B, rn.xs[tt], rn.ys[tt], add2(rn.xs[tt], rn.ys[tt]));
-#pragma unroll
-      for (int i = 0; i < 8; i++) bn[tt - 1][i] = B[i];
-      if (tt == 4) normalise(B);
-    }
-  }
-}
-
-// rebuild only: aw[t] = alpha_{8w+t} from ack = alpha_{8w}
-B200_HD void rebuild_alpha(uint32_t aw[8][8], const uint32_t ack[8], const WinRegs& r)
-{
-  uint32_t A[8];
-#pragma unroll
-  for (int i = 0; i < 8; i++) A[i] = aw[0][i] = ack[i];
-#pragma unroll
-  for (int t = 0; t < 7; t++) {
-    alpha_update(A, r.xs[t], r.ys[t], add2(r.xs[t], r.ys[t]));
-    if (t == 3) normalise(A);
-#pragma unroll
-    for (int i = 0; i < 8; i++) aw[t + 1][i] = A[i];
-  }
-}
-
-// backward LLR steps of the current window (vectors aw, inputs r) + rebuild of the next (lower) window's alpha vectors
-template <bool HAVE_NEXT>
-B200_HD void bwd_window_pipe(uint32_t U[8], const uint32_t aw[8][8], const WinRegs& r, const CrcPow* cw, LaneResult& res, WinOut& o,
-                             uint32_t an[8][8], const uint32_t ackn[8], const WinRegs& rn)
-{
-  uint32_t A[8];
-  if (HAVE_NEXT) {
-#pragma unroll
-    for (int i = 0; i < 8; i++) A[i] = an[0][i] = ackn[i];
-  }
-  o.bits = 0;
-#pragma unroll
-  for (int t = 7; t >= 0; t--) {
-    const uint32_t xy = add2(r.xs[t], r.ys[t]);
-    const uint32_t L  = llr_step<false>(const_cast<uint32_t*>(aw[t]), U, r.xs[t], r.ys[t], xy);
-    if ((t & 3) == 3) normalise(U);
-    beta_step(U, r.xs[t], r.ys[t], xy);
-    win_emit(o, res, cw, t, L, r.es[t]);
-    if (HAVE_NEXT && t > 0) {
-      const int tt = 7 - t; // 0..6
-      alpha_update(A, rn.xs[tt], rn.ys[tt], add2(rn.xs[tt], rn.ys[tt]));
-      if (tt == 3) normalise(A);
-#pragma unroll
-      for (int i = 0; i < 8; i++) an[tt + 1][i] = A[i];
-    }
-  }
-}
-
 // Warp F, phase 1: 8 forward steps, no output
 B200_HD void alpha_window(uint32_t A[8], const WinRegs& r)
 {
@@ -582,7 +489,7 @@ B200_HD void beta_tail(uint32_t B[8], const u4& st, const u4& pt)
   }
 }
 
-template <bool DEC2, bool FIRST, bool IN8, bool PIPE = false>
+template <bool DEC2, bool FIRST, bool IN8>
 B200_HD void siso_pass_lane(const TdecView& v, int tile, int lane, int pass_idx)
 {
   CbStatus* st     = v.status + ((size_t)tile * TDEC_TILE_CB + 2 * (size_t)lane);
@@ -644,57 +551,20 @@ B200_HD void siso_pass_lane(const TdecView& v, int tile, int lane, int pass_idx)
   LaneResult res = {0u, 0u};
   WinOut     o;
   uint32_t   c[8];
-  if (!PIPE) {
-    for (int w = ws; w < nw; w++) {
-      load_window_direct<DEC2, FIRST, IN8>(v, tile, lane, w, r, pos);
-      ck_load(v, tile, lane, w, c);
-      fwd_window(A, c, 8 * w + 8 < K, r, cbase ? cbase + 8 * w : nullptr, res, o);
-      for (int t = 0; t < 8; t++) v.E[e_idx(v, tile, (int)pos[t], lane)] = o.enew[t];
-      hb_store(&v.HB[hb_idx(v, tile, w, lane)], o.bits, act_lo, act_hi);
-    }
-    // phase 2, warp B
-    for (int w = ws - 1; w >= 0; w--) {
-      load_window_direct<DEC2, FIRST, IN8>(v, tile, lane, w, r, pos);
-      ck_load(v, tile, lane, w, c);
-      bwd_window(B, c, r, cbase ? cbase + 8 * w : nullptr, res, o);
-      for (int t = 0; t < 8; t++) v.E[e_idx(v, tile, (int)pos[t], lane)] = o.enew[t];
-      hb_store(&v.HB[hb_idx(v, tile, w, lane)], o.bits, act_lo, act_hi);
-    }
-  } else {
-    // the software-pipelined forms the GPU kernel runs: LLR steps of window w interleaved with the rebuild of the next one
-    uint32_t vec[2][8][8];
-    WinRegs  rr[2];
-    uint32_t pp[2][8];
-    load_window_direct<DEC2, FIRST, IN8>(v, tile, lane, ws, rr[0], pp[0]);
-    ck_load(v, tile, lane, ws, c);
-    rebuild_beta(vec[0], c, 8 * ws + 8 < K, rr[0]);
-    for (int w = ws, i = 0; w < nw; w++, i ^= 1) {
-      const CrcPow* cw = cbase ? cbase + 8 * w : nullptr;
-      if (w + 1 < nw) {
-        load_window_direct<DEC2, FIRST, IN8>(v, tile, lane, w + 1, rr[i ^ 1], pp[i ^ 1]);
-        ck_load(v, tile, lane, w + 1, c);
-        fwd_window_pipe<true>(A, vec[i], rr[i], cw, res, o, vec[i ^ 1], c, 8 * (w + 1) + 8 < K, rr[i ^ 1]);
-      } else {
-        fwd_window_pipe<false>(A, vec[i], rr[i], cw, res, o, vec[i ^ 1], c, false, rr[i ^ 1]);
-      }
-      for (int t = 0; t < 8; t++) v.E[e_idx(v, tile, (int)pp[i][t], lane)] = o.enew[t];
-      hb_store(&v.HB[hb_idx(v, tile, w, lane)], o.bits, act_lo, act_hi);
-    }
-    load_window_direct<DEC2, FIRST, IN8>(v, tile, lane, ws - 1, rr[0], pp[0]);
-    ck_load(v, tile, lane, ws - 1, c);
-    rebuild_alpha(vec[0], c, rr[0]);
-    for (int w = ws - 1, i = 0; w >= 0; w--, i ^= 1) {
-      const CrcPow* cw = cbase ? cbase + 8 * w : nullptr;
-      if (w > 0) {
-        load_window_direct<DEC2, FIRST, IN8>(v, tile, lane, w - 1, rr[i ^ 1], pp[i ^ 1]);
-        ck_load(v, tile, lane, w - 1, c);
-        bwd_window_pipe<true>(B, vec[i], rr[i], cw, res, o, vec[i ^ 1], c, rr[i ^ 1]);
-      } else {
-        bwd_window_pipe<false>(B, vec[i], rr[i], cw, res, o, vec[i ^ 1], c, rr[i ^ 1]);
-      }
-      for (int t = 0; t < 8; t++) v.E[e_idx(v, tile, (int)pp[i][t], lane)] = o.enew[t];
-      hb_store(&v.HB[hb_idx(v, tile, w, lane)], o.bits, act_lo, act_hi);
-    }
+  for (int w = ws; w < nw; w++) {
+    load_window_direct<DEC2, FIRST, IN8>(v, tile, lane, w, r, pos);
+    ck_load(v, tile, lane, w, c);
+    fwd_window(A, c, 8 * w + 8 < K, r, cbase ? cbase + 8 * w : nullptr, res, o);
+    for (int t = 0; t < 8; t++) v.E[e_idx(v, tile, (int)pos[t], lane)] = o.enew[t];
+    hb_store(&v.HB[hb_idx(v, tile, w, lane)], o.bits, act_lo, act_hi);
+  }
+  // phase 2, warp B
+  for (int w = ws - 1; w >= 0; w--) {
+    load_window_direct<DEC2, FIRST, IN8>(v, tile, lane, w, r, pos);
+    ck_load(v, tile, lane, w, c);
+    bwd_window(B, c, r, cbase ? cbase + 8 * w : nullptr, res, o);
+    for (int t = 0; t < 8; t++) v.E[e_idx(v, tile, (int)pos[t], lane)] = o.enew[t];
+    hb_store(&v.HB[hb_idx(v, tile, w, lane)], o.bits, act_lo, act_hi);
   }
   finish_pass(v, st, s_lo, s_hi, act_lo, act_hi, res, pass_idx);
 }

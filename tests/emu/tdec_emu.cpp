@@ -17,7 +17,7 @@ extern "C" int emu_tdec_batch2(const int16_t* llr,
                                uint32_t       max_pass,
                                int            crc_kind, /* 0 = CRC24B, 1 = CRC24A, 2 = none */
                                int            early_stop,
-                               int            force_int16, /* bit 0: never use the int8 tile format; bit 1: software-pipelined phase 2 */
+                               int            force_int16, /* never use the int8 tile format */
                                int            split_percent,
                                uint8_t*       out,
                                uint8_t*       crc_ok,
@@ -52,7 +52,7 @@ extern "C" int emu_tdec_batch2(const int16_t* llr,
   const size_t nllr = 3 * (size_t)K + 12;
   std::vector<int16_t> zeros(nllr, 0);
   for (int tile = 0; tile < ntiles; tile++) {
-    bool fits = !(force_int16 & 1);
+    bool fits = !force_int16;
     for (uint32_t c = 0; c < TDEC_TILE_CB && fits; c++) {
       const uint32_t cb = (uint32_t)tile * TDEC_TILE_CB + c;
       if (cb >= ncb) break;
@@ -105,25 +105,26 @@ extern "C" int emu_tdec_batch2(const int16_t* llr,
       st[cb1] = CbStatus{(uint8_t)(cb1 < ncb), 0, 0, 0};
     }
   }
-  const bool pipe = (force_int16 & 2) != 0;
   for (uint32_t p = 0; p < max_pass; p++) {
     for (int tile = 0; tile < ntiles; tile++) {
       for (int lane = 0; lane < 32; lane++) {
-#define RUN(D2, F, I8)                                                          \
-  do {                                                                          \
-    if (pipe) siso_pass_lane<D2, F, I8, true>(v, tile, lane, (int)p);           \
-    else siso_pass_lane<D2, F, I8, false>(v, tile, lane, (int)p);               \
-  } while (0)
         if (fmt[tile] == 0) {
-          if (p == 0) RUN(false, true, true);
-          else if (p & 1) RUN(true, false, true);
-          else RUN(false, false, true);
+          if (p == 0) {
+            siso_pass_lane<false, true, true>(v, tile, lane, (int)p);
+          } else if (p & 1) {
+            siso_pass_lane<true, false, true>(v, tile, lane, (int)p);
+          } else {
+            siso_pass_lane<false, false, true>(v, tile, lane, (int)p);
+          }
         } else {
-          if (p == 0) RUN(false, true, false);
-          else if (p & 1) RUN(true, false, false);
-          else RUN(false, false, false);
+          if (p == 0) {
+            siso_pass_lane<false, true, false>(v, tile, lane, (int)p);
+          } else if (p & 1) {
+            siso_pass_lane<true, false, false>(v, tile, lane, (int)p);
+          } else {
+            siso_pass_lane<false, false, false>(v, tile, lane, (int)p);
+          }
         }
-#undef RUN
       }
     }
   }

@@ -26,14 +26,14 @@ def emu():
     return C.CDLL(so)
 
 
-def run_emu(emu, llr, K, max_pass, crc_kind, early, force16=False, split=47, pipe=True):
+def run_emu(emu, llr, K, max_pass, crc_kind, early, force16=False, split=47):
     ncb = llr.shape[0]
     out = np.zeros((ncb, K // 8), np.uint8)
     ok = np.zeros(ncb, np.uint8)
     nc = np.zeros(ncb, np.uint8)
     nr = np.zeros(ncb, np.uint8)
     p = lambda a: a.ctypes.data_as(C.c_void_p)
-    assert emu.emu_tdec_batch2(p(llr), ncb, K, max_pass, crc_kind, int(early), int(force16) | (2 if pipe else 0), split, p(out), p(ok), p(nc), p(nr)) == 0
+    assert emu.emu_tdec_batch2(p(llr), ncb, K, max_pass, crc_kind, int(early), int(force16), split, p(out), p(ok), p(nc), p(nr)) == 0
     return out, ok, nc, nr
 
 
@@ -45,8 +45,8 @@ def test_emulated_kernels_match_oracle(emu, port, K, ncb, sigma, scale, clip):
     for early in (True, False):
         for mp in (8, 5, 1):
             o1, k1, n1, _ = port.decode_batch(llr, K, mp, "B", 0, early)
-            for force16, split, pipe in ((False, 47, True), (True, 47, True), (False, 1, True), (True, 99, True), (False, 47, False)):
-                o2, k2, nc, nr = run_emu(emu, llr, K, mp, 0, early, force16, split, pipe)
+            for force16, split in ((False, 47), (True, 47), (False, 1), (True, 99)):
+                o2, k2, nc, nr = run_emu(emu, llr, K, mp, 0, early, force16, split)
                 assert (o1 == o2).all(), (early, mp, force16, split)
                 assert (k1 == k2).all() and (n1 == npass_of(k2, nc, nr)).all(), (early, mp, force16, split)
 
