@@ -254,6 +254,26 @@ def run_ours(args):
     barrier()
     ms_e2e = max_over_ranks((time.perf_counter() - t0) * 1e3) / n_e2e
     e2e_val = world * ncb * K / (ms_e2e * 1e-3) / 1e9
+    # the same call with the LLRs in the reference's 8-bit soft-bit container (SRSRAN_B200_FLAG_LLR_INT8): identical values
+    # (|LLR| <= 31 here), identical int16 arithmetic after widening on the device, half the PCIe bytes.  Reported beside e2e.
+    h_llr8 = torch.empty((ncb, 3 * K + 12), dtype=torch.int8, pin_memory=True)
+    h_llr8.copy_(llr.to(torch.int8))
+    h_out8 = torch.empty((ncb, K // 8), dtype=torch.uint8, pin_memory=True)
+    torch.cuda.synchronize()
+
+    def step_e2e8():
+        dec.decode_pinned(h_llr8.data_ptr(), ncb, K, h_out8.data_ptr(), h_ok.data_ptr(), h_np.data_ptr(), MAX_PASSES, "B", False,
+                          llr_int8=True)
+
+    step_e2e8()
+    same8 = bool((h_out8 == h_out).all().item())
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(n_e2e):
+        step_e2e8()
+    barrier()
+    ms_e2e8 = max_over_ranks((time.perf_counter() - t0) * 1e3) / n_e2e
+    del h_llr8
     e2e_match = bool((h_out.to(dev) == out).all().item()) if False else None  # (out now holds the early-stop decode)
 
     # ---- roofline of the dominant kernel (tdec_siso_pass_kernel) -----------------------------------------------
@@ -270,6 +290,17 @@ def run_ours(args):
                 "avg_launch_ms": siso_ms, "launches_timed": prof["siso_launches"],
                 "algorithmic_bytes_per_launch": ncb * alg_per_cb,
                 "share_of_step": prof["siso_ms"] / max(1e-9, prof["total_ms"])}
+    # Second ceiling: the decoder's integer work against the packed-int16 issue peak.  Literal operation count of the
+    # reference's generic SISO (turbodecoder_gen.c: beta 2+12+8+7/4, alpha 2+12+16+14+8+1+7/4) = 78.5 int16 ops per trellis step
+    # and pass; one packed instruction lane carries two code blocks.  Peak = 127 lanes/clk/SM measured for VIADD.16x2 +
+    # VIADDMNMX.S16x2 issued together (tools/ubench_int16.cu, profiles/r01_int16_issue.txt) x SMs x the SM clock under load.
+    sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+    sm_hz = (clocks or {}).get("sm_mhz") or 1965.0
+    alu_peak = 127.0 * sm_count * sm_hz * 1e6
+    alu_ach = ncb * K * 78.5 / 2.0 / (siso_ms * 1e-3) if siso_ms > 0 else 0.0
+    roofline_alu = {"bound": "packed-int16 issue", "kernel": "tdec_siso_pass_kernel", "achieved": alu_ach / 1e12, "peak": alu_peak / 1e12,
+                    "unit": "T lane-ops/s", "frac": alu_ach / alu_peak,
+                    "note": "78.5 int16 ops per trellis step and pass (reference's literal count) / 2 blocks per lane; peak 127 lanes/clk/SM measured"}
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
@@ -332,7 +363,10 @@ def run_ours(args):
         "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(ncb * (3 * K + 12) * 2),
                 "d2h_bytes_per_step": int(ncb * (K // 8 + 2)), "ms_per_step": ms_e2e, "steps": n_e2e,
                 "note": "host pinned LLRs in, bits+crc+passes out, chunk-pipelined; bounded by PCIe (6 B per info bit)"},
-        "roofline": roofline, "cpu_baseline": cpu,
+        "e2e_int8_container": {"value": world * ncb * K / (ms_e2e8 * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms_e2e8,
+                               "h2d_bytes_per_step": int(ncb * (3 * K + 12)), "same_bytes_out_as_int16_call": same8,
+                               "note": "same LLR values handed over as int8 (the reference's 8-bit soft-bit container), widened on the device"},
+        "roofline": roofline, "roofline_int16_alu": roofline_alu, "cpu_baseline": cpu,
         "early_stop": {"value": world * ncb * K / (ms_es * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms_es, "mean_passes": mean_pass,
                        "crc_ok_fraction": frac_ok, "ebn0_db": EBN0_DB},
         "checks": {"crc_ok_fraction_fixed8": frac_ok_fixed, "crc_ok_blocks_equal_transmitted_bits": ber_ok},

@@ -31,6 +31,10 @@ extern "C" {
 /* flags */
 #define SRSRAN_B200_FLAG_DEVICE_PTRS 0x1u    /* data pointers are device memory on the object's GPU (else host memory) */
 #define SRSRAN_B200_FLAG_SOFT_ON_DEVICE 0x2u /* only the HARQ soft-buffer pool is device memory (stays resident) */
+#define SRSRAN_B200_FLAG_LLR_INT8 0x4u       /* srsran_b200_tdec_run: `llr` points to int8_t values (the reference's 8-bit soft-bit
+                                                container, rm_turbo.h:80 / demod_soft.h srsran_demod_soft_demodulate_b); they are
+                                                widened to int16 on the device and decoded with the SAME int16 arithmetic, so the
+                                                result equals the int16 entry on the widened values.  Halves the PCIe bytes. */
 
 /* int16 values per code block in a soft-buffer pool: SOFTBUFFER_SIZE of lib/include/srsran/phy/fec/softbuffer.h:56 */
 #define SRSRAN_B200_SOFTBUFFER_SIZE 18600

@@ -248,21 +248,30 @@ int TdecEngine::run(const int16_t* llr,
   }
   B200_CUDA_TRY(cudaSetDevice(ctx->device));
 
+  const bool   llr8 = (flags & SRSRAN_B200_FLAG_LLR_INT8) != 0;
+  const size_t nllr = 3 * (size_t)K + 12;
   if (flags & SRSRAN_B200_FLAG_DEVICE_PTRS) {
     if (arena.reserve(workspace_bytes((int)K, ncb)) != B200_SUCCESS) {
       return B200_ERROR;
+    }
+    if (llr8) { // widen into a scratch vector first (one extra pass over 3 bytes per value, ~6 % of an 8-pass decode)
+      if (pipe_io[0].reserve((size_t)ncb * nllr * sizeof(int16_t) + 1024) != B200_SUCCESS) return B200_ERROR;
+      pipe_io[0].reset();
+      int16_t* wide = (int16_t*)pipe_io[0].take((size_t)ncb * nllr * sizeof(int16_t));
+      launch_widen_i8(reinterpret_cast<const int8_t*>(llr), wide, (size_t)ncb * nllr, stream);
+      g_kernel_launches++;
+      return run_device(arena, wide, ncb, (int)K, cb_idx, max_passes, crc_kind, early_stop, out, crc_ok, npass, stream);
     }
     return run_device(arena, llr, ncb, (int)K, cb_idx, max_passes, crc_kind, early_stop, out, crc_ok, npass, stream);
   }
 
   // Host pointers: cut the batch into chunks and ping-pong two streams so the copy of chunk c+1 overlaps the decode
   // of chunk c.  6 input bytes per info bit cross PCIe here, which is what bounds this path.
-  const size_t   nllr  = 3 * (size_t)K + 12;
   const size_t   nb    = K / 8;
   const uint32_t chunk = ncb < 2 * kPipeChunkCb ? (ncb + 1) / 2 : kPipeChunkCb;
   for (int i = 0; i < 2; i++) {
     if (pipe_arena[i].reserve(workspace_bytes((int)K, chunk)) != B200_SUCCESS ||
-        pipe_io[i].reserve(chunk * (nllr * sizeof(int16_t) + nb + 2) + 1024) != B200_SUCCESS) {
+        pipe_io[i].reserve(chunk * (nllr * (sizeof(int16_t) + (llr8 ? 1 : 0)) + nb + 2) + 2048) != B200_SUCCESS) {
       return B200_ERROR;
     }
   }
@@ -279,7 +288,14 @@ int TdecEngine::run(const int16_t* llr,
     uint8_t* d_out = (uint8_t*)pipe_io[s].take(n * nb);
     uint8_t* d_ok  = (uint8_t*)pipe_io[s].take(n);
     uint8_t* d_np  = (uint8_t*)pipe_io[s].take(n);
-    B200_CUDA_TRY(cudaMemcpyAsync(d_llr, llr + first * nllr, n * nllr * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+    if (llr8) {
+      int8_t* d_llr8 = (int8_t*)pipe_io[s].take(n * nllr);
+      B200_CUDA_TRY(cudaMemcpyAsync(d_llr8, reinterpret_cast<const int8_t*>(llr) + first * nllr, n * nllr, cudaMemcpyHostToDevice, st));
+      launch_widen_i8(d_llr8, d_llr, (size_t)n * nllr, st);
+      g_kernel_launches++;
+    } else {
+      B200_CUDA_TRY(cudaMemcpyAsync(d_llr, llr + first * nllr, n * nllr * sizeof(int16_t), cudaMemcpyHostToDevice, st));
+    }
     rc = run_device(pipe_arena[s], d_llr, n, (int)K, cb_idx, max_passes, crc_kind, early_stop, d_out, d_ok, d_np, st);
     if (rc != B200_SUCCESS) break;
     B200_CUDA_TRY(cudaMemcpyAsync(out + first * nb, d_out, n * nb, cudaMemcpyDeviceToHost, st));

@@ -708,4 +708,39 @@ void launch_decide(const TdecView& v,
   tdec_decide_kernel<<<(unsigned)v.ntiles, 256, smem, stream>>>(v, qpp_rev_dev, out_dev, crc_ok_dev, npass_dev, npass_run_dev, ncb);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// int8 container -> int16.  16 values per thread and step when both pointers allow 16-byte accesses.
+__global__ void __launch_bounds__(256) tdec_widen_i8_kernel(const int8_t* __restrict__ in, int16_t* __restrict__ out, size_t n)
+{
+  const size_t stride = (size_t)gridDim.x * blockDim.x, t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15u) == 0) {
+    const size_t nv = n / 16;
+    for (size_t i = t0; i < nv; i += stride) {
+      const uint4 q = __ldcs(reinterpret_cast<const uint4*>(in) + i);
+      const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+      uint32_t       o[8];
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        o[2 * k]     = sext8x2(w[k], 0);
+        o[2 * k + 1] = sext8x2(w[k], 1);
+      }
+      uint4* dst = reinterpret_cast<uint4*>(out) + 2 * i;
+      __stcs(dst, make_uint4(o[0], o[1], o[2], o[3]));
+      __stcs(dst + 1, make_uint4(o[4], o[5], o[6], o[7]));
+    }
+    for (size_t i = nv * 16 + t0; i < n; i += stride) out[i] = (int16_t)in[i];
+  } else {
+    for (size_t i = t0; i < n; i += stride) out[i] = (int16_t)in[i];
+  }
+}
+
+void launch_widen_i8(const int8_t* in, int16_t* out, size_t n, cudaStream_t stream)
+{
+  if (n == 0) return;
+  size_t blocks = (n / 16 + 255) / 256;
+  if (blocks < 1) blocks = 1;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  tdec_widen_i8_kernel<<<(unsigned)blocks, 256, 0, stream>>>(in, out, n);
+}
+
 } // namespace b200

@@ -24,4 +24,7 @@ void launch_decide(const TdecView& v,
                    uint32_t        ncb,
                    cudaStream_t    stream);
 
+// int8 LLR container -> int16 (sign extension), n values
+void launch_widen_i8(const int8_t* in, int16_t* out, size_t n, cudaStream_t stream);
+
 } // namespace b200

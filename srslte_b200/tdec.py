@@ -64,10 +64,11 @@ class TurboDecoderBatch:
         return out, ok, npass
 
     def decode_pinned(self, llr_ptr: int, ncb: int, K: int, out_ptr: int, ok_ptr: int, npass_ptr: int,
-                      max_passes: int = 8, crc: str | None = "B", early_stop: bool = True):
-        """Host path on raw (pinned) host pointers, for the end-to-end benchmark."""
+                      max_passes: int = 8, crc: str | None = "B", early_stop: bool = True, llr_int8: bool = False):
+        """Host path on raw (pinned) host pointers, for the end-to-end benchmark.  llr_int8: the buffer holds int8 values
+        (SRSRAN_B200_FLAG_LLR_INT8), decoded with the same int16 arithmetic after widening on the device."""
         rc = self._lib.srsran_b200_tdec_run(self._h, llr_ptr, ncb, K, max_passes, _CRC[crc], int(early_stop),
-                                            out_ptr, ok_ptr, npass_ptr, 0, None)
+                                            out_ptr, ok_ptr, npass_ptr, _lib.FLAG_LLR_INT8 if llr_int8 else 0, None)
         if rc != _lib.SUCCESS:
             raise RuntimeError(f"srsran_b200_tdec_run failed ({rc})")
 
@@ -83,7 +84,7 @@ class TurboDecoderBatch:
         rc = self._lib.srsran_b200_tdec_run(self._h, llr.data_ptr(), ncb, K, max_passes, _CRC[crc], int(early_stop),
                                             out.data_ptr(), ok.data_ptr() if ok is not None else None,
                                             npass.data_ptr() if npass is not None else None,
-                                            _lib.FLAG_DEVICE_PTRS, stream_ptr)
+                                            _lib.FLAG_DEVICE_PTRS | (_lib.FLAG_LLR_INT8 if llr.dtype == torch.int8 else 0), stream_ptr)
         if rc != _lib.SUCCESS:
             raise RuntimeError(f"srsran_b200_tdec_run failed ({rc})")
 

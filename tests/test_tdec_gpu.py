@@ -136,3 +136,33 @@ def test_mixed_int8_and_int16_tiles_in_one_batch(dec, port):
         o1, k1, n1, _ = port.decode_batch(llr, K, 6, "B", 0, early, nthreads=8)
         o2, k2, n2 = dec.decode(llr, K, 6, "B", early)
         assert (o1 == o2).all() and (k1 == k2).all() and (n1 == n2).all(), early
+
+
+def test_int8_llr_container_decodes_like_int16(dec, port):
+    """SRSRAN_B200_FLAG_LLR_INT8: the same values in an int8 buffer (host and device path) give the int16 entry's results."""
+    import ctypes as C
+
+    import torch
+
+    from srslte_b200 import _lib
+    from helpers import coded_llrs
+
+    for K, ncb in ((6144, 70), (40, 129), (1008, 65)):
+        llr, _ = coded_llrs(port, K, ncb, 0.9, 16.0, 31, seed=K)
+        assert np.abs(llr).max() <= 127
+        want = dec.decode(llr, K, 8, "B", True)
+        l8 = np.ascontiguousarray(llr.astype(np.int8))
+        out = np.zeros((ncb, K // 8), np.uint8)
+        ok = np.zeros(ncb, np.uint8)
+        npass = np.zeros(ncb, np.uint8)
+        rc = dec._lib.srsran_b200_tdec_run(dec._h, l8.ctypes.data, ncb, K, 8, _lib.CRC24B, 1, out.ctypes.data, ok.ctypes.data,
+                                           npass.ctypes.data, _lib.FLAG_LLR_INT8, None)
+        assert rc == 0
+        assert (out == want[0]).all() and (ok == want[1]).all() and (npass == want[2]).all()
+        d8 = torch.from_numpy(l8).cuda()
+        o = torch.empty((ncb, K // 8), dtype=torch.uint8, device="cuda")
+        k = torch.empty(ncb, dtype=torch.uint8, device="cuda")
+        n = torch.empty(ncb, dtype=torch.uint8, device="cuda")
+        dec.decode_device(d8, K, o, k, n, 8, "B", True)
+        torch.cuda.synchronize()
+        assert (o.cpu().numpy() == want[0]).all() and (k.cpu().numpy() == want[1]).all() and (n.cpu().numpy() == want[2]).all()
