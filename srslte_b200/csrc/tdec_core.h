@@ -277,12 +277,13 @@ struct WinOut {
   uint32_t bits;    // decisions (turbodecoder_gen.c:266: LLR > 0 -> 1): bit 7-t = step t, low block in bits 0..7, high in 16..23
 };
 
-// sink(t, e_new) receives the new extrinsic of step t: the GPU kernel stores it straight away (the value dies at once
-// instead of occupying a register until the end of the window), the plain overload below keeps it in o.enew[]
+// sink(t, L) receives the a-posteriori LLR of step t and disposes of the new extrinsic L - e (turbodecoder_iter.h:108,118-127):
+// the GPU kernel re-reads e from its shared-memory stage and stores the difference straight away, so that neither e nor the
+// result occupies a register beyond the step; the plain overloads below keep both in WinRegs / WinOut.
 template <class Sink>
-B200_HD void win_emit(WinOut& o, LaneResult& res, const CrcPow* cw, int t, uint32_t L, uint32_t e, Sink&& sink)
+B200_HD void win_emit(WinOut& o, LaneResult& res, const CrcPow* cw, int t, uint32_t L, Sink&& sink)
 {
-  sink(t, sub2(L, e));
+  sink(t, L);
   const uint32_t one = pos2(L);
   o.bits |= one << (7 - t);
   if (cw) {
@@ -293,13 +294,10 @@ B200_HD void win_emit(WinOut& o, LaneResult& res, const CrcPow* cw, int t, uint3
   }
 }
 struct KeepInWinOut {
-  WinOut& o;
-  B200_HD void operator()(int t, uint32_t e) const { o.enew[t] = e; }
+  WinOut&        o;
+  const WinRegs& r;
+  B200_HD void   operator()(int t, uint32_t L) const { o.enew[t] = sub2(L, r.es[t]); }
 };
-B200_HD void win_emit(WinOut& o, LaneResult& res, const CrcPow* cw, int t, uint32_t L, uint32_t e)
-{
-  win_emit(o, res, cw, t, L, e, KeepInWinOut{o});
-}
 
 // Warp F, phase 2.  A = alpha_{8w} on entry, alpha_{8w+8} on exit.  ck = beta_{8w+8} un-normalised; norm_ck = (8w+8 < K):
 // the recursion continues from the normalised value except at the very end of the block (turbodecoder_gen.c:105).
@@ -325,12 +323,12 @@ B200_HD void fwd_window(uint32_t A[8], const uint32_t ck[8], bool norm_ck, const
   for (int t = 0; t < 8; t++) {
     const uint32_t L = llr_step<true>(A, bw[t], r.xs[t], r.ys[t], add2(r.xs[t], r.ys[t]));
     if ((t & 3) == 3) normalise(A); // forward index k = 8w+t+1 (turbodecoder_gen.c:186)
-    win_emit(o, res, cw, t, L, r.es[t], sink);
+    win_emit(o, res, cw, t, L, sink);
   }
 }
 B200_HD void fwd_window(uint32_t A[8], const uint32_t ck[8], bool norm_ck, const WinRegs& r, const CrcPow* cw, LaneResult& res, WinOut& o)
 {
-  fwd_window(A, ck, norm_ck, r, cw, res, o, KeepInWinOut{o});
+  fwd_window(A, ck, norm_ck, r, cw, res, o, KeepInWinOut{o, r});
 }
 
 // Warp B, phase 2.  U = beta_{8w+8} un-normalised on entry (8w+8 < K always: this warp works below the split),
@@ -357,12 +355,12 @@ B200_HD void bwd_window(uint32_t U[8], const uint32_t ack[8], const WinRegs& r, 
     const uint32_t L  = llr_step<false>(aw[t], U, r.xs[t], r.ys[t], xy);
     if ((t & 3) == 3) normalise(U); // U is beta_{8w+t+1}: a multiple of 4 (and < K)
     beta_step(U, r.xs[t], r.ys[t], xy);
-    win_emit(o, res, cw, t, L, r.es[t], sink);
+    win_emit(o, res, cw, t, L, sink);
   }
 }
 B200_HD void bwd_window(uint32_t U[8], const uint32_t ack[8], const WinRegs& r, const CrcPow* cw, LaneResult& res, WinOut& o)
 {
-  bwd_window(U, ack, r, cw, res, o, KeepInWinOut{o});
+  bwd_window(U, ack, r, cw, res, o, KeepInWinOut{o, r});
 }
 
 // Warp F, phase 1: 8 forward steps, no output

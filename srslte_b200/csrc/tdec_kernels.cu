@@ -168,6 +168,17 @@ struct WarpRing {
     *reinterpret_cast<u4*>(tCK + (w * 1024u + l16))        = u4{c[0], c[1], c[2], c[3]};
     *reinterpret_cast<u4*>(tCK + (w * 1024u + 512u + l16)) = u4{c[4], c[5], c[6], c[7]};
   }
+  // what is subtracted from the LLR of step t to form the new extrinsic (turbodecoder_iter.h:108,118): nothing on the first pass,
+  // DEC2 its systematic input (already in a register), DEC1 the a-priori value, re-read from the stage
+  __device__ __forceinline__ uint32_t e_in(const uint8_t* st, const WinRegs& r, int t) const
+  {
+    if (FIRST) return 0u;
+    if (DEC2) return r.xs[t];
+    // volatile: keep the load at the step that consumes it (hoisted to the top of the window it would pin 8 registers)
+    uint32_t e;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(e) : "r"(smem_u32(st) + L::OFF_E + (uint32_t)t * 128u + l4));
+    return e;
+  }
   // where the new extrinsic of step t of window w goes; q = the window's interleaver entries (DEC2)
   __device__ __forceinline__ uint32_t* e_out(uint32_t w, const u4& q, int t) const
   {
@@ -293,7 +304,7 @@ __device__ __forceinline__ void siso_pass_tile(const TdecView& v, int pass_idx, 
       u4 q = {};
       if (DEC2) q = *reinterpret_cast<const u4*>(st + RG::L::OFF_QPP);
       fwd_window(M, c, 8u * w + 8u < K, r, have_crc ? reinterpret_cast<const CrcPow*>(st + RG::L::OFF_CRC) : nullptr, res, o,
-                 [&](int t, uint32_t e) { *rg.e_out(w, q, t) = e; });
+                 [&](int t, uint32_t L) { *rg.e_out(w, q, t) = sub2(L, rg.e_in(st, r, t)); });
       rg.store_hb(w, o.bits, act_lo, act_hi);
     });
   } else {
@@ -304,7 +315,7 @@ __device__ __forceinline__ void siso_pass_tile(const TdecView& v, int pass_idx, 
       u4 q = {};
       if (DEC2) q = *reinterpret_cast<const u4*>(st + RG::L::OFF_QPP);
       bwd_window(M, c, r, have_crc ? reinterpret_cast<const CrcPow*>(st + RG::L::OFF_CRC) : nullptr, res, o,
-                 [&](int t, uint32_t e) { *rg.e_out(w, q, t) = e; });
+                 [&](int t, uint32_t L) { *rg.e_out(w, q, t) = sub2(L, rg.e_in(st, r, t)); });
       rg.store_hb(w, o.bits, act_lo, act_hi);
     });
     xres[lane] = res;
