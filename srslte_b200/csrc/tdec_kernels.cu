@@ -592,6 +592,137 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Streaming form of tdec_load8_kernel for 8-byte aligned block vectors (the common case): a CTA owns (tile, segment of
+// consecutive 64-row chunks) and double-buffers the chunks with cp.async, so the global-memory latency of chunk c+1 is
+// hidden behind the packing of chunk c (the one-chunk-per-CTA kernel above spends 2/3 of its time waiting on its loads:
+// profiles/README.md).  Staging layout: block c of the tile at row (c & 1) * 32 + (c >> 1), 400 bytes per row, so that a lane
+// finds its two blocks at rows lane and lane + 32 and the 16-byte reads of a quarter warp fall into 32 different banks.
+constexpr int    LS_PITCH  = 400;                               // bytes per staged block row (384 used)
+constexpr size_t LS_BUF    = (size_t)TDEC_TILE_CB * LS_PITCH;   // one chunk of a tile
+constexpr size_t LS_SMEM   = 2 * LS_BUF + TDEC_TILE_CB * sizeof(uint64_t);
+constexpr int    LS_CHUNKS = 12;                                // chunks per CTA (K=6144: 96 chunks -> 8 segments per tile)
+
+__device__ __forceinline__ void cp_async8_raw(uint32_t dst, const void* src)
+{
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(__cvta_generic_to_global(src)) : "memory");
+}
+
+__global__ void __launch_bounds__(256)
+    tdec_load8_stream_kernel(TdecView v, const int16_t* __restrict__ llr, const uint64_t* __restrict__ offsets, uint32_t ncb)
+{
+  extern __shared__ __align__(16) uint8_t sm[];
+  const uint8_t** sbase = reinterpret_cast<const uint8_t**>(sm + 2 * LS_BUF); // byte address of every block's vector
+  const int    tile = blockIdx.y, seg = blockIdx.x;
+  const int    K    = v.K;
+  const size_t nllr = 3 * (size_t)K + 12;
+  const int    tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int    nchunk = (K + LOAD_ROWS - 1) / LOAD_ROWS;
+  const int    c_lo = seg * LS_CHUNKS, c_hi = min(nchunk, c_lo + LS_CHUNKS);
+  if (tid < TDEC_TILE_CB) {
+    const uint32_t cb = (uint32_t)tile * TDEC_TILE_CB + tid;
+    sbase[tid]        = cb < ncb ? reinterpret_cast<const uint8_t*>(llr + (offsets ? offsets[cb] : cb * nllr)) : nullptr;
+  }
+  // rows of blocks past the end of the batch stay zero in both buffers
+  for (int i = tid; i < (int)(2 * LS_BUF / 16); i += 256) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0u, 0u, 0u, 0u);
+  __syncthreads();
+  const uint32_t sm_u32 = smem_u32(sm);
+
+  // warp w stages blocks w, w+8, ..., w+56; lane q takes the 8-byte pieces q and q+32 of the block's chunk (48 per full chunk)
+  auto prefetch = [&](int chunk, int buf) {
+    const int k0   = chunk * LOAD_ROWS;
+    const int nvec = min(LOAD_ROWS, K - k0) * 3 / 4;
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const int      c   = wid + 8 * u;
+      const uint8_t* src = sbase[c];
+      if (src != nullptr) {
+        const uint32_t dst = sm_u32 + (uint32_t)buf * (uint32_t)LS_BUF + (uint32_t)(((c & 1) * 32 + (c >> 1)) * LS_PITCH);
+        src += 6 * (size_t)k0;
+        if (lane < nvec) cp_async8_raw(dst + 8u * lane, src + 8 * lane);
+        if (lane + 32 < nvec) cp_async8_raw(dst + 8u * (lane + 32), src + 8 * (lane + 32));
+      }
+    }
+    cp_commit();
+  };
+
+  uint32_t acc = 0; // v ^ (v << 1) has bits 15..8 clear <=> v fits int8 (per int16 half)
+  if (c_lo < c_hi) prefetch(c_lo, 0);
+  for (int chunk = c_lo; chunk < c_hi; chunk++) {
+    const int buf = (chunk - c_lo) & 1;
+    cp_wait<0>();
+    __syncthreads(); // this chunk has landed; everybody is done with the other buffer
+    if (chunk + 1 < c_hi) prefetch(chunk + 1, buf ^ 1);
+    const int      k0   = chunk * LOAD_ROWS;
+    const int      rows = min(LOAD_ROWS, K - k0); // multiple of 8
+    const uint8_t* bsm  = sm + (size_t)buf * LS_BUF;
+    // warp = window of the chunk; a lane reads the 48 bytes of its two blocks, pairs and packs them with byte permutes and
+    // writes its 16 bytes of each int8 tile row
+    for (int w8 = wid; w8 < rows / 8; w8 += 8) {
+      uint32_t a[12], b[12];
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        const uint4 x = *reinterpret_cast<const uint4*>(bsm + lane * LS_PITCH + w8 * 48 + 16 * j);
+        const uint4 y = *reinterpret_cast<const uint4*>(bsm + (lane + 32) * LS_PITCH + w8 * 48 + 16 * j);
+        a[4 * j] = x.x; a[4 * j + 1] = x.y; a[4 * j + 2] = x.z; a[4 * j + 3] = x.w;
+        b[4 * j] = y.x; b[4 * j + 1] = y.y; b[4 * j + 2] = y.z; b[4 * j + 3] = y.w;
+      }
+#pragma unroll
+      for (int j = 0; j < 12; j++) acc |= (a[j] ^ (a[j] << 1)) | (b[j] ^ (b[j] << 1));
+#pragma unroll
+      for (int s_ = 0; s_ < 3; s_++) {
+        uint32_t w[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          // rows 2q, 2q+1 of stream s_: value index i = 3*row + s_ inside the window's 24 values of a block
+          const int      i0 = 3 * (2 * q) + s_, i1 = 3 * (2 * q + 1) + s_;
+          const uint32_t p0 = __byte_perm(a[i0 >> 1], b[i0 >> 1], (i0 & 1) ? 0x7632 : 0x5410); // (a, b) as an int16 pair
+          const uint32_t p1 = __byte_perm(a[i1 >> 1], b[i1 >> 1], (i1 & 1) ? 0x7632 : 0x5410);
+          w[q]              = __byte_perm(p0, p1, 0x6420);                                     // their low bytes
+        }
+        u4* dst = s_ == 0 ? v.S8 : (s_ == 1 ? v.P08 : v.P18);
+        dst[row8(v, tile, k0 / 8 + w8, lane)] = u4{w[0], w[1], w[2], w[3]};
+      }
+    }
+  }
+  if (__syncthreads_or((acc & 0xFF00FF00u) != 0u) && tid == 0) atomicOr(v.fmt + tile, 1u);
+
+  // the last segment also writes the tail row (the 12 tail values: row K/8 of S8/P08/P18 and S2T) and arms the block state
+  if (seg == (int)gridDim.x - 1 && tid < 32) {
+    uint32_t w16[4][4];
+    bool     bad = false;
+#pragma unroll
+    for (int s_ = 0; s_ < 4; s_++) {
+#pragma unroll
+      for (int t = 0; t < 4; t++) {
+        int16_t        a0 = 0, b0 = 0;
+        const uint32_t cb0 = (uint32_t)tile * TDEC_TILE_CB + 2 * lane;
+        if (cb0 < ncb) a0 = natural_pick(llr + (offsets ? offsets[cb0] : cb0 * nllr), K, s_, K + t);
+        if (cb0 + 1 < ncb) b0 = natural_pick(llr + (offsets ? offsets[cb0 + 1] : (cb0 + 1) * nllr), K, s_, K + t);
+        w16[s_][t] = pack2(a0, b0);
+        if (s_ < 3) bad |= !fits8(a0) || !fits8(b0); // S2T stays int16
+      }
+    }
+    if (__any_sync(0xFFFFFFFFu, bad) && lane == 0) atomicOr(v.fmt + tile, 1u);
+#pragma unroll
+    for (int s_ = 0; s_ < 3; s_++) {
+      uint32_t w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+      for (int t = 0; t < 4; t++) {
+        const uint32_t lo = w16[s_][t] & 0xFFu, hi = (w16[s_][t] >> 16) & 0xFFu;
+        w[t >> 1] |= (lo | (hi << 8)) << (16 * (t & 1));
+      }
+      u4* dst = s_ == 0 ? v.S8 : (s_ == 1 ? v.P08 : v.P18);
+      dst[row8(v, tile, K / 8, lane)] = u4{w[0], w[1], w[2], w[3]};
+    }
+    v.S2T[(size_t)tile * 32 + lane] = u4{w16[3][0], w16[3][1], w16[3][2], w16[3][3]};
+    const uint32_t cb0 = (uint32_t)tile * TDEC_TILE_CB + 2 * lane;
+    v.status[cb0]      = CbStatus{(uint8_t)(cb0 < ncb), 0, 0, 0};
+    v.status[cb0 + 1]  = CbStatus{(uint8_t)(cb0 + 1 < ncb), 0, 0, 0};
+  }
+}
+
+
 void launch_load_natural(const TdecView& v,
                          const int16_t*  llr_dev,
                          const uint64_t* offsets_dev,
@@ -615,7 +746,20 @@ void launch_load_natural(const TdecView& v,
   }
   cudaMemsetAsync(v.fmt, 0, (size_t)v.ntiles * sizeof(uint32_t), stream);
   if (aligned8) {
-    tdec_load8_kernel<true><<<grid, block, LOAD_SMEM, stream>>>(v, llr_dev, offsets_dev, ncb);
+    static const bool one_chunk = getenv("SRSLTE_B200_LOAD_ONE_CHUNK") != nullptr; // the earlier kernel, for comparison
+    if (one_chunk) {
+      tdec_load8_kernel<true><<<grid, block, LOAD_SMEM, stream>>>(v, llr_dev, offsets_dev, ncb);
+    } else {
+      static bool attr_s = false;
+      if (!attr_s) {
+        cudaFuncSetAttribute(tdec_load8_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LS_SMEM);
+        cudaFuncSetAttribute(tdec_load8_stream_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        attr_s = true;
+      }
+      const int nchunk = (v.K + LOAD_ROWS - 1) / LOAD_ROWS;
+      dim3      gs((unsigned)((nchunk + LS_CHUNKS - 1) / LS_CHUNKS), (unsigned)v.ntiles);
+      tdec_load8_stream_kernel<<<gs, block, LS_SMEM, stream>>>(v, llr_dev, offsets_dev, ncb);
+    }
     tdec_load16_kernel<true><<<grid16, block, LOAD_SMEM, stream>>>(v, llr_dev, offsets_dev, ncb);
   } else {
     tdec_load8_kernel<false><<<grid, block, LOAD_SMEM, stream>>>(v, llr_dev, offsets_dev, ncb);
