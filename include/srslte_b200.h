@@ -109,6 +109,10 @@ SRSRAN_B200_API int  srsran_b200_sch_init(srsran_b200_sch_t** q, int device);
 SRSRAN_B200_API void srsran_b200_sch_free(srsran_b200_sch_t* q);
 /* srsran_sch_set_max_noi (sch.c:222-229): maximum SISO passes per code block, 0 selects the default of 10 */
 SRSRAN_B200_API void srsran_b200_sch_set_max_noi(srsran_b200_sch_t* q, uint32_t max_iterations);
+/* The NEXT srsran_b200_sch_decode_batch call reads device buffers that are still being produced on `producer_stream`
+ * (e.g. the soft bits of srsran_b200_pusch_rx_batch): its kernels are ordered after everything queued on that stream at
+ * the time of the call, so the caller need not synchronise first and the call's host-side bookkeeping overlaps the producer. */
+SRSRAN_B200_API void srsran_b200_sch_decode_after(srsran_b200_sch_t* q, void* producer_stream);
 
 /* One srsran_rm_turbo_rx_lut_(input, output, in_len, cb_idx, rv_idx, enable_input_tdec=false) call (rm_turbo.c:403) */
 typedef struct {

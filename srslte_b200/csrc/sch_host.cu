@@ -5,6 +5,7 @@
 //   decode_tb_cb  lib/src/phy/phch/sch.c:370-492   (E split with its off-by-one, de-match into the HARQ soft buffer, up to
 //                                                   max_iterations passes with a CRC check after each, cb_crc bookkeeping)
 // Code blocks of all transport blocks are pooled, grouped by (K, CRC kind) and each group runs as ONE batched decode.
+#include <chrono>
 #include <map>
 #include <new>
 #include <vector>
@@ -108,18 +109,24 @@ struct SchEngine {
   DeviceArena    io;   // staged e_bits / soft pool / data when the caller hands host memory
   DeviceArena    meta; // descriptor arrays, per-group decision buffers
   uint32_t       max_iterations = 10; // SRSRAN_PDSCH_MAX_TDEC_ITERS, sch.c:35
+  size_t         last_ncb = 0;        // code blocks of the previous batch (sizes the bookkeeping vectors)
+  cudaStream_t   after  = nullptr;    // srsran_b200_sch_decode_after: producer stream of the next decode_batch's device inputs
+  bool           have_after = false;
+  cudaEvent_t    after_ev = nullptr;
 
   int init(int device)
   {
     if (tdec.init(device, 0) != B200_SUCCESS) return B200_ERROR;
     ctx = tdec.ctx;
     B200_CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    B200_CUDA_TRY(cudaEventCreateWithFlags(&after_ev, cudaEventDisableTiming));
     return B200_SUCCESS;
   }
   void destroy()
   {
     if (ctx) cudaSetDevice(ctx->device);
     if (stream) cudaStreamDestroy(stream);
+    if (after_ev) cudaEventDestroy(after_ev);
     io.release();
     meta.release();
     tdec.destroy();
@@ -144,6 +151,9 @@ static int build_rm_descs(DeviceContext* ctx, const srsran_b200_rm_cb_t* cbs, ui
                           std::vector<RmDescDev>& out)
 {
   out.resize(n);
+  // consecutive jobs mostly share (cb_idx, rv): remember the last table instead of taking the context's lock per job
+  uint32_t        last_idx = 0xFFFFFFFFu, last_rv = 0xFFFFFFFFu;
+  const uint16_t* last_inv = nullptr;
   for (uint32_t i = 0; i < n; i++) {
     const srsran_b200_rm_cb_t& c = cbs[i];
     if (c.rv > 3 || c.cb_idx >= (uint32_t)NOF_CB_SIZES) {
@@ -157,7 +167,12 @@ static int build_rm_descs(DeviceContext* ctx, const srsran_b200_rm_cb_t* cbs, ui
       return B200_ERROR_INVALID_INPUTS;
     }
     RmDescDev& d  = out[i];
-    d.inv         = ctx->rm_table((int)c.cb_idx, (int)c.rv);
+    if (c.cb_idx != last_idx || c.rv != last_rv) {
+      last_inv = ctx->rm_table((int)c.cb_idx, (int)c.rv);
+      last_idx = c.cb_idx;
+      last_rv  = c.rv;
+    }
+    d.inv         = last_inv;
     d.in_offset   = c.in_offset;
     d.soft_offset = c.soft_offset;
     d.E           = c.E;
@@ -219,12 +234,22 @@ int SchEngine::decode_batch(const int16_t* e_bits, uint64_t e_len, int16_t* soft
   const bool   all_dev  = (flags & SRSRAN_B200_FLAG_DEVICE_PTRS) != 0;
   const bool   soft_dev = all_dev || (flags & SRSRAN_B200_FLAG_SOFT_ON_DEVICE) != 0;
   cudaStream_t st       = stream;
+  if (have_after) { // the device inputs are produced on another stream: order this batch after what is queued there now
+    B200_CUDA_TRY(cudaEventRecord(after_ev, after));
+    B200_CUDA_TRY(cudaStreamWaitEvent(st, after_ev, 0));
+    have_after = false;
+  }
 
+  static const bool timing = getenv("SRSLTE_B200_SCH_TIMING") != nullptr;
+  auto              now    = [] { return std::chrono::steady_clock::now(); };
+  auto              t_0    = now();
   // ---- host-side bookkeeping: segmentation and the per-code-block E split of sch.c:392-406 ---------------------------
   std::vector<CbRec>               cbs;
   std::vector<srsran_b200_rm_cb_t> rm;
   std::vector<TbCrcJob>            crc_jobs(n_tb);
   bool                             any_skip = false;
+  cbs.reserve(last_ncb + 64);
+  rm.reserve(last_ncb + 64);
   for (uint32_t t = 0; t < n_tb; t++) {
     srsran_b200_tb_t& tb = tbs[t];
     tb.result            = B200_ERROR;
@@ -298,6 +323,8 @@ int SchEngine::decode_batch(const int16_t* e_bits, uint64_t e_len, int16_t* soft
     }
   }
 
+  auto t_1 = now();
+  last_ncb = cbs.size();
   // ---- stage buffers ---------------------------------------------------------------------------------------------------
   const int16_t* d_e    = e_bits;
   int16_t*       d_soft = soft_pool;
@@ -321,6 +348,7 @@ int SchEngine::decode_batch(const int16_t* e_bits, uint64_t e_len, int16_t* soft
   std::vector<RmDescDev> descs;
   int                    rc = build_rm_descs(ctx, rm.data(), (uint32_t)rm.size(), e_len, soft_len, descs);
   if (rc != B200_SUCCESS) return rc;
+  auto   t_2       = now();
   size_t meta_need = descs.size() * sizeof(RmDescDev) + cbs.size() * (sizeof(uint64_t) + sizeof(ScatterJob) + 8) +
                      n_tb * (sizeof(TbCrcJob) + 8) + (size_t(2) << 20);
   for (const CbRec& r : cbs) meta_need += r.K / 8 + 64;
@@ -333,6 +361,7 @@ int SchEngine::decode_batch(const int16_t* e_bits, uint64_t e_len, int16_t* soft
     g_kernel_launches++;
   }
 
+  auto t_3 = now();
   // ---- group by (K, CRC kind) and decode each group as one batch -----------------------------------------------------
   std::map<std::pair<uint32_t, uint32_t>, std::vector<uint32_t>> groups;
   for (uint32_t i = 0; i < cbs.size(); i++) groups[{cbs[i].K, cbs[i].crc_kind}].push_back(i);
@@ -374,6 +403,7 @@ int SchEngine::decode_batch(const int16_t* e_bits, uint64_t e_len, int16_t* soft
     // run_device reuses one workspace: the next group may only start once this one has drained (same stream: it has)
   }
 
+  auto t_4 = now();
   // ---- transport block CRC + results -------------------------------------------------------------------------------------
   TbCrcJob* d_cj = nullptr;
   if (upload(meta, crc_jobs, &d_cj, st) != B200_SUCCESS) return B200_ERROR;
@@ -394,8 +424,15 @@ int SchEngine::decode_batch(const int16_t* e_bits, uint64_t e_len, int16_t* soft
     B200_CUDA_TRY(cudaMemcpyAsync(data, d_data, data_len, cudaMemcpyDeviceToHost, st));
     if (!soft_dev) B200_CUDA_TRY(cudaMemcpyAsync(soft_pool, d_soft, soft_len * sizeof(int16_t), cudaMemcpyDeviceToHost, st));
   }
+  auto t_5 = now();
   B200_CUDA_TRY(cudaStreamSynchronize(st));
   B200_CUDA_TRY(cudaGetLastError());
+  auto t_6 = now();
+  if (timing) {
+    auto us = [](auto a, auto b) { return (double)std::chrono::duration_cast<std::chrono::nanoseconds>(b - a).count() / 1e3; };
+    fprintf(stderr, "[sch timing] bookkeeping %.0f us, rm descs %.0f, upload+dematch launch %.0f, groups+decode launches %.0f, tail launches %.0f, "
+                    "wait for the device %.0f\n", us(t_0, t_1), us(t_1, t_2), us(t_2, t_3), us(t_3, t_4), us(t_4, t_5), us(t_5, t_6));
+  }
   for (size_t p = 0; p < pend.size(); p++) {
     for (size_t j = 0; j < pend[p].idx->size(); j++) {
       h_ok[(*pend[p].idx)[j]] = tmp_ok[p][j];
@@ -449,6 +486,14 @@ void srsran_b200_sch_free(srsran_b200_sch_t* q)
   if (q) {
     q->eng.destroy();
     delete q;
+  }
+}
+
+void srsran_b200_sch_decode_after(srsran_b200_sch_t* q, void* producer_stream)
+{
+  if (q) {
+    q->eng.after      = (cudaStream_t)producer_stream;
+    q->eng.have_after = true;
   }
 }
 

@@ -84,7 +84,9 @@ class PuschRx:
         d = self.tb_np
         soft_stride = self.soft.shape[1]
         d["rv"][:nsf], d["new_data"][:nsf], d["cb_crc_mask"][:nsf] = rv, 1, 0
-        t.cuda.current_stream(self.dev).synchronize()  # the decode loop runs on the library's own stream
+        # the decode loop runs on the library's own stream: order it after the front end instead of synchronising, so that
+        # the call's host-side bookkeeping (segmentation, de-matching descriptors) overlaps the front-end kernels
+        self._lib.srsran_b200_sch_decode_after(self.sch._h, t.cuda.current_stream(self.dev).cuda_stream)
         rc = self._lib.srsran_b200_sch_decode_batch(self.sch._h, self.llr.data_ptr(), nsf * self.G, self.soft.data_ptr(),
                                                     nsf * soft_stride, self.data.data_ptr(), nsf * self.data_stride,
                                                     d.ctypes.data, nsf, _lib.FLAG_DEVICE_PTRS)
