@@ -44,6 +44,11 @@ extern "C" {
 #define SRSRAN_B200_CRC24A 1 /* single-code-block transport block: CRC24A over the K = tbs+24 bits */
 #define SRSRAN_B200_CRC24B 2 /* segmented transport block: CRC24B over the K bits of each code block */
 
+#define SRSRAN_B200_FLAG_IQ_INT16 0x8u       /* srsran_b200_ofdm_rx_sf_batch: `in` holds int16 I/Q pairs (the radio's wire format, what
+                                                the RF front ends convert with srsran_vec_convert_if(.., 32768, ..) on the host): the
+                                                first FFT pass converts (x / 32768, exact in float) so the result equals the float
+                                                entry on the converted samples.  Halves the PCIe bytes per subframe. */
+
 SRSRAN_B200_API int srsran_b200_device_count(void);
 
 /* Number of CUDA kernels this library has launched so far in this process (all objects, all devices). */

@@ -17,6 +17,7 @@ ERROR_INVALID_INPUTS = -2
 
 FLAG_DEVICE_PTRS = 0x1
 FLAG_LLR_INT8 = 0x4
+FLAG_IQ_INT16 = 0x8
 CRC_NONE, CRC24A, CRC24B = 0, 1, 2
 
 vp = C.c_void_p

@@ -176,7 +176,11 @@ struct OfdmEngine {
     if (!in || !out) return B200_ERROR_INVALID_INPUTS;
     if (nsf == 0) return B200_SUCCESS;
     B200_CUDA_TRY(cudaSetDevice(ctx->device));
-    const size_t in_b = (size_t)nsf * plan.sf_sz * sizeof(float2), out_b = (size_t)nsf * plan.nsym * plan.R * sizeof(float2);
+    OfdmPlanDev plan = this->plan; // per call: the sample format is a property of the call, not of the object
+    plan.iq16        = (flags & SRSRAN_B200_FLAG_IQ_INT16) ? 1 : 0;
+    plan.iq_scale    = 1.0f / 32768.0f;
+    const size_t in_b = (size_t)nsf * plan.sf_sz * (plan.iq16 ? 2 * sizeof(int16_t) : sizeof(float2)),
+                 out_b = (size_t)nsf * plan.nsym * plan.R * sizeof(float2);
     if (flags & SRSRAN_B200_FLAG_DEVICE_PTRS) {
       int rc = launch_ofdm_rx(plan, in, out, nsf, sm_count, user);
       g_kernel_launches++;

@@ -41,6 +41,12 @@ __device__ __forceinline__ float2 mul_mi(float2 a)
   return make_float2(a.y, -a.x);
 }
 
+// int16 I/Q sample -> float2 (exact: the scale is a power of two)
+__device__ __forceinline__ float2 iq16_to_f2(uint32_t w, float scale)
+{
+  return make_float2((float)(int16_t)(w & 0xFFFFu) * scale, (float)(int16_t)(w >> 16) * scale);
+}
+
 template <int R>
 __device__ __forceinline__ void dft_small(float2* u);
 
@@ -181,7 +187,7 @@ __device__ __forceinline__ void fft_pass(const OfdmPlanDev& p,
     for (int q = 0; q < RADIX; q++) {
       const int idx = j + q * T;
       if (first) {
-        float2 v = gin[idx];
+        float2 v = p.iq16 ? iq16_to_f2(reinterpret_cast<const uint32_t*>(gin)[idx], p.iq_scale) : gin[idx];
         if (p.shift) v = cmul(v, p.shift[idx]);
         if (eq_h) { // precoding.c:224-262: (y conj(h)) / (|h|^2 [+ noise when noise > 0])
           const float2 h  = eq_h[idx];
@@ -243,8 +249,9 @@ __global__ void __launch_bounds__(OFDM_THREADS) ofdm_rx_kernel(OfdmPlanDev p, co
     const bool     active = !spare && sidx < nsymtot;
     const uint32_t sf = (active && !p.generic) ? sidx / p.nsym : 0, l = (active && !p.generic) ? sidx % p.nsym : 0;
     const int      slot = (int)l / half, ls = (int)l % half;
+    const size_t   woff = (size_t)sf * p.sf_sz + (size_t)slot * p.slot_sz + p.cp1 + (size_t)ls * (p.N + p.cp2) - p.noff;
     const float2*  gin  = p.generic ? in + (size_t)sidx * p.idist
-                                    : in + (size_t)sf * p.sf_sz + (size_t)slot * p.slot_sz + p.cp1 + (size_t)ls * (p.N + p.cp2) - p.noff;
+                                    : (p.iq16 ? reinterpret_cast<const float2*>(reinterpret_cast<const uint32_t*>(in) + woff) : in + woff);
     float2*        gout = p.generic ? out + (size_t)sidx * p.odist : out + (size_t)sidx * p.R;
     const float2*  eq_h  = nullptr;
     float          eq_n0 = 0.f;
@@ -296,7 +303,7 @@ __global__ void __launch_bounds__(OFDM_THREADS) ofdm_rx_kernel(OfdmPlanDev p, co
 // derives at run time (pass sequence, strides, index divisions) is a compile-time constant, N/16 threads hold 16 points
 // each in registers through every pass, and the passes exchange IN PLACE through one padded shared buffer (all loads of
 // a pass, barrier, all stores), which halves the shared memory per symbol and doubles the resident warps.
-template <int N, int RADIX, int NS, bool FIRST, bool LAST>
+template <int N, int RADIX, int NS, bool FIRST, bool LAST, bool IQ16 = false>
 __device__ __forceinline__ void pass_ct(const OfdmPlanDev& p, const float2* __restrict__ gin, float2* buf, float2* __restrict__ gout, int t,
                                         bool active)
 {
@@ -317,7 +324,7 @@ __device__ __forceinline__ void pass_ct(const OfdmPlanDev& p, const float2* __re
       for (int q = 0; q < RADIX; q++) {
         const int idx = j + q * T;
         if (FIRST) { // gin = this symbol's window, already staged in shared memory (natural order)
-          float2 v = gin[idx];
+          float2 v = IQ16 ? iq16_to_f2(reinterpret_cast<const uint32_t*>(gin)[idx], p.iq_scale) : gin[idx];
           if (p.shift) {
             v  = cmul(v, sh);
             sh = cmul(sh, c1);
@@ -384,7 +391,14 @@ __device__ __forceinline__ void cp_async8(float2* dst_smem, const float2* src)
 
 // Persistent blocks; the window of the NEXT symbol is fetched with cp.async into a staging buffer while the current
 // symbol's passes run, so the global-memory latency is off the critical path.
-template <int N, int R0, int R1, int R2>
+__device__ __forceinline__ void cp_async4(void* dst_smem, const void* src)
+{
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)),
+               "l"(__cvta_generic_to_global(src))
+               : "memory");
+}
+
+template <int N, int R0, int R1, int R2, bool IQ16>
 __global__ void __launch_bounds__(OFDM_THREADS, 6) ofdm_rx_kernel_ct(OfdmPlanDev p, const float2* __restrict__ in, float2* __restrict__ out,
                                                                      uint32_t nsf)
 {
@@ -401,13 +415,20 @@ __global__ void __launch_bounds__(OFDM_THREADS, 6) ofdm_rx_kernel_ct(OfdmPlanDev
   auto window = [&](uint32_t sidx) {
     const uint32_t sf = sidx / p.nsym, l = sidx % p.nsym;
     const int      slot = (int)l / half, ls = (int)l % half;
-    return in + (size_t)sf * p.sf_sz + (size_t)slot * p.slot_sz + p.cp1 + (size_t)ls * (N + p.cp2) - p.noff;
+    return (size_t)sf * p.sf_sz + (size_t)slot * p.slot_sz + p.cp1 + (size_t)ls * (N + p.cp2) - p.noff; // in samples
   };
   auto prefetch = [&](uint32_t sidx) {
     if (sidx < nsymtot) {
-      const float2* gin = window(sidx);
+      if (IQ16) { // 4-byte samples: the staging buffer holds them as they come, the first pass converts
+        const uint32_t* gin = reinterpret_cast<const uint32_t*>(in) + window(sidx);
+        uint32_t*       st4 = reinterpret_cast<uint32_t*>(stage);
 #pragma unroll
-      for (int q = 0; q < 16; q++) cp_async8(stage + t + q * TPS, gin + t + q * TPS);
+        for (int q = 0; q < 16; q++) cp_async4(st4 + t + q * TPS, gin + t + q * TPS);
+      } else {
+        const float2* gin = in + window(sidx);
+#pragma unroll
+        for (int q = 0; q < 16; q++) cp_async8(stage + t + q * TPS, gin + t + q * TPS);
+      }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
@@ -418,7 +439,7 @@ __global__ void __launch_bounds__(OFDM_THREADS, 6) ofdm_rx_kernel_ct(OfdmPlanDev
     float2*        gout   = out + (size_t)sidx * p.R;
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads(); // the staged window is complete and visible to the whole group
-    pass_ct<N, R0, 1, true, false>(p, stage, buf, gout, t, active);
+    pass_ct<N, R0, 1, true, false, IQ16>(p, stage, buf, gout, t, active);
     prefetch(sidx + gridDim.x * SPB); // the barrier that ended the first pass: every thread has read its staged points
     if (R2 > 1) {
       pass_ct<N, R1, R0, false, false>(p, stage, buf, gout, t, active);
@@ -430,15 +451,15 @@ __global__ void __launch_bounds__(OFDM_THREADS, 6) ofdm_rx_kernel_ct(OfdmPlanDev
   }
 }
 
-template <int N, int R0, int R1, int R2>
-static int launch_ct(const OfdmPlanDev& p, const float2* in_dev, float2* out_dev, uint32_t nsf, int sm_count, cudaStream_t stream)
+template <int N, int R0, int R1, int R2, bool IQ16>
+static int launch_ct_t(const OfdmPlanDev& p, const float2* in_dev, float2* out_dev, uint32_t nsf, int sm_count, cudaStream_t stream)
 {
   constexpr int    SPB  = OFDM_THREADS / (N / 16);
   constexpr size_t smem = (size_t)SPB * (2 * N + (N >> 4) + 1) * sizeof(float2); // work buffer + staged next window
   static bool      attr_done = false;
   if (!attr_done) {
-    B200_CUDA_TRY(cudaFuncSetAttribute(ofdm_rx_kernel_ct<N, R0, R1, R2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    B200_CUDA_TRY(cudaFuncSetAttribute(ofdm_rx_kernel_ct<N, R0, R1, R2>, cudaFuncAttributePreferredSharedMemoryCarveout,
+    B200_CUDA_TRY(cudaFuncSetAttribute(ofdm_rx_kernel_ct<N, R0, R1, R2, IQ16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200_CUDA_TRY(cudaFuncSetAttribute(ofdm_rx_kernel_ct<N, R0, R1, R2, IQ16>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                        cudaSharedmemCarveoutMaxShared));
     attr_done = true;
   }
@@ -446,9 +467,16 @@ static int launch_ct(const OfdmPlanDev& p, const float2* in_dev, float2* out_dev
   uint32_t       blocks  = (nsymtot + SPB - 1) / SPB;
   const uint32_t cap     = (uint32_t)sm_count * 12u; // persistent: the resident blocks loop over the symbols
   if (blocks > cap) blocks = cap;
-  ofdm_rx_kernel_ct<N, R0, R1, R2><<<blocks, OFDM_THREADS, smem, stream>>>(p, in_dev, out_dev, nsf);
+  ofdm_rx_kernel_ct<N, R0, R1, R2, IQ16><<<blocks, OFDM_THREADS, smem, stream>>>(p, in_dev, out_dev, nsf);
   B200_CUDA_TRY(cudaGetLastError());
   return B200_SUCCESS;
+}
+
+template <int N, int R0, int R1, int R2>
+static int launch_ct(const OfdmPlanDev& p, const float2* in_dev, float2* out_dev, uint32_t nsf, int sm_count, cudaStream_t stream)
+{
+  return p.iq16 ? launch_ct_t<N, R0, R1, R2, true>(p, in_dev, out_dev, nsf, sm_count, stream)
+                : launch_ct_t<N, R0, R1, R2, false>(p, in_dev, out_dev, nsf, sm_count, stream);
 }
 
 

@@ -27,6 +27,8 @@ struct OfdmPlanDev {
   int idist;
   int odist;
   int inverse; // 1: e^{+2 pi i kn/N} (conjugate in, conjugate out)
+  int   iq16;     // OFDM mode: the input samples are int16 I/Q pairs (the radio's wire format); value = int16 * iq_scale
+  float iq_scale; // 1/32768: what the host-side conversion to float does (power of two, so the float result is the same)
   float gscale; // generic mode: every output bin is multiplied by this when non-zero (1/sqrt(N) of dft_fftw.c:343-350)
   // PUSCH transform de-precoding mode (generic = 2): transform h = (subframe sf = h / pusch_nd, data symbol d = h % pusch_nd) reads
   // the 12*L_prb allocated elements of OFDM symbol pusch_l[d] out of the subframe's resource grid, EQUALISED on the fly with

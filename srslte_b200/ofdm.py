@@ -56,7 +56,9 @@ class OfdmRx:
 
         if stream_ptr is None:
             stream_ptr = torch.cuda.current_stream(x.device).cuda_stream
-        rc = self._lib.srsran_b200_ofdm_rx_sf_batch(self._h, x.data_ptr(), out.data_ptr(), nsf, _lib.FLAG_DEVICE_PTRS, stream_ptr)
+        # int16 tensors (nsf, sf_sz, 2) are I/Q pairs in the radio's wire format (SRSRAN_B200_FLAG_IQ_INT16)
+        fl = _lib.FLAG_DEVICE_PTRS | (_lib.FLAG_IQ_INT16 if x.dtype == torch.int16 else 0)
+        rc = self._lib.srsran_b200_ofdm_rx_sf_batch(self._h, x.data_ptr(), out.data_ptr(), nsf, fl, stream_ptr)
         if rc != _lib.SUCCESS:
             raise RuntimeError(f"srsran_b200_ofdm_rx_sf_batch failed ({rc})")
 

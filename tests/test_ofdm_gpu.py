@@ -107,3 +107,32 @@ def test_demod_bit_exact(port):
     for mod in (1, 2, 3):
         want = np.concatenate([port.demod_s(mod, s[i * 1001:(i + 1) * 1001]) for i in range(3)])
         assert (demod_soft_s(mod, s, symbols_per_call=1001) == want).all()
+
+
+@pytest.mark.parametrize("prb,N", [(100, 2048), (100, 0), (25, 512), (6, 128), (75, 0)])
+def test_int16_iq_input_equals_float_input(prb, N):
+    """SRSRAN_B200_FLAG_IQ_INT16: the radio's int16 I/Q pairs give bit for bit what the float entry gives on x / 32768
+    (the conversion is exact), on the specialised and the generic kernel, host and device pointers."""
+    import ctypes as C
+
+    import torch
+
+    from srslte_b200 import _lib
+    from srslte_b200.ofdm import OfdmRx
+
+    rx = OfdmRx(prb, False, N, -0.5, 0.5, False, False)
+    rng = np.random.default_rng(prb + N)
+    nsf = 3
+    iq = rng.integers(-20000, 20000, (nsf, rx.sf_sz, 2)).astype(np.int16)
+    iq[0, :4] = [[-32768, 32767], [0, -1], [1, 0], [32767, -32768]]
+    xf = (iq[..., 0].astype(np.float32) / np.float32(32768.0) + 1j * (iq[..., 1].astype(np.float32) / np.float32(32768.0))).astype(np.complex64)
+    want = rx.rx_sf(xf.reshape(-1))
+    out = np.zeros_like(want)
+    rc = rx._lib.srsran_b200_ofdm_rx_sf_batch(rx._h, iq.ctypes.data, out.ctypes.data, nsf, _lib.FLAG_IQ_INT16, None)
+    assert rc == 0
+    assert (out.view(np.uint32) == want.view(np.uint32)).all()
+    d_out = torch.empty((nsf, rx.nof_symbols, rx.nof_re), dtype=torch.complex64, device="cuda")
+    rx.rx_sf_device(torch.from_numpy(iq).cuda(), d_out, nsf)
+    torch.cuda.synchronize()
+    assert (d_out.cpu().numpy().view(np.uint32) == want.view(np.uint32)).all()
+    rx.close()
