@@ -240,6 +240,37 @@ B200_HD uint32_t llr_step(uint32_t A[8], const uint32_t b[8], uint32_t x, uint32
   return sub2(one_side, zero_side);
 }
 
+// LLR of one step AND the backward update in one go, for warp B's steps that need no normalisation in between: the sixteen
+// terms beta_{k+1}[s'] + gamma of the backward recursion (turbodecoder_gen.c:76-92) are also, grouped by the PREVIOUS state s,
+// the second summands of the sixteen LLR candidates alpha_k[s] + (gamma + beta_{k+1}[s']) (:160-176).  int16 addition wraps and
+// is associative, so every candidate and every new beta is the same 16-bit value the reference computes with
+// (alpha + gamma) + beta; 39 packed operations instead of the 43 of llr_step<false> + beta_step.
+//   previous state s -> (next state, gamma) on bit 0: 0->(0,0) 1->(4,0) 2->(5,y) 3->(1,y) 4->(2,y) 5->(6,y) 6->(7,0) 7->(3,0)
+//                                         on bit 1: 0->(4,xy) 1->(0,xy) 2->(1,x) 3->(5,x) 4->(6,x) 5->(2,x) 6->(3,xy) 7->(7,xy)
+B200_HD uint32_t llr_beta_step(const uint32_t A[8], uint32_t U[8], uint32_t x, uint32_t y, uint32_t xy)
+{
+  const uint32_t z0 = U[0], z1 = U[4], z2 = add2(U[5], y), z3 = add2(U[1], y);
+  const uint32_t z4 = add2(U[2], y), z5 = add2(U[6], y), z6 = U[7], z7 = U[3];
+  const uint32_t o0 = add2(U[4], xy), o1 = add2(U[0], xy), o2 = add2(U[1], x), o3 = add2(U[5], x);
+  const uint32_t o4 = add2(U[6], x), o5 = add2(U[2], x), o6 = add2(U[3], xy), o7 = add2(U[7], xy);
+  uint32_t a0 = add2(A[0], z0), a1 = add2(A[4], z4), b0 = add2(A[0], o0), b1 = add2(A[4], o4);
+  a0 = addmax2(A[1], z1, a0);
+  a1 = addmax2(A[5], z5, a1);
+  b0 = addmax2(A[1], o1, b0);
+  b1 = addmax2(A[5], o5, b1);
+  a0 = addmax2(A[2], z2, a0);
+  a1 = addmax2(A[6], z6, a1);
+  b0 = addmax2(A[2], o2, b0);
+  b1 = addmax2(A[6], o6, b1);
+  a0 = addmax2(A[3], z3, a0);
+  a1 = addmax2(A[7], z7, a1);
+  b0 = addmax2(A[3], o3, b0);
+  b1 = addmax2(A[7], o7, b1);
+  U[0] = max2(z0, o0); U[1] = max2(z1, o1); U[2] = max2(z2, o2); U[3] = max2(z3, o3);
+  U[4] = max2(z4, o4); U[5] = max2(z5, o5); U[6] = max2(z6, o6); U[7] = max2(z7, o7);
+  return sub2(max2(b0, b1), max2(a0, a1));
+}
+
 // ---- one window of 8 trellis steps in registers ---------------------------------------------------------------
 struct WinRegs {
   uint32_t xs[8]; // systematic (+ a-priori) input of the constituent decoder
@@ -352,9 +383,14 @@ B200_HD void bwd_window(uint32_t U[8], const uint32_t ack[8], const WinRegs& r, 
 #pragma unroll
   for (int t = 7; t >= 0; t--) {
     const uint32_t xy = add2(r.xs[t], r.ys[t]);
-    const uint32_t L  = llr_step<false>(aw[t], U, r.xs[t], r.ys[t], xy);
-    if ((t & 3) == 3) normalise(U); // U is beta_{8w+t+1}: a multiple of 4 (and < K)
-    beta_step(U, r.xs[t], r.ys[t], xy);
+    uint32_t       L;
+    if ((t & 3) == 3) { // U is beta_{8w+t+1}, index a multiple of 4 (and < K): the LLR takes it as stored, the recursion normalised
+      L = llr_step<false>(aw[t], U, r.xs[t], r.ys[t], xy);
+      normalise(U);
+      beta_step(U, r.xs[t], r.ys[t], xy);
+    } else {
+      L = llr_beta_step(aw[t], U, r.xs[t], r.ys[t], xy);
+    }
     win_emit(o, res, cw, t, L, sink);
   }
 }
