@@ -89,7 +89,7 @@ struct TdecView {
 };
 
 // Split of the trellis between the two warps.  Per step warp F spends ~15 instructions below the split and ~56 above,
-// warp B ~62 below (its alpha rebuild cannot share the branch sums with the LLR) and ~15 above: measured best at ws = 0.48 nw (sweep 45..53 %, profiles/README.md).
+// warp B ~62 below (its alpha rebuild cannot share the branch sums with the LLR) and ~15 above: measured best at ws = 0.51 nw since warp B shares its backward terms with the LLR (sweeps in profiles/README.md).
 B200_HD int tdec_split(int K, int percent)
 {
   const int nw = K / 8;

@@ -33,16 +33,23 @@ size_t TdecEngine::workspace_bytes(int K, uint32_t ncb)
   return total;
 }
 
-// share of the trellis windows below the split (tdec_core.h: tdec_split); SRSLTE_B200_TDEC_SPLIT is a tuning knob
-static int split_percent()
+// share of the trellis windows below the split (tdec_core.h: tdec_split), per kind of pass: 0 = first pass, 1 = DEC2 (odd),
+// 2 = DEC1 (even, with a-priori input).  SRSLTE_B200_TDEC_SPLIT[_FIRST|_DEC2|_DEC1] are tuning knobs.
+static int split_percent(int kind)
 {
-  static int pct = -1;
-  if (pct < 0) {
-    const char* e = getenv("SRSLTE_B200_TDEC_SPLIT");
-    pct           = e ? atoi(e) : 48;
-    if (pct < 1 || pct > 99) pct = 48;
+  static int pct[3] = {-1, -1, -1};
+  if (pct[0] < 0) {
+    static const char* names[3] = {"SRSLTE_B200_TDEC_SPLIT_FIRST", "SRSLTE_B200_TDEC_SPLIT_DEC2", "SRSLTE_B200_TDEC_SPLIT_DEC1"};
+    static const int   dflt[3]  = {51, 51, 51};
+    const char*        all      = getenv("SRSLTE_B200_TDEC_SPLIT");
+    for (int k = 2; k >= 0; k--) {
+      const char* e = getenv(names[k]);
+      int         p = e ? atoi(e) : (all ? atoi(all) : dflt[k]);
+      if (p < 1 || p > 99) p = dflt[k];
+      pct[k] = p;
+    }
   }
-  return pct;
+  return pct[kind];
 }
 
 int TdecEngine::carve(DeviceArena& arena, int K, uint32_t ncb, TdecView& v) const
@@ -59,7 +66,7 @@ int TdecEngine::carve(DeviceArena& arena, int K, uint32_t ncb, TdecView& v) cons
   v.P08               = (u4*)arena.take(rows8);
   v.P18               = (u4*)arena.take(rows8);
   v.fmt               = (uint32_t*)arena.take(ntiles * sizeof(uint32_t));
-  v.ws                = tdec_split(K, split_percent());
+  v.ws                = tdec_split(K, split_percent(2));
   v.S2T               = (u4*)arena.take(ntiles * 32 * sizeof(u4));
   v.E                 = (uint32_t*)arena.take(ntiles * (size_t)K * 32 * sizeof(uint32_t));
   v.CK                = (u4*)arena.take(ntiles * (size_t)(K / 8) * 2 * 32 * sizeof(u4));
@@ -211,6 +218,7 @@ int TdecEngine::run_device(DeviceArena&   ws,
   g_kernel_launches += 2;
   for (uint32_t p = 0; p < max_passes; p++) {
     prof_begin(1, stream);
+    v.ws = tdec_split(K, split_percent(p == 0 ? 0 : ((p & 1) ? 1 : 2))); // the checkpoints are per-pass scratch: each kind of pass splits where it balances
     launch_siso_pass(v, (int)p, stream);
     prof_end(stream);
     g_kernel_launches++;
