@@ -42,6 +42,35 @@ void DeviceArena::release()
   cap = used = 0;
 }
 
+int PinnedArena::reserve(size_t bytes)
+{
+  if (bytes <= cap) return B200_SUCCESS;
+  if (base) {
+    B200_CUDA_TRY(cudaFreeHost(base));
+    base = nullptr;
+    cap  = 0;
+  }
+  size_t want = (bytes + (size_t(4) << 20)) & ~((size_t(4) << 20) - 1);
+  B200_CUDA_TRY(cudaHostAlloc(&base, want, cudaHostAllocDefault));
+  cap = want;
+  return B200_SUCCESS;
+}
+
+void* PinnedArena::take(size_t bytes)
+{
+  size_t off = (used + 63) & ~size_t(63);
+  if (off + bytes > cap) return nullptr;
+  used = off + bytes;
+  return static_cast<char*>(base) + off;
+}
+
+void PinnedArena::release()
+{
+  if (base) cudaFreeHost(base);
+  base = nullptr;
+  cap = used = 0;
+}
+
 int DeviceContext::init(int dev)
 {
   device = dev;

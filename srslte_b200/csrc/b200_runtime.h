@@ -47,6 +47,20 @@ struct DeviceArena {
   void  release();
 };
 
+// Grow-only PINNED host buffer for descriptor uploads: cudaMemcpyAsync from pageable memory first synchronises the stream,
+// which serialises the host-side launches with the device; from page-locked memory it is a plain enqueue.  reset() once the
+// stream that consumed the previous contents has been synchronised.
+struct PinnedArena {
+  void*  base = nullptr;
+  size_t cap  = 0;
+  size_t used = 0;
+
+  int   reserve(size_t bytes);
+  void  reset() { used = 0; }
+  void* take(size_t bytes); // 64-byte aligned; nullptr when not reserved large enough
+  void  release();
+};
+
 struct RmTableKey {
   int  cb_idx, rv;
   bool operator<(const RmTableKey& o) const { return cb_idx != o.cb_idx ? cb_idx < o.cb_idx : rv < o.rv; }

@@ -232,13 +232,22 @@ struct PuschRx {
   float2*       d_d   = nullptr;
   float*        d_meas = nullptr;
   uint32_t      cap_sf = 0;
-  std::vector<PuschSfParam> h_prm;
+  // per-subframe parameters are staged in two page-locked buffers used in turn (a copy from pageable memory would first
+  // synchronise the stream, i.e. wait for the OFDM kernel queued just before this call)
+  PuschSfParam* h_prm[2]   = {nullptr, nullptr};
+  cudaEvent_t   prm_ev[2]  = {nullptr, nullptr};
+  uint32_t      h_prm_cap  = 0;
+  int           prm_cur    = 0;
 
   ~PuschRx()
   {
     if (ctx) cudaSetDevice(ctx->device);
     for (void* p : {(void*)dW, (void*)d_dmrs, (void*)d_x1w, (void*)d_jump, (void*)d_prm, (void*)d_seq, (void*)d_ce, (void*)d_d, (void*)d_meas}) {
       if (p) cudaFree(p);
+    }
+    for (int i = 0; i < 2; i++) {
+      if (h_prm[i]) cudaFreeHost(h_prm[i]);
+      if (prm_ev[i]) cudaEventDestroy(prm_ev[i]);
     }
   }
 
@@ -392,17 +401,30 @@ struct PuschRx {
   // per-subframe parameters -> device (the copy is stream ordered; the host vector is staged by the runtime)
   int upload_params(uint32_t nsf, const uint32_t* rnti, const uint32_t* tti, const uint32_t* n_dmrs, cudaStream_t st)
   {
-    h_prm.resize(nsf);
+    if (nsf > h_prm_cap) {
+      for (int i = 0; i < 2; i++) {
+        if (prm_ev[i]) B200_CUDA_TRY(cudaEventSynchronize(prm_ev[i]));
+        if (h_prm[i]) cudaFreeHost(h_prm[i]);
+        h_prm[i] = nullptr;
+        B200_CUDA_TRY(cudaHostAlloc((void**)&h_prm[i], (size_t)nsf * sizeof(PuschSfParam), cudaHostAllocDefault));
+        if (!prm_ev[i]) B200_CUDA_TRY(cudaEventCreateWithFlags(&prm_ev[i], cudaEventDisableTiming));
+      }
+      h_prm_cap = nsf;
+    }
+    prm_cur ^= 1;
+    B200_CUDA_TRY(cudaEventSynchronize(prm_ev[prm_cur])); // the copy that last read this buffer has completed
+    PuschSfParam* hp = h_prm[prm_cur];
     for (uint32_t i = 0; i < nsf; i++) {
       const uint32_t sf_idx = tti ? tti[i] % 10 : 0, nd_ = n_dmrs ? n_dmrs[i] : 0, r = rnti ? rnti[i] : 0;
       if (nd_ > 7) {
         B200_LOG_ERROR("n_dmrs %u out of range (refsignal_ul.c:327)", nd_);
         return B200_ERROR_INVALID_INPUTS;
       }
-      h_prm[i].c_init   = ((r & 0xFFFFu) << 14) + (sf_idx << 9) + cfg.cell_id;
-      h_prm[i].dmrs_idx = nd_ * 10 + sf_idx;
+      hp[i].c_init   = ((r & 0xFFFFu) << 14) + (sf_idx << 9) + cfg.cell_id;
+      hp[i].dmrs_idx = nd_ * 10 + sf_idx;
     }
-    B200_CUDA_TRY(cudaMemcpyAsync(d_prm, h_prm.data(), (size_t)nsf * sizeof(PuschSfParam), cudaMemcpyHostToDevice, st));
+    B200_CUDA_TRY(cudaMemcpyAsync(d_prm, hp, (size_t)nsf * sizeof(PuschSfParam), cudaMemcpyHostToDevice, st));
+    B200_CUDA_TRY(cudaEventRecord(prm_ev[prm_cur], st));
     return B200_SUCCESS;
   }
 

@@ -108,6 +108,7 @@ struct SchEngine {
   cudaStream_t   stream = nullptr;
   DeviceArena    io;   // staged e_bits / soft pool / data when the caller hands host memory
   DeviceArena    meta; // descriptor arrays, per-group decision buffers
+  PinnedArena    hmeta; // page-locked staging of the descriptor arrays (decode_batch: truly asynchronous uploads)
   uint32_t       max_iterations = 10; // SRSRAN_PDSCH_MAX_TDEC_ITERS, sch.c:35
   size_t         last_ncb = 0;        // code blocks of the previous batch (sizes the bookkeeping vectors)
   cudaStream_t   after  = nullptr;    // srsran_b200_sch_decode_after: producer stream of the next decode_batch's device inputs
@@ -129,15 +130,24 @@ struct SchEngine {
     if (after_ev) cudaEventDestroy(after_ev);
     io.release();
     meta.release();
+    hmeta.release();
     tdec.destroy();
   }
 
   template <class T>
-  int upload(DeviceArena& a, const std::vector<T>& h, T** d, cudaStream_t st)
+  int upload(DeviceArena& a, const std::vector<T>& h, T** d, cudaStream_t st, PinnedArena* stage = nullptr)
   {
     *d = (T*)a.take(h.size() * sizeof(T) + 16);
     if (!*d) return B200_ERROR;
-    B200_CUDA_TRY(cudaMemcpyAsync(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+    const void* src = h.data();
+    if (stage) { // through page-locked memory: the copy is a plain enqueue instead of a stream synchronisation
+      void* p = stage->take(h.size() * sizeof(T) + 16);
+      if (p) {
+        memcpy(p, h.data(), h.size() * sizeof(T));
+        src = p;
+      }
+    }
+    B200_CUDA_TRY(cudaMemcpyAsync(*d, src, h.size() * sizeof(T), cudaMemcpyHostToDevice, st));
     return B200_SUCCESS;
   }
 
@@ -354,9 +364,15 @@ int SchEngine::decode_batch(const int16_t* e_bits, uint64_t e_len, int16_t* soft
   for (const CbRec& r : cbs) meta_need += r.K / 8 + 64;
   if (meta.reserve(meta_need) != B200_SUCCESS) return B200_ERROR;
   meta.reset();
+  // the previous call ended with a stream synchronisation, so its staged descriptors are free again
+  if (hmeta.reserve(descs.size() * sizeof(RmDescDev) + cbs.size() * (sizeof(uint64_t) + sizeof(ScatterJob)) + n_tb * sizeof(TbCrcJob) +
+                    (size_t(1) << 20)) != B200_SUCCESS) {
+    return B200_ERROR;
+  }
+  hmeta.reset();
   if (!descs.empty()) {
     RmDescDev* d_descs = nullptr;
-    if (upload(meta, descs, &d_descs, st) != B200_SUCCESS) return B200_ERROR;
+    if (upload(meta, descs, &d_descs, st, &hmeta) != B200_SUCCESS) return B200_ERROR;
     if (launch_rm_rx(d_e, d_soft, d_descs, (uint32_t)descs.size(), st) != B200_SUCCESS) return B200_ERROR;
     g_kernel_launches++;
   }
@@ -388,7 +404,7 @@ int SchEngine::decode_batch(const int16_t* e_bits, uint64_t e_len, int16_t* soft
     }
     uint64_t*   d_offs = nullptr;
     ScatterJob* d_jobs = nullptr;
-    if (upload(meta, offs, &d_offs, st) != B200_SUCCESS || upload(meta, jobs, &d_jobs, st) != B200_SUCCESS) return B200_ERROR;
+    if (upload(meta, offs, &d_offs, st, &hmeta) != B200_SUCCESS || upload(meta, jobs, &d_jobs, st, &hmeta) != B200_SUCCESS) return B200_ERROR;
     uint8_t* d_dec = (uint8_t*)meta.take((size_t)n * (K / 8));
     uint8_t* d_ok  = (uint8_t*)meta.take(n);
     uint8_t* d_np  = (uint8_t*)meta.take(n);
@@ -406,7 +422,7 @@ int SchEngine::decode_batch(const int16_t* e_bits, uint64_t e_len, int16_t* soft
   auto t_4 = now();
   // ---- transport block CRC + results -------------------------------------------------------------------------------------
   TbCrcJob* d_cj = nullptr;
-  if (upload(meta, crc_jobs, &d_cj, st) != B200_SUCCESS) return B200_ERROR;
+  if (upload(meta, crc_jobs, &d_cj, st, &hmeta) != B200_SUCCESS) return B200_ERROR;
   uint8_t* d_tbok = (uint8_t*)meta.take(n_tb);
   if (!d_tbok) return B200_ERROR;
   sch_tb_crc_kernel<<<(n_tb + 3) / 4, 128, 0, st>>>(d_data, d_cj, n_tb, d_tbok);
