@@ -790,32 +790,31 @@ __global__ void __launch_bounds__(256) tdec_decide_kernel(TdecView v,
   for (int i = tid; i < nb * 4; i += 256) reinterpret_cast<uint4*>(hb)[i] = src[i];
   __syncthreads();
 
-  // a warp takes 4 output bytes (32 decisions) at a time for all 64 blocks; lane = block within a half tile
+  // a warp takes 4 output bytes (32 decisions) at a time; lane = lane of the tile = the block pair (2 lane, 2 lane + 1) whose
+  // decisions share a 16-bit HB word (low byte = even block), so one shared-memory read serves two blocks
+  const CbStatus st_lo = v.status[(size_t)tile * TDEC_TILE_CB + 2 * lane], st_hi = v.status[(size_t)tile * TDEC_TILE_CB + 2 * lane + 1];
+  // last pass was DEC2: HB is in its visiting order
+  const bool     perm_lo = st_lo.npass_run > 0 && ((st_lo.npass_run - 1) & 1), perm_hi = st_hi.npass_run > 0 && ((st_hi.npass_run - 1) & 1);
+  const bool     any_perm = __any_sync(0xFFFFFFFFu, perm_lo || perm_hi);
+  const uint32_t keep_nat = (perm_lo ? 0u : 0x00FFu) | (perm_hi ? 0u : 0xFF00u); // halves that take the natural-order word
   for (int j0 = wid * 4; j0 < nb; j0 += 32) {
     const int      nj  = min(4, nb - j0);
     const uint32_t rev = (8 * j0 + lane < v.K) ? qpp_rev[8 * j0 + lane] : 0u; // visiting index of bit 8*j0+lane
+    for (int j = 0; j < nj; j++) {
+      const uint32_t nat = hb[(j0 + j) * 32 + lane];
+      uint32_t       w2  = nat;
+      if (any_perm) {
+        uint32_t acc = 0; // bit 0 / bit 8: the low / high block's decision, shifted in MSB first
 #pragma unroll
-    for (int h = 0; h < 2; h++) {
-      const int      c    = 32 * h + lane; // block within the tile
-      const CbStatus st   = v.status[(size_t)tile * TDEC_TILE_CB + c];
-      const bool     perm = st.npass_run > 0 && ((st.npass_run - 1) & 1); // last pass was DEC2: HB is in its visiting order
-      const int      sh   = (c & 1) ? 8 : 0;
-      for (int j = 0; j < nj; j++) {
-        uint32_t byte;
-        if (!__any_sync(0xFFFFFFFFu, perm)) {
-          byte = (hb[(j0 + j) * 32 + (c >> 1)] >> sh) & 0xFFu;
-        } else {
-          byte = 0;
-#pragma unroll
-          for (int t = 0; t < 8; t++) {
-            const uint32_t i   = __shfl_sync(0xFFFFFFFFu, rev, 8 * j + t);
-            const uint32_t w   = hb[(i >> 3) * 32 + (c >> 1)] >> sh;
-            byte               = (byte << 1) | ((w >> (7 - (i & 7))) & 1u);
-          }
-          if (!perm) byte = (hb[(j0 + j) * 32 + (c >> 1)] >> sh) & 0xFFu;
+        for (int t = 0; t < 8; t++) {
+          const uint32_t i = __shfl_sync(0xFFFFFFFFu, rev, 8 * j + t);
+          const uint32_t w = hb[(i >> 3) * 32 + lane];
+          acc              = (acc << 1) | ((w >> (7 - (i & 7))) & 0x0101u);
         }
-        so[c * pitch + j0 + j] = (uint8_t)byte;
+        w2 = (nat & keep_nat) | (acc & ~keep_nat);
       }
+      so[(2 * lane) * pitch + j0 + j]     = (uint8_t)(w2 & 0xFFu);
+      so[(2 * lane + 1) * pitch + j0 + j] = (uint8_t)((w2 >> 8) & 0xFFu);
     }
   }
   __syncthreads();
