@@ -53,7 +53,29 @@ __global__ void __launch_bounds__(RM_THREADS) rm_rx_gather_kernel(const int16_t*
     __syncthreads();
     // two outputs per thread and step: n_out = 3K+12 is even and every soft buffer starts on a 4-byte boundary when its
     // offset is even (the decode loop's 18600-value slots are), so pairs move as aligned 32-bit words
-    if (((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(inv)) & 3u) == 0) {
+    if (((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(inv)) & 7u) == 0 && (N & 3u) == 0) {
+      // four outputs per thread and step (n_out = 3K+12 is a multiple of 4, the decode loop's soft-buffer slots start on 8-byte
+      // boundaries): 8-byte table loads and 8-byte stores, half the instructions of the pair form below
+      const uint2* inv4 = reinterpret_cast<const uint2*>(inv);
+      uint2*       out4 = reinterpret_cast<uint2*>(out);
+      for (uint32_t o4 = threadIdx.x; o4 < N / 4; o4 += RM_THREADS) {
+        const uint2    ii = inv4[o4];
+        const uint32_t i0 = ii.x & 0xFFFFu, i1 = ii.x >> 16, i2 = ii.y & 0xFFFFu, i3 = ii.y >> 16;
+        uint2          w  = make_uint2(0u, 0u);
+        if (base == 0) {
+          if (!fresh) w = out4[o4];
+        } else {
+          if (i0 >= len && i1 >= len && i2 >= len && i3 >= len) continue;
+          w = out4[o4];
+        }
+        int a = (int)(int16_t)(w.x & 0xFFFFu), b2 = (int)(int16_t)(w.x >> 16), c2 = (int)(int16_t)(w.y & 0xFFFFu), d2 = (int)(int16_t)(w.y >> 16);
+        if (i0 < len) a += (int)stage[i0];
+        if (i1 < len) b2 += (int)stage[i1];
+        if (i2 < len) c2 += (int)stage[i2];
+        if (i3 < len) d2 += (int)stage[i3];
+        out4[o4] = make_uint2(((uint32_t)a & 0xFFFFu) | ((uint32_t)b2 << 16), ((uint32_t)c2 & 0xFFFFu) | ((uint32_t)d2 << 16));
+      }
+    } else if (((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(inv)) & 3u) == 0) {
       const uint32_t* inv2 = reinterpret_cast<const uint32_t*>(inv);
       uint32_t*       out2 = reinterpret_cast<uint32_t*>(out);
       for (uint32_t o2 = threadIdx.x; o2 < N / 2; o2 += RM_THREADS) {
