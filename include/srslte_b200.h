@@ -323,6 +323,56 @@ SRSRAN_B200_API int srsran_b200_pusch_rx_batch(srsran_b200_pusch_t* q, const voi
                                                void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * One cell's PUSCH receiver for a batch of subframes in ONE call: time samples in, transport-block bytes out.  Replaces, per
+ * subframe, srsran_enb_ul_fft (lib/src/phy/enb/enb_ul.c:151-154) and get_pusch (enb_ul.c:262-290: srsran_chest_ul_estimate_pusch +
+ * srsran_pusch_decode) for subframes that all carry the configured allocation.  The object owns the three engines above, the
+ * device buffers between them and the HARQ soft buffers (slot i = subframe index i of the batch; the caller maps
+ * (UE, HARQ process) to slots and passes new_data[i] = 0, rv[i] for a retransmission into slot i).  With host samples the
+ * host->device copies are chunked on a second stream and overlap the front-end kernels.
+ */
+typedef struct srsran_b200_enb_ul srsran_b200_enb_ul_t; /* opaque; one per host thread */
+
+typedef struct {
+  uint32_t cell_id;
+  uint32_t cell_nof_prb;
+  int      cp_ext;
+  uint32_t symbol_sz;           /* 0 = srsran_symbol_sz(cell_nof_prb) */
+  uint32_t dmrs_cyclic_shift;   /* srsran_refsignal_dmrs_pusch_cfg_t */
+  uint32_t dmrs_delta_ss;
+  int      group_hopping_en;
+  int      sequence_hopping_en;
+  uint32_t L_prb;               /* the allocation of every subframe of a batch */
+  uint32_t n_prb;
+  int      modulation;          /* 1 QPSK, 2 16QAM, 3 64QAM */
+  uint32_t tbs;                 /* transport block size in bits (a standard size: no filler bits) */
+  uint32_t llr_shift;           /* see srsran_b200_pusch_cfg_t */
+  uint32_t max_iterations;      /* decoder passes per code block, 0 = 8 */
+} srsran_b200_enb_ul_cfg_t;
+
+typedef struct {
+  int32_t crc_ok;          /* srsran_pusch_res_t.crc */
+  float   avg_iterations;  /* srsran_pusch_res_t.avg_iterations_block */
+  float   noise_estimate;  /* srsran_chest_ul_res_t */
+  float   snr;
+  float   cfo_hz;
+} srsran_b200_pusch_res_t;
+
+SRSRAN_B200_API int  srsran_b200_enb_ul_init(srsran_b200_enb_ul_t** q, int device, const srsran_b200_enb_ul_cfg_t* cfg);
+SRSRAN_B200_API void srsran_b200_enb_ul_free(srsran_b200_enb_ul_t* q);
+SRSRAN_B200_API int  srsran_b200_enb_ul_geometry(const srsran_b200_enb_ul_t* q, uint32_t* sf_sz, uint32_t* tb_bytes);
+/*
+ * samples  nsf x sf_sz I/Q samples: cf_t, or int16 pairs with SRSRAN_B200_FLAG_IQ_INT16; host memory (page-locked for full PCIe
+ *          speed) or, with SRSRAN_B200_FLAG_DEVICE_PTRS, device memory (then `data` is device memory too)
+ * rnti, tti, n_dmrs, rv, new_data   per-subframe host arrays; NULL = 0 (new_data: NULL = all new)
+ * data     nsf x tb_bytes (= tbs/8 + 3: payload + CRC24A), rows tightly packed
+ * res      nsf results (host)
+ * Synchronous: returns when data and res are complete.
+ */
+SRSRAN_B200_API int srsran_b200_enb_ul_pusch_batch(srsran_b200_enb_ul_t* q, const void* samples, uint32_t nsf, const uint32_t* rnti,
+                                                   const uint32_t* tti, const uint32_t* n_dmrs, const uint32_t* rv, const uint32_t* new_data,
+                                                   uint8_t* data, srsran_b200_pusch_res_t* res, uint32_t flags);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Synthetic workload (bench / tests only, never on the decode path): fills llr_dev[ncb][3K+12] (device memory) with
  * the quantised channel output of randomly drawn, CRC24B-terminated, turbo-encoded blocks:
  * llr = clip(rint(scale * ((2c-1) + sigma*n)), +-clip), the recipe of turbodecoder_test.c:211-255 plus a clip.

@@ -73,6 +73,11 @@ def lib() -> C.CDLL:
     L.srsran_b200_pusch_equalize_deprecode_batch.argtypes = [vp, vp, vp, vp, vp, u32, u32, vp]
     L.srsran_b200_pusch_demod_descramble_batch.argtypes = [vp, vp, vp, u32, vp, vp, u32, vp]
     L.srsran_b200_pusch_rx_batch.argtypes = [vp, vp, vp, vp, u32, vp, vp, vp, u32, vp]
+    L.srsran_b200_enb_ul_init.argtypes = [C.POINTER(vp), C.c_int, vp]
+    L.srsran_b200_enb_ul_free.argtypes = [vp]
+    L.srsran_b200_enb_ul_free.restype = None
+    L.srsran_b200_enb_ul_geometry.argtypes = [vp, C.POINTER(u32), C.POINTER(u32)]
+    L.srsran_b200_enb_ul_pusch_batch.argtypes = [vp, vp, u32, vp, vp, vp, vp, vp, vp, vp, u32]
     L.srsran_b200_synth_llr.argtypes = [C.c_int, vp, vp, u32, u32, C.c_float, C.c_float, C.c_int, C.c_uint64, C.c_int, vp]
     return L
 
@@ -96,6 +101,10 @@ EXPORTED_SYMBOLS = [
     "srsran_b200_pusch_equalize_deprecode_batch",
     "srsran_b200_pusch_demod_descramble_batch",
     "srsran_b200_pusch_rx_batch",
+    "srsran_b200_enb_ul_init",
+    "srsran_b200_enb_ul_free",
+    "srsran_b200_enb_ul_geometry",
+    "srsran_b200_enb_ul_pusch_batch",
     "srsran_b200_synth_llr",
     "srsran_b200_sch_init",
     "srsran_b200_sch_free",

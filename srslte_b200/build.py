@@ -20,6 +20,7 @@ SOURCES = [
     "ofdm_host.cu",
     "demod_kernels.cu",
     "pusch_kernels.cu",
+    "enb_ul.cu",
     "srsran_compat.cu",
     "synth.cu",
 ]

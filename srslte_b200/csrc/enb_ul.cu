@@ -1,0 +1,251 @@
+// Native PUSCH receive pipeline of one cell for a batch of subframes: what srsran_enb_ul_fft (lib/src/phy/enb/enb_ul.c:151-154)
+// and get_pusch (enb_ul.c:262-290: srsran_chest_ul_estimate_pusch + srsran_pusch_decode) do per subframe, as ONE call with time
+// samples in and transport-block bytes out.  It only orchestrates the batched entries of this library
+//     srsran_b200_ofdm_rx_sf_batch -> srsran_b200_pusch_rx_batch -> srsran_b200_sch_decode_batch
+// on device buffers it owns: with host samples the batch is cut into chunks whose host->device copies (second stream) overlap the
+// front-end kernels of the previous chunk, the decode loop then runs over the whole batch (it needs the batch to fill the GPU)
+// while its host-side bookkeeping overlaps the tail of the front end.  HARQ soft buffers live in the object, one slot per
+// subframe index of the batch (the caller maps (UE, HARQ process) to slots).
+#include <cuda_runtime.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "../../include/srslte_b200.h"
+#include "b200_runtime.h"
+#include "tdec_engine.h"
+
+namespace b200 {
+
+struct EnbUl {
+  int                       device = 0;
+  srsran_b200_enb_ul_cfg_t  cfg{};
+  srsran_b200_ofdm_t*       ofdm  = nullptr;
+  srsran_b200_pusch_t*      pusch = nullptr;
+  srsran_b200_sch_t*        sch   = nullptr;
+  cudaStream_t              compute = nullptr, copy = nullptr;
+  std::vector<cudaEvent_t>  ev;
+  uint32_t sf_sz = 0, nsym = 0, nre = 0, nbits = 0, ncb = 0, data_stride = 0;
+  // device buffers, grow-only
+  uint32_t cap_sf = 0;
+  void*    d_iq   = nullptr;
+  float2*  d_grid = nullptr;
+  int16_t* d_llr  = nullptr;
+  int16_t* d_soft = nullptr;
+  uint8_t* d_data = nullptr;
+  float*   d_meas = nullptr;
+  std::vector<srsran_b200_tb_t> tbs;
+  std::vector<uint32_t>         crc_mask; // per slot, carried across retransmissions (sch.c:474-488)
+  std::vector<float>            h_meas;
+
+  ~EnbUl()
+  {
+    cudaSetDevice(device);
+    if (ofdm) srsran_b200_ofdm_rx_free(ofdm);
+    if (pusch) srsran_b200_pusch_free(pusch);
+    if (sch) srsran_b200_sch_free(sch);
+    for (void* p : {d_iq, (void*)d_grid, (void*)d_llr, (void*)d_soft, (void*)d_data, (void*)d_meas}) {
+      if (p) cudaFree(p);
+    }
+    for (cudaEvent_t e : ev) cudaEventDestroy(e);
+    if (compute) cudaStreamDestroy(compute);
+    if (copy) cudaStreamDestroy(copy);
+  }
+
+  int init(int dev, const srsran_b200_enb_ul_cfg_t& c)
+  {
+    device = dev;
+    cfg    = c;
+    if (c.modulation < 1 || c.modulation > 3 || c.tbs == 0) return B200_ERROR_INVALID_INPUTS;
+    B200_CUDA_TRY(cudaSetDevice(dev));
+    // the eNB's uplink OFDM configuration (enb_ul.c:50-58): half-subcarrier shift, window advanced by half a CP, no normalisation
+    srsran_b200_ofdm_cfg_t oc;
+    memset(&oc, 0, sizeof(oc));
+    oc.nof_prb          = c.cell_nof_prb;
+    oc.cp_ext           = c.cp_ext;
+    oc.symbol_sz        = c.symbol_sz;
+    oc.freq_shift_f     = -0.5f;
+    oc.rx_window_offset = 0.5f;
+    int rc              = srsran_b200_ofdm_rx_init(&ofdm, dev, &oc);
+    if (rc != B200_SUCCESS) return rc;
+    srsran_b200_pusch_cfg_t pc;
+    memset(&pc, 0, sizeof(pc));
+    pc.cell_id             = c.cell_id;
+    pc.cell_nof_prb        = c.cell_nof_prb;
+    pc.cp_ext              = c.cp_ext;
+    pc.L_prb               = c.L_prb;
+    pc.n_prb               = c.n_prb;
+    pc.modulation          = c.modulation;
+    pc.llr_shift           = c.llr_shift;
+    pc.dmrs_cyclic_shift   = c.dmrs_cyclic_shift;
+    pc.dmrs_delta_ss       = c.dmrs_delta_ss;
+    pc.group_hopping_en    = c.group_hopping_en;
+    pc.sequence_hopping_en = c.sequence_hopping_en;
+    if ((rc = srsran_b200_pusch_init(&pusch, dev, &pc)) != B200_SUCCESS) return rc;
+    if ((rc = srsran_b200_sch_init(&sch, dev)) != B200_SUCCESS) return rc;
+    srsran_b200_sch_set_max_noi(sch, c.max_iterations ? c.max_iterations : 8);
+    uint32_t symsz = 0;
+    srsran_b200_ofdm_rx_geometry(ofdm, &symsz, &sf_sz, &nsym, &nre);
+    uint32_t nof_re = 0, nd = 0;
+    srsran_b200_pusch_geometry(pusch, &nof_re, &nbits, &nd);
+    // code blocks of the transport block (36.212 5.1.2): B = tbs + 24, C = ceil(B / (6144 - 24)) when B > 6144
+    const uint32_t B = c.tbs + 24;
+    ncb              = B <= 6144 ? 1 : (B + 6119) / 6120;
+    data_stride      = (c.tbs / 8 + 3 + 768 + 15) / 16 * 16;
+    B200_CUDA_TRY(cudaStreamCreateWithFlags(&compute, cudaStreamNonBlocking));
+    B200_CUDA_TRY(cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking));
+    return B200_SUCCESS;
+  }
+
+  int reserve(uint32_t nsf, bool host_samples, size_t sample_bytes)
+  {
+    if (nsf > cap_sf) {
+      for (void* p : {(void*)d_grid, (void*)d_llr, (void*)d_soft, (void*)d_data, (void*)d_meas, d_iq}) {
+        if (p) cudaFree(p);
+      }
+      d_grid = nullptr; d_llr = nullptr; d_soft = nullptr; d_data = nullptr; d_meas = nullptr; d_iq = nullptr;
+      cap_sf = 0;
+      B200_CUDA_TRY(cudaMalloc(&d_grid, (size_t)nsf * nsym * nre * sizeof(float2)));
+      B200_CUDA_TRY(cudaMalloc(&d_llr, (size_t)nsf * nbits * sizeof(int16_t)));
+      B200_CUDA_TRY(cudaMalloc(&d_soft, (size_t)nsf * ncb * SRSRAN_B200_SOFTBUFFER_SIZE * sizeof(int16_t)));
+      B200_CUDA_TRY(cudaMemset(d_soft, 0, (size_t)nsf * ncb * SRSRAN_B200_SOFTBUFFER_SIZE * sizeof(int16_t)));
+      B200_CUDA_TRY(cudaMalloc(&d_data, (size_t)nsf * data_stride));
+      B200_CUDA_TRY(cudaMemset(d_data, 0, (size_t)nsf * data_stride));
+      B200_CUDA_TRY(cudaMalloc(&d_meas, (size_t)nsf * 4 * sizeof(float)));
+      B200_CUDA_TRY(cudaMalloc(&d_iq, (size_t)nsf * sf_sz * sizeof(float2))); // sized for float samples
+      cap_sf = nsf;
+      tbs.assign(nsf, srsran_b200_tb_t{});
+      crc_mask.assign(nsf, 0u);
+      h_meas.assign((size_t)nsf * 4, 0.f);
+      for (uint32_t i = 0; i < nsf; i++) {
+        tbs[i].tbs         = cfg.tbs;
+        tbs[i].Qm          = 2u * (uint32_t)cfg.modulation;
+        tbs[i].nof_e_bits  = nbits;
+        tbs[i].e_offset    = (uint64_t)i * nbits;
+        tbs[i].soft_offset = (uint64_t)i * ncb * SRSRAN_B200_SOFTBUFFER_SIZE;
+        tbs[i].data_offset = (uint64_t)i * data_stride;
+      }
+    }
+    (void)host_samples;
+    (void)sample_bytes;
+    return B200_SUCCESS;
+  }
+
+  int run(const void* samples, uint32_t nsf, const uint32_t* rnti, const uint32_t* tti, const uint32_t* n_dmrs, const uint32_t* rv,
+          const uint32_t* new_data, uint8_t* data, srsran_b200_pusch_res_t* res, uint32_t flags)
+  {
+    if (!samples || !data || !res) return B200_ERROR_INVALID_INPUTS;
+    if (nsf == 0) return B200_SUCCESS;
+    B200_CUDA_TRY(cudaSetDevice(device));
+    const bool   dev_ptrs = (flags & SRSRAN_B200_FLAG_DEVICE_PTRS) != 0;
+    const bool   iq16     = (flags & SRSRAN_B200_FLAG_IQ_INT16) != 0;
+    const size_t ssz      = iq16 ? 2 * sizeof(int16_t) : sizeof(float2);
+    int          rc       = reserve(nsf, !dev_ptrs, ssz);
+    if (rc != B200_SUCCESS) return rc;
+    const uint32_t fe_flags = SRSRAN_B200_FLAG_DEVICE_PTRS | (iq16 ? SRSRAN_B200_FLAG_IQ_INT16 : 0u);
+
+    // ---- front end, chunk by chunk -----------------------------------------------------------------------------------------
+    const uint32_t chunk   = dev_ptrs ? nsf : (nsf > 1024 ? 512u : (nsf + 1) / 2);
+    const uint32_t nchunks = (nsf + chunk - 1) / chunk;
+    while (ev.size() < nchunks) {
+      cudaEvent_t e;
+      B200_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      ev.push_back(e);
+    }
+    for (uint32_t c = 0; c < nchunks; c++) {
+      const uint32_t first = c * chunk, n = (nsf - first) < chunk ? (nsf - first) : chunk;
+      const char*    in    = (const char*)samples + (size_t)first * sf_sz * ssz;
+      const void*    d_in  = in;
+      if (!dev_ptrs) {
+        char* dst = (char*)d_iq + (size_t)first * sf_sz * ssz;
+        B200_CUDA_TRY(cudaMemcpyAsync(dst, in, (size_t)n * sf_sz * ssz, cudaMemcpyHostToDevice, copy));
+        B200_CUDA_TRY(cudaEventRecord(ev[c], copy));
+        B200_CUDA_TRY(cudaStreamWaitEvent(compute, ev[c], 0));
+        d_in = dst;
+      }
+      float2* grid_c = d_grid + (size_t)first * nsym * nre;
+      if ((rc = srsran_b200_ofdm_rx_sf_batch(ofdm, d_in, grid_c, n, fe_flags, compute)) != B200_SUCCESS) return rc;
+      if ((rc = srsran_b200_pusch_rx_batch(pusch, grid_c, d_llr + (size_t)first * nbits, d_meas + (size_t)first * 4, n, rnti ? rnti + first : nullptr,
+                                           tti ? tti + first : nullptr, n_dmrs ? n_dmrs + first : nullptr, SRSRAN_B200_FLAG_DEVICE_PTRS,
+                                           compute)) != B200_SUCCESS) {
+        return rc;
+      }
+    }
+
+    // ---- decode loop over the whole batch ------------------------------------------------------------------------------------
+    for (uint32_t i = 0; i < nsf; i++) {
+      const bool fresh   = new_data ? new_data[i] != 0 : true;
+      tbs[i].rv          = rv ? rv[i] : 0u;
+      tbs[i].new_data    = fresh ? 1u : 0u;
+      tbs[i].cb_crc_mask = fresh ? 0u : crc_mask[i];
+    }
+    srsran_b200_sch_decode_after(sch, compute);
+    rc = srsran_b200_sch_decode_batch(sch, d_llr, (uint64_t)nsf * nbits, d_soft, (uint64_t)cap_sf * ncb * SRSRAN_B200_SOFTBUFFER_SIZE, d_data,
+                                      (uint64_t)cap_sf * data_stride, tbs.data(), nsf, SRSRAN_B200_FLAG_DEVICE_PTRS);
+    if (rc != B200_SUCCESS) return rc;
+    // (the decode call has synchronised its stream, which was ordered after `compute`: front end, meas copy and decode are done)
+    B200_CUDA_TRY(cudaMemcpyAsync(h_meas.data(), d_meas, (size_t)nsf * 4 * sizeof(float), cudaMemcpyDeviceToHost, compute));
+    const size_t out_b = (size_t)cfg.tbs / 8 + 3;
+    if (dev_ptrs) {
+      B200_CUDA_TRY(cudaMemcpy2DAsync(data, out_b, d_data, data_stride, out_b, nsf, cudaMemcpyDeviceToDevice, compute));
+    } else {
+      B200_CUDA_TRY(cudaMemcpy2DAsync(data, out_b, d_data, data_stride, out_b, nsf, cudaMemcpyDeviceToHost, compute));
+    }
+    B200_CUDA_TRY(cudaStreamSynchronize(compute));
+    for (uint32_t i = 0; i < nsf; i++) {
+      crc_mask[i]           = tbs[i].cb_crc_mask;
+      res[i].crc_ok         = tbs[i].result == B200_SUCCESS ? 1 : 0;
+      res[i].avg_iterations = tbs[i].avg_iterations;
+      res[i].noise_estimate = h_meas[4 * (size_t)i + 0];
+      res[i].snr            = h_meas[4 * (size_t)i + 1];
+      res[i].cfo_hz         = h_meas[4 * (size_t)i + 2];
+    }
+    return B200_SUCCESS;
+  }
+};
+
+} // namespace b200
+
+using namespace b200;
+
+struct srsran_b200_enb_ul {
+  EnbUl e;
+};
+
+extern "C" SRSRAN_B200_API int srsran_b200_enb_ul_init(srsran_b200_enb_ul_t** q, int device, const srsran_b200_enb_ul_cfg_t* cfg)
+{
+  if (!q || !cfg) return B200_ERROR_INVALID_INPUTS;
+  *q                      = nullptr;
+  srsran_b200_enb_ul_t* h = new (std::nothrow) srsran_b200_enb_ul_t();
+  if (!h) return B200_ERROR;
+  const int rc = h->e.init(device, *cfg);
+  if (rc != B200_SUCCESS) {
+    delete h;
+    return rc;
+  }
+  *q = h;
+  return B200_SUCCESS;
+}
+
+extern "C" SRSRAN_B200_API void srsran_b200_enb_ul_free(srsran_b200_enb_ul_t* q)
+{
+  delete q;
+}
+
+extern "C" SRSRAN_B200_API int srsran_b200_enb_ul_geometry(const srsran_b200_enb_ul_t* q, uint32_t* sf_sz, uint32_t* tb_bytes)
+{
+  if (!q) return B200_ERROR_INVALID_INPUTS;
+  if (sf_sz) *sf_sz = q->e.sf_sz;
+  if (tb_bytes) *tb_bytes = q->e.cfg.tbs / 8 + 3;
+  return B200_SUCCESS;
+}
+
+extern "C" SRSRAN_B200_API int srsran_b200_enb_ul_pusch_batch(srsran_b200_enb_ul_t* q, const void* samples, uint32_t nsf, const uint32_t* rnti,
+                                                             const uint32_t* tti, const uint32_t* n_dmrs, const uint32_t* rv,
+                                                             const uint32_t* new_data, uint8_t* data, srsran_b200_pusch_res_t* res,
+                                                             uint32_t flags)
+{
+  if (!q) return B200_ERROR_INVALID_INPUTS;
+  return q->e.run(samples, nsf, rnti, tti, n_dmrs, rv, new_data, data, res, flags);
+}

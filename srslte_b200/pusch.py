@@ -245,3 +245,61 @@ class PuschRxFull(PuschRx):
     def run(self, iq, nsf: int, rnti=None, tti=None, n_dmrs=None, rv: int = 0):
         self.front_end(iq, nsf, rnti, tti, n_dmrs)
         return self.decode(nsf, rv)
+
+
+class EnbUlCfg(C.Structure):
+    """srsran_b200_enb_ul_cfg_t"""
+    _fields_ = [("cell_id", C.c_uint32), ("cell_nof_prb", C.c_uint32), ("cp_ext", C.c_int), ("symbol_sz", C.c_uint32),
+                ("dmrs_cyclic_shift", C.c_uint32), ("dmrs_delta_ss", C.c_uint32), ("group_hopping_en", C.c_int),
+                ("sequence_hopping_en", C.c_int), ("L_prb", C.c_uint32), ("n_prb", C.c_uint32), ("modulation", C.c_int), ("tbs", C.c_uint32),
+                ("llr_shift", C.c_uint32), ("max_iterations", C.c_uint32)]
+
+
+PUSCH_RES_DTYPE = np.dtype([("crc_ok", "<i4"), ("avg_iterations", "<f4"), ("noise_estimate", "<f4"), ("snr", "<f4"), ("cfo_hz", "<f4")])
+
+
+class EnbUl:
+    """srsran_b200_enb_ul_*: the native one-call PUSCH receiver (time samples in, transport-block bytes out)."""
+
+    def __init__(self, cell_id=1, nof_prb=100, tbs=75376, mod=3, llr_shift=4, max_noi=8, device=0, symbol_sz=0, L_prb=None, n_prb=0,
+                 cyclic_shift=0, delta_ss=0, cp_ext=False):
+        self._lib = _lib.lib()
+        self.cfg = EnbUlCfg(cell_id, nof_prb, int(cp_ext), symbol_sz, cyclic_shift, delta_ss, 0, 0, L_prb if L_prb is not None else nof_prb,
+                            n_prb, mod, tbs, llr_shift, max_noi)
+        self._h = C.c_void_p()
+        rc = self._lib.srsran_b200_enb_ul_init(C.byref(self._h), device, C.byref(self.cfg))
+        if rc != _lib.SUCCESS:
+            raise RuntimeError(f"srsran_b200_enb_ul_init failed ({rc})")
+        a, b = C.c_uint32(), C.c_uint32()
+        self._lib.srsran_b200_enb_ul_geometry(self._h, C.byref(a), C.byref(b))
+        self.sf_sz, self.tb_bytes = a.value, b.value
+
+    def close(self):
+        if self._h:
+            self._lib.srsran_b200_enb_ul_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def run_ptr(self, samples_ptr: int, nsf: int, rnti, tti, data_ptr: int, res: np.ndarray, n_dmrs=None, rv=None, new_data=None,
+                flags: int = 0):
+        """Raw pointers (host unless FLAG_DEVICE_PTRS); res: numpy array of PUSCH_RES_DTYPE with nsf entries."""
+        k = [PuschChain._u32(a, nsf) for a in (rnti, tti, n_dmrs, rv, new_data)]
+        rc = self._lib.srsran_b200_enb_ul_pusch_batch(self._h, samples_ptr, nsf, k[0][1], k[1][1], k[2][1], k[3][1], k[4][1], data_ptr,
+                                                      res.ctypes.data, flags)
+        if rc != _lib.SUCCESS:
+            raise RuntimeError(f"srsran_b200_enb_ul_pusch_batch failed ({rc})")
+
+    def run(self, samples: np.ndarray, rnti, tti, n_dmrs=None, rv=None, new_data=None):
+        """samples: (nsf, sf_sz) complex64 or (nsf, sf_sz, 2) int16 host array.  Returns (bytes (nsf, tb_bytes) uint8, results)."""
+        samples = np.ascontiguousarray(samples)
+        nsf = samples.shape[0]
+        fl = _lib.FLAG_IQ_INT16 if samples.dtype == np.int16 else 0
+        data = np.zeros((nsf, self.tb_bytes), np.uint8)
+        res = np.zeros(nsf, PUSCH_RES_DTYPE)
+        self.run_ptr(samples.ctypes.data, nsf, rnti, tti, data.ctypes.data, res, n_dmrs, rv, new_data, fl)
+        return data, res

@@ -238,3 +238,40 @@ def test_full_pipeline_from_time_samples(port):
     ok2, _ = rx.run(torch.from_numpy(iq).cuda(), nsf, rnti + 1, tti)
     assert not ok2.any()
     rx.close()
+
+
+def test_native_enb_ul_pipeline_with_harq(port):
+    """srsran_b200_enb_ul_pusch_batch: host samples in (float and int16), transport-block bytes out, results, and a HARQ
+    retransmission into the same slots (first transmission too noisy to decode, second one combines)."""
+    from srslte_b200 import synth_pusch as sp
+    from srslte_b200.pusch import EnbUl, PuschChain
+
+    tbs, nsf = 75376, 5
+    ch = PuschChain(17, 100, False, 100, 0, 3, 4)
+    dm = {sf: ch.dmrs(sf, 0) for sf in range(10)}
+    ch.close()
+    rnti = np.array([62, 159, 4000, 65535, 7], np.uint32)
+    tti = np.array([0, 13, 26, 9, 1234], np.uint32)
+    qpp = sp.qpp_interleaver(5824)
+    iq, payload, _ = sp.make_subframes_full(17, 100, 2048, tbs, 6, 0, qpp, nsf, rnti, tti, lambda sf: dm[sf], 23.0, seed=3)
+    enb = EnbUl(17, 100, tbs, 3, llr_shift=4, max_noi=8, symbol_sz=2048)
+    data, res = enb.run(iq, rnti, tti)
+    assert res["crc_ok"].all() and (data == payload).all()
+    assert (np.abs(10 * np.log10(res["snr"]) - 23.0) < 1.5).all()
+    # int16 samples (scaled to about half of full scale)
+    peak = np.abs(iq.view(np.float32)).max()
+    iq16 = np.round(iq.view(np.float32).reshape(nsf, -1, 2) * (16384.0 / peak)).astype(np.int16)
+    data16, res16 = enb.run(iq16, rnti, tti)
+    assert res16["crc_ok"].all() and (data16 == payload).all()
+    # HARQ: rv 0 at 14 dB fails, rv 2 of the same transport blocks into the same slots succeeds
+    iq_a, payload2, _ = sp.make_subframes_full(17, 100, 2048, tbs, 6, 0, qpp, nsf, rnti, tti, lambda sf: dm[sf], 14.0, seed=9, fading=False)
+    iq_b, payload2b, _ = sp.make_subframes_full(17, 100, 2048, tbs, 6, 2, qpp, nsf, rnti, tti, lambda sf: dm[sf], 14.0, seed=9, fading=False)
+    assert (payload2 == payload2b).all()
+    _, r1 = enb.run(iq_a, rnti, tti, rv=np.zeros(nsf, np.uint32), new_data=np.ones(nsf, np.uint32))
+    assert not r1["crc_ok"].any()
+    d2, r2 = enb.run(iq_b, rnti, tti, rv=np.full(nsf, 2, np.uint32), new_data=np.zeros(nsf, np.uint32))
+    assert r2["crc_ok"].all() and (d2 == payload2).all()
+    # ... while the retransmission alone does not decode
+    _, r3 = enb.run(iq_b, rnti, tti, rv=np.full(nsf, 2, np.uint32), new_data=np.ones(nsf, np.uint32))
+    assert not r3["crc_ok"].any()
+    enb.close()
