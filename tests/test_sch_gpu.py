@@ -134,3 +134,49 @@ def test_filler_bits_rejected(sch):
     rc, res = sch.decode(np.zeros(20000, np.int16), soft, data, [dict(tbs=tbs, Qm=2, rv=0, nof_e_bits=20000, e_offset=0, soft_offset=0,
                                                                      data_offset=0)])
     assert rc == 0 and res[0]["result"] == -2
+
+
+def test_config2_all_188_sizes_in_one_dematch_and_decode_batch(sch, port):
+    """BASELINE.json configs[2]: every LTE QPP size K = 40..6144 in ONE batch through rate de-matching + turbo decoding, with
+    punctured (E < 3K+12), exactly fitting and repeated (E > 3K+12) transmissions and all four redundancy versions.
+    One single-code-block transport block per size (TBS = K - 24, CRC24A): bytes, verdicts, pass counts and the combined soft
+    buffers must equal the oracle's decode_tb."""
+    Ks = port.cb_sizes()
+    assert len(Ks) == 188
+    e_all, tbs_desc, want = [], [], []
+    e_off = soft_off = data_off = 0
+    for i, K in enumerate(Ks):
+        K = int(K)
+        tbs, Qm = K - 24, 2
+        ratio = (0.45, 1.0, 1.7)[i % 3]
+        G = max(2 * Qm, int(ratio * (3 * K + 12)) // Qm * Qm)
+        if ratio == 1.0:
+            G = 3 * K + 12
+        rv = i % 4 if ratio > 0.9 else 0          # heavily punctured blocks only decode from rv 0
+        sigma = 0.55 if ratio < 0.9 else 0.85
+        e, _, s = make_tb(port, tbs, Qm, G, rv, sigma, seed=3000 + i)
+        assert s["C"] == 1 and s["K1"] == K and s["F"] == 0
+        soft = np.zeros(SB, np.int16)
+        cbcrc = np.zeros(1, np.uint8)
+        data = np.zeros(tbs // 8 + 3 + 768, np.uint8)
+        ret, iters = port.decode_tb(e, tbs, Qm, rv, 8, soft, cbcrc, data)
+        want.append((ret, iters, int(cbcrc[0]), data[:tbs // 8 + 3].copy(), soft[:3 * K + 12].copy(), data_off, soft_off, tbs, K))
+        tbs_desc.append(dict(tbs=tbs, Qm=Qm, rv=rv, nof_e_bits=G, e_offset=e_off, soft_offset=soft_off, data_offset=data_off, new_data=1))
+        e_all.append(e)
+        e_off += G
+        soft_off += SB
+        data_off += (tbs // 8 + 3 + 768 + 15) // 16 * 16
+    e_all = np.concatenate(e_all)
+    soft_pool = np.zeros(soft_off, np.int16)
+    data = np.zeros(data_off + 1024, np.uint8)
+    rc, res = sch.decode(e_all, soft_pool, data, tbs_desc)
+    assert rc == 0
+    n_ok = 0
+    for r, (ret, iters, cbok, d, soft, doff, soff, tbs, K) in zip(res, want):
+        assert r["result"] == ret and r["nof_cb"] == 1, K
+        assert abs(r["avg_iterations"] - iters) < 1e-6, K
+        assert r["cb_crc_mask"] == cbok, K
+        assert (data[doff: doff + tbs // 8 + 3] == d).all(), K
+        assert (soft_pool[soff: soff + 3 * K + 12] == soft).all(), K
+        n_ok += ret == 0
+    assert n_ok > 150  # the point is parity, but most of the batch should decode
