@@ -98,7 +98,7 @@ struct EnbUl {
     return B200_SUCCESS;
   }
 
-  int reserve(uint32_t nsf, bool host_samples, size_t sample_bytes)
+  int reserve(uint32_t nsf)
   {
     if (nsf > cap_sf) {
       for (void* p : {(void*)d_grid, (void*)d_llr, (void*)d_soft, (void*)d_data, (void*)d_meas, d_iq}) {
@@ -127,8 +127,6 @@ struct EnbUl {
         tbs[i].data_offset = (uint64_t)i * data_stride;
       }
     }
-    (void)host_samples;
-    (void)sample_bytes;
     return B200_SUCCESS;
   }
 
@@ -141,7 +139,7 @@ struct EnbUl {
     const bool   dev_ptrs = (flags & SRSRAN_B200_FLAG_DEVICE_PTRS) != 0;
     const bool   iq16     = (flags & SRSRAN_B200_FLAG_IQ_INT16) != 0;
     const size_t ssz      = iq16 ? 2 * sizeof(int16_t) : sizeof(float2);
-    int          rc       = reserve(nsf, !dev_ptrs, ssz);
+    int          rc       = reserve(nsf);
     if (rc != B200_SUCCESS) return rc;
     const uint32_t fe_flags = SRSRAN_B200_FLAG_DEVICE_PTRS | (iq16 ? SRSRAN_B200_FLAG_IQ_INT16 : 0u);
 
