@@ -275,3 +275,37 @@ def test_native_enb_ul_pipeline_with_harq(port):
     _, r3 = enb.run(iq_b, rnti, tti, rv=np.full(nsf, 2, np.uint32), new_data=np.ones(nsf, np.uint32))
     assert not r3["crc_ok"].any()
     enb.close()
+
+
+def test_entries_reject_bad_arguments():
+    """Error behaviour in the reference's style: SRSRAN_ERROR_INVALID_INPUTS (-2) for missing pointers, host pointers where the
+    stage works on device buffers, and out-of-range per-subframe parameters; nothing is launched."""
+    import torch
+
+    from srslte_b200 import _lib
+    from srslte_b200.pusch import EnbUl, PuschChain
+
+    L = _lib.lib()
+    ch = PuschChain(1, 25, False, 25, 0, 2, 0)
+    grid = torch.zeros((1, 14, 300), dtype=torch.complex64, device="cuda")
+    ce = torch.zeros((1, 2, 300), dtype=torch.complex64, device="cuda")
+    meas = torch.zeros((1, 4), dtype=torch.float32, device="cuda")
+    g = torch.zeros((1, ch.nof_bits), dtype=torch.int16, device="cuda")
+    assert L.srsran_b200_chest_ul_pusch_batch(ch._h, None, 1, None, None, ce.data_ptr(), meas.data_ptr(), 1, None) == -2
+    assert L.srsran_b200_chest_ul_pusch_batch(ch._h, grid.data_ptr(), 1, None, None, ce.data_ptr(), meas.data_ptr(), 0, None) == -2
+    assert L.srsran_b200_pusch_rx_batch(None, grid.data_ptr(), g.data_ptr(), None, 1, None, None, None, 1, None) == -2
+    assert L.srsran_b200_pusch_rx_batch(ch._h, grid.data_ptr(), g.data_ptr(), None, 1, None, None, None, 0, None) == -2
+    bad = np.array([8], np.uint32)  # n_dmrs > 7 (refsignal_ul.c:327)
+    assert L.srsran_b200_pusch_rx_batch(ch._h, grid.data_ptr(), g.data_ptr(), None, 1, None, None, bad.ctypes.data, 1, None) == -2
+    assert L.srsran_b200_pusch_rx_batch(ch._h, grid.data_ptr(), g.data_ptr(), None, 0, None, None, None, 1, None) == 0  # empty batch
+    r = np.zeros(2 * 300, np.complex64)
+    assert L.srsran_b200_refsignal_dmrs_pusch_gen(ch._h, 10, 0, r.ctypes.data) == -2
+    ch.close()
+    with pytest.raises(RuntimeError):
+        EnbUl(1, 25, 0, 2)        # no transport block
+    with pytest.raises(RuntimeError):
+        EnbUl(1, 25, 4584, 5)     # unknown modulation
+    enb = EnbUl(1, 25, 4584, 2, llr_shift=3, symbol_sz=512)
+    res = np.zeros(1, np.dtype([("a", "<i4"), ("b", "<f4"), ("c", "<f4"), ("d", "<f4"), ("e", "<f4")]))
+    assert L.srsran_b200_enb_ul_pusch_batch(enb._h, None, 1, None, None, None, None, None, None, res.ctypes.data, 0) == -2
+    enb.close()
