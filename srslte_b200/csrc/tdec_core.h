@@ -316,7 +316,13 @@ B200_HD void win_emit(WinOut& o, LaneResult& res, const CrcPow* cw, int t, uint3
 {
   sink(t, L);
   const uint32_t one = pos2(L);
+#if defined(__CUDA_ARCH__)
+  // bits += one * 2^(7-t) as an integer multiply-add: it issues on the FMA pipe, which idles while the packed-halfword
+  // instructions keep the ALU pipe busy (a shift + OR would go there as well); the bit positions never collide, so + is |
+  asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(o.bits) : "r"(one), "r"(1u << (7 - t)));
+#else
   o.bits |= one << (7 - t);
+#endif
   if (cw) {
     const CrcPow   c    = cw[t];
     const uint32_t mask = one * 0xFFFFu;
