@@ -10,6 +10,13 @@ iterations, turbodecoder_iter.h:104-140), CRC24B evaluated after every pass.
           Extra keys report the same batch with CRC early stop on (the reference's decode_tb_cb loop, sch.c:425-454).
   e2e   : the same metric through the C ABI with HOST buffers (pinned): H2D of the LLRs and D2H of bits/flags inside
           the timed region, chunk-pipelined by the library.
+  e2e_int8_container : e2e with the same LLR values in the 8-bit soft-bit container (half the PCIe bytes)
+  roofline / roofline_int16_alu : SISO launch time against the measured HBM copy peak (algorithmic bytes) and against the
+          measured packed-int16 issue peak (the reference's literal operation count)
+  early_stop / early_stop_sweep : the batch (and fresh batches at 0.5 / 1 / 2.5 / 4 dB) with CRC early stop on
+  pusch      : BASELINE's second metric, 20 MHz PUSCH subframes/s through OFDM rx -> demap -> de-match -> decode (identity channel)
+  pusch_full : the same subframe through the complete receiver (channel estimation, equaliser, transform de-precoding,
+          descrambling, de-interleave); its e2e is ONE native call per step (srsran_b200_enb_ul_pusch_batch) with host samples
   --impl reference : the reference's own CPU decoder (AVX2 16-lane window, srsran_tdec AUTO) from oracle/_ref on all
           host cores, same config, bounded sample per step.
 
