@@ -92,12 +92,36 @@ SRSRAN_B200_API int srsran_b200_tdec_run(srsran_b200_tdec_t* h,
                                          void*               stream);
 
 /*
+ * BASELINE config 3: code blocks of SEVERAL lengths in one batch (turbodecoder.c:510-525 re-arms the reference's decoder per
+ * block length; here every tile of 64 blocks carries its own K and one launch per pass covers all of them, longest first).
+ *   llr     group after group: ncb[0] vectors of 3*K[0]+12 int16, then ncb[1] vectors of 3*K[1]+12, ...
+ *   out     group after group: K[g]/8 bytes per block;  crc_ok, npass: one entry per block in the same order
+ *   K, ncb  host arrays of n_groups entries; every K must be one of the 188 sizes (else SRSRAN_ERROR like srsran_tdec_new_cb)
+ * Other arguments and the host / device pointer rule as srsran_b200_tdec_run (no int8 container here).
+ */
+SRSRAN_B200_API int srsran_b200_tdec_run_mixed(srsran_b200_tdec_t* h,
+                                               const int16_t*      llr,
+                                               uint32_t            n_groups,
+                                               const uint32_t*     K,
+                                               const uint32_t*     ncb,
+                                               uint32_t            max_passes,
+                                               int                 crc_kind,
+                                               int                 early_stop,
+                                               uint8_t*            out,
+                                               uint8_t*            crc_ok,
+                                               uint8_t*            npass,
+                                               uint32_t            flags,
+                                               void*               stream);
+
+/*
  * Optional kernel timing: with enable != 0 every kernel the object launches is bracketed by CUDA events on the
  * launching stream; profile_get synchronises the device and returns accumulated milliseconds and launch counts for
  * the three kernel classes [0] layout load, [1] SISO pass, [2] decision/pack.  Reset clears the history.
  */
 SRSRAN_B200_API void srsran_b200_tdec_profile_reset(srsran_b200_tdec_t* h, int enable);
 SRSRAN_B200_API int  srsran_b200_tdec_profile_get(srsran_b200_tdec_t* h, double* ms_by_class, uint64_t* launches_by_class);
+/* Same with nclasses entries: [3] = re-packing of the still-running blocks between the passes of an early-stop decode. */
+SRSRAN_B200_API int  srsran_b200_tdec_profile_get_ex(srsran_b200_tdec_t* h, double* ms_by_class, uint64_t* launches_by_class, int nclasses);
 /* Resident CTAs (tiles of 64 code blocks) per SM of the SISO pass kernel on the current device, as the CUDA occupancy
  * calculator reports it; -1 on error.  Diagnostic: a 65,536-block batch is one wave when this is >= 7 on 148 SMs. */
 SRSRAN_B200_API int  srsran_b200_tdec_resident_tiles_per_sm(void);
@@ -371,24 +395,6 @@ SRSRAN_B200_API int  srsran_b200_enb_ul_geometry(const srsran_b200_enb_ul_t* q, 
 SRSRAN_B200_API int srsran_b200_enb_ul_pusch_batch(srsran_b200_enb_ul_t* q, const void* samples, uint32_t nsf, const uint32_t* rnti,
                                                    const uint32_t* tti, const uint32_t* n_dmrs, const uint32_t* rv, const uint32_t* new_data,
                                                    uint8_t* data, srsran_b200_pusch_res_t* res, uint32_t flags);
-
-/* ---------------------------------------------------------------------------------------------------------------
- * Synthetic workload (bench / tests only, never on the decode path): fills llr_dev[ncb][3K+12] (device memory) with
- * the quantised channel output of randomly drawn, CRC24B-terminated, turbo-encoded blocks:
- * llr = clip(rint(scale * ((2c-1) + sigma*n)), +-clip), the recipe of turbodecoder_test.c:211-255 plus a clip.
- * truth_dev (optional) receives the transmitted K bits of every block, packed MSB first, [ncb][K/8].
- */
-SRSRAN_B200_API int srsran_b200_synth_llr(int      device,
-                                          int16_t* llr_dev,
-                                          uint8_t* truth_dev,
-                                          uint32_t ncb,
-                                          uint32_t K,
-                                          float    sigma,
-                                          float    scale,
-                                          int      clip,
-                                          uint64_t seed,
-                                          int      attach_crc,
-                                          void*    stream);
 
 #ifdef __cplusplus
 }

@@ -41,6 +41,8 @@ def lib() -> C.CDLL:
     L.srsran_b200_tdec_free.argtypes = [vp]
     L.srsran_b200_tdec_free.restype = None
     L.srsran_b200_tdec_run.argtypes = [vp, vp, u32, u32, u32, C.c_int, C.c_int, vp, vp, vp, u32, vp]
+    L.srsran_b200_tdec_run_mixed.argtypes = [vp, vp, u32, vp, vp, u32, C.c_int, C.c_int, vp, vp, vp, u32, vp]
+    L.srsran_b200_tdec_profile_get_ex.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.c_int]
     L.srsran_b200_tdec_profile_reset.argtypes = [vp, C.c_int]
     L.srsran_b200_tdec_profile_reset.restype = None
     L.srsran_b200_tdec_profile_get.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
@@ -78,7 +80,6 @@ def lib() -> C.CDLL:
     L.srsran_b200_enb_ul_free.restype = None
     L.srsran_b200_enb_ul_geometry.argtypes = [vp, C.POINTER(u32), C.POINTER(u32)]
     L.srsran_b200_enb_ul_pusch_batch.argtypes = [vp, vp, u32, vp, vp, vp, vp, vp, vp, vp, u32]
-    L.srsran_b200_synth_llr.argtypes = [C.c_int, vp, vp, u32, u32, C.c_float, C.c_float, C.c_int, C.c_uint64, C.c_int, vp]
     return L
 
 
@@ -89,6 +90,8 @@ EXPORTED_SYMBOLS = [
     "srsran_b200_tdec_init",
     "srsran_b200_tdec_free",
     "srsran_b200_tdec_run",
+    "srsran_b200_tdec_run_mixed",
+    "srsran_b200_tdec_profile_get_ex",
     "srsran_b200_tdec_profile_reset",
     "srsran_b200_tdec_profile_get",
     "srsran_b200_tdec_resident_tiles_per_sm",
@@ -105,7 +108,6 @@ EXPORTED_SYMBOLS = [
     "srsran_b200_enb_ul_free",
     "srsran_b200_enb_ul_geometry",
     "srsran_b200_enb_ul_pusch_batch",
-    "srsran_b200_synth_llr",
     "srsran_b200_sch_init",
     "srsran_b200_sch_free",
     "srsran_b200_sch_decode_after",

@@ -20,6 +20,7 @@ int DeviceArena::reserve(size_t bytes)
   size_t want = (bytes + (size_t(64) << 20)) & ~((size_t(64) << 20) - 1);
   B200_CUDA_TRY(cudaMalloc(&base, want));
   cap = want;
+  generation++;
   return B200_SUCCESS;
 }
 
@@ -40,6 +41,7 @@ void DeviceArena::release()
   }
   base = nullptr;
   cap = used = 0;
+  generation++;
 }
 
 int PinnedArena::reserve(size_t bytes)

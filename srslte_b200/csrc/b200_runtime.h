@@ -6,6 +6,7 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
 #include <map>
 #include <mutex>
 #include <vector>
@@ -34,11 +35,22 @@
 
 namespace b200 {
 
+// cudaFuncSetAttribute applies to the CURRENT device: true the first time this is called for (flag word, current device),
+// so that an object created on a second GPU of the same process sets its kernels' attributes there as well.
+inline bool once_per_device(std::atomic<uint64_t>& done)
+{
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const uint64_t bit = 1ull << (dev & 63);
+  return (done.fetch_or(bit) & bit) == 0;
+}
+
 // Grow-only device buffer: steady-state calls never touch cudaMalloc.
 struct DeviceArena {
-  void*  base = nullptr;
-  size_t cap  = 0;
-  size_t used = 0;
+  void*    base = nullptr;
+  size_t   cap  = 0;
+  size_t   used = 0;
+  uint64_t generation = 0; // bumped whenever the memory is (re)allocated: whatever was cached inside is gone
 
   int  reserve(size_t bytes);
   void reset() { used = 0; }

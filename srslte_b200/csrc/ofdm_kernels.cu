@@ -456,12 +456,11 @@ static int launch_ct_t(const OfdmPlanDev& p, const float2* in_dev, float2* out_d
 {
   constexpr int    SPB  = OFDM_THREADS / (N / 16);
   constexpr size_t smem = (size_t)SPB * (2 * N + (N >> 4) + 1) * sizeof(float2); // work buffer + staged next window
-  static bool      attr_done = false;
-  if (!attr_done) {
+  static std::atomic<uint64_t> attr_done{0}; // function attributes are per device
+  if (once_per_device(attr_done)) {
     B200_CUDA_TRY(cudaFuncSetAttribute(ofdm_rx_kernel_ct<N, R0, R1, R2, IQ16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     B200_CUDA_TRY(cudaFuncSetAttribute(ofdm_rx_kernel_ct<N, R0, R1, R2, IQ16>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                        cudaSharedmemCarveoutMaxShared));
-    attr_done = true;
   }
   const uint32_t nsymtot = nsf * (uint32_t)p.nsym;
   uint32_t       blocks  = (nsymtot + SPB - 1) / SPB;
@@ -642,12 +641,11 @@ static int launch_dft_ct(const OfdmPlanDev& p, const float2* in_dev, float2* out
 {
   using C = DftCt<N, R0, R1, R2, R3>;
   constexpr size_t smem = (size_t)C::SPB * (C::PADN + 2 * N) * sizeof(float2); // work buffer + staged next inputs per symbol
-  static bool      attr_done = false;
-  if (!attr_done) {
+  static std::atomic<uint64_t> attr_done{0}; // function attributes are per device
+  if (once_per_device(attr_done)) {
     B200_CUDA_TRY(cudaFuncSetAttribute(dft_batch_kernel_ct<N, R0, R1, R2, R3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     B200_CUDA_TRY(cudaFuncSetAttribute(dft_batch_kernel_ct<N, R0, R1, R2, R3>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                        cudaSharedmemCarveoutMaxShared));
-    attr_done = true;
   }
   uint32_t       blocks = (ntot + C::SPB - 1) / C::SPB;
   const uint32_t cap    = (uint32_t)sm_count * 8u;

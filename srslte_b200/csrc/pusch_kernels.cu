@@ -433,10 +433,8 @@ struct PuschRx {
     const float  w   = 0.3333f;                                                         // chest_ul.c:82-83
     const float  cal = (float)((7.419 * w * w + 0.1117 * w - 0.005387) * 0.8);           // chest_ul.c:216-219
     const size_t sm  = (size_t)2 * M * sizeof(float2);
-    static size_t attr = 0;
-    if (sm > 48 * 1024 && sm > attr) {
+    if (sm > 48 * 1024) { // per device and cheap: set before every launch that needs the opt-in
       B200_CUDA_TRY(cudaFuncSetAttribute(pusch_chest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-      attr = sm;
     }
     pusch_chest_kernel<<<nsf, 256, sm, st>>>(grid, d_dmrs, d_prm, ce, meas, nsym, R, plan.grid_off, M, w, cal);
     g_kernel_launches++;

@@ -114,11 +114,10 @@ __global__ void __launch_bounds__(RM_THREADS) rm_rx_gather_kernel(const int16_t*
 int launch_rm_rx(const int16_t* e_bits_dev, int16_t* soft_pool_dev, const RmDescDev* descs_dev, uint32_t n, cudaStream_t stream)
 {
   if (n == 0) return B200_SUCCESS;
-  static bool attr = false;
+  static std::atomic<uint64_t> attr{0}; // function attributes are per device
   const size_t smem = RM_MAX_STAGE * sizeof(int16_t);
-  if (!attr) {
+  if (once_per_device(attr)) {
     B200_CUDA_TRY(cudaFuncSetAttribute(rm_rx_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
   }
   rm_rx_gather_kernel<<<n, RM_THREADS, smem, stream>>>(e_bits_dev, soft_pool_dev, descs_dev, n);
   B200_CUDA_TRY(cudaGetLastError());

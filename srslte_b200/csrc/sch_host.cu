@@ -24,17 +24,18 @@ namespace b200 {
 // contributes rlen/8 bytes (its 3 CRC bytes are overwritten by the next block) -- reproduced without the overlap.
 struct ScatterJob {
   uint64_t dst;    // byte offset in data
-  uint32_t src_cb; // index inside the group's decision buffer
+  uint64_t src;    // byte offset in the decision buffer of the batch
   uint32_t nbytes;
+  uint32_t pad;
 };
 
-__global__ void sch_scatter_payload_kernel(const uint8_t* __restrict__ dec, uint32_t bytes_per_cb, uint8_t* __restrict__ data,
+__global__ void sch_scatter_payload_kernel(const uint8_t* __restrict__ dec, uint8_t* __restrict__ data,
                                            const ScatterJob* __restrict__ jobs, uint32_t n)
 {
   const uint32_t j = blockIdx.x;
   if (j >= n) return;
   const ScatterJob  job = jobs[j];
-  const uint8_t*    src = dec + (size_t)job.src_cb * bytes_per_cb;
+  const uint8_t*    src = dec + job.src;
   for (uint32_t i = threadIdx.x; i < job.nbytes; i += blockDim.x) data[job.dst + i] = src[i];
 }
 
@@ -77,6 +78,10 @@ __global__ void __launch_bounds__(128) sch_tb_crc_kernel(const uint8_t* __restri
   const uint32_t t    = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (t >= n) return;
   const TbCrcJob j      = jobs[t];
+  if (j.pad == 0) { // not a valid transport block of this batch (rejected inputs): nothing to read
+    if (lane == 0) ok[t] = 0;
+    return;
+  }
   const uint8_t* p      = data + j.data_off;
   const int      nbytes = (int)(j.tbs / 8);
   const int      L      = (nbytes + 31) / 32;
@@ -347,7 +352,10 @@ int SchEngine::decode_batch(const int16_t* e_bits, uint64_t e_len, int16_t* soft
     d_data      = (uint8_t*)io.take(data_len);
     B200_CUDA_TRY(cudaMemcpyAsync(de, e_bits, e_len * sizeof(int16_t), cudaMemcpyHostToDevice, st));
     d_e = de;
+    // the whole staged buffer travels back at the end: start from the caller's bytes when blocks decoded earlier must be
+    // kept (sch.c:466-471), else from zeros, so that gaps, slack and rejected transport blocks never receive stale memory
     if (any_skip) B200_CUDA_TRY(cudaMemcpyAsync(d_data, data, data_len, cudaMemcpyHostToDevice, st));
+    else B200_CUDA_TRY(cudaMemsetAsync(d_data, 0, data_len, st));
     if (!soft_dev) {
       d_soft = (int16_t*)io.take(soft_len * sizeof(int16_t));
       B200_CUDA_TRY(cudaMemcpyAsync(d_soft, soft_pool, soft_len * sizeof(int16_t), cudaMemcpyHostToDevice, st));
@@ -378,45 +386,46 @@ int SchEngine::decode_batch(const int16_t* e_bits, uint64_t e_len, int16_t* soft
   }
 
   auto t_3 = now();
-  // ---- group by (K, CRC kind) and decode each group as one batch -----------------------------------------------------
+  // ---- group by (K, CRC kind); ONE batched decode over all groups (one launch per pass, tiles ordered by length) ------
   std::map<std::pair<uint32_t, uint32_t>, std::vector<uint32_t>> groups;
   for (uint32_t i = 0; i < cbs.size(); i++) groups[{cbs[i].K, cbs[i].crc_kind}].push_back(i);
   std::vector<uint8_t> h_ok(cbs.size(), 0), h_np(cbs.size(), 0);
-  struct Pending {
-    uint8_t *d_ok, *d_np;
-    const std::vector<uint32_t>* idx;
-  };
-  std::vector<Pending> pend;
-  for (auto& g : groups) {
-    const uint32_t               K   = g.first.first;
-    const std::vector<uint32_t>& idx = g.second;
-    const uint32_t               n   = (uint32_t)idx.size();
-    std::vector<uint64_t>        offs(n);
-    std::vector<ScatterJob>      jobs(n);
-    bool                         al8 = (reinterpret_cast<uintptr_t>(d_soft) & 7u) == 0;
-    for (uint32_t j = 0; j < n; j++) {
-      const CbRec& r = cbs[idx[j]];
-      offs[j]        = r.soft_off;
-      al8            = al8 && (r.soft_off % 4 == 0);
-      jobs[j].dst    = tbs[r.tb].data_offset + (uint64_t)r.c * (r.rlen / 8);
-      jobs[j].src_cb = j;
-      jobs[j].nbytes = r.last_of_tb ? r.K / 8 : r.rlen / 8;
+  uint8_t *            d_ok = nullptr, *d_np = nullptr;
+  std::vector<uint32_t> slot_of(cbs.size()); // position of code block i in the decoder's per-block arrays
+  if (!cbs.empty()) {
+    std::vector<TdecGroupSpec> specs;
+    std::vector<uint64_t>      offs(cbs.size());
+    std::vector<ScatterJob>    jobs(cbs.size());
+    bool                       al8     = (reinterpret_cast<uintptr_t>(d_soft) & 7u) == 0;
+    uint32_t                   slot    = 0;
+    uint64_t                   dec_off = 0;
+    for (auto& g : groups) {
+      const uint32_t K = g.first.first;
+      specs.push_back(TdecGroupSpec{(int)K, cb_index_exact(K), (int)g.first.second, (uint32_t)g.second.size(), slot, 0, dec_off});
+      for (uint32_t i : g.second) {
+        const CbRec& r    = cbs[i];
+        slot_of[i]        = slot;
+        offs[slot]        = r.soft_off;
+        al8               = al8 && (r.soft_off % 4 == 0);
+        jobs[slot].dst    = tbs[r.tb].data_offset + (uint64_t)r.c * (r.rlen / 8);
+        jobs[slot].src    = dec_off;
+        jobs[slot].nbytes = r.last_of_tb ? r.K / 8 : r.rlen / 8;
+        jobs[slot].pad    = 0;
+        dec_off += K / 8;
+        slot++;
+      }
     }
     uint64_t*   d_offs = nullptr;
     ScatterJob* d_jobs = nullptr;
     if (upload(meta, offs, &d_offs, st, &hmeta) != B200_SUCCESS || upload(meta, jobs, &d_jobs, st, &hmeta) != B200_SUCCESS) return B200_ERROR;
-    uint8_t* d_dec = (uint8_t*)meta.take((size_t)n * (K / 8));
-    uint8_t* d_ok  = (uint8_t*)meta.take(n);
-    uint8_t* d_np  = (uint8_t*)meta.take(n);
+    uint8_t* d_dec = (uint8_t*)meta.take(dec_off);
+    d_ok           = (uint8_t*)meta.take(cbs.size());
+    d_np           = (uint8_t*)meta.take(cbs.size());
     if (!d_dec || !d_ok || !d_np) return B200_ERROR;
-    if (tdec.arena.reserve(TdecEngine::workspace_bytes((int)K, n)) != B200_SUCCESS) return B200_ERROR;
-    rc = tdec.run_device(tdec.arena, d_soft, n, (int)K, cb_index_exact(K), max_iterations, (int)g.first.second, 1, d_dec, d_ok,
-                         d_np, st, d_offs, al8);
+    rc = tdec.run_groups(tdec.ws, d_soft, specs, max_iterations, 1, d_dec, d_ok, d_np, st, d_offs, al8);
     if (rc != B200_SUCCESS) return rc;
-    sch_scatter_payload_kernel<<<n, 128, 0, st>>>(d_dec, K / 8, d_data, d_jobs, n);
+    sch_scatter_payload_kernel<<<(unsigned)cbs.size(), 128, 0, st>>>(d_dec, d_data, d_jobs, (uint32_t)cbs.size());
     g_kernel_launches++;
-    pend.push_back(Pending{d_ok, d_np, &idx});
-    // run_device reuses one workspace: the next group may only start once this one has drained (same stream: it has)
   }
 
   auto t_4 = now();
@@ -429,12 +438,10 @@ int SchEngine::decode_batch(const int16_t* e_bits, uint64_t e_len, int16_t* soft
   g_kernel_launches++;
   std::vector<uint8_t> h_tbok(n_tb, 0);
   B200_CUDA_TRY(cudaMemcpyAsync(h_tbok.data(), d_tbok, n_tb, cudaMemcpyDeviceToHost, st));
-  std::vector<std::vector<uint8_t>> tmp_ok(pend.size()), tmp_np(pend.size());
-  for (size_t p = 0; p < pend.size(); p++) {
-    tmp_ok[p].resize(pend[p].idx->size());
-    tmp_np[p].resize(pend[p].idx->size());
-    B200_CUDA_TRY(cudaMemcpyAsync(tmp_ok[p].data(), pend[p].d_ok, tmp_ok[p].size(), cudaMemcpyDeviceToHost, st));
-    B200_CUDA_TRY(cudaMemcpyAsync(tmp_np[p].data(), pend[p].d_np, tmp_np[p].size(), cudaMemcpyDeviceToHost, st));
+  std::vector<uint8_t> tmp_ok(cbs.size()), tmp_np(cbs.size());
+  if (!cbs.empty()) {
+    B200_CUDA_TRY(cudaMemcpyAsync(tmp_ok.data(), d_ok, cbs.size(), cudaMemcpyDeviceToHost, st));
+    B200_CUDA_TRY(cudaMemcpyAsync(tmp_np.data(), d_np, cbs.size(), cudaMemcpyDeviceToHost, st));
   }
   if (!all_dev) {
     B200_CUDA_TRY(cudaMemcpyAsync(data, d_data, data_len, cudaMemcpyDeviceToHost, st));
@@ -449,11 +456,9 @@ int SchEngine::decode_batch(const int16_t* e_bits, uint64_t e_len, int16_t* soft
     fprintf(stderr, "[sch timing] bookkeeping %.0f us, rm descs %.0f, upload+dematch launch %.0f, groups+decode launches %.0f, tail launches %.0f, "
                     "wait for the device %.0f\n", us(t_0, t_1), us(t_1, t_2), us(t_2, t_3), us(t_3, t_4), us(t_4, t_5), us(t_5, t_6));
   }
-  for (size_t p = 0; p < pend.size(); p++) {
-    for (size_t j = 0; j < pend[p].idx->size(); j++) {
-      h_ok[(*pend[p].idx)[j]] = tmp_ok[p][j];
-      h_np[(*pend[p].idx)[j]] = tmp_np[p][j];
-    }
+  for (size_t i = 0; i < cbs.size(); i++) {
+    h_ok[i] = tmp_ok[slot_of[i]];
+    h_np[i] = tmp_np[slot_of[i]];
   }
   std::vector<uint32_t> iters(n_tb, 0);
   for (size_t i = 0; i < cbs.size(); i++) {

@@ -201,6 +201,7 @@ int srsran_rm_turbo_rx_lut_8bit(int8_t*, int8_t*, uint32_t, uint32_t, uint32_t)
 struct CompatTdec {
   TdecEngine eng;
   TdecView   view{};
+  int        K      = 0;
   int        cb_idx = -1;
   uint8_t *  d_out = nullptr;
   int16_t*   d_llr = nullptr;
@@ -221,7 +222,7 @@ int srsran_tdec_init_manual(srsran_tdec_t* h, uint32_t max_long_cb, srsran_tdec_
   if (!c) return SRSRAN_ERROR;
   if (c->eng.init(compat_device(), 0) != B200_SUCCESS || cudaMalloc(&c->d_out, MAX_CB_LEN / 8) != cudaSuccess ||
       cudaMalloc(&c->d_llr, (3 * MAX_CB_LEN + 12) * sizeof(int16_t)) != cudaSuccess ||
-      c->eng.arena.reserve(TdecEngine::workspace_bytes(MAX_CB_LEN, 1)) != B200_SUCCESS) {
+      c->eng.ws.arena.reserve(TdecEngine::workspace_bytes(MAX_CB_LEN, 1)) != B200_SUCCESS) {
     c->eng.destroy();
     delete c;
     return SRSRAN_ERROR;
@@ -296,16 +297,17 @@ static int tdec_one_pass(srsran_tdec_t* h, int16_t* input)
   cudaStream_t st = c->eng.pipe_stream[0];
   if (cudaSetDevice(c->eng.ctx->device) != cudaSuccess) return SRSRAN_ERROR;
   if (h->n_iter == 0) { // first pass reads the input (turbodecoder_iter.h:99-101)
-    c->eng.arena.reset();
-    if (c->eng.carve(c->eng.arena, K, 1, c->view) != B200_SUCCESS) return SRSRAN_ERROR;
-    c->view.qpp_fwd    = c->eng.ctx->qpp_fwd(h->current_cbidx);
-    c->view.crc_nat    = nullptr;
-    c->view.crc_perm   = nullptr;
-    c->view.early_stop = 0;
-    c->view.max_pass   = 1 << 30;
-    c->cb_idx          = h->current_cbidx;
+    std::vector<TdecGroupSpec> one(1);
+    one[0] = TdecGroupSpec{K, h->current_cbidx, SRSRAN_B200_CRC_NONE, 1, 0, 0, 0};
+    if (c->eng.prepare(c->eng.ws, one, st) != B200_SUCCESS) return SRSRAN_ERROR;
+    c->view               = c->eng.ws.plan.v;
+    c->view.early_stop    = 0;
+    c->view.max_pass      = 1 << 30;
+    c->view.split_percent = 51;
+    c->K                  = K;
+    c->cb_idx             = h->current_cbidx;
     B200_CUDA_TRY(cudaMemcpyAsync(c->d_llr, input, (3 * (size_t)K + 12) * sizeof(int16_t), cudaMemcpyHostToDevice, st));
-    launch_load_natural(c->view, c->d_llr, nullptr, true, 1, st);
+    launch_load_natural(c->view, K, c->d_llr, nullptr, true, st);
     g_kernel_launches++;
   }
   launch_siso_pass(c->view, h->n_iter, st);
@@ -318,7 +320,7 @@ static int tdec_decide(srsran_tdec_t* h, uint8_t* output)
 {
   CompatTdec*  c  = tdec_of(h);
   cudaStream_t st = c->eng.pipe_stream[0];
-  launch_decide(c->view, c->eng.ctx->qpp_rev(c->cb_idx), c->d_out, nullptr, nullptr, nullptr, 1, st);
+  launch_decide(c->view, c->K, c->d_out, nullptr, nullptr, nullptr, st);
   g_kernel_launches++;
   B200_CUDA_TRY(cudaMemcpyAsync(output, c->d_out, h->current_long_cb / 8, cudaMemcpyDeviceToHost, st));
   B200_CUDA_TRY(cudaStreamSynchronize(st));

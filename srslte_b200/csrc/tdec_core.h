@@ -20,15 +20,22 @@
 //     No beta array (98 KB/block in the reference, turbodecoder_gen.c:206) is ever materialised.  beta checkpoints hold
 //     the value BEFORE the every-4th-step normalisation, like the reference's beta[] does (turbodecoder_gen.c:98-110);
 //     alpha checkpoints sit on multiples of 8 and are therefore freshly normalised (turbodecoder_gen.c:186-191).
-//   * Everything is stored k-major / code-block-minor so that one trellis step of a warp is one contiguous row:
-//       int16 inputs  S, P0, P1 : uint4 [tile][(K+4)/4][32 lanes]  4 consecutive steps of a lane's block pair per 16 B
-//       int8 inputs   S8,P08,P18: uint4 [tile][K/8+1][32 lanes]    8 consecutive steps x 2 blocks per 16 B
+//   * Everything is stored k-major / code-block-minor so that one trellis step of a warp is one contiguous row.  A batch
+//     may mix code block lengths: every tile has its own K and its own arrays (TileDesc), tiles are ordered by
+//     descending K so that one launch per pass covers the whole batch, longest tiles first:
+//       int16 inputs  S, P0, P1 : uint4 [(K+4)/4][32 lanes]  4 consecutive steps of a lane's block pair per 16 B
+//       int8 inputs   S8,P08,P18: uint4 [K/8+1][32 lanes]    8 consecutive steps x 2 blocks per 16 B
 //                   (used for a tile when every channel LLR of its 64 blocks fits int8: half the bytes per sweep;
 //                    fmt[tile] says which set is valid; rows past K hold the three tail steps; S2T = encoder 2's
 //                    systematic tail, always int16)
-//       E         : u32   [tile][K][32 lanes]         the one extrinsic array, natural bit order, updated in place
-//       CK        : uint4 [tile][K/8][2][32 lanes]    checkpoints (scratch), alpha below the split, beta above
-//       HB        : u16   [tile][K/8][32 lanes]       hard decisions of the last pass run, 8 per block per entry
+//       E         : u32   [K][32 lanes]         the one extrinsic array, natural bit order, updated in place
+//       CK        : uint4 [K/8][2][32 lanes]    checkpoints (scratch), alpha below the split, beta above
+//       HB        : u16   [K/8][32 lanes]       hard decisions of the last pass run, 8 per block per entry
+//   * Block-granular early stop: a lane slot (tile, lane) HOLDS a block pair, named by LaneMap {st0, hb0} = where the
+//     pair's status records and decision words live (its HOME, the slot it was loaded into).  Between passes the lanes
+//     that still run are re-packed into fewer tiles (compact_* below move a lane's S8/P08/P18/S2T/E columns and its
+//     LaneMap into a free slot of an earlier tile of the same K and CRC kind); status and HB stay at home, so the
+//     decision kernel and the caller never see the move, and tiles left without a running lane exit at once.
 //   * The two constituent decoders share E in place:
 //       DEC1 (even pass): a-priori = E[j];              x = S[j] + E[j];  E[j]     <- L1[j] - E[j]
 //       DEC2 (odd pass) : x = E[PI(i)] (no a-priori);                      E[PI(i)] <- L2[i] - x
@@ -64,28 +71,59 @@ struct alignas(8) CrcPow {
   uint32_t hi8x2;
 };
 
-struct TdecView {
-  int K;      // code block length (one of the 188 LTE sizes, multiple of 8)
-  int ntiles; // tiles of 64 blocks
-  int ws;     // split window: 1 <= ws <= K/8-1 (see tdec_split)
-  u4*             S;
-  u4*             P0;
-  u4*             P1;
-  u4*             S8;
+constexpr uint32_t LANE_EMPTY = 0xFFFFFFFFu;
+
+// which block pair a lane slot holds
+struct LaneMap {
+  uint32_t st0; // index of the pair's first record in status[] (LANE_EMPTY: the slot holds nothing)
+  uint32_t hb0; // index of the pair's window-0 decision word in HB[] (window w at hb0 + 32 w)
+};
+
+// per tile of 64 code blocks of equal K
+struct alignas(16) TileDesc {
+  u4*             S8;   // int8 rows  [K/8+1][32]
   u4*             P08;
   u4*             P18;
-  uint32_t*       fmt;  // [ntiles] 0: the int8 arrays hold the tile, 1: the int16 arrays do
-  u4*             S2T;  // [tile][32] : x,y,z = systematic tail of encoder 2 (app2[K..K+2])
-  uint32_t*       E;
-  u4*             CK;
-  uint16_t*       HB;
-  CbStatus*       status; // [ntiles*64]
+  u4*             S;    // int16 rows [(K+4)/4][32], valid when fmt[tile] != 0
+  u4*             P0;
+  u4*             P1;
+  uint32_t*       E;    // [K][32]
+  u4*             CK;   // [K/8][2][32]
   const uint16_t* qpp_fwd; // PI(i), K entries (tc_interl_lte.c:89-93)
+  const uint16_t* qpp_rev; // inverse table
   // CRC syndrome weights in VISITING order, nullptr = no CRC:
   const CrcPow*   crc_nat;  // [j] = x^(K-1-j) mod g        (DEC1 visits natural position j)
   const CrcPow*   crc_perm; // [i] = x^(K-1-PI(i)) mod g    (DEC2 visits natural position PI(i) at step i)
-  int             early_stop; // stop a block at its first CRC match (sch.c:446-449)
-  int             max_pass;
+  uint64_t        llr_off;  // int16 offset of the natural input vector of the tile's first block (contiguous inputs)
+  uint64_t        out_off;  // byte offset of the tile's first block in the decision output
+  uint32_t        K;        // code block length (one of the 188 LTE sizes, multiple of 8)
+  uint32_t        hb_row0;  // first row (of 32 u16) of the tile's decisions in HB
+  uint32_t        cb0;      // index of the tile's first code block in the per-block arrays (offset list, crc_ok, npass)
+  uint32_t        nblk;     // code blocks in this tile (1..64)
+  uint32_t        group;    // (K, CRC kind) group the tile belongs to: lanes are only re-packed inside a group
+  uint32_t        pad[3];
+};
+
+// consecutive tiles of equal K and CRC kind
+struct TileGroup {
+  uint32_t first_tile, ntiles;
+};
+
+struct MoveRec {
+  uint32_t src, dst; // lane slots: tile * 32 + lane
+};
+
+struct TdecView {
+  int              ntiles; // tiles of 64 blocks
+  int              split_percent; // share of a tile's trellis windows below the split (tdec_split)
+  const TileDesc*  tiles;  // [ntiles]
+  uint32_t*        fmt;    // [ntiles] 0: the int8 arrays hold the tile, 1: the int16 arrays do
+  u4*              S2T;    // [ntiles*32] : x,y,z = systematic tail of encoder 2 (app2[K..K+2]) of the pair in that slot
+  LaneMap*         lanes;  // [ntiles*32]
+  uint16_t*        HB;
+  CbStatus*        status; // [ntiles*64], index = home tile * 64 + block of the tile
+  int              early_stop; // stop a block at its first CRC match (sch.c:446-449)
+  int              max_pass;
 };
 
 // Split of the trellis between the two warps.  Per step warp F spends ~15 instructions below the split and ~56 above,
@@ -99,25 +137,32 @@ B200_HD int tdec_split(int K, int percent)
   return ws;
 }
 
-B200_HD size_t vec_row(const TdecView& v, int tile, int k4, int lane)
+// rows of a tile's arrays (all offsets fit 32 bits: a tile's largest array, E, is K * 128 bytes < 1 MB)
+B200_HD uint32_t vec_row(int k4, int lane)
 {
-  return ((size_t)tile * (size_t)((v.K + 4) / 4) + (size_t)k4) * 32 + (size_t)lane;
+  return (uint32_t)k4 * 32u + (uint32_t)lane;
 }
-B200_HD size_t row8(const TdecView& v, int tile, int w, int lane)
+B200_HD uint32_t row8(int w, int lane)
 {
-  return ((size_t)tile * (size_t)(v.K / 8 + 1) + (size_t)w) * 32 + (size_t)lane;
+  return (uint32_t)w * 32u + (uint32_t)lane;
 }
-B200_HD size_t e_idx(const TdecView& v, int tile, int k, int lane)
+B200_HD uint32_t e_idx(int k, int lane)
 {
-  return ((size_t)tile * (size_t)v.K + (size_t)k) * 32 + (size_t)lane;
+  return (uint32_t)k * 32u + (uint32_t)lane;
 }
-B200_HD size_t ck_idx(const TdecView& v, int tile, int w, int half, int lane)
+B200_HD uint32_t ck_idx(int w, int half, int lane)
 {
-  return (((size_t)tile * (size_t)(v.K / 8) + (size_t)w) * 2 + (size_t)half) * 32 + (size_t)lane;
+  return ((uint32_t)w * 2u + (uint32_t)half) * 32u + (uint32_t)lane;
 }
-B200_HD size_t hb_idx(const TdecView& v, int tile, int w, int lane)
+// decision word of window w of the pair whose home is hb0
+B200_HD size_t hb_idx(uint32_t hb0, int w)
 {
-  return ((size_t)tile * (size_t)(v.K / 8) + (size_t)w) * 32 + (size_t)lane;
+  return (size_t)hb0 + (size_t)w * 32u;
+}
+// home of the pair loaded into (tile, lane)
+B200_HD LaneMap lane_home(const TileDesc& td, int tile, int lane)
+{
+  return LaneMap{(uint32_t)tile * (uint32_t)TDEC_TILE_CB + 2u * (uint32_t)lane, td.hb_row0 * 32u + (uint32_t)lane};
 }
 
 B200_HD uint32_t u4_get(const u4& q, int i)
@@ -445,6 +490,7 @@ B200_HD void hb_store(uint16_t* dst, uint32_t bits, bool act_lo, bool act_hi)
 
 // ---- end of a pass: CRC verdict, pass counters, stop flag (sch.c:431-452) ---------------------------------------
 B200_HD void finish_pass(const TdecView&   v,
+                         bool              have_crc,
                          CbStatus*         st,
                          CbStatus          s_lo,
                          CbStatus          s_hi,
@@ -455,7 +501,7 @@ B200_HD void finish_pass(const TdecView&   v,
 {
   const bool last = (pass_idx + 1 >= v.max_pass);
   if (act_lo) {
-    bool ok        = v.crc_nat && ((r.crc_lo16x2 & 0xFFFFu) == 0) && ((r.crc_hi8x2 & 0xFFu) == 0);
+    bool ok        = have_crc && ((r.crc_lo16x2 & 0xFFFFu) == 0) && ((r.crc_hi8x2 & 0xFFu) == 0);
     s_lo.npass_run = (uint8_t)(pass_idx + 1);
     if (ok && !s_lo.crc_ok) {
       s_lo.crc_ok    = 1;
@@ -465,7 +511,7 @@ B200_HD void finish_pass(const TdecView&   v,
     st[0] = s_lo;
   }
   if (act_hi) {
-    bool ok        = v.crc_nat && ((r.crc_lo16x2 >> 16) == 0) && (((r.crc_hi8x2 >> 16) & 0xFFu) == 0);
+    bool ok        = have_crc && ((r.crc_lo16x2 >> 16) == 0) && (((r.crc_hi8x2 >> 16) & 0xFFu) == 0);
     s_hi.npass_run = (uint8_t)(pass_idx + 1);
     if (ok && !s_hi.crc_ok) {
       s_hi.crc_ok    = 1;
@@ -480,38 +526,38 @@ B200_HD void finish_pass(const TdecView&   v,
 // The CPU emulation (tests/emu) runs this; it is also the readable statement of the schedule.  The GPU kernel in
 // tdec_kernels.cu runs the same window functions, two warps at a time, fed through shared-memory rings.
 template <bool DEC2, bool FIRST, bool IN8>
-B200_HD void load_window_direct(const TdecView& v, int tile, int lane, int w, WinRegs& r, uint32_t pos[8])
+B200_HD void load_window_direct(const TileDesc& td, int lane, int w, WinRegs& r, uint32_t pos[8])
 {
   u4       s[2] = {}, p[2] = {};
   uint32_t e[8] = {};
   if (IN8) {
-    p[0] = (DEC2 ? v.P18 : v.P08)[row8(v, tile, w, lane)];
-    if (!DEC2) s[0] = v.S8[row8(v, tile, w, lane)];
+    p[0] = (DEC2 ? td.P18 : td.P08)[row8(w, lane)];
+    if (!DEC2) s[0] = td.S8[row8(w, lane)];
   } else {
-    const u4* P = DEC2 ? v.P1 : v.P0;
-    p[0]        = P[vec_row(v, tile, 2 * w, lane)];
-    p[1]        = P[vec_row(v, tile, 2 * w + 1, lane)];
+    const u4* P = DEC2 ? td.P1 : td.P0;
+    p[0]        = P[vec_row(2 * w, lane)];
+    p[1]        = P[vec_row(2 * w + 1, lane)];
     if (!DEC2) {
-      s[0] = v.S[vec_row(v, tile, 2 * w, lane)];
-      s[1] = v.S[vec_row(v, tile, 2 * w + 1, lane)];
+      s[0] = td.S[vec_row(2 * w, lane)];
+      s[1] = td.S[vec_row(2 * w + 1, lane)];
     }
   }
   for (int t = 0; t < 8; t++) {
-    pos[t] = DEC2 ? (uint32_t)v.qpp_fwd[8 * w + t] : (uint32_t)(8 * w + t);
-    if (!FIRST) e[t] = v.E[e_idx(v, tile, (int)pos[t], lane)];
+    pos[t] = DEC2 ? (uint32_t)td.qpp_fwd[8 * w + t] : (uint32_t)(8 * w + t);
+    if (!FIRST) e[t] = td.E[e_idx((int)pos[t], lane)];
   }
   win_unpack<DEC2, FIRST, IN8>(r, s, p, e);
 }
 
-B200_HD void ck_load(const TdecView& v, int tile, int lane, int w, uint32_t c[8])
+B200_HD void ck_load(const TileDesc& td, int lane, int w, uint32_t c[8])
 {
-  const u4 c0 = v.CK[ck_idx(v, tile, w, 0, lane)], c1 = v.CK[ck_idx(v, tile, w, 1, lane)];
+  const u4 c0 = td.CK[ck_idx(w, 0, lane)], c1 = td.CK[ck_idx(w, 1, lane)];
   c[0] = c0.x; c[1] = c0.y; c[2] = c0.z; c[3] = c0.w; c[4] = c1.x; c[5] = c1.y; c[6] = c1.z; c[7] = c1.w;
 }
-B200_HD void ck_store(const TdecView& v, int tile, int lane, int w, const uint32_t c[8])
+B200_HD void ck_store(const TileDesc& td, int lane, int w, const uint32_t c[8])
 {
-  v.CK[ck_idx(v, tile, w, 0, lane)] = u4{c[0], c[1], c[2], c[3]};
-  v.CK[ck_idx(v, tile, w, 1, lane)] = u4{c[4], c[5], c[6], c[7]};
+  td.CK[ck_idx(w, 0, lane)] = u4{c[0], c[1], c[2], c[3]};
+  td.CK[ck_idx(w, 1, lane)] = u4{c[4], c[5], c[6], c[7]};
 }
 
 // the three tail steps k = K+2, K+1, K: no a-priori, no normalisation (turbodecoder_gen.c:73-75,105)
@@ -532,15 +578,20 @@ B200_HD void beta_tail(uint32_t B[8], const u4& st, const u4& pt)
 template <bool DEC2, bool FIRST, bool IN8>
 B200_HD void siso_pass_lane(const TdecView& v, int tile, int lane, int pass_idx)
 {
-  CbStatus* st     = v.status + ((size_t)tile * TDEC_TILE_CB + 2 * (size_t)lane);
-  CbStatus  s_lo   = st[0];
-  CbStatus  s_hi   = st[1];
-  bool      act_lo = s_lo.active != 0, act_hi = s_hi.active != 0;
+  const LaneMap lm = v.lanes[(size_t)tile * 32 + lane];
+  if (lm.st0 == LANE_EMPTY) {
+    return;
+  }
+  const TileDesc& td   = v.tiles[tile];
+  CbStatus*       st   = v.status + lm.st0;
+  CbStatus        s_lo = st[0];
+  CbStatus        s_hi = st[1];
+  bool            act_lo = s_lo.active != 0, act_hi = s_hi.active != 0;
   if (!act_lo && !act_hi) {
     return;
   }
-  const int     K = v.K, nw = K / 8, ws = v.ws;
-  const CrcPow* cbase = DEC2 ? v.crc_perm : v.crc_nat;
+  const int     K = (int)td.K, nw = K / 8, ws = tdec_split(K, v.split_percent);
+  const CrcPow* cbase = DEC2 ? td.crc_perm : td.crc_nat;
   WinRegs       r;
   uint32_t      pos[8];
 
@@ -549,8 +600,8 @@ B200_HD void siso_pass_lane(const TdecView& v, int tile, int lane, int pass_idx)
   A[0] = 0;
   for (int i = 1; i < 8; i++) A[i] = NEG_INF2;
   for (int w = 0; w < ws; w++) {
-    ck_store(v, tile, lane, w, A);
-    load_window_direct<DEC2, FIRST, IN8>(v, tile, lane, w, r, pos);
+    ck_store(td, lane, w, A);
+    load_window_direct<DEC2, FIRST, IN8>(td, lane, w, r, pos);
     alpha_window(A, r);
   }
   // phase 1, warp B
@@ -559,11 +610,11 @@ B200_HD void siso_pass_lane(const TdecView& v, int tile, int lane, int pass_idx)
     // encoder 2's systematic tail is always int16 (S2T); widen an int8 parity tail to match by using IN8 on both
     u4 pt, stl;
     if (IN8) {
-      pt  = (DEC2 ? v.P18 : v.P08)[row8(v, tile, nw, lane)];
-      stl = v.S8[row8(v, tile, nw, lane)];
+      pt  = (DEC2 ? td.P18 : td.P08)[row8(nw, lane)];
+      stl = td.S8[row8(nw, lane)];
     } else {
-      pt  = (DEC2 ? v.P1 : v.P0)[vec_row(v, tile, K / 4, lane)];
-      stl = v.S[vec_row(v, tile, K / 4, lane)];
+      pt  = (DEC2 ? td.P1 : td.P0)[vec_row(K / 4, lane)];
+      stl = td.S[vec_row(K / 4, lane)];
     }
     if (DEC2) {
       const u4 s2 = v.S2T[(size_t)tile * 32 + lane];
@@ -578,12 +629,12 @@ B200_HD void siso_pass_lane(const TdecView& v, int tile, int lane, int pass_idx)
       beta_tail<IN8>(B, stl, pt);
     }
   }
-  ck_store(v, tile, lane, nw - 1, B);
+  ck_store(td, lane, nw - 1, B);
   for (int w = nw - 1; w >= ws; w--) {
-    load_window_direct<DEC2, FIRST, IN8>(v, tile, lane, w, r, pos);
+    load_window_direct<DEC2, FIRST, IN8>(td, lane, w, r, pos);
     beta_window(B, r);
     if (w > ws) {
-      ck_store(v, tile, lane, w - 1, B);
+      ck_store(td, lane, w - 1, B);
       normalise(B);
     }
   }
@@ -592,21 +643,147 @@ B200_HD void siso_pass_lane(const TdecView& v, int tile, int lane, int pass_idx)
   WinOut     o;
   uint32_t   c[8];
   for (int w = ws; w < nw; w++) {
-    load_window_direct<DEC2, FIRST, IN8>(v, tile, lane, w, r, pos);
-    ck_load(v, tile, lane, w, c);
+    load_window_direct<DEC2, FIRST, IN8>(td, lane, w, r, pos);
+    ck_load(td, lane, w, c);
     fwd_window(A, c, 8 * w + 8 < K, r, cbase ? cbase + 8 * w : nullptr, res, o);
-    for (int t = 0; t < 8; t++) v.E[e_idx(v, tile, (int)pos[t], lane)] = o.enew[t];
-    hb_store(&v.HB[hb_idx(v, tile, w, lane)], o.bits, act_lo, act_hi);
+    for (int t = 0; t < 8; t++) td.E[e_idx((int)pos[t], lane)] = o.enew[t];
+    hb_store(&v.HB[hb_idx(lm.hb0, w)], o.bits, act_lo, act_hi);
   }
   // phase 2, warp B
   for (int w = ws - 1; w >= 0; w--) {
-    load_window_direct<DEC2, FIRST, IN8>(v, tile, lane, w, r, pos);
-    ck_load(v, tile, lane, w, c);
+    load_window_direct<DEC2, FIRST, IN8>(td, lane, w, r, pos);
+    ck_load(td, lane, w, c);
     bwd_window(B, c, r, cbase ? cbase + 8 * w : nullptr, res, o);
-    for (int t = 0; t < 8; t++) v.E[e_idx(v, tile, (int)pos[t], lane)] = o.enew[t];
-    hb_store(&v.HB[hb_idx(v, tile, w, lane)], o.bits, act_lo, act_hi);
+    for (int t = 0; t < 8; t++) td.E[e_idx((int)pos[t], lane)] = o.enew[t];
+    hb_store(&v.HB[hb_idx(lm.hb0, w)], o.bits, act_lo, act_hi);
   }
-  finish_pass(v, st, s_lo, s_hi, act_lo, act_hi, res, pass_idx);
+  finish_pass(v, cbase != nullptr, st, s_lo, s_hi, act_lo, act_hi, res, pass_idx);
+}
+
+// ---- block-granular early stop: re-packing the lanes that still run into fewer tiles -------------------------------
+// One group (equal K and CRC kind, consecutive tiles) is planned by one thread block; the steps below are written for
+// `nthr` cooperating threads with `sync()` between them, so the CPU emulation runs the very same code with nthr = 1.
+// Scratch (per tile, global memory): mask[t] = lanes of tile t holding a pair that still runs, pref[t] = running count
+// (free lanes in receiver tiles / running lanes in donor tiles).  plan[g] = {receivers, first move, moves, go}.
+struct GroupPlan {
+  uint32_t receivers; // the group's running lanes fit its first `receivers` tiles
+  uint32_t base;      // first entry of this group in the move list
+  uint32_t moves;
+  uint32_t go;
+};
+
+B200_HD bool lane_running(const TdecView& v, uint32_t slot)
+{
+  const LaneMap lm = v.lanes[slot];
+  if (lm.st0 == LANE_EMPTY) return false;
+  return (v.status[lm.st0].active | v.status[lm.st0 + 1].active) != 0;
+}
+
+// step 1: per-tile masks.  Returns false for a tile whose inputs are kept in int16 (such a group is left alone).
+B200_HD bool compact_scan_tile(const TdecView& v, uint32_t tile, uint32_t* mask)
+{
+  uint32_t m = 0;
+  for (uint32_t l = 0; l < 32; l++) {
+    if (lane_running(v, tile * 32 + l)) m |= 1u << l;
+  }
+  mask[tile] = m;
+  return v.fmt[tile] == 0u;
+}
+
+B200_HD uint32_t popc32(uint32_t x)
+{
+#if defined(__CUDA_ARCH__)
+  return (uint32_t)__popc(x);
+#else
+  return (uint32_t)__builtin_popcount(x);
+#endif
+}
+
+// step 2 (one thread): decide whether re-packing pays and lay out the moves.  `min_gain_tiles`: tiles that must be
+// freed for the copy to be worth its traffic (a lane's columns are ~60 KB at K=6144).
+B200_HD void compact_plan_group(const TileGroup& g, const uint32_t* mask, uint32_t* pref, bool all_int8, uint32_t min_gain_tiles,
+                                uint32_t* move_counter, uint32_t move_cap, GroupPlan& plan)
+{
+  uint32_t running = 0, tiles_now = 0;
+  for (uint32_t t = 0; t < g.ntiles; t++) {
+    const uint32_t n = popc32(mask[g.first_tile + t]);
+    running += n;
+    if (n) tiles_now = t + 1;
+  }
+  const uint32_t need = (running + 31) / 32;
+  plan = GroupPlan{need, 0, 0, 0};
+  if (!all_int8 || tiles_now < need + min_gain_tiles || 5 * need > 4 * tiles_now) return;
+  uint32_t nfree = 0, nrun = 0;
+  for (uint32_t t = 0; t < need; t++) {
+    pref[g.first_tile + t] = nfree;
+    nfree += 32 - popc32(mask[g.first_tile + t]);
+  }
+  for (uint32_t t = need; t < tiles_now; t++) {
+    pref[g.first_tile + t] = nrun;
+    nrun += popc32(mask[g.first_tile + t]);
+  }
+  for (uint32_t t = tiles_now; t < g.ntiles; t++) pref[g.first_tile + t] = nrun;
+  if (nrun == 0 || nrun > nfree) return; // nrun <= nfree always holds (running <= 32 need); belt and braces
+#if defined(__CUDA_ARCH__)
+  const uint32_t base = atomicAdd(move_counter, nrun);
+#else
+  const uint32_t base = *move_counter;
+  *move_counter += nrun;
+#endif
+  if (base + nrun > move_cap) return; // the list is sized for every lane, cannot happen
+  plan.base  = base;
+  plan.moves = nrun;
+  plan.go    = 1;
+}
+
+// step 3: tile t of the group writes its side of the moves (receiver: destinations, donor: sources)
+B200_HD void compact_emit_tile(const TileGroup& g, uint32_t t, const uint32_t* mask, const uint32_t* pref, const GroupPlan& plan, MoveRec* moves)
+{
+  if (!plan.go) return;
+  const uint32_t tile = g.first_tile + t;
+  uint32_t       k    = pref[tile];
+  if (t < plan.receivers) {
+    uint32_t fr = ~mask[tile];
+    for (uint32_t l = 0; l < 32 && k < plan.moves; l++) {
+      if ((fr >> l) & 1u) moves[plan.base + k++].dst = tile * 32 + l;
+    }
+  } else {
+    const uint32_t m = mask[tile];
+    for (uint32_t l = 0; l < 32; l++) {
+      if ((m >> l) & 1u) moves[plan.base + k++].src = tile * 32 + l;
+    }
+  }
+}
+
+// step 4: the moved pair's name follows its data; the source slot holds nothing afterwards
+B200_HD void compact_rename(const TdecView& v, const MoveRec& mv)
+{
+  v.lanes[mv.dst]     = v.lanes[mv.src];
+  v.lanes[mv.src].st0 = LANE_EMPTY;
+}
+
+// the data of one move, element i of n = compact_move_elems(K): a lane's column of S8, P08, P18, E and its S2T entry
+B200_HD uint32_t compact_move_elems(uint32_t K)
+{
+  return 3u * (K / 8u + 1u) + K + 1u;
+}
+B200_HD void compact_move_elem(const TdecView& v, const MoveRec& mv, uint32_t i)
+{
+  const uint32_t  ts = mv.src >> 5, ls = mv.src & 31u, td_ = mv.dst >> 5, ld = mv.dst & 31u;
+  const TileDesc& a = v.tiles[ts];
+  const TileDesc& b = v.tiles[td_];
+  const uint32_t  r8 = a.K / 8u + 1u;
+  if (i < 3u * r8) {
+    const uint32_t s = i / r8, w = i % r8;
+    const u4*      src = s == 0 ? a.S8 : (s == 1 ? a.P08 : a.P18);
+    u4*            dst = s == 0 ? b.S8 : (s == 1 ? b.P08 : b.P18);
+    dst[row8((int)w, (int)ld)] = src[row8((int)w, (int)ls)];
+  } else if (i < 3u * r8 + a.K) {
+    const uint32_t k = i - 3u * r8;
+    b.E[e_idx((int)k, (int)ld)] = a.E[e_idx((int)k, (int)ls)];
+  } else {
+    v.S2T[(size_t)td_ * 32 + ld] = v.S2T[(size_t)ts * 32 + ls];
+  }
 }
 
 } // namespace b200
@@ -640,22 +817,25 @@ B200_HD int16_t natural_pick(const int16_t* in, int K, int which, int k)
   }
 }
 
-// Decided byte jb (bits 8jb..8jb+7, MSB first, natural order) of code block cb after its last pass.
+// Decided byte jb (bits 8jb..8jb+7, MSB first, natural order) of block c (0..63) of tile `tile` after its last pass.
 // rev = inverse QPP table (tc_interl_lte.c:93); after an odd pass HB is in DEC2's visiting order and bit j sits at
 // visiting index rev[j] (the reference instead de-interleaves the whole LLR vector, turbodecoder_iter.h:127).
-B200_HD uint8_t decide_byte(const TdecView& v, const uint16_t* rev, int cb, int jb)
+// Status and HB are addressed by the block's HOME slot, wherever its data was moved in between.
+B200_HD uint8_t decide_byte(const TdecView& v, int tile, int c, int jb)
 {
-  const int      tile = cb / TDEC_TILE_CB, lane = (cb % TDEC_TILE_CB) >> 1, half = cb & 1;
-  const CbStatus st   = v.status[cb];
-  const bool     perm = st.npass_run > 0 && ((st.npass_run - 1) & 1);
+  const TileDesc& td   = v.tiles[tile];
+  const int       lane = c >> 1, half = c & 1;
+  const LaneMap   home = lane_home(td, tile, lane);
+  const CbStatus  st   = v.status[home.st0 + half];
+  const bool      perm = st.npass_run > 0 && ((st.npass_run - 1) & 1);
   if (!perm) {
-    uint16_t hb = v.HB[hb_idx(v, tile, jb, lane)];
+    uint16_t hb = v.HB[hb_idx(home.hb0, jb)];
     return (uint8_t)(half ? (hb >> 8) : (hb & 0xFF));
   }
   uint32_t byte = 0;
   for (int t = 0; t < 8; t++) {
-    int      i  = rev[8 * jb + t];
-    uint16_t hb = v.HB[hb_idx(v, tile, i >> 3, lane)];
+    int      i  = td.qpp_rev[8 * jb + t];
+    uint16_t hb = v.HB[hb_idx(home.hb0, i >> 3)];
     uint32_t b  = half ? (hb >> 8) : (hb & 0xFF);
     byte        = (byte << 1) | ((b >> (7 - (i & 7))) & 1u);
   }

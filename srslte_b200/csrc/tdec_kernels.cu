@@ -8,8 +8,11 @@
 #include <cuda_runtime.h>
 #include <stdlib.h>
 
+#include <algorithm>
+#include <atomic>
 #include <type_traits>
 
+#include "b200_runtime.h"
 #include "tdec_core.h"
 #include "tdec_kernels.h"
 
@@ -77,27 +80,29 @@ struct WarpRing {
   const uint8_t* tP;
   uint8_t*       tE;
   uint8_t*       tCK;
-  uint8_t*       tHB;
+  uint8_t*       gHB;  // the decision array; hb_off = byte offset of this lane's pair (its home, not this tile)
+  uint32_t       hb_off;
   const uint8_t* gCRC; // syndrome weights in this decoder's visiting order, or nullptr
   uint32_t       fill = 0, drain = 0; // byte offsets of the next stage to fill / to consume
 
-  __device__ WarpRing(const TdecView& v, uint8_t* smem, int tile, int lane)
+  __device__ WarpRing(const TdecView& v, const TileDesc& td, uint8_t* smem, int lane, uint32_t hb0)
   {
     gen  = smem;
     base = smem_u32(smem);
     l16  = (uint32_t)lane * 16u;
     l4   = (uint32_t)lane * 4u;
     if (IN8) {
-      tS = reinterpret_cast<const uint8_t*>(v.S8 + row8(v, tile, 0, 0));
-      tP = reinterpret_cast<const uint8_t*>((DEC2 ? v.P18 : v.P08) + row8(v, tile, 0, 0));
+      tS = reinterpret_cast<const uint8_t*>(td.S8);
+      tP = reinterpret_cast<const uint8_t*>(DEC2 ? td.P18 : td.P08);
     } else {
-      tS = reinterpret_cast<const uint8_t*>(v.S + vec_row(v, tile, 0, 0));
-      tP = reinterpret_cast<const uint8_t*>((DEC2 ? v.P1 : v.P0) + vec_row(v, tile, 0, 0));
+      tS = reinterpret_cast<const uint8_t*>(td.S);
+      tP = reinterpret_cast<const uint8_t*>(DEC2 ? td.P1 : td.P0);
     }
-    tE   = reinterpret_cast<uint8_t*>(v.E + e_idx(v, tile, 0, 0));
-    tCK  = reinterpret_cast<uint8_t*>(v.CK + ck_idx(v, tile, 0, 0, 0));
-    tHB  = reinterpret_cast<uint8_t*>(v.HB + hb_idx(v, tile, 0, 0));
-    gCRC = reinterpret_cast<const uint8_t*>(DEC2 ? v.crc_perm : v.crc_nat);
+    tE     = reinterpret_cast<uint8_t*>(td.E);
+    tCK    = reinterpret_cast<uint8_t*>(td.CK);
+    gHB    = reinterpret_cast<uint8_t*>(v.HB);
+    hb_off = hb0 * 2u;
+    gCRC   = reinterpret_cast<const uint8_t*>(DEC2 ? td.crc_perm : td.crc_nat);
   }
 
   __device__ __forceinline__ void restart() { fill = drain = 0; }
@@ -187,7 +192,7 @@ struct WarpRing {
   // hard decisions of window w
   __device__ __forceinline__ void store_hb(uint32_t w, uint32_t bits, bool act_lo, bool act_hi) const
   {
-    hb_store(reinterpret_cast<uint16_t*>(tHB + (w * 64u + (l4 >> 1))), bits, act_lo, act_hi);
+    hb_store(reinterpret_cast<uint16_t*>(gHB + (size_t)hb_off + w * 64u), bits, act_lo, act_hi);
   }
 };
 
@@ -203,17 +208,22 @@ __device__ __forceinline__ void siso_pass_tile(const TdecView& v, int pass_idx, 
   const int tile = blockIdx.x;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
-  // whole tile finished (early stop): nothing to do.  Both warps read the same flags, so the exit is CTA-uniform.
-  CbStatus*  stp  = v.status + ((size_t)tile * TDEC_TILE_CB + 2 * (size_t)lane);
-  const bool act_lo = stp[0].active != 0, act_hi = stp[1].active != 0; // the records themselves are re-read at the end of the pass
+  // whole tile finished or emptied by the re-packing (early stop): nothing to do.  Both warps read the same flags, so the
+  // exit is CTA-uniform.
+  const LaneMap lm   = v.lanes[(size_t)tile * 32 + lane];
+  const bool    held = lm.st0 != LANE_EMPTY;
+  CbStatus*     stp  = v.status + (held ? lm.st0 : 0u);
+  const bool act_lo = held && stp[0].active != 0, act_hi = held && stp[1].active != 0; // the records themselves are re-read at the end of the pass
   if (__ballot_sync(0xFFFFFFFFu, act_lo || act_hi) == 0u) return;
 
   using RG = WarpRing<DEC2, FIRST, IN8>;
-  constexpr int  NST = RG::L::NST;
-  const uint32_t K   = (uint32_t)v.K;
-  const uint32_t nw  = K / 8u, ws = (uint32_t)v.ws;
-  RG             rg(v, smem + warp * ring::RING_BYTES, tile, lane);
-  const bool     have_crc = (DEC2 ? v.crc_perm : v.crc_nat) != nullptr;
+  constexpr int   NST = RG::L::NST;
+  const TileDesc& td  = v.tiles[tile];
+  const uint32_t  K   = td.K;
+  const uint32_t  nw  = K / 8u, ws = (uint32_t)tdec_split((int)K, v.split_percent);
+  RG              rg(v, td, smem + warp * ring::RING_BYTES, lane, lm.hb0);
+  const bool      have_crc = (DEC2 ? td.crc_perm : td.crc_nat) != nullptr;
+  const uint16_t* qpp_fwd  = td.qpp_fwd;
 
   WinRegs    r;
   LaneResult res = {0u, 0u};
@@ -225,11 +235,11 @@ __device__ __forceinline__ void siso_pass_tile(const TdecView& v, int pass_idx, 
     constexpr bool PH2 = decltype(ph2_tag)::value;
     rg.restart();
     uint32_t nxt = first, left = count;
-    if (DEC2) qn = ldg_q(v.qpp_fwd, first);
+    if (DEC2) qn = ldg_q(qpp_fwd, first);
     auto issue_next = [&]() {
       if (left > 0) {
         const u4 q = qn;
-        if (DEC2 && left > 1) qn = ldg_q(v.qpp_fwd, nxt + dir);
+        if (DEC2 && left > 1) qn = ldg_q(qpp_fwd, nxt + dir);
         rg.template issue<PH2>(nxt, q);
         nxt += dir;
         left--;
@@ -324,7 +334,7 @@ __device__ __forceinline__ void siso_pass_tile(const TdecView& v, int pass_idx, 
   if (warp == 0) {
     res.crc_lo16x2 ^= xres[lane].crc_lo16x2;
     res.crc_hi8x2 ^= xres[lane].crc_hi8x2;
-    finish_pass(v, stp, stp[0], stp[1], act_lo, act_hi, res, pass_idx);
+    finish_pass(v, have_crc, stp, stp[0], stp[1], act_lo, act_hi, res, pass_idx);
   }
 }
 
@@ -346,8 +356,8 @@ __global__ void __maxnreg__(128) tdec_siso_pass_kernel(TdecView v, int pass_idx)
 static void siso_set_attributes()
 {
   const size_t smem = 2 * ring::RING_BYTES;
-  static bool  attr_done = false;
-  if (!attr_done) {
+  static std::atomic<uint64_t> attr_done{0}; // function attributes are per device
+  if (once_per_device(attr_done)) {
     cudaFuncSetAttribute(tdec_siso_pass_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(tdec_siso_pass_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(tdec_siso_pass_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -355,7 +365,6 @@ static void siso_set_attributes()
     cudaFuncSetAttribute(tdec_siso_pass_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(tdec_siso_pass_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(tdec_siso_pass_kernel<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    attr_done = true;
   }
 }
 
@@ -400,15 +409,21 @@ __device__ __forceinline__ bool fits8(int16_t a)
   return (int16_t)(int8_t)a == a;
 }
 
-// `offsets` (optional): int16 offset of each block's vector inside llr (soft buffers scattered in a HARQ pool); without it
-// the vectors are contiguous, block cb at cb*(3K+12).  ALIGNED8: every vector starts on an 8-byte boundary.
-// Returns (to all threads) whether every staged value fits int8.
-template <bool ALIGNED8>
-__device__ __forceinline__ bool load_stage_chunk(uint8_t* sm, const TdecView& v, const int16_t* __restrict__ llr,
-                                                 const uint64_t* __restrict__ offsets, uint32_t ncb, int tile, int k0, int rows)
+// Source of block c (0..63) of a tile: `offsets` (optional) holds the int16 offset of every block's vector inside llr,
+// indexed by the block's position in the batch (soft buffers scattered in a HARQ pool); without it the vectors of a
+// tile are contiguous from llr + td.llr_off.  nullptr past the tile's last block.
+__device__ __forceinline__ const int16_t* block_src(const TileDesc& td, const int16_t* __restrict__ llr, const uint64_t* __restrict__ offsets, int c)
 {
-  const size_t nllr = 3 * (size_t)v.K + 12;
-  const int    nvec = rows * 3 / 4; // 8-byte vectors per block in this chunk (<= 48)
+  if ((uint32_t)c >= td.nblk) return nullptr;
+  return llr + (offsets ? offsets[td.cb0 + (uint32_t)c] : td.llr_off + (uint64_t)c * (3ull * td.K + 12ull));
+}
+
+// ALIGNED8: every vector starts on an 8-byte boundary.  Returns (to all threads) whether every staged value fits int8.
+template <bool ALIGNED8>
+__device__ __forceinline__ bool load_stage_chunk(uint8_t* sm, const TileDesc& td, const int16_t* __restrict__ llr,
+                                                 const uint64_t* __restrict__ offsets, int k0, int rows)
+{
+  const int nvec = rows * 3 / 4; // 8-byte vectors per block in this chunk (<= 48)
   // warp w stages blocks w, w+8, ...; lane q takes the q-th 8-byte piece of the block's chunk (no divisions).  Two
   // blocks per round keep 6 independent 8-byte loads per thread in flight.
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
@@ -419,14 +434,14 @@ __device__ __forceinline__ bool load_stage_chunk(uint8_t* sm, const TdecView& v,
     uint2 val[NB][NH];
 #pragma unroll
     for (int u = 0; u < NB; u++) {
-      const int      c  = c0 + u * nwarp;
-      const uint32_t cb = (uint32_t)tile * TDEC_TILE_CB + c;
+      const int      c    = c0 + u * nwarp;
+      const int16_t* base = c < TDEC_TILE_CB ? block_src(td, llr, offsets, c) : nullptr;
 #pragma unroll
       for (int h = 0; h < NH; h++) {
         const int q = lane + 32 * h;
         val[u][h]   = make_uint2(0u, 0u);
-        if (c < TDEC_TILE_CB && cb < ncb && q < nvec) {
-          const int16_t* src = llr + (offsets ? offsets[cb] : cb * nllr) + 3 * (size_t)k0 + 4 * (size_t)q;
+        if (base != nullptr && q < nvec) {
+          const int16_t* src = base + 3 * (size_t)k0 + 4 * (size_t)q;
           if (ALIGNED8) {
             val[u][h] = __ldcs(reinterpret_cast<const uint2*>(src));
           } else {
@@ -453,21 +468,63 @@ __device__ __forceinline__ bool load_stage_chunk(uint8_t* sm, const TdecView& v,
   return __syncthreads_or(bad) == 0;
 }
 
+// The 12 tail values of a tile's blocks (row K/8 of S8/P08/P18 and S2T), the per-block state of a fresh decode
+// (srsran_tdec_new_cb, turbodecoder.c:510-525) and the lane map (every pair starts at home).  One warp.
+__device__ __forceinline__ void load_tail_and_arm(const TdecView& v, const TileDesc& td, int tile, const int16_t* __restrict__ llr,
+                                                  const uint64_t* __restrict__ offsets, int lane)
+{
+  const int K = (int)td.K;
+  uint32_t  w16[4][4];
+  bool      bad = false;
+  const int16_t* src0 = block_src(td, llr, offsets, 2 * lane);
+  const int16_t* src1 = block_src(td, llr, offsets, 2 * lane + 1);
+#pragma unroll
+  for (int s_ = 0; s_ < 4; s_++) {
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+      int16_t a0 = 0, b0 = 0;
+      if (src0) a0 = natural_pick(src0, K, s_, K + t);
+      if (src1) b0 = natural_pick(src1, K, s_, K + t);
+      w16[s_][t] = pack2(a0, b0);
+      if (s_ < 3) bad |= !fits8(a0) || !fits8(b0); // S2T stays int16
+    }
+  }
+  if (__any_sync(0xFFFFFFFFu, bad) && lane == 0) atomicOr(v.fmt + tile, 1u);
+#pragma unroll
+  for (int s_ = 0; s_ < 3; s_++) {
+    uint32_t w[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int t = 0; t < 4; t++) {
+      const uint32_t lo = w16[s_][t] & 0xFFu, hi = (w16[s_][t] >> 16) & 0xFFu;
+      w[t >> 1] |= (lo | (hi << 8)) << (16 * (t & 1));
+    }
+    u4* dst = s_ == 0 ? td.S8 : (s_ == 1 ? td.P08 : td.P18);
+    dst[row8(K / 8, lane)] = u4{w[0], w[1], w[2], w[3]};
+  }
+  v.S2T[(size_t)tile * 32 + lane] = u4{w16[3][0], w16[3][1], w16[3][2], w16[3][3]};
+  const LaneMap home  = lane_home(td, tile, lane);
+  v.lanes[(size_t)tile * 32 + lane] = home;
+  v.status[home.st0]     = CbStatus{(uint8_t)(src0 != nullptr), 0, 0, 0};
+  v.status[home.st0 + 1] = CbStatus{(uint8_t)(src1 != nullptr), 0, 0, 0};
+}
+
 template <bool ALIGNED8>
 __global__ void __launch_bounds__(256)
-    tdec_load8_kernel(TdecView v, const int16_t* __restrict__ llr, const uint64_t* __restrict__ offsets, uint32_t ncb)
+    tdec_load8_kernel(TdecView v, const int16_t* __restrict__ llr, const uint64_t* __restrict__ offsets)
 {
   extern __shared__ __align__(16) uint8_t sm[];
-  const int    tile  = blockIdx.y;
-  const int    chunk = blockIdx.x;
-  const int    K     = v.K;
-  const int    k0    = chunk * LOAD_ROWS;
-  const size_t nllr  = 3 * (size_t)K + 12;
-  const int    tid   = threadIdx.x;
+  const int       tile  = blockIdx.y;
+  const int       chunk = blockIdx.x;
+  const TileDesc& td    = v.tiles[tile];
+  const int       K     = (int)td.K;
+  const int       k0    = chunk * LOAD_ROWS;
+  const int       tid   = threadIdx.x;
+  const int       nchunk = (K + LOAD_ROWS - 1) / LOAD_ROWS;
+  if (chunk > nchunk) return; // a shorter tile of a mixed batch
 
   if (k0 < K) {
     const int  rows = min(LOAD_ROWS, K - k0); // multiple of 8
-    const bool ok   = load_stage_chunk<ALIGNED8>(sm, v, llr, offsets, ncb, tile, k0, rows);
+    const bool ok   = load_stage_chunk<ALIGNED8>(sm, td, llr, offsets, k0, rows);
     if (!ok && tid == 0) atomicOr(v.fmt + tile, 1u);
     // warp = window of the chunk; a lane reads the 48 bytes of its two blocks, pairs and packs them with byte permutes
     // and writes its 16 bytes of each int8 tile row
@@ -491,68 +548,35 @@ __global__ void __launch_bounds__(256)
           const uint32_t p1 = __byte_perm(a[i1 >> 1], b[i1 >> 1], (i1 & 1) ? 0x7632 : 0x5410);
           w[q]              = __byte_perm(p0, p1, 0x6420);                                     // their low bytes
         }
-        u4* dst = s == 0 ? v.S8 : (s == 1 ? v.P08 : v.P18);
-        dst[row8(v, tile, k0 / 8 + w8, lane)] = u4{w[0], w[1], w[2], w[3]};
+        u4* dst = s == 0 ? td.S8 : (s == 1 ? td.P08 : td.P18);
+        dst[row8(k0 / 8 + w8, lane)] = u4{w[0], w[1], w[2], w[3]};
       }
     }
-  } else {
-    // the chunk past the payload carries the 12 tail values: row K/8 of S8/P08/P18 and S2T
-    if (tid < 32) {
-      const int lane = tid;
-      uint32_t  w16[4][4];
-      bool      bad = false;
-#pragma unroll
-      for (int s = 0; s < 4; s++) {
-#pragma unroll
-        for (int t = 0; t < 4; t++) {
-          int16_t a = 0, b = 0;
-          const uint32_t cb0 = (uint32_t)tile * TDEC_TILE_CB + 2 * lane;
-          if (cb0 < ncb) a = natural_pick(llr + (offsets ? offsets[cb0] : cb0 * nllr), K, s, K + t);
-          if (cb0 + 1 < ncb) b = natural_pick(llr + (offsets ? offsets[cb0 + 1] : (cb0 + 1) * nllr), K, s, K + t);
-          w16[s][t] = pack2(a, b);
-          if (s < 3) bad |= !fits8(a) || !fits8(b); // S2T stays int16
-        }
-      }
-      if (__any_sync(0xFFFFFFFFu, bad) && lane == 0) atomicOr(v.fmt + tile, 1u);
-#pragma unroll
-      for (int s = 0; s < 3; s++) {
-        uint32_t w[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-        for (int t = 0; t < 4; t++) {
-          const uint32_t lo = w16[s][t] & 0xFFu, hi = (w16[s][t] >> 16) & 0xFFu;
-          w[t >> 1] |= (lo | (hi << 8)) << (16 * (t & 1));
-        }
-        u4* dst = s == 0 ? v.S8 : (s == 1 ? v.P08 : v.P18);
-        dst[row8(v, tile, K / 8, lane)] = u4{w[0], w[1], w[2], w[3]};
-      }
-      v.S2T[(size_t)tile * 32 + lane] = u4{w16[3][0], w16[3][1], w16[3][2], w16[3][3]};
-      // arm the per-block state for a fresh decode (srsran_tdec_new_cb, turbodecoder.c:510-525)
-      const uint32_t cb0 = (uint32_t)tile * TDEC_TILE_CB + 2 * lane;
-      v.status[cb0]      = CbStatus{(uint8_t)(cb0 < ncb), 0, 0, 0};
-      v.status[cb0 + 1]  = CbStatus{(uint8_t)(cb0 + 1 < ncb), 0, 0, 0};
-    }
+  } else if (tid < 32) {
+    // the chunk past the payload carries the 12 tail values
+    load_tail_and_arm(v, td, tile, llr, offsets, tid);
   }
 }
 
 template <bool ALIGNED8>
 __global__ void __launch_bounds__(256)
-    tdec_load16_kernel(TdecView v, const int16_t* __restrict__ llr, const uint64_t* __restrict__ offsets, uint32_t ncb)
+    tdec_load16_kernel(TdecView v, const int16_t* __restrict__ llr, const uint64_t* __restrict__ offsets, int max_chunks)
 {
   extern __shared__ __align__(16) uint8_t sm[];
-  const int    K      = v.K;
-  const size_t nllr   = 3 * (size_t)K + 12;
-  const int    tid    = threadIdx.x;
-  const int    chunks = (K + LOAD_ROWS - 1) / LOAD_ROWS + 1;
+  const int tid = threadIdx.x;
   // few CTAs walking all (tile, chunk) items: in the common case no tile is raised and this costs microseconds
-  for (int item = blockIdx.x; item < v.ntiles * chunks; item += gridDim.x) {
-  const int tile = item / chunks, chunk = item % chunks;
-  const int k0   = chunk * LOAD_ROWS;
+  for (int item = blockIdx.x; item < v.ntiles * max_chunks; item += gridDim.x) {
+  const int tile = item / max_chunks, chunk = item % max_chunks;
   if (v.fmt[tile] == 0u) continue; // the tile lives in the int8 arrays
+  const TileDesc& td = v.tiles[tile];
+  const int       K  = (int)td.K;
+  const int       k0 = chunk * LOAD_ROWS;
+  if (chunk > (K + LOAD_ROWS - 1) / LOAD_ROWS) continue;
   __syncthreads();                 // the previous item's readers of sm are done
 
   if (k0 < K) {
     const int rows = min(LOAD_ROWS, K - k0); // multiple of 8
-    load_stage_chunk<ALIGNED8>(sm, v, llr, offsets, ncb, tile, k0, rows);
+    load_stage_chunk<ALIGNED8>(sm, td, llr, offsets, k0, rows);
     const int lane = tid & 31;
     for (int r4 = tid >> 5; r4 < rows / 4; r4 += 8) {
       uint32_t w[3][4];
@@ -565,29 +589,30 @@ __global__ void __launch_bounds__(256)
                               reinterpret_cast<const int16_t*>(sm + (2 * lane + 1) * RAW_PITCH)[o]);
         }
       }
-      const size_t row = vec_row(v, tile, k0 / 4 + r4, lane);
-      v.S[row]         = u4{w[0][0], w[0][1], w[0][2], w[0][3]};
-      v.P0[row]        = u4{w[1][0], w[1][1], w[1][2], w[1][3]};
-      v.P1[row]        = u4{w[2][0], w[2][1], w[2][2], w[2][3]};
+      const uint32_t row = vec_row(k0 / 4 + r4, lane);
+      td.S[row]          = u4{w[0][0], w[0][1], w[0][2], w[0][3]};
+      td.P0[row]         = u4{w[1][0], w[1][1], w[1][2], w[1][3]};
+      td.P1[row]         = u4{w[2][0], w[2][1], w[2][2], w[2][3]};
     }
   } else if (tid < 32) {
     const int lane = tid;
     uint32_t  w[3][4];
+    const int16_t* src0 = block_src(td, llr, offsets, 2 * lane);
+    const int16_t* src1 = block_src(td, llr, offsets, 2 * lane + 1);
 #pragma unroll
     for (int s = 0; s < 3; s++) {
 #pragma unroll
       for (int t = 0; t < 4; t++) {
         int16_t a = 0, b = 0;
-        const uint32_t cb0 = (uint32_t)tile * TDEC_TILE_CB + 2 * lane;
-        if (cb0 < ncb) a = natural_pick(llr + (offsets ? offsets[cb0] : cb0 * nllr), K, s, K + t);
-        if (cb0 + 1 < ncb) b = natural_pick(llr + (offsets ? offsets[cb0 + 1] : (cb0 + 1) * nllr), K, s, K + t);
+        if (src0) a = natural_pick(src0, K, s, K + t);
+        if (src1) b = natural_pick(src1, K, s, K + t);
         w[s][t] = pack2(a, b);
       }
     }
-    const size_t row = vec_row(v, tile, K / 4, lane);
-    v.S[row]         = u4{w[0][0], w[0][1], w[0][2], w[0][3]};
-    v.P0[row]        = u4{w[1][0], w[1][1], w[1][2], w[1][3]};
-    v.P1[row]        = u4{w[2][0], w[2][1], w[2][2], w[2][3]};
+    const uint32_t row = vec_row(K / 4, lane);
+    td.S[row]          = u4{w[0][0], w[0][1], w[0][2], w[0][3]};
+    td.P0[row]         = u4{w[1][0], w[1][1], w[1][2], w[1][3]};
+    td.P1[row]         = u4{w[2][0], w[2][1], w[2][2], w[2][3]};
   }
   }
 }
@@ -609,20 +634,19 @@ __device__ __forceinline__ void cp_async8_raw(uint32_t dst, const void* src)
 }
 
 __global__ void __launch_bounds__(256)
-    tdec_load8_stream_kernel(TdecView v, const int16_t* __restrict__ llr, const uint64_t* __restrict__ offsets, uint32_t ncb)
+    tdec_load8_stream_kernel(TdecView v, const int16_t* __restrict__ llr, const uint64_t* __restrict__ offsets)
 {
   extern __shared__ __align__(16) uint8_t sm[];
   const uint8_t** sbase = reinterpret_cast<const uint8_t**>(sm + 2 * LS_BUF); // byte address of every block's vector
-  const int    tile = blockIdx.y, seg = blockIdx.x;
-  const int    K    = v.K;
-  const size_t nllr = 3 * (size_t)K + 12;
-  const int    tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int    nchunk = (K + LOAD_ROWS - 1) / LOAD_ROWS;
-  const int    c_lo = seg * LS_CHUNKS, c_hi = min(nchunk, c_lo + LS_CHUNKS);
-  if (tid < TDEC_TILE_CB) {
-    const uint32_t cb = (uint32_t)tile * TDEC_TILE_CB + tid;
-    sbase[tid]        = cb < ncb ? reinterpret_cast<const uint8_t*>(llr + (offsets ? offsets[cb] : cb * nllr)) : nullptr;
-  }
+  const int       tile = blockIdx.y, seg = blockIdx.x;
+  const TileDesc& td   = v.tiles[tile];
+  const int       K    = (int)td.K;
+  const int       tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int       nchunk = (K + LOAD_ROWS - 1) / LOAD_ROWS;
+  const int       nseg   = (nchunk + LS_CHUNKS - 1) / LS_CHUNKS;
+  if (seg >= nseg) return; // a shorter tile of a mixed batch
+  const int       c_lo = seg * LS_CHUNKS, c_hi = min(nchunk, c_lo + LS_CHUNKS);
+  if (tid < TDEC_TILE_CB) sbase[tid] = reinterpret_cast<const uint8_t*>(block_src(td, llr, offsets, tid));
   // rows of blocks past the end of the batch stay zero in both buffers
   for (int i = tid; i < (int)(2 * LS_BUF / 16); i += 256) reinterpret_cast<uint4*>(sm)[i] = make_uint4(0u, 0u, 0u, 0u);
   __syncthreads();
@@ -680,90 +704,49 @@ __global__ void __launch_bounds__(256)
           const uint32_t p1 = __byte_perm(a[i1 >> 1], b[i1 >> 1], (i1 & 1) ? 0x7632 : 0x5410);
           w[q]              = __byte_perm(p0, p1, 0x6420);                                     // their low bytes
         }
-        u4* dst = s_ == 0 ? v.S8 : (s_ == 1 ? v.P08 : v.P18);
-        dst[row8(v, tile, k0 / 8 + w8, lane)] = u4{w[0], w[1], w[2], w[3]};
+        u4* dst = s_ == 0 ? td.S8 : (s_ == 1 ? td.P08 : td.P18);
+        dst[row8(k0 / 8 + w8, lane)] = u4{w[0], w[1], w[2], w[3]};
       }
     }
   }
   if (__syncthreads_or((acc & 0xFF00FF00u) != 0u) && tid == 0) atomicOr(v.fmt + tile, 1u);
 
-  // the last segment also writes the tail row (the 12 tail values: row K/8 of S8/P08/P18 and S2T) and arms the block state
-  if (seg == (int)gridDim.x - 1 && tid < 32) {
-    uint32_t w16[4][4];
-    bool     bad = false;
-#pragma unroll
-    for (int s_ = 0; s_ < 4; s_++) {
-#pragma unroll
-      for (int t = 0; t < 4; t++) {
-        int16_t        a0 = 0, b0 = 0;
-        const uint32_t cb0 = (uint32_t)tile * TDEC_TILE_CB + 2 * lane;
-        if (cb0 < ncb) a0 = natural_pick(llr + (offsets ? offsets[cb0] : cb0 * nllr), K, s_, K + t);
-        if (cb0 + 1 < ncb) b0 = natural_pick(llr + (offsets ? offsets[cb0 + 1] : (cb0 + 1) * nllr), K, s_, K + t);
-        w16[s_][t] = pack2(a0, b0);
-        if (s_ < 3) bad |= !fits8(a0) || !fits8(b0); // S2T stays int16
-      }
-    }
-    if (__any_sync(0xFFFFFFFFu, bad) && lane == 0) atomicOr(v.fmt + tile, 1u);
-#pragma unroll
-    for (int s_ = 0; s_ < 3; s_++) {
-      uint32_t w[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-      for (int t = 0; t < 4; t++) {
-        const uint32_t lo = w16[s_][t] & 0xFFu, hi = (w16[s_][t] >> 16) & 0xFFu;
-        w[t >> 1] |= (lo | (hi << 8)) << (16 * (t & 1));
-      }
-      u4* dst = s_ == 0 ? v.S8 : (s_ == 1 ? v.P08 : v.P18);
-      dst[row8(v, tile, K / 8, lane)] = u4{w[0], w[1], w[2], w[3]};
-    }
-    v.S2T[(size_t)tile * 32 + lane] = u4{w16[3][0], w16[3][1], w16[3][2], w16[3][3]};
-    const uint32_t cb0 = (uint32_t)tile * TDEC_TILE_CB + 2 * lane;
-    v.status[cb0]      = CbStatus{(uint8_t)(cb0 < ncb), 0, 0, 0};
-    v.status[cb0 + 1]  = CbStatus{(uint8_t)(cb0 + 1 < ncb), 0, 0, 0};
-  }
+  // the tile's last segment also writes the tail row and arms the block state
+  if (seg == nseg - 1 && tid < 32) load_tail_and_arm(v, td, tile, llr, offsets, lane);
 }
 
 
 void launch_load_natural(const TdecView& v,
+                         int             max_K,
                          const int16_t*  llr_dev,
                          const uint64_t* offsets_dev,
                          bool            aligned8,
-                         uint32_t        ncb,
                          cudaStream_t    stream)
 {
-  const int chunks = (v.K + LOAD_ROWS - 1) / LOAD_ROWS + 1; // +1: the tail chunk
+  const int chunks = (max_K + LOAD_ROWS - 1) / LOAD_ROWS + 1; // +1: the tail chunk
   dim3      grid((unsigned)chunks, (unsigned)v.ntiles), block(256);
   const long items = (long)chunks * v.ntiles;
   dim3       grid16((unsigned)(items < 148 * 8 ? items : 148 * 8));
-  static bool attr_done = false;
-  if (!attr_done) { // 8 CTAs of 25 KB per SM
+  static std::atomic<uint64_t> attr_done{0};
+  if (once_per_device(attr_done)) { // 8 CTAs of 25 KB per SM
     cudaFuncSetAttribute(tdec_load8_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(tdec_load8_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(tdec_load8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LOAD_SMEM);
     cudaFuncSetAttribute(tdec_load8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LOAD_SMEM);
     cudaFuncSetAttribute(tdec_load16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LOAD_SMEM);
     cudaFuncSetAttribute(tdec_load16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LOAD_SMEM);
-    attr_done = true;
+    cudaFuncSetAttribute(tdec_load8_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LS_SMEM);
+    cudaFuncSetAttribute(tdec_load8_stream_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   }
   cudaMemsetAsync(v.fmt, 0, (size_t)v.ntiles * sizeof(uint32_t), stream);
   if (aligned8) {
-    static const bool one_chunk = getenv("SRSLTE_B200_LOAD_ONE_CHUNK") != nullptr; // the earlier kernel, for comparison
-    if (one_chunk) {
-      tdec_load8_kernel<true><<<grid, block, LOAD_SMEM, stream>>>(v, llr_dev, offsets_dev, ncb);
-    } else {
-      static bool attr_s = false;
-      if (!attr_s) {
-        cudaFuncSetAttribute(tdec_load8_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LS_SMEM);
-        cudaFuncSetAttribute(tdec_load8_stream_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        attr_s = true;
-      }
-      const int nchunk = (v.K + LOAD_ROWS - 1) / LOAD_ROWS;
-      dim3      gs((unsigned)((nchunk + LS_CHUNKS - 1) / LS_CHUNKS), (unsigned)v.ntiles);
-      tdec_load8_stream_kernel<<<gs, block, LS_SMEM, stream>>>(v, llr_dev, offsets_dev, ncb);
-    }
-    tdec_load16_kernel<true><<<grid16, block, LOAD_SMEM, stream>>>(v, llr_dev, offsets_dev, ncb);
+    const int nchunk = (max_K + LOAD_ROWS - 1) / LOAD_ROWS;
+    dim3      gs((unsigned)((nchunk + LS_CHUNKS - 1) / LS_CHUNKS), (unsigned)v.ntiles);
+    tdec_load8_stream_kernel<<<gs, block, LS_SMEM, stream>>>(v, llr_dev, offsets_dev);
+    tdec_load16_kernel<true><<<grid16, block, LOAD_SMEM, stream>>>(v, llr_dev, offsets_dev, chunks);
   } else {
-    tdec_load8_kernel<false><<<grid, block, LOAD_SMEM, stream>>>(v, llr_dev, offsets_dev, ncb);
-    tdec_load16_kernel<false><<<grid16, block, LOAD_SMEM, stream>>>(v, llr_dev, offsets_dev, ncb);
+    tdec_load8_kernel<false><<<grid, block, LOAD_SMEM, stream>>>(v, llr_dev, offsets_dev);
+    tdec_load16_kernel<false><<<grid16, block, LOAD_SMEM, stream>>>(v, llr_dev, offsets_dev, chunks);
   }
 }
 
@@ -771,22 +754,24 @@ void launch_load_natural(const TdecView& v,
 // HB -> bytes.  One CTA per tile: the tile's decisions (K/8 x 64 bytes) are staged in shared memory, so the gather
 // through the inverse interleaver that a block ending on a DEC2 pass needs (eight 1-bit lookups per output byte)
 // never leaves the SM; the 64 x K/8 output bytes are assembled in shared memory too and leave as one contiguous run.
+// Tiles are HOME tiles here: status and HB never move when the lanes are re-packed between passes.
 __global__ void __launch_bounds__(256) tdec_decide_kernel(TdecView v,
-                                                          const uint16_t* __restrict__ qpp_rev,
                                                           uint8_t* __restrict__ out,
                                                           uint8_t* __restrict__ crc_ok,
                                                           uint8_t* __restrict__ npass,
-                                                          uint8_t* __restrict__ npass_run,
-                                                          uint32_t ncb)
+                                                          uint8_t* __restrict__ npass_run)
 {
   extern __shared__ __align__(16) uint8_t dsm[];
-  const int      tile  = blockIdx.x;
-  const int      nb    = v.K / 8; // bytes per block = windows per block
-  const int      pitch = nb + 4;
-  uint16_t*      hb    = reinterpret_cast<uint16_t*>(dsm);           // [nb][32]
-  uint8_t*       so    = dsm + (((size_t)nb * 64 + 15) / 16) * 16;   // [64][pitch]
-  const int      tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const uint4*   src = reinterpret_cast<const uint4*>(v.HB + hb_idx(v, tile, 0, 0));
+  const int       tile  = blockIdx.x;
+  const TileDesc& td    = v.tiles[tile];
+  const int       K     = (int)td.K;
+  const int       nb    = K / 8; // bytes per block = windows per block
+  const int       pitch = nb + 4;
+  uint16_t*       hb    = reinterpret_cast<uint16_t*>(dsm);           // [nb][32]
+  uint8_t*        so    = dsm + (((size_t)nb * 64 + 15) / 16) * 16;   // [64][pitch]
+  const int       tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const uint4*    src = reinterpret_cast<const uint4*>(v.HB + (size_t)td.hb_row0 * 32);
+  const uint16_t* __restrict__ qpp_rev = td.qpp_rev;
   for (int i = tid; i < nb * 4; i += 256) reinterpret_cast<uint4*>(hb)[i] = src[i];
   __syncthreads();
 
@@ -799,7 +784,7 @@ __global__ void __launch_bounds__(256) tdec_decide_kernel(TdecView v,
   const uint32_t keep_nat = (perm_lo ? 0u : 0x00FFu) | (perm_hi ? 0u : 0xFF00u); // halves that take the natural-order word
   for (int j0 = wid * 4; j0 < nb; j0 += 32) {
     const int      nj  = min(4, nb - j0);
-    const uint32_t rev = (8 * j0 + lane < v.K) ? qpp_rev[8 * j0 + lane] : 0u; // visiting index of bit 8*j0+lane
+    const uint32_t rev = (8 * j0 + lane < K) ? qpp_rev[8 * j0 + lane] : 0u; // visiting index of bit 8*j0+lane
     for (int j = 0; j < nj; j++) {
       const uint32_t nat = hb[(j0 + j) * 32 + lane];
       uint32_t       w2  = nat;
@@ -818,9 +803,8 @@ __global__ void __launch_bounds__(256) tdec_decide_kernel(TdecView v,
     }
   }
   __syncthreads();
-  const size_t   first = (size_t)tile * TDEC_TILE_CB;
-  const uint32_t nblk  = first < ncb ? (uint32_t)min((size_t)TDEC_TILE_CB, (size_t)ncb - first) : 0u;
-  uint8_t*       dst   = out + first * nb;
+  const uint32_t nblk = td.nblk;
+  uint8_t*       dst  = out + td.out_off;
   if ((nb & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
     const int q = nb / 16;
     for (uint32_t i = tid; i < nblk * q; i += 256) {
@@ -831,35 +815,86 @@ __global__ void __launch_bounds__(256) tdec_decide_kernel(TdecView v,
   } else {
     for (uint32_t i = tid; i < nblk * nb; i += 256) dst[i] = so[(i / nb) * pitch + (i % nb)];
   }
-  if (tid < TDEC_TILE_CB) {
-    const uint32_t cb = (uint32_t)first + tid;
-    if (cb < ncb) {
-      const CbStatus s = v.status[cb];
-      if (crc_ok) crc_ok[cb] = s.crc_ok;
-      // the caller's loop counter (sch.c:431-432): pass at which the CRC matched, else the passes spent
-      if (npass) npass[cb] = s.crc_ok ? s.npass_crc : s.npass_run;
-      if (npass_run) npass_run[cb] = s.npass_run;
-    }
+  if (tid < TDEC_TILE_CB && (uint32_t)tid < nblk) {
+    const uint32_t cb = td.cb0 + tid;
+    const CbStatus s  = v.status[(size_t)tile * TDEC_TILE_CB + tid];
+    if (crc_ok) crc_ok[cb] = s.crc_ok;
+    // the caller's loop counter (sch.c:431-432): pass at which the CRC matched, else the passes spent
+    if (npass) npass[cb] = s.crc_ok ? s.npass_crc : s.npass_run;
+    if (npass_run) npass_run[cb] = s.npass_run;
   }
 }
 
 void launch_decide(const TdecView& v,
-                   const uint16_t* qpp_rev_dev,
+                   int             max_K,
                    uint8_t*        out_dev,
                    uint8_t*        crc_ok_dev,
                    uint8_t*        npass_dev,
                    uint8_t*        npass_run_dev,
-                   uint32_t        ncb,
                    cudaStream_t    stream)
 {
-  const int    nb   = v.K / 8;
+  const int    nb   = max_K / 8;
   const size_t smem = (((size_t)nb * 64 + 15) / 16) * 16 + (size_t)TDEC_TILE_CB * (nb + 4);
-  static bool  attr_done = false;
-  if (!attr_done) {
+  static std::atomic<uint64_t> attr_done{0};
+  if (once_per_device(attr_done)) {
     cudaFuncSetAttribute(tdec_decide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    attr_done = true;
   }
-  tdec_decide_kernel<<<(unsigned)v.ntiles, 256, smem, stream>>>(v, qpp_rev_dev, out_dev, crc_ok_dev, npass_dev, npass_run_dev, ncb);
+  tdec_decide_kernel<<<(unsigned)v.ntiles, 256, smem, stream>>>(v, out_dev, crc_ok_dev, npass_dev, npass_run_dev);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Block-granular early stop (tdec_core.h: compact_*).  After a pass, per group of equal-K tiles: find the lanes that
+// still run, and if they fit markedly fewer tiles, move the running lanes of the group's last tiles into the free lane
+// slots of its first ones.  Everything is decided on the device; the host enqueues the two kernels after every pass of
+// an early-stop decode and the next pass launches over all tiles as before (emptied tiles exit at once).
+__global__ void __launch_bounds__(256) tdec_compact_plan_kernel(TdecView v, const TileGroup* __restrict__ groups, uint32_t* __restrict__ mask,
+                                                                uint32_t* __restrict__ pref, GroupPlan* __restrict__ plans,
+                                                                MoveRec* __restrict__ moves, uint32_t* __restrict__ move_counter,
+                                                                uint32_t move_cap, uint32_t min_gain_tiles)
+{
+  __shared__ GroupPlan plan;
+  const TileGroup g = groups[blockIdx.x];
+  // step 1: a warp per tile, a lane per lane slot
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  bool      int8_only = true;
+  for (uint32_t t = wid; t < g.ntiles; t += 8) {
+    const uint32_t tile = g.first_tile + t;
+    const uint32_t m    = __ballot_sync(0xFFFFFFFFu, lane_running(v, tile * 32 + lane));
+    if (lane == 0) mask[tile] = m;
+    int8_only = int8_only && v.fmt[tile] == 0u;
+  }
+  const bool all_int8 = __syncthreads_and(int8_only) != 0;
+  if (threadIdx.x == 0) {
+    compact_plan_group(g, mask, pref, all_int8, min_gain_tiles, move_counter, move_cap, plan);
+    plans[blockIdx.x] = plan;
+  }
+  __syncthreads();
+  if (!plan.go) return;
+  for (uint32_t t = threadIdx.x; t < g.ntiles; t += blockDim.x) compact_emit_tile(g, t, mask, pref, plan, moves);
+}
+
+// One CTA per move (grid-stride): copies the lane's columns; the last thread block to finish nothing else -- the lane map
+// is renamed by the thread block that copied the data, after its copy.
+__global__ void __launch_bounds__(256) tdec_compact_move_kernel(TdecView v, const MoveRec* __restrict__ moves, const uint32_t* __restrict__ move_counter)
+{
+  const uint32_t n = *move_counter;
+  for (uint32_t m = blockIdx.x; m < n; m += gridDim.x) {
+    const MoveRec  mv = moves[m];
+    const uint32_t ne = compact_move_elems(v.tiles[mv.src >> 5].K);
+    for (uint32_t i = threadIdx.x; i < ne; i += blockDim.x) compact_move_elem(v, mv, i);
+    if (threadIdx.x == 0) compact_rename(v, mv);
+  }
+}
+
+void launch_compact(const TdecView& v, const TileGroup* groups_dev, uint32_t ngroups, uint32_t* mask_dev, uint32_t* pref_dev,
+                    GroupPlan* plans_dev, MoveRec* moves_dev, uint32_t* move_counter_dev, uint32_t min_gain_tiles, int sm_count,
+                    cudaStream_t stream)
+{
+  cudaMemsetAsync(move_counter_dev, 0, sizeof(uint32_t), stream);
+  tdec_compact_plan_kernel<<<ngroups, 256, 0, stream>>>(v, groups_dev, mask_dev, pref_dev, plans_dev, moves_dev, move_counter_dev,
+                                                        (uint32_t)v.ntiles * 32u, min_gain_tiles);
+  const unsigned nmove = (unsigned)std::min<long>((long)v.ntiles * 32, (long)sm_count * 8);
+  tdec_compact_move_kernel<<<nmove, 256, 0, stream>>>(v, moves_dev, move_counter_dev);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -41,13 +41,51 @@ class TurboDecoderBatch:
         self._lib.srsran_b200_tdec_profile_reset(self._h, int(enable))
 
     def profile_get(self) -> dict:
-        ms = (C.c_double * 3)()
-        n = (C.c_uint64 * 3)()
-        rc = self._lib.srsran_b200_tdec_profile_get(self._h, ms, n)
+        ms = (C.c_double * 4)()
+        n = (C.c_uint64 * 4)()
+        rc = self._lib.srsran_b200_tdec_profile_get_ex(self._h, ms, n, 4)
         if rc != _lib.SUCCESS:
-            raise RuntimeError(f"srsran_b200_tdec_profile_get failed ({rc})")
-        return {"load_ms": ms[0], "siso_ms": ms[1], "decide_ms": ms[2], "total_ms": ms[0] + ms[1] + ms[2],
-                "load_launches": int(n[0]), "siso_launches": int(n[1]), "decide_launches": int(n[2])}
+            raise RuntimeError(f"srsran_b200_tdec_profile_get_ex failed ({rc})")
+        return {"load_ms": ms[0], "siso_ms": ms[1], "decide_ms": ms[2], "repack_ms": ms[3], "total_ms": ms[0] + ms[1] + ms[2] + ms[3],
+                "load_launches": int(n[0]), "siso_launches": int(n[1]), "decide_launches": int(n[2]), "repack_launches": int(n[3])}
+
+    # -- several code block lengths in one batch (BASELINE config 3) ---------------------------------------------
+    def decode_mixed(self, llrs, Ks, max_passes: int = 8, crc: str | None = "B", early_stop: bool = True):
+        """llrs: list of (ncb_g, 3K_g+12) int16 numpy arrays, Ks: their code block lengths.  Host buffers.
+        Returns a list of (bytes (ncb_g,K_g/8), crc_ok (ncb_g,), npass (ncb_g,)) per group."""
+        ncbs = [int(np.asarray(a).reshape(-1, 3 * K + 12).shape[0]) for a, K in zip(llrs, Ks)]
+        flat = np.ascontiguousarray(np.concatenate([np.asarray(a, np.int16).ravel() for a in llrs]) if llrs else np.zeros(0, np.int16))
+        tot = sum(ncbs)
+        out = np.zeros(sum(n * (K // 8) for n, K in zip(ncbs, Ks)), np.uint8)
+        ok = np.zeros(tot, np.uint8)
+        npass = np.zeros(tot, np.uint8)
+        Ka = np.array(Ks, np.uint32)
+        na = np.array(ncbs, np.uint32)
+        rc = self._lib.srsran_b200_tdec_run_mixed(self._h, flat.ctypes.data, len(Ks), Ka.ctypes.data, na.ctypes.data, max_passes,
+                                                  _CRC[crc], int(early_stop), out.ctypes.data, ok.ctypes.data, npass.ctypes.data, 0, None)
+        if rc != _lib.SUCCESS:
+            raise RuntimeError(f"srsran_b200_tdec_run_mixed failed ({rc})")
+        res, o0, c0 = [], 0, 0
+        for n, K in zip(ncbs, Ks):
+            res.append((out[o0:o0 + n * (K // 8)].reshape(n, K // 8), ok[c0:c0 + n], npass[c0:c0 + n]))
+            o0 += n * (K // 8)
+            c0 += n
+        return res
+
+    def decode_mixed_device(self, llr, Ks, ncbs, out, ok, npass, max_passes: int = 8, crc: str | None = "B",
+                            early_stop: bool = True, stream_ptr: int | None = None):
+        """llr / out / ok / npass: flat torch CUDA tensors laid out group after group; asynchronous."""
+        import torch
+
+        if stream_ptr is None:
+            stream_ptr = torch.cuda.current_stream(llr.device).cuda_stream
+        Ka = np.array(Ks, np.uint32)
+        na = np.array(ncbs, np.uint32)
+        rc = self._lib.srsran_b200_tdec_run_mixed(self._h, llr.data_ptr(), len(Ks), Ka.ctypes.data, na.ctypes.data, max_passes,
+                                                  _CRC[crc], int(early_stop), out.data_ptr(), ok.data_ptr() if ok is not None else None,
+                                                  npass.data_ptr() if npass is not None else None, _lib.FLAG_DEVICE_PTRS, stream_ptr)
+        if rc != _lib.SUCCESS:
+            raise RuntimeError(f"srsran_b200_tdec_run_mixed failed ({rc})")
 
     # -- host buffers ------------------------------------------------------------------------------------
     def decode(self, llr: np.ndarray, K: int, max_passes: int = 8, crc: str | None = "B", early_stop: bool = True):
@@ -91,15 +129,22 @@ class TurboDecoderBatch:
 
 def synth_llr(device: int, ncb: int, K: int, sigma: float, scale: float = 16.0, clip: int = 31, seed: int = 0xB200,
               attach_crc: bool = True):
-    """Synthetic AWGN workload generated on the GPU: returns (llr int16 (ncb,3K+12), truth uint8 (ncb,K/8)) torch CUDA."""
+    """Synthetic AWGN workload generated on the GPU by the test/bench helper library tools/synth/libsrslte_b200_synth.so
+    (not part of the product library): returns (llr int16 (ncb,3K+12), truth uint8 (ncb,K/8)) torch CUDA tensors."""
+    import ctypes as C
+
     import torch
 
+    from .build import SYNTH_LIB_PATH
+
+    L = C.CDLL(SYNTH_LIB_PATH)
+    L.b200_synth_llr.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_float, C.c_float, C.c_int,
+                                 C.c_uint64, C.c_int, C.c_void_p]
     dev = torch.device("cuda", device)
     llr = torch.empty((ncb, 3 * K + 12), dtype=torch.int16, device=dev)
     truth = torch.empty((ncb, K // 8), dtype=torch.uint8, device=dev)
     st = torch.cuda.current_stream(dev).cuda_stream
-    rc = _lib.lib().srsran_b200_synth_llr(device, llr.data_ptr(), truth.data_ptr(), ncb, K, sigma, scale, clip, seed,
-                                          int(attach_crc), st)
-    if rc != _lib.SUCCESS:
-        raise RuntimeError(f"srsran_b200_synth_llr failed ({rc})")
+    rc = L.b200_synth_llr(device, llr.data_ptr(), truth.data_ptr(), ncb, K, sigma, scale, clip, seed, int(attach_crc), st)
+    if rc != 0:
+        raise RuntimeError(f"b200_synth_llr failed ({rc})")
     return llr, truth

@@ -166,3 +166,86 @@ def test_int8_llr_container_decodes_like_int16(dec, port):
         dec.decode_device(d8, K, o, k, n, 8, "B", True)
         torch.cuda.synchronize()
         assert (o.cpu().numpy() == want[0]).all() and (k.cpu().numpy() == want[1]).all() and (n.cpu().numpy() == want[2]).all()
+
+
+def test_mixed_sizes_in_one_batch(dec, port):
+    """BASELINE config 3 through srsran_b200_tdec_run_mixed: all 188 lengths in ONE batch (one launch per pass over every
+    tile, ordered by length), 64+ blocks for a spread of sizes and a few blocks for every other one, bit-exact per block."""
+    sizes = [int(k) for k in port.cb_sizes()]
+    big = set(sizes[::12] + [40, 6144])
+    Ks, llrs = [], []
+    for i, K in enumerate(sizes):
+        n = (66 if K <= 1024 else 64) if K in big else 2
+        if K > 3000 and K in big:
+            n = 64
+        Ks.append(K)
+        llrs.append(coded_llrs(port, K, n, 0.85 + 0.3 * (i % 3), 16, 31, seed=100 + i)[0])
+    for early in (True, False):
+        res = dec.decode_mixed(llrs, Ks, 6, "B", early)
+        for (o2, k2, n2), llr, K in zip(res, llrs, Ks):
+            o1, k1, n1, _ = port.decode_batch(llr, K, 6, "B", 0, early, nthreads=8)
+            assert (o1 == o2).all() and (k1 == k2).all() and (n1 == n2).all(), (K, early)
+    # an invalid length anywhere in the list is rejected like srsran_tdec_new_cb
+    with pytest.raises(RuntimeError):
+        dec.decode_mixed([np.zeros((1, 3 * 100 + 12), np.int16)], [100])
+
+
+def test_lane_repacking_between_passes(dec, port, monkeypatch):
+    """Block-granular early stop on the device: running lanes are re-packed into fewer tiles after every pass.  Blocks with
+    very different convergence share tiles so lanes really move; results must equal the oracle's per block, and equal the
+    run with re-packing switched off."""
+    K, ncb = 104, 64 * 40 - 7
+    rng = np.random.default_rng(9)
+    parts = []
+    for i in range(ncb):
+        sigma = 1.3 if rng.random() < 0.15 else 0.5
+        parts.append(coded_llrs(port, K, 1, sigma, 16, 31, seed=7000 + i)[0])
+    llr = np.concatenate(parts)
+    llr2, _ = coded_llrs(port, 40, 700, 1.0, 16, 31, seed=11)
+    monkeypatch.setenv("SRSLTE_B200_TDEC_COMPACT_MIN_TILES", "1")
+    dec.profile_reset(True)
+    (a, b) = dec.decode_mixed([llr, llr2], [K, 40], 8, "B", True)
+    prof = dec.profile_get()
+    dec.profile_reset(False)
+    assert prof["repack_launches"] == 7
+    o1, k1, n1, _ = port.decode_batch(llr, K, 8, "B", 0, True, nthreads=8)
+    p1, q1, r1, _ = port.decode_batch(llr2, 40, 8, "B", 0, True, nthreads=8)
+    assert n1.max() > n1.min() + 2
+    assert (a[0] == o1).all() and (a[1] == k1).all() and (a[2] == n1).all()
+    assert (b[0] == p1).all() and (b[1] == q1).all() and (b[2] == r1).all()
+    monkeypatch.setenv("SRSLTE_B200_TDEC_NO_COMPACT", "1")
+    (c, d) = dec.decode_mixed([llr, llr2], [K, 40], 8, "B", True)
+    assert (c[0] == a[0]).all() and (c[2] == a[2]).all() and (d[0] == b[0]).all()
+
+
+def test_lane_repacking_full_size_properties(dec, port):
+    """65,536 blocks of K=6144 near the waterfall (blocks finish after very different numbers of passes): with and without
+    re-packing the decoder must return the same bytes, flags and pass counts; a sample is checked against the oracle."""
+    import torch
+
+    from srslte_b200.tdec import synth_llr
+
+    K, ncb = 6144, 65536
+    llr, truth = synth_llr(0, ncb, K, sigma=0.86, scale=16.0, clip=31, seed=123)
+    outs = []
+    for no_compact in (False, True):
+        if no_compact:
+            os.environ["SRSLTE_B200_TDEC_NO_COMPACT"] = "1"
+        try:
+            out = torch.empty((ncb, K // 8), dtype=torch.uint8, device="cuda")
+            ok = torch.empty(ncb, dtype=torch.uint8, device="cuda")
+            npass = torch.empty(ncb, dtype=torch.uint8, device="cuda")
+            dec.decode_device(llr, K, out, ok, npass, 8, "B", True)
+            torch.cuda.synchronize()
+            outs.append((out, ok, npass))
+        finally:
+            os.environ.pop("SRSLTE_B200_TDEC_NO_COMPACT", None)
+    (o_a, k_a, n_a), (o_b, k_b, n_b) = outs
+    assert (k_a == k_b).all() and (n_a == n_b).all() and (o_a == o_b).all()
+    okb = k_a.bool()
+    assert 0.5 < okb.float().mean().item() and n_a.float().std().item() > 0.5
+    assert (o_a[okb] == truth[okb]).all()
+    idx = torch.arange(0, ncb, 2731)
+    sub = llr[idx].cpu().numpy()
+    o1, k1, n1, _ = port.decode_batch(sub, K, 8, "B", 0, True, nthreads=8)
+    assert (o1 == o_a[idx].cpu().numpy()).all() and (k1 == k_a[idx].cpu().numpy()).all() and (n1 == n_a[idx].cpu().numpy()).all()

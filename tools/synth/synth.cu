@@ -3,14 +3,16 @@
 // BPSK over AWGN, quantisation to int16.  This is the recipe of SURVEY.md section 8(d) config 2 and follows what
 // lib/src/phy/fec/turbo/test/turbodecoder_test.c:211-255 does on the CPU (encode -> +-1 + noise -> scale to int16),
 // with an explicit clip so the inputs stay inside the range where the reference's generic decoder never wraps.
-// Not on the decode path; nothing here is timed.
+// Not on the decode path; nothing here is timed.  Built as tools/synth/libsrslte_b200_synth.so by srslte_b200/build.py: a
+// test/bench helper OUTSIDE the product library (libsrslte_b200.so does not contain or link it).
 #include <cuda_runtime.h>
 #include <math.h>
 
-#include "../../include/srslte_b200.h"
-#include "b200_runtime.h"
-#include "lte_tables.h"
-#include "tdec_engine.h"
+#include <stdio.h>
+
+#include <vector>
+
+#include "lte_tables.h" // header-only host tables of the library (QPP parameters, CRC polynomials); nothing is linked
 
 namespace b200 {
 
@@ -112,40 +114,50 @@ __global__ void synth_channel_kernel(const uint8_t* __restrict__ coded,
 
 using namespace b200;
 
-extern "C" SRSRAN_B200_API int srsran_b200_synth_llr(int      device,
-                                                     int16_t* llr_dev,
-                                                     uint8_t* truth_dev,
-                                                     uint32_t ncb,
-                                                     uint32_t K,
-                                                     float    sigma,
-                                                     float    scale,
-                                                     int      clip,
-                                                     uint64_t seed,
-                                                     int      attach_crc,
-                                                     void*    stream)
+#define SYNTH_CUDA_TRY(expr)                                                                                           \
+  do {                                                                                                                 \
+    cudaError_t e__ = (expr);                                                                                          \
+    if (e__ != cudaSuccess) {                                                                                          \
+      fprintf(stderr, "[b200_synth] %s: %s\n", #expr, cudaGetErrorString(e__));                                        \
+      return -1;                                                                                                       \
+    }                                                                                                                  \
+  } while (0)
+
+extern "C" __attribute__((visibility("default"))) int b200_synth_llr(int      device,
+                                                                     int16_t* llr_dev,
+                                                                     uint8_t* truth_dev,
+                                                                     uint32_t ncb,
+                                                                     uint32_t K,
+                                                                     float    sigma,
+                                                                     float    scale,
+                                                                     int      clip,
+                                                                     uint64_t seed,
+                                                                     int      attach_crc,
+                                                                     void*    stream)
 {
   const int cb_idx = cb_index_exact(K);
   if (cb_idx < 0 || !llr_dev) {
-    return B200_ERROR_INVALID_INPUTS;
+    return -2;
   }
-  DeviceContext* ctx = device_context(device);
-  if (!ctx) {
-    return B200_ERROR;
-  }
-  B200_CUDA_TRY(cudaSetDevice(device));
+  SYNTH_CUDA_TRY(cudaSetDevice(device));
+  std::vector<uint16_t> fwd, rev;
+  qpp_tables(cb_idx, fwd, rev);
+  uint16_t* d_qpp = nullptr;
+  SYNTH_CUDA_TRY(cudaMalloc(&d_qpp, fwd.size() * sizeof(uint16_t)));
+  SYNTH_CUDA_TRY(cudaMemcpy(d_qpp, fwd.data(), fwd.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
   cudaStream_t st   = (cudaStream_t)stream;
   const size_t nllr = 3 * (size_t)K + 12;
   uint8_t *    bits = nullptr, *coded = nullptr;
   // generate in slabs so the byte-per-bit scratch stays small next to a multi-GB LLR batch
   const uint32_t slab = 8192;
-  B200_CUDA_TRY(cudaMalloc(&bits, (size_t)slab * K));
-  B200_CUDA_TRY(cudaMalloc(&coded, (size_t)slab * nllr));
+  SYNTH_CUDA_TRY(cudaMalloc(&bits, (size_t)slab * K));
+  SYNTH_CUDA_TRY(cudaMalloc(&coded, (size_t)slab * nllr));
   for (uint32_t first = 0; first < ncb; first += slab) {
     const uint32_t n = (ncb - first) < slab ? (ncb - first) : slab;
     synth_encode_kernel<<<(n + 63) / 64, 64, 0, st>>>(bits,
                                                       coded,
                                                       truth_dev ? truth_dev + (size_t)first * (K / 8) : nullptr,
-                                                      ctx->qpp_fwd(cb_idx),
+                                                      d_qpp,
                                                       n,
                                                       (int)K,
                                                       seed + 0x1000003ull * first,
@@ -154,9 +166,10 @@ extern "C" SRSRAN_B200_API int srsran_b200_synth_llr(int      device,
     synth_channel_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(
         coded, llr_dev + (size_t)first * nllr, tot, sigma, scale, clip, seed + 0x9E37ull * (first + 1));
   }
-  B200_CUDA_TRY(cudaStreamSynchronize(st));
-  B200_CUDA_TRY(cudaFree(bits));
-  B200_CUDA_TRY(cudaFree(coded));
-  B200_CUDA_TRY(cudaGetLastError());
-  return B200_SUCCESS;
+  SYNTH_CUDA_TRY(cudaStreamSynchronize(st));
+  SYNTH_CUDA_TRY(cudaFree(bits));
+  SYNTH_CUDA_TRY(cudaFree(coded));
+  SYNTH_CUDA_TRY(cudaFree(d_qpp));
+  SYNTH_CUDA_TRY(cudaGetLastError());
+  return 0;
 }
