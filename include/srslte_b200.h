@@ -121,6 +121,8 @@ SRSRAN_B200_API int srsran_b200_tdec_run_mixed(srsran_b200_tdec_t* h,
 SRSRAN_B200_API void srsran_b200_tdec_profile_reset(srsran_b200_tdec_t* h, int enable);
 SRSRAN_B200_API int  srsran_b200_tdec_profile_get(srsran_b200_tdec_t* h, double* ms_by_class, uint64_t* launches_by_class);
 /* Same with nclasses entries: [3] = re-packing of the still-running blocks between the passes of an early-stop decode. */
+/* Every timed span since the last reset in launch order: ms[i] and its class cls[i]; returns the number written (<= max_spans). */
+SRSRAN_B200_API int  srsran_b200_tdec_profile_spans(srsran_b200_tdec_t* h, float* ms, int* cls, int max_spans);
 SRSRAN_B200_API int  srsran_b200_tdec_profile_get_ex(srsran_b200_tdec_t* h, double* ms_by_class, uint64_t* launches_by_class, int nclasses);
 /* Resident CTAs (tiles of 64 code blocks) per SM of the SISO pass kernel on the current device, as the CUDA occupancy
  * calculator reports it; -1 on error.  Diagnostic: a 65,536-block batch is one wave when this is >= 7 on 148 SMs. */

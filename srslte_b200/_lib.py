@@ -43,6 +43,7 @@ def lib() -> C.CDLL:
     L.srsran_b200_tdec_run.argtypes = [vp, vp, u32, u32, u32, C.c_int, C.c_int, vp, vp, vp, u32, vp]
     L.srsran_b200_tdec_run_mixed.argtypes = [vp, vp, u32, vp, vp, u32, C.c_int, C.c_int, vp, vp, vp, u32, vp]
     L.srsran_b200_tdec_profile_get_ex.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.c_int]
+    L.srsran_b200_tdec_profile_spans.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_int), C.c_int]
     L.srsran_b200_tdec_profile_reset.argtypes = [vp, C.c_int]
     L.srsran_b200_tdec_profile_reset.restype = None
     L.srsran_b200_tdec_profile_get.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]
@@ -92,6 +93,7 @@ EXPORTED_SYMBOLS = [
     "srsran_b200_tdec_run",
     "srsran_b200_tdec_run_mixed",
     "srsran_b200_tdec_profile_get_ex",
+    "srsran_b200_tdec_profile_spans",
     "srsran_b200_tdec_profile_reset",
     "srsran_b200_tdec_profile_get",
     "srsran_b200_tdec_resident_tiles_per_sm",

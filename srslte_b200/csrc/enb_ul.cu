@@ -98,27 +98,41 @@ struct EnbUl {
     return B200_SUCCESS;
   }
 
+  // Grows the per-slot buffers.  Slots are HARQ processes: the soft buffers, the payload bytes of code blocks decoded in an
+  // earlier transmission and the per-slot CRC masks of the slots that already exist survive the growth (a retransmission
+  // into slot i after a larger batch still combines with what slot i received before).
   int reserve(uint32_t nsf)
   {
     if (nsf > cap_sf) {
+      const size_t soft_slot = (size_t)ncb * SRSRAN_B200_SOFTBUFFER_SIZE * sizeof(int16_t);
+      int16_t*     n_soft = nullptr;
+      uint8_t*     n_data = nullptr;
+      B200_CUDA_TRY(cudaMalloc(&n_soft, (size_t)nsf * soft_slot));
+      B200_CUDA_TRY(cudaMalloc(&n_data, (size_t)nsf * data_stride));
+      B200_CUDA_TRY(cudaMemset(n_soft, 0, (size_t)nsf * soft_slot));
+      B200_CUDA_TRY(cudaMemset(n_data, 0, (size_t)nsf * data_stride));
+      if (cap_sf) { // (cudaMemcpy: synchronous with respect to the host, after whatever the object's streams still run)
+        B200_CUDA_TRY(cudaDeviceSynchronize());
+        B200_CUDA_TRY(cudaMemcpy(n_soft, d_soft, (size_t)cap_sf * soft_slot, cudaMemcpyDeviceToDevice));
+        B200_CUDA_TRY(cudaMemcpy(n_data, d_data, (size_t)cap_sf * data_stride, cudaMemcpyDeviceToDevice));
+      }
       for (void* p : {(void*)d_grid, (void*)d_llr, (void*)d_soft, (void*)d_data, (void*)d_meas, d_iq}) {
         if (p) cudaFree(p);
       }
-      d_grid = nullptr; d_llr = nullptr; d_soft = nullptr; d_data = nullptr; d_meas = nullptr; d_iq = nullptr;
+      d_soft = n_soft;
+      d_data = n_data;
+      d_grid = nullptr; d_llr = nullptr; d_meas = nullptr; d_iq = nullptr;
+      const uint32_t old_sf = cap_sf;
       cap_sf = 0;
       B200_CUDA_TRY(cudaMalloc(&d_grid, (size_t)nsf * nsym * nre * sizeof(float2)));
       B200_CUDA_TRY(cudaMalloc(&d_llr, (size_t)nsf * nbits * sizeof(int16_t)));
-      B200_CUDA_TRY(cudaMalloc(&d_soft, (size_t)nsf * ncb * SRSRAN_B200_SOFTBUFFER_SIZE * sizeof(int16_t)));
-      B200_CUDA_TRY(cudaMemset(d_soft, 0, (size_t)nsf * ncb * SRSRAN_B200_SOFTBUFFER_SIZE * sizeof(int16_t)));
-      B200_CUDA_TRY(cudaMalloc(&d_data, (size_t)nsf * data_stride));
-      B200_CUDA_TRY(cudaMemset(d_data, 0, (size_t)nsf * data_stride));
       B200_CUDA_TRY(cudaMalloc(&d_meas, (size_t)nsf * 4 * sizeof(float)));
       B200_CUDA_TRY(cudaMalloc(&d_iq, (size_t)nsf * sf_sz * sizeof(float2))); // sized for float samples
       cap_sf = nsf;
-      tbs.assign(nsf, srsran_b200_tb_t{});
-      crc_mask.assign(nsf, 0u);
+      tbs.resize(nsf, srsran_b200_tb_t{});
+      crc_mask.resize(nsf, 0u); // existing slots keep their masks
       h_meas.assign((size_t)nsf * 4, 0.f);
-      for (uint32_t i = 0; i < nsf; i++) {
+      for (uint32_t i = old_sf; i < nsf; i++) {
         tbs[i].tbs         = cfg.tbs;
         tbs[i].Qm          = 2u * (uint32_t)cfg.modulation;
         tbs[i].nof_e_bits  = nbits;

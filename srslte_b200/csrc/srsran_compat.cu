@@ -549,8 +549,9 @@ void srsran_dft_run_c(srsran_dft_plan_t* plan, const cf_t* in, cf_t* out)
   }
   if (plan->db) {
     for (int i = 0; i < N; i++) {
-      float pw = f[2 * i] * f[2 * i] + f[2 * i + 1] * f[2 * i + 1]; // srsran_convert_power_to_dB on |x| as the cast does
-      f[2 * i]     = 10.0f * log10f(sqrtf(pw));
+      // dft_fftw.c:346-349 hands a COMPLEX value to srsran_convert_power_to_dB(float): the C conversion keeps the real part
+      // only, so the reference's result is 10 log10(Re x) (NaN for a negative real part), imaginary part zero -- reproduced
+      f[2 * i]     = 10.0f * log10f(f[2 * i]);
       f[2 * i + 1] = 0.0f;
     }
   }
@@ -641,9 +642,19 @@ int srsran_dft_precoding(srsran_dft_precoding_t* q, cf_t* input, cf_t* output, u
 
 // ===================================================================================================================
 // srsran_ofdm_t (receive side)
+//
+// A receive object set up here keeps the batched engine's handle in fft_plan.p and marks itself with two self-pointers in
+// the plan's (otherwise unused) buffer fields.  The mark matters because srsran_ofdm_set_freq_shift / set_normalize /
+// set_non_mbsfn_region are shared with the TRANSMIT objects of the reference's own ofdm.c (srsran_ofdm_tx_init), whose
+// fft_plan is an ordinary DFT plan of this library: those calls must then do what ofdm.c does on the struct, nothing else.
+static bool ofdm_is_ours(const srsran_ofdm_t* q)
+{
+  return q && q->fft_plan.p && q->fft_plan.in == (const void*)q && q->fft_plan.out == (const void*)&q->fft_plan;
+}
+
 static srsran_b200_ofdm_t* ofdm_of(srsran_ofdm_t* q)
 {
-  return q ? (srsran_b200_ofdm_t*)q->fft_plan.p : nullptr;
+  return ofdm_is_ours(q) ? (srsran_b200_ofdm_t*)q->fft_plan.p : nullptr;
 }
 
 static int ofdm_apply(srsran_ofdm_t* q)
@@ -663,6 +674,8 @@ static int ofdm_apply(srsran_ofdm_t* q)
     srsran_b200_ofdm_t* h = nullptr;
     rc                    = srsran_b200_ofdm_rx_init(&h, compat_device(), &c);
     q->fft_plan.p         = h;
+    q->fft_plan.in        = (void*)q;
+    q->fft_plan.out       = (void*)&q->fft_plan;
   }
   if (rc != SRSRAN_SUCCESS) return SRSRAN_ERROR;
   uint32_t N, sf, ns, nre;
@@ -771,12 +784,39 @@ int srsran_ofdm_set_freq_shift(srsran_ofdm_t* q, float freq_shift)
 {
   if (!q) return SRSRAN_ERROR_INVALID_INPUTS;
   q->cfg.freq_shift_f = freq_shift;
-  return ofdm_apply(q);
+  if (ofdm_is_ours(q)) return ofdm_apply(q);
+  // a transmit object of the reference's ofdm.c: ofdm.c:334-360 on its own struct (the per-sample rotation it multiplies its
+  // output with, in the reference's precision: the angle in double, rounded to float, cexpf)
+  if (!isnormal(freq_shift)) {
+    q->fft_plan.dc = true;
+    return SRSRAN_SUCCESS;
+  }
+  if (!q->shift_buffer) return SRSRAN_ERROR;
+  const uint32_t N   = q->cfg.symbol_sz;
+  float*         ptr = (float*)q->shift_buffer;
+  for (uint32_t n = 0; n < 2; n++) {
+    for (uint32_t i = 0; i < q->nof_symbols; i++) {
+      // SRSRAN_CP_LEN_NORM / SRSRAN_CP_LEN_EXT (phy_common.h:125-128): ceil(c * symbol_sz / 2048) with c = 160 / 144 / 512
+      const float    c     = q->cfg.cp == SRSRAN_CP_NORM ? (i == 0 ? 160.0f : 144.0f) : 512.0f;
+      const uint32_t cplen = (uint32_t)(int)ceilf((c * (float)N) / 2048.0f);
+      for (uint32_t t = 0; t < N + cplen; t++) {
+        const float a = (float)(2.0 * M_PI * (double)((float)t - (float)cplen) * (double)freq_shift / (double)N);
+        sincosf(a, &ptr[2 * t + 1], &ptr[2 * t]);
+      }
+      ptr += 2 * (N + cplen);
+    }
+  }
+  q->fft_plan.dc = false; // ofdm.c:359
+  return SRSRAN_SUCCESS;
 }
 
 void srsran_ofdm_set_normalize(srsran_ofdm_t* q, bool normalize_enable)
 {
   if (!q) return;
+  if (!ofdm_is_ours(q)) { // ofdm.c:557-560
+    q->fft_plan.norm = normalize_enable;
+    return;
+  }
   q->cfg.normalize = normalize_enable;
   ofdm_apply(q);
 }

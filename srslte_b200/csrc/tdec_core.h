@@ -712,7 +712,7 @@ B200_HD void compact_plan_group(const TileGroup& g, const uint32_t* mask, uint32
   }
   const uint32_t need = (running + 31) / 32;
   plan = GroupPlan{need, 0, 0, 0};
-  if (!all_int8 || tiles_now < need + min_gain_tiles || 5 * need > 4 * tiles_now) return;
+  if (!all_int8 || tiles_now < need + min_gain_tiles || 5 * need > 3 * tiles_now) return; // pays when the tiles shrink to 60 % or less
   uint32_t nfree = 0, nrun = 0;
   for (uint32_t t = 0; t < need; t++) {
     pref[g.first_tile + t] = nfree;

@@ -36,6 +36,7 @@ struct TdecPlan {
   GroupPlan* plans   = nullptr;
   MoveRec*   moves   = nullptr; // [ntiles*32]
   uint32_t*  move_counter = nullptr;
+  uint32_t*  gsrc    = nullptr; // [ntiles*32] source slot of every lane slot during a re-packing, LANE_EMPTY otherwise
 };
 
 // Decoder workspace of one stream: device arrays, the page-locked staging of the tile descriptors and the last batch

@@ -40,7 +40,7 @@ size_t TdecEngine::workspace_bytes(const std::vector<TdecGroupSpec>& groups)
   }
   total += hb_rows * 32 * sizeof(uint16_t) + 256;                         // HB
   total += ntiles * (sizeof(uint32_t) * 3 + 32 * sizeof(u4) + 32 * sizeof(LaneMap) + TDEC_TILE_CB * sizeof(CbStatus) +
-                     sizeof(TileDesc) + 32 * sizeof(MoveRec));             // fmt, mask, pref, S2T, lanes, status, descriptors, moves
+                     sizeof(TileDesc) + 32 * sizeof(MoveRec) + 32 * sizeof(uint32_t));             // fmt, mask, pref, S2T, lanes, status, descriptors, moves
   total += groups.size() * (sizeof(TileGroup) + sizeof(GroupPlan));
   return total + 16 * 256 + 4096;
 }
@@ -118,12 +118,13 @@ int TdecEngine::prepare(TdecWorkspace& w, const std::vector<TdecGroupSpec>& grou
   p.pref          = (uint32_t*)a.take(ntiles * sizeof(uint32_t));
   p.move_counter  = (uint32_t*)a.take(sizeof(uint32_t));
   p.moves         = (MoveRec*)a.take(ntiles * 32 * sizeof(MoveRec));
+  p.gsrc          = (uint32_t*)a.take(ntiles * 32 * sizeof(uint32_t));
   p.v.S2T         = (u4*)a.take(ntiles * 32 * sizeof(u4));
   p.v.lanes       = (LaneMap*)a.take(ntiles * 32 * sizeof(LaneMap));
   p.v.status      = (CbStatus*)a.take(ntiles * TDEC_TILE_CB * sizeof(CbStatus));
   p.v.HB          = (uint16_t*)a.take(hb_rows * 32 * sizeof(uint16_t));
   p.v.tiles       = d_tiles;
-  if (!d_tiles || !p.groups || !p.plans || !p.v.fmt || !p.mask || !p.pref || !p.move_counter || !p.moves || !p.v.S2T || !p.v.lanes ||
+  if (!d_tiles || !p.groups || !p.plans || !p.v.fmt || !p.mask || !p.pref || !p.move_counter || !p.moves || !p.gsrc || !p.v.S2T || !p.v.lanes ||
       !p.v.status || !p.v.HB) {
     B200_LOG_ERROR("decoder workspace too small");
     return B200_ERROR;
@@ -331,9 +332,9 @@ int TdecEngine::run_groups(TdecWorkspace&                    w,
     g_kernel_launches++;
     if (compact && ps + 1 < max_passes) {
       prof_begin(3, stream);
-      launch_compact(v, p.groups, p.ngroups, p.mask, p.pref, p.plans, p.moves, p.move_counter, min_env ? 0u : 4u, sm_count, stream);
+      launch_compact(v, p.groups, p.ngroups, p.mask, p.pref, p.plans, p.moves, p.move_counter, p.gsrc, min_env ? 0u : 4u, sm_count, stream);
       prof_end(stream);
-      g_kernel_launches += 2;
+      g_kernel_launches += 4;
     }
   }
   prof_begin(2, stream);
@@ -611,6 +612,24 @@ int srsran_b200_tdec_profile_get(srsran_b200_tdec_t* h, double* ms_by_class, uin
     return B200_ERROR_INVALID_INPUTS;
   }
   return h->eng.prof_get(ms_by_class, launches_by_class, 3);
+}
+
+int srsran_b200_tdec_profile_spans(srsran_b200_tdec_t* h, float* ms, int* cls, int max_spans)
+{
+  if (!h || !ms || !cls || max_spans < 0) {
+    return B200_ERROR_INVALID_INPUTS;
+  }
+  if (cudaDeviceSynchronize() != cudaSuccess) return B200_ERROR;
+  int n = 0;
+  for (auto& s : h->eng.spans) {
+    if (n >= max_spans) break;
+    float t = 0;
+    if (cudaEventElapsedTime(&t, s.a, s.b) != cudaSuccess) continue;
+    ms[n]  = t;
+    cls[n] = s.cls;
+    n++;
+  }
+  return n;
 }
 
 int srsran_b200_tdec_profile_get_ex(srsran_b200_tdec_t* h, double* ms_by_class, uint64_t* launches_by_class, int nclasses)

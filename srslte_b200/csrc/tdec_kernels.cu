@@ -847,54 +847,186 @@ void launch_decide(const TdecView& v,
 // still run, and if they fit markedly fewer tiles, move the running lanes of the group's last tiles into the free lane
 // slots of its first ones.  Everything is decided on the device; the host enqueues the two kernels after every pass of
 // an early-stop decode and the next pass launches over all tiles as before (emptied tiles exit at once).
-__global__ void __launch_bounds__(256) tdec_compact_plan_kernel(TdecView v, const TileGroup* __restrict__ groups, uint32_t* __restrict__ mask,
+// step 1, a warp per tile (all groups at once): which lane slots hold a pair that still runs
+__global__ void __launch_bounds__(256) tdec_compact_scan_kernel(TdecView v, uint32_t* __restrict__ mask)
+{
+  const uint32_t tile = blockIdx.x * 8u + (threadIdx.x >> 5), lane = threadIdx.x & 31u;
+  if (tile >= (uint32_t)v.ntiles) return;
+  const uint32_t m = __ballot_sync(0xFFFFFFFFu, lane_running(v, tile * 32u + lane));
+  if (lane == 0) mask[tile] = m;
+}
+
+// steps 2 and 3, one thread block per group: the same decisions as compact_plan_group / compact_emit_tile (tdec_core.h, run
+// by the CPU emulation), with the sums and the running counts computed by the block instead of one thread.
+__global__ void __launch_bounds__(256) tdec_compact_plan_kernel(TdecView v, const TileGroup* __restrict__ groups, const uint32_t* __restrict__ mask,
                                                                 uint32_t* __restrict__ pref, GroupPlan* __restrict__ plans,
                                                                 MoveRec* __restrict__ moves, uint32_t* __restrict__ move_counter,
                                                                 uint32_t move_cap, uint32_t min_gain_tiles)
 {
+  __shared__ uint32_t  part[256];
+  __shared__ uint32_t  red_run[8], red_last[8], red_int8[8];
   __shared__ GroupPlan plan;
-  const TileGroup g = groups[blockIdx.x];
-  // step 1: a warp per tile, a lane per lane slot
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  bool      int8_only = true;
-  for (uint32_t t = wid; t < g.ntiles; t += 8) {
-    const uint32_t tile = g.first_tile + t;
-    const uint32_t m    = __ballot_sync(0xFFFFFFFFu, lane_running(v, tile * 32 + lane));
-    if (lane == 0) mask[tile] = m;
-    int8_only = int8_only && v.fmt[tile] == 0u;
+  const TileGroup g   = groups[blockIdx.x];
+  const uint32_t  tid = threadIdx.x, lane = tid & 31u, wid = tid >> 5;
+  // every thread owns a contiguous run of the group's tiles
+  const uint32_t per = (g.ntiles + 255u) / 256u, t_lo = min(g.ntiles, tid * per), t_hi = min(g.ntiles, t_lo + per);
+  uint32_t       run = 0, last = 0, int8_only = 1;
+  for (uint32_t t = t_lo; t < t_hi; t++) {
+    const uint32_t n = popc32(mask[g.first_tile + t]);
+    run += n;
+    if (n) last = t + 1;
+    int8_only &= (v.fmt[g.first_tile + t] == 0u) ? 1u : 0u;
   }
-  const bool all_int8 = __syncthreads_and(int8_only) != 0;
-  if (threadIdx.x == 0) {
-    compact_plan_group(g, mask, pref, all_int8, min_gain_tiles, move_counter, move_cap, plan);
-    plans[blockIdx.x] = plan;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    run += __shfl_xor_sync(0xFFFFFFFFu, run, o);
+    last = max(last, __shfl_xor_sync(0xFFFFFFFFu, last, o));
+    int8_only &= __shfl_xor_sync(0xFFFFFFFFu, int8_only, o);
+  }
+  if (lane == 0) {
+    red_run[wid]  = run;
+    red_last[wid] = last;
+    red_int8[wid] = int8_only;
+  }
+  __syncthreads();
+  uint32_t running = 0, tiles_now = 0, all_int8 = 1;
+#pragma unroll
+  for (int w = 0; w < 8; w++) {
+    running += red_run[w];
+    tiles_now = max(tiles_now, red_last[w]);
+    all_int8 &= red_int8[w];
+  }
+  const uint32_t need = (running + 31u) / 32u;
+  const bool     go   = all_int8 && tiles_now >= need + min_gain_tiles && 5u * need <= 3u * tiles_now && tiles_now > need;
+  if (!go) {
+    if (tid == 0) plans[blockIdx.x] = GroupPlan{need, 0, 0, 0};
+    return;
+  }
+  // running counts: free lane slots over the receiver tiles [0, need), running lanes over the donor tiles [need, tiles_now)
+  uint32_t sum = 0;
+  for (uint32_t t = t_lo; t < t_hi; t++) {
+    const uint32_t n = popc32(mask[g.first_tile + t]);
+    sum += t < need ? 32u - n : (t < tiles_now ? n : 0u);
+  }
+  part[tid] = sum;
+  __syncthreads();
+  if (tid == 0) {
+    uint32_t acc = 0;
+    for (int i = 0; i < 256; i++) {
+      const uint32_t x = part[i];
+      part[i]          = acc;
+      acc += x;
+    }
+  }
+  __syncthreads();
+  // the free slots of the receivers come first in the running count: donors count from the receivers' total
+  uint32_t nfree_thread = 0; // receivers' total = count in front of the thread that owns tile `need`
+  {
+    const uint32_t owner = min(255u, need / per);
+    nfree_thread         = part[owner];
+    for (uint32_t t = min(g.ntiles, owner * per); t < need; t++) nfree_thread += 32u - popc32(mask[g.first_tile + t]);
+  }
+  const uint32_t nfree = nfree_thread;
+  uint32_t       acc   = part[tid];
+  for (uint32_t t = t_lo; t < t_hi; t++) {
+    const uint32_t n = popc32(mask[g.first_tile + t]);
+    pref[g.first_tile + t] = t < need ? acc : acc - nfree;
+    acc += t < need ? 32u - n : (t < tiles_now ? n : 0u);
+  }
+  if (tid == 0) {
+    const uint32_t nrun = running - (32u * need - nfree); // running lanes outside the receivers
+    GroupPlan      p    = GroupPlan{need, 0, 0, 0};
+    if (nrun > 0 && nrun <= nfree) {
+      const uint32_t base = atomicAdd(move_counter, nrun);
+      if (base + nrun <= move_cap) {
+        p.base  = base;
+        p.moves = nrun;
+        p.go    = 1;
+      }
+    }
+    plan              = p;
+    plans[blockIdx.x] = p;
   }
   __syncthreads();
   if (!plan.go) return;
-  for (uint32_t t = threadIdx.x; t < g.ntiles; t += blockDim.x) compact_emit_tile(g, t, mask, pref, plan, moves);
+  for (uint32_t t = t_lo; t < t_hi; t++) {
+    if (t < tiles_now) compact_emit_tile(g, t, mask, pref, plan, moves);
+  }
 }
 
-// One CTA per move (grid-stride): copies the lane's columns; the last thread block to finish nothing else -- the lane map
-// is renamed by the thread block that copied the data, after its copy.
-__global__ void __launch_bounds__(256) tdec_compact_move_kernel(TdecView v, const MoveRec* __restrict__ moves, const uint32_t* __restrict__ move_counter)
+// The data follows in GATHER form, one thread block per receiver tile: gsrc[slot] = the lane slot whose pair moves into
+// `slot` (LANE_EMPTY: the slot keeps what it has).  A warp walks the tile's rows; lane l reads its new value from its source
+// (lanes that share a donor tile share its 128-byte row) and the row leaves as one full, coalesced store.  (The first version
+// copied column by column, 4 bytes per row and request: three times the time of a SISO pass's worth of sectors.)
+__global__ void __launch_bounds__(256) tdec_compact_gsrc_kernel(TdecView v, const MoveRec* __restrict__ moves, const uint32_t* __restrict__ move_counter,
+                                                                uint32_t* __restrict__ gsrc)
 {
   const uint32_t n = *move_counter;
-  for (uint32_t m = blockIdx.x; m < n; m += gridDim.x) {
-    const MoveRec  mv = moves[m];
-    const uint32_t ne = compact_move_elems(v.tiles[mv.src >> 5].K);
-    for (uint32_t i = threadIdx.x; i < ne; i += blockDim.x) compact_move_elem(v, mv, i);
-    if (threadIdx.x == 0) compact_rename(v, mv);
+  for (uint32_t m = blockIdx.x * blockDim.x + threadIdx.x; m < n; m += gridDim.x * blockDim.x) gsrc[moves[m].dst] = moves[m].src;
+}
+
+constexpr int COMPACT_SPLIT = 4; // thread blocks per receiver tile (rows are dealt out among them)
+
+__global__ void __launch_bounds__(256) tdec_compact_move_kernel(TdecView v, const TileGroup* __restrict__ groups, const GroupPlan* __restrict__ plans,
+                                                                const uint32_t* __restrict__ gsrc, const uint32_t* __restrict__ move_counter)
+{
+  if (*move_counter == 0u) return;
+  const uint32_t  tile = blockIdx.x, part = blockIdx.y, lane = threadIdx.x & 31u, wid = threadIdx.x >> 5;
+  const TileDesc& b    = v.tiles[tile];
+  const GroupPlan pl   = plans[b.group];
+  if (!pl.go || tile - groups[b.group].first_tile >= pl.receivers) return; // only receiver tiles of a re-packed group take lanes
+  const uint32_t src = gsrc[tile * 32u + lane];
+  if (__ballot_sync(0xFFFFFFFFu, src != LANE_EMPTY) == 0u) return;
+  const bool      mv  = src != LANE_EMPTY;
+  const uint32_t  ts  = mv ? (src >> 5) : tile, ls = mv ? (src & 31u) : lane;
+  const TileDesc& a   = v.tiles[ts];
+  const uint32_t  K   = b.K, r8 = K / 8u + 1u;
+  const uint32_t  w0  = part * 8u + wid; // this warp's first row; rows advance by 8 * COMPACT_SPLIT
+  constexpr uint32_t STEP = 8u * COMPACT_SPLIT;
+  if (mv) { // 16 bytes per lane and window row of each input stream; lanes that stay keep their rows untouched
+    const u4 *s0 = a.S8 + ls, *s1 = a.P08 + ls, *s2 = a.P18 + ls;
+    u4 *      d0 = b.S8 + lane, *d1 = b.P08 + lane, *d2 = b.P18 + lane;
+    uint32_t  w  = w0;
+    for (; w + STEP < r8; w += 2u * STEP) {
+      const u4 x0 = s0[w * 32u], y0 = s1[w * 32u], z0 = s2[w * 32u];
+      const u4 x1 = s0[(w + STEP) * 32u], y1 = s1[(w + STEP) * 32u], z1 = s2[(w + STEP) * 32u];
+      d0[w * 32u] = x0; d1[w * 32u] = y0; d2[w * 32u] = z0;
+      d0[(w + STEP) * 32u] = x1; d1[(w + STEP) * 32u] = y1; d2[(w + STEP) * 32u] = z1;
+    }
+    for (; w < r8; w += STEP) {
+      const u4 x = s0[w * 32u], y = s1[w * 32u], z = s2[w * 32u];
+      d0[w * 32u] = x; d1[w * 32u] = y; d2[w * 32u] = z;
+    }
+  }
+  // E: every lane takes part (a lane that stays re-writes its own value), so each row leaves as one full 128-byte store
+  const uint32_t* es = a.E + ls;
+  uint32_t*       ed = b.E + lane;
+  uint32_t        k  = w0;
+  for (; k + 7u * STEP < K; k += 8u * STEP) { // eight independent rows in flight per warp
+    uint32_t e[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) e[u] = es[(k + (uint32_t)u * STEP) * 32u];
+#pragma unroll
+    for (int u = 0; u < 8; u++) ed[(k + (uint32_t)u * STEP) * 32u] = e[u];
+  }
+  for (; k < K; k += STEP) ed[k * 32u] = es[k * 32u];
+  if (part == 0 && wid == 0 && mv) { // nothing in this kernel reads the lane map or S2T of another slot
+    v.S2T[(size_t)tile * 32 + lane] = v.S2T[(size_t)ts * 32 + ls];
+    compact_rename(v, MoveRec{src, tile * 32u + lane});
   }
 }
 
 void launch_compact(const TdecView& v, const TileGroup* groups_dev, uint32_t ngroups, uint32_t* mask_dev, uint32_t* pref_dev,
-                    GroupPlan* plans_dev, MoveRec* moves_dev, uint32_t* move_counter_dev, uint32_t min_gain_tiles, int sm_count,
-                    cudaStream_t stream)
+                    GroupPlan* plans_dev, MoveRec* moves_dev, uint32_t* move_counter_dev, uint32_t* gsrc_dev, uint32_t min_gain_tiles,
+                    int sm_count, cudaStream_t stream)
 {
   cudaMemsetAsync(move_counter_dev, 0, sizeof(uint32_t), stream);
+  cudaMemsetAsync(gsrc_dev, 0xFF, (size_t)v.ntiles * 32 * sizeof(uint32_t), stream); // LANE_EMPTY: every slot keeps what it has
+  tdec_compact_scan_kernel<<<(unsigned)((v.ntiles + 7) / 8), 256, 0, stream>>>(v, mask_dev);
   tdec_compact_plan_kernel<<<ngroups, 256, 0, stream>>>(v, groups_dev, mask_dev, pref_dev, plans_dev, moves_dev, move_counter_dev,
                                                         (uint32_t)v.ntiles * 32u, min_gain_tiles);
-  const unsigned nmove = (unsigned)std::min<long>((long)v.ntiles * 32, (long)sm_count * 8);
-  tdec_compact_move_kernel<<<nmove, 256, 0, stream>>>(v, moves_dev, move_counter_dev);
+  tdec_compact_gsrc_kernel<<<(unsigned)std::min<long>(((long)v.ntiles * 32 + 255) / 256, (long)sm_count * 4), 256, 0, stream>>>(v, moves_dev, move_counter_dev, gsrc_dev);
+  tdec_compact_move_kernel<<<dim3((unsigned)v.ntiles, COMPACT_SPLIT), 256, 0, stream>>>(v, groups_dev, plans_dev, gsrc_dev, move_counter_dev);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

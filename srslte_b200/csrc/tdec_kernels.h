@@ -25,8 +25,8 @@ void launch_decide(const TdecView& v,
                    cudaStream_t    stream);
 // re-packs the lanes that still run into fewer tiles (two kernels, all decisions on the device)
 void launch_compact(const TdecView& v, const TileGroup* groups_dev, uint32_t ngroups, uint32_t* mask_dev, uint32_t* pref_dev,
-                    GroupPlan* plans_dev, MoveRec* moves_dev, uint32_t* move_counter_dev, uint32_t min_gain_tiles, int sm_count,
-                    cudaStream_t stream);
+                    GroupPlan* plans_dev, MoveRec* moves_dev, uint32_t* move_counter_dev, uint32_t* gsrc_dev, uint32_t min_gain_tiles,
+                    int sm_count, cudaStream_t stream);
 
 // int8 LLR container -> int16 (sign extension), n values
 void launch_widen_i8(const int8_t* in, int16_t* out, size_t n, cudaStream_t stream);

@@ -49,6 +49,15 @@ class TurboDecoderBatch:
         return {"load_ms": ms[0], "siso_ms": ms[1], "decide_ms": ms[2], "repack_ms": ms[3], "total_ms": ms[0] + ms[1] + ms[2] + ms[3],
                 "load_launches": int(n[0]), "siso_launches": int(n[1]), "decide_launches": int(n[2]), "repack_launches": int(n[3])}
 
+    def profile_spans(self, max_spans: int = 8192):
+        """[(class, ms), ...] of every timed span since the last reset, in launch order (0 load, 1 SISO pass, 2 decide, 3 re-packing)."""
+        ms = (C.c_float * max_spans)()
+        cls = (C.c_int * max_spans)()
+        n = self._lib.srsran_b200_tdec_profile_spans(self._h, ms, cls, max_spans)
+        if n < 0:
+            raise RuntimeError(f"srsran_b200_tdec_profile_spans failed ({n})")
+        return [(int(cls[i]), float(ms[i])) for i in range(n)]
+
     # -- several code block lengths in one batch (BASELINE config 3) ---------------------------------------------
     def decode_mixed(self, llrs, Ks, max_passes: int = 8, crc: str | None = "B", early_stop: bool = True):
         """llrs: list of (ncb_g, 3K_g+12) int16 numpy arrays, Ks: their code block lengths.  Host buffers.

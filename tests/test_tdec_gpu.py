@@ -226,7 +226,7 @@ def test_lane_repacking_full_size_properties(dec, port):
     from srslte_b200.tdec import synth_llr
 
     K, ncb = 6144, 65536
-    llr, truth = synth_llr(0, ncb, K, sigma=0.86, scale=16.0, clip=31, seed=123)
+    llr, truth = synth_llr(0, ncb, K, sigma=0.90, scale=16.0, clip=31, seed=123)
     outs = []
     for no_compact in (False, True):
         if no_compact:
@@ -243,7 +243,7 @@ def test_lane_repacking_full_size_properties(dec, port):
     (o_a, k_a, n_a), (o_b, k_b, n_b) = outs
     assert (k_a == k_b).all() and (n_a == n_b).all() and (o_a == o_b).all()
     okb = k_a.bool()
-    assert 0.5 < okb.float().mean().item() and n_a.float().std().item() > 0.5
+    assert 0.5 < okb.float().mean().item() and n_a.max().item() >= n_a.min().item() + 3
     assert (o_a[okb] == truth[okb]).all()
     idx = torch.arange(0, ncb, 2731)
     sub = llr[idx].cpu().numpy()
