@@ -28,7 +28,7 @@ struct EnbUl {
   std::vector<cudaEvent_t>  ev;
   uint32_t sf_sz = 0, nsym = 0, nre = 0, nbits = 0, ncb = 0, data_stride = 0;
   // device buffers, grow-only
-  uint32_t cap_sf = 0;
+  uint32_t cap_sf = 0, cap_iq = 0;
   void*    d_iq   = nullptr;
   float2*  d_grid = nullptr;
   int16_t* d_llr  = nullptr;
@@ -127,7 +127,7 @@ struct EnbUl {
       B200_CUDA_TRY(cudaMalloc(&d_grid, (size_t)nsf * nsym * nre * sizeof(float2)));
       B200_CUDA_TRY(cudaMalloc(&d_llr, (size_t)nsf * nbits * sizeof(int16_t)));
       B200_CUDA_TRY(cudaMalloc(&d_meas, (size_t)nsf * 4 * sizeof(float)));
-      B200_CUDA_TRY(cudaMalloc(&d_iq, (size_t)nsf * sf_sz * sizeof(float2))); // sized for float samples
+      cap_iq = 0; // the staging buffer of host samples is allocated when host samples arrive (run)
       cap_sf = nsf;
       tbs.resize(nsf, srsran_b200_tb_t{});
       crc_mask.resize(nsf, 0u); // existing slots keep their masks
@@ -155,6 +155,12 @@ struct EnbUl {
     const size_t ssz      = iq16 ? 2 * sizeof(int16_t) : sizeof(float2);
     int          rc       = reserve(nsf);
     if (rc != B200_SUCCESS) return rc;
+    if (!dev_ptrs && cap_iq < cap_sf) {
+      if (d_iq) cudaFree(d_iq);
+      d_iq = nullptr;
+      B200_CUDA_TRY(cudaMalloc(&d_iq, (size_t)cap_sf * sf_sz * sizeof(float2))); // sized for float samples
+      cap_iq = cap_sf;
+    }
     const uint32_t fe_flags = SRSRAN_B200_FLAG_DEVICE_PTRS | (iq16 ? SRSRAN_B200_FLAG_IQ_INT16 : 0u);
 
     // ---- front end, chunk by chunk -----------------------------------------------------------------------------------------

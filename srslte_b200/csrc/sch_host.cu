@@ -5,6 +5,8 @@
 //   decode_tb_cb  lib/src/phy/phch/sch.c:370-492   (E split with its off-by-one, de-match into the HARQ soft buffer, up to
 //                                                   max_iterations passes with a CRC check after each, cb_crc bookkeeping)
 // Code blocks of all transport blocks are pooled, grouped by (K, CRC kind) and each group runs as ONE batched decode.
+#include <string.h>
+
 #include <chrono>
 #include <map>
 #include <new>
@@ -107,6 +109,46 @@ __global__ void __launch_bounds__(128) sch_tb_crc_kernel(const uint8_t* __restri
   }
 }
 
+struct CbRec {
+  uint32_t tb, c, K, cb_idx, E, rlen, crc_kind;
+  uint64_t in_off, soft_off;
+  bool     last_of_tb;
+};
+
+// Everything decode_batch derives from the transport block list alone: segmentation, E split, de-matching descriptors,
+// decoder groups, payload assembly and CRC jobs -- on the host and, uploaded, on the device.  It is kept between calls: a
+// receiver in steady state hands over the same list again (same grants, offsets and HARQ flags) and then none of it is
+// rebuilt or uploaded; only a list that differs in any input field is planned anew.
+struct SchPlan {
+  bool                          valid = false;
+  std::vector<srsran_b200_tb_t> key;   // the input fields of the list this plan was built for (outputs zeroed)
+  uint64_t                      e_len = 0, soft_len = 0, data_len = 0;
+  uint64_t                      meta_generation = ~0ull;
+  // host side
+  std::vector<CbRec>            cbs;
+  std::vector<int32_t>          tb_result0; // verdict known from the inputs alone (rejected lists, empty blocks), else SRSRAN_ERROR
+  std::vector<uint32_t>         tb_nof_cb;
+  std::vector<uint8_t>          tb_valid;
+  bool                          any_skip = false;
+  std::vector<TdecGroupSpec>    specs;
+  std::vector<uint32_t>         slot_of;    // position of code block i in the decoder's per-block arrays
+  bool                          soft_offsets_aligned8 = true;
+  uint64_t                      dec_bytes = 0;
+  // device side (carved from SchEngine::meta)
+  RmDescDev*  d_descs = nullptr;
+  uint64_t*   d_offs  = nullptr;
+  ScatterJob* d_jobs  = nullptr;
+  TbCrcJob*   d_cj    = nullptr;
+  uint8_t *   d_dec = nullptr, *d_ok = nullptr, *d_np = nullptr, *d_tbok = nullptr;
+};
+
+// the input fields only, compared one by one: the caller's structs may carry anything in their output fields and padding
+static bool tb_same_inputs(const srsran_b200_tb_t& a, const srsran_b200_tb_t& b)
+{
+  return a.tbs == b.tbs && a.Qm == b.Qm && a.rv == b.rv && a.nof_e_bits == b.nof_e_bits && a.e_offset == b.e_offset &&
+         a.soft_offset == b.soft_offset && a.data_offset == b.data_offset && a.new_data == b.new_data && a.cb_crc_mask == b.cb_crc_mask;
+}
+
 struct SchEngine {
   DeviceContext* ctx = nullptr;
   TdecEngine     tdec;
@@ -119,6 +161,9 @@ struct SchEngine {
   cudaStream_t   after  = nullptr;    // srsran_b200_sch_decode_after: producer stream of the next decode_batch's device inputs
   bool           have_after = false;
   cudaEvent_t    after_ev = nullptr;
+  SchPlan        plan;                // of the last transport block list (reused when the next list repeats it)
+  std::vector<uint8_t>          h_tbok, tmp_ok, tmp_np;
+  std::vector<uint32_t>         iters_scratch;
 
   int init(int device)
   {
@@ -158,6 +203,8 @@ struct SchEngine {
 
   int rm_batch(const int16_t* e_bits, uint64_t e_len, int16_t* soft_pool, uint64_t soft_len, const srsran_b200_rm_cb_t* cbs,
                uint32_t n, uint32_t flags, cudaStream_t user_stream);
+  int build_plan(SchPlan& p, uint64_t e_len, uint64_t soft_len, uint64_t data_len, const srsran_b200_tb_t* tbs, uint32_t n_tb,
+                 cudaStream_t st);
   int decode_batch(const int16_t* e_bits, uint64_t e_len, int16_t* soft_pool, uint64_t soft_len, uint8_t* data, uint64_t data_len,
                    srsran_b200_tb_t* tbs, uint32_t n_tb, uint32_t flags);
 };
@@ -212,6 +259,7 @@ int SchEngine::rm_batch(const int16_t* e_bits, uint64_t e_len, int16_t* soft_poo
   cudaStream_t st       = dev_ptrs ? user_stream : stream;
   if (meta.reserve(descs.size() * sizeof(RmDescDev) + 4096) != B200_SUCCESS) return B200_ERROR;
   meta.reset();
+  plan.valid = false; // the decode loop's kept descriptors lived in this arena
   RmDescDev* d_descs = nullptr;
   if (upload(meta, descs, &d_descs, st) != B200_SUCCESS) return B200_ERROR;
   if (dev_ptrs) {
@@ -234,76 +282,57 @@ int SchEngine::rm_batch(const int16_t* e_bits, uint64_t e_len, int16_t* soft_poo
   return rc;
 }
 
-struct CbRec {
-  uint32_t tb, c, K, cb_idx, E, rlen, crc_kind;
-  uint64_t in_off, soft_off;
-  bool     last_of_tb;
-};
-
-int SchEngine::decode_batch(const int16_t* e_bits, uint64_t e_len, int16_t* soft_pool, uint64_t soft_len, uint8_t* data,
-                            uint64_t data_len, srsran_b200_tb_t* tbs, uint32_t n_tb, uint32_t flags)
+int SchEngine::build_plan(SchPlan& p, uint64_t e_len, uint64_t soft_len, uint64_t data_len, const srsran_b200_tb_t* tbs, uint32_t n_tb,
+                          cudaStream_t st)
 {
-  if (!e_bits || !soft_pool || !data || (!tbs && n_tb)) return B200_ERROR_INVALID_INPUTS;
-  if (n_tb == 0) return B200_SUCCESS;
-  B200_CUDA_TRY(cudaSetDevice(ctx->device));
-  const bool   all_dev  = (flags & SRSRAN_B200_FLAG_DEVICE_PTRS) != 0;
-  const bool   soft_dev = all_dev || (flags & SRSRAN_B200_FLAG_SOFT_ON_DEVICE) != 0;
-  cudaStream_t st       = stream;
-  if (have_after) { // the device inputs are produced on another stream: order this batch after what is queued there now
-    B200_CUDA_TRY(cudaEventRecord(after_ev, after));
-    B200_CUDA_TRY(cudaStreamWaitEvent(st, after_ev, 0));
-    have_after = false;
-  }
-
-  static const bool timing = getenv("SRSLTE_B200_SCH_TIMING") != nullptr;
-  auto              now    = [] { return std::chrono::steady_clock::now(); };
-  auto              t_0    = now();
-  // ---- host-side bookkeeping: segmentation and the per-code-block E split of sch.c:392-406 ---------------------------
-  std::vector<CbRec>               cbs;
+  p.valid = false;
+  p.cbs.clear();
+  p.cbs.reserve(last_ncb + 64);
+  p.tb_result0.assign(n_tb, B200_ERROR);
+  p.tb_nof_cb.assign(n_tb, 0);
+  p.tb_valid.assign(n_tb, 0);
+  p.any_skip = false;
   std::vector<srsran_b200_rm_cb_t> rm;
   std::vector<TbCrcJob>            crc_jobs(n_tb);
-  bool                             any_skip = false;
-  cbs.reserve(last_ncb + 64);
   rm.reserve(last_ncb + 64);
+  // ---- segmentation and the per-code-block E split of sch.c:392-406 ----------------------------------------------------
   for (uint32_t t = 0; t < n_tb; t++) {
-    srsran_b200_tb_t& tb = tbs[t];
-    tb.result            = B200_ERROR;
-    tb.nof_cb            = 0;
-    tb.avg_iterations    = 0;
-    CbSegm s;
+    const srsran_b200_tb_t& tb = tbs[t];
+    CbSegm                  s;
     if (tb.Qm == 0 || cb_segmentation(tb.tbs, s) != 0) {
-      tb.result = B200_ERROR_INVALID_INPUTS;
+      p.tb_result0[t] = B200_ERROR_INVALID_INPUTS;
       continue;
     }
     if (s.tbs == 0 || s.C == 0) {
-      tb.result = B200_SUCCESS; // sch.c:517-519
+      p.tb_result0[t] = B200_SUCCESS; // sch.c:517-519
       continue;
     }
     if (s.F) {
       fprintf(stderr, "Error filler bits are not supported. Use standard TBS\n"); // sch.c:521-524
-      tb.result = B200_ERROR_INVALID_INPUTS;
+      p.tb_result0[t] = B200_ERROR_INVALID_INPUTS;
       continue;
     }
     if (s.C > 32) { // SRSRAN_MAX_CODEBLOCKS, sch.c:382-385
-      tb.result = B200_ERROR_INVALID_INPUTS;
+      p.tb_result0[t] = B200_ERROR_INVALID_INPUTS;
       continue;
     }
     if (tb.e_offset + tb.nof_e_bits > e_len || tb.soft_offset + (uint64_t)s.C * SRSRAN_B200_SOFTBUFFER_SIZE > soft_len ||
         tb.data_offset + tb.tbs / 8 + 3 + MAX_CB_LEN / 8 > data_len) {
       B200_LOG_ERROR("transport block %u exceeds its buffers", t);
-      tb.result = B200_ERROR_INVALID_INPUTS;
+      p.tb_result0[t] = B200_ERROR_INVALID_INPUTS;
       continue;
     }
-    tb.nof_cb             = s.C;
-    crc_jobs[t].data_off  = tb.data_offset;
-    crc_jobs[t].tbs       = tb.tbs;
-    crc_jobs[t].pad       = 1; // valid
-    const uint32_t Gp     = tb.nof_e_bits / tb.Qm;
-    const uint32_t gamma  = Gp % s.C;
-    const uint32_t n_e    = tb.Qm * (Gp / s.C);
+    p.tb_nof_cb[t]       = s.C;
+    p.tb_valid[t]        = 1;
+    crc_jobs[t].data_off = tb.data_offset;
+    crc_jobs[t].tbs      = tb.tbs;
+    crc_jobs[t].pad      = 1; // valid
+    const uint32_t Gp    = tb.nof_e_bits / tb.Qm;
+    const uint32_t gamma = Gp % s.C;
+    const uint32_t n_e   = tb.Qm * (Gp / s.C);
     for (uint32_t c = 0; c < s.C; c++) {
       if (tb.cb_crc_mask & (1u << c)) { // sch.c:390: already decoded in an earlier transmission
-        any_skip = true;
+        p.any_skip = true;
         continue;
       }
       CbRec r;
@@ -323,10 +352,10 @@ int SchEngine::decode_batch(const int16_t* e_bits, uint64_t e_len, int16_t* soft
       r.crc_kind   = s.C > 1 ? SRSRAN_B200_CRC24B : SRSRAN_B200_CRC24A; // sch.c:437-444
       r.last_of_tb = (c == s.C - 1);
       if (r.in_off + r.E > e_len) {
-        tb.result = B200_ERROR_INVALID_INPUTS;
+        p.tb_result0[t] = B200_ERROR_INVALID_INPUTS;
         continue;
       }
-      cbs.push_back(r);
+      p.cbs.push_back(r);
       srsran_b200_rm_cb_t j;
       j.cb_idx      = r.cb_idx;
       j.rv          = tb.rv;
@@ -337,9 +366,117 @@ int SchEngine::decode_batch(const int16_t* e_bits, uint64_t e_len, int16_t* soft
       rm.push_back(j);
     }
   }
+  const std::vector<CbRec>& cbs = p.cbs;
+  last_ncb                      = cbs.size();
+  // ---- de-matching descriptors, decoder groups (K, CRC kind), payload assembly -------------------------------------------
+  std::vector<RmDescDev> descs;
+  int                    rc = build_rm_descs(ctx, rm.data(), (uint32_t)rm.size(), e_len, soft_len, descs);
+  if (rc != B200_SUCCESS) return rc;
+  std::map<std::pair<uint32_t, uint32_t>, std::vector<uint32_t>> groups;
+  for (uint32_t i = 0; i < cbs.size(); i++) groups[{cbs[i].K, cbs[i].crc_kind}].push_back(i);
+  p.specs.clear();
+  p.slot_of.assign(cbs.size(), 0);
+  std::vector<uint64_t>   offs(cbs.size());
+  std::vector<ScatterJob> jobs(cbs.size());
+  p.soft_offsets_aligned8 = true;
+  p.dec_bytes             = 0;
+  {
+    uint32_t slot = 0;
+    for (auto& g : groups) {
+      const uint32_t K = g.first.first;
+      p.specs.push_back(TdecGroupSpec{(int)K, cb_index_exact(K), (int)g.first.second, (uint32_t)g.second.size(), slot, 0, p.dec_bytes});
+      for (uint32_t i : g.second) {
+        const CbRec& r          = cbs[i];
+        p.slot_of[i]            = slot;
+        offs[slot]              = r.soft_off;
+        p.soft_offsets_aligned8 = p.soft_offsets_aligned8 && (r.soft_off % 4 == 0);
+        jobs[slot].dst          = tbs[r.tb].data_offset + (uint64_t)r.c * (r.rlen / 8);
+        jobs[slot].src          = p.dec_bytes;
+        jobs[slot].nbytes       = r.last_of_tb ? r.K / 8 : r.rlen / 8;
+        jobs[slot].pad          = 0;
+        p.dec_bytes += K / 8;
+        slot++;
+      }
+    }
+  }
+  // ---- upload ------------------------------------------------------------------------------------------------------------
+  size_t meta_need = descs.size() * sizeof(RmDescDev) + cbs.size() * (sizeof(uint64_t) + sizeof(ScatterJob) + 8) +
+                     n_tb * (sizeof(TbCrcJob) + 8) + p.dec_bytes + (size_t(2) << 20);
+  if (meta.reserve(meta_need) != B200_SUCCESS) return B200_ERROR;
+  meta.reset();
+  // the previous call ended with a stream synchronisation, so its staged descriptors are free again
+  if (hmeta.reserve(descs.size() * sizeof(RmDescDev) + cbs.size() * (sizeof(uint64_t) + sizeof(ScatterJob)) + n_tb * sizeof(TbCrcJob) +
+                    (size_t(1) << 20)) != B200_SUCCESS) {
+    return B200_ERROR;
+  }
+  hmeta.reset();
+  p.d_descs = nullptr;
+  p.d_offs  = nullptr;
+  p.d_jobs  = nullptr;
+  p.d_dec = p.d_ok = p.d_np = nullptr;
+  if (!descs.empty() && upload(meta, descs, &p.d_descs, st, &hmeta) != B200_SUCCESS) return B200_ERROR;
+  if (!cbs.empty()) {
+    if (upload(meta, offs, &p.d_offs, st, &hmeta) != B200_SUCCESS || upload(meta, jobs, &p.d_jobs, st, &hmeta) != B200_SUCCESS) return B200_ERROR;
+    p.d_dec = (uint8_t*)meta.take(p.dec_bytes);
+    p.d_ok  = (uint8_t*)meta.take(cbs.size());
+    p.d_np  = (uint8_t*)meta.take(cbs.size());
+    if (!p.d_dec || !p.d_ok || !p.d_np) return B200_ERROR;
+  }
+  if (upload(meta, crc_jobs, &p.d_cj, st, &hmeta) != B200_SUCCESS) return B200_ERROR;
+  p.d_tbok = (uint8_t*)meta.take(n_tb);
+  if (!p.d_tbok) return B200_ERROR;
+  p.key.assign(tbs, tbs + n_tb);
+  p.e_len           = e_len;
+  p.soft_len        = soft_len;
+  p.data_len        = data_len;
+  p.meta_generation = meta.generation;
+  p.valid           = true;
+  return B200_SUCCESS;
+}
 
+int SchEngine::decode_batch(const int16_t* e_bits, uint64_t e_len, int16_t* soft_pool, uint64_t soft_len, uint8_t* data,
+                            uint64_t data_len, srsran_b200_tb_t* tbs, uint32_t n_tb, uint32_t flags)
+{
+  if (!e_bits || !soft_pool || !data || (!tbs && n_tb)) return B200_ERROR_INVALID_INPUTS;
+  if (n_tb == 0) return B200_SUCCESS;
+  B200_CUDA_TRY(cudaSetDevice(ctx->device));
+  const bool   all_dev  = (flags & SRSRAN_B200_FLAG_DEVICE_PTRS) != 0;
+  const bool   soft_dev = all_dev || (flags & SRSRAN_B200_FLAG_SOFT_ON_DEVICE) != 0;
+  cudaStream_t st       = stream;
+  if (have_after) { // the device inputs are produced on another stream: order this batch after what is queued there now
+    B200_CUDA_TRY(cudaEventRecord(after_ev, after));
+    B200_CUDA_TRY(cudaStreamWaitEvent(st, after_ev, 0));
+    have_after = false;
+  }
+
+  static const bool timing = getenv("SRSLTE_B200_SCH_TIMING") != nullptr;
+  auto              now    = [] { return std::chrono::steady_clock::now(); };
+  auto              t_0    = now();
+  // ---- the plan of this list: taken over from the previous call when nothing it depends on has changed -------------------
+  SchPlan& p    = plan;
+  bool     same = p.valid && p.key.size() == n_tb && p.e_len == e_len && p.soft_len == soft_len && p.data_len == data_len &&
+              p.meta_generation == meta.generation;
+  for (uint32_t t = 0; same && t < n_tb; t++) same = tb_same_inputs(tbs[t], p.key[t]);
+  if (!same) {
+    if (timing) {
+      fprintf(stderr, "[sch timing] new plan: valid %d, size %zu/%u, lens %d%d%d, arena generation %llu/%llu\n", (int)p.valid, p.key.size(), n_tb,
+              (int)(p.e_len == e_len), (int)(p.soft_len == soft_len), (int)(p.data_len == data_len), (unsigned long long)p.meta_generation,
+              (unsigned long long)meta.generation);
+    }
+    int rc = build_plan(p, e_len, soft_len, data_len, tbs, n_tb, st);
+    if (rc != B200_SUCCESS) {
+      p.valid = false;
+      return rc;
+    }
+  }
+  const std::vector<CbRec>& cbs = p.cbs;
+  for (uint32_t t = 0; t < n_tb; t++) {
+    tbs[t].result         = p.tb_result0[t];
+    tbs[t].nof_cb         = p.tb_nof_cb[t];
+    tbs[t].avg_iterations = 0;
+  }
   auto t_1 = now();
-  last_ncb = cbs.size();
+
   // ---- stage buffers ---------------------------------------------------------------------------------------------------
   const int16_t* d_e    = e_bits;
   int16_t*       d_soft = soft_pool;
@@ -354,7 +491,7 @@ int SchEngine::decode_batch(const int16_t* e_bits, uint64_t e_len, int16_t* soft
     d_e = de;
     // the whole staged buffer travels back at the end: start from the caller's bytes when blocks decoded earlier must be
     // kept (sch.c:466-471), else from zeros, so that gaps, slack and rejected transport blocks never receive stale memory
-    if (any_skip) B200_CUDA_TRY(cudaMemcpyAsync(d_data, data, data_len, cudaMemcpyHostToDevice, st));
+    if (p.any_skip) B200_CUDA_TRY(cudaMemcpyAsync(d_data, data, data_len, cudaMemcpyHostToDevice, st));
     else B200_CUDA_TRY(cudaMemsetAsync(d_data, 0, data_len, st));
     if (!soft_dev) {
       d_soft = (int16_t*)io.take(soft_len * sizeof(int16_t));
@@ -363,117 +500,86 @@ int SchEngine::decode_batch(const int16_t* e_bits, uint64_t e_len, int16_t* soft
   }
 
   // ---- rate de-matching of every pending code block -------------------------------------------------------------------
-  std::vector<RmDescDev> descs;
-  int                    rc = build_rm_descs(ctx, rm.data(), (uint32_t)rm.size(), e_len, soft_len, descs);
-  if (rc != B200_SUCCESS) return rc;
-  auto   t_2       = now();
-  size_t meta_need = descs.size() * sizeof(RmDescDev) + cbs.size() * (sizeof(uint64_t) + sizeof(ScatterJob) + 8) +
-                     n_tb * (sizeof(TbCrcJob) + 8) + (size_t(2) << 20);
-  for (const CbRec& r : cbs) meta_need += r.K / 8 + 64;
-  if (meta.reserve(meta_need) != B200_SUCCESS) return B200_ERROR;
-  meta.reset();
-  // the previous call ended with a stream synchronisation, so its staged descriptors are free again
-  if (hmeta.reserve(descs.size() * sizeof(RmDescDev) + cbs.size() * (sizeof(uint64_t) + sizeof(ScatterJob)) + n_tb * sizeof(TbCrcJob) +
-                    (size_t(1) << 20)) != B200_SUCCESS) {
-    return B200_ERROR;
-  }
-  hmeta.reset();
-  if (!descs.empty()) {
-    RmDescDev* d_descs = nullptr;
-    if (upload(meta, descs, &d_descs, st, &hmeta) != B200_SUCCESS) return B200_ERROR;
-    if (launch_rm_rx(d_e, d_soft, d_descs, (uint32_t)descs.size(), st) != B200_SUCCESS) return B200_ERROR;
+  if (!cbs.empty()) {
+    if (launch_rm_rx(d_e, d_soft, p.d_descs, (uint32_t)cbs.size(), st) != B200_SUCCESS) return B200_ERROR;
     g_kernel_launches++;
   }
-
   auto t_3 = now();
-  // ---- group by (K, CRC kind); ONE batched decode over all groups (one launch per pass, tiles ordered by length) ------
-  std::map<std::pair<uint32_t, uint32_t>, std::vector<uint32_t>> groups;
-  for (uint32_t i = 0; i < cbs.size(); i++) groups[{cbs[i].K, cbs[i].crc_kind}].push_back(i);
-  std::vector<uint8_t> h_ok(cbs.size(), 0), h_np(cbs.size(), 0);
-  uint8_t *            d_ok = nullptr, *d_np = nullptr;
-  std::vector<uint32_t> slot_of(cbs.size()); // position of code block i in the decoder's per-block arrays
-  if (!cbs.empty()) {
-    std::vector<TdecGroupSpec> specs;
-    std::vector<uint64_t>      offs(cbs.size());
-    std::vector<ScatterJob>    jobs(cbs.size());
-    bool                       al8     = (reinterpret_cast<uintptr_t>(d_soft) & 7u) == 0;
-    uint32_t                   slot    = 0;
-    uint64_t                   dec_off = 0;
-    for (auto& g : groups) {
-      const uint32_t K = g.first.first;
-      specs.push_back(TdecGroupSpec{(int)K, cb_index_exact(K), (int)g.first.second, (uint32_t)g.second.size(), slot, 0, dec_off});
-      for (uint32_t i : g.second) {
-        const CbRec& r    = cbs[i];
-        slot_of[i]        = slot;
-        offs[slot]        = r.soft_off;
-        al8               = al8 && (r.soft_off % 4 == 0);
-        jobs[slot].dst    = tbs[r.tb].data_offset + (uint64_t)r.c * (r.rlen / 8);
-        jobs[slot].src    = dec_off;
-        jobs[slot].nbytes = r.last_of_tb ? r.K / 8 : r.rlen / 8;
-        jobs[slot].pad    = 0;
-        dec_off += K / 8;
-        slot++;
-      }
-    }
-    uint64_t*   d_offs = nullptr;
-    ScatterJob* d_jobs = nullptr;
-    if (upload(meta, offs, &d_offs, st, &hmeta) != B200_SUCCESS || upload(meta, jobs, &d_jobs, st, &hmeta) != B200_SUCCESS) return B200_ERROR;
-    uint8_t* d_dec = (uint8_t*)meta.take(dec_off);
-    d_ok           = (uint8_t*)meta.take(cbs.size());
-    d_np           = (uint8_t*)meta.take(cbs.size());
-    if (!d_dec || !d_ok || !d_np) return B200_ERROR;
-    rc = tdec.run_groups(tdec.ws, d_soft, specs, max_iterations, 1, d_dec, d_ok, d_np, st, d_offs, al8);
-    if (rc != B200_SUCCESS) return rc;
-    sch_scatter_payload_kernel<<<(unsigned)cbs.size(), 128, 0, st>>>(d_dec, d_data, d_jobs, (uint32_t)cbs.size());
-    g_kernel_launches++;
-  }
 
-  auto t_4 = now();
-  // ---- transport block CRC + results -------------------------------------------------------------------------------------
-  TbCrcJob* d_cj = nullptr;
-  if (upload(meta, crc_jobs, &d_cj, st, &hmeta) != B200_SUCCESS) return B200_ERROR;
-  uint8_t* d_tbok = (uint8_t*)meta.take(n_tb);
-  if (!d_tbok) return B200_ERROR;
-  sch_tb_crc_kernel<<<(n_tb + 3) / 4, 128, 0, st>>>(d_data, d_cj, n_tb, d_tbok);
-  g_kernel_launches++;
-  std::vector<uint8_t> h_tbok(n_tb, 0);
-  B200_CUDA_TRY(cudaMemcpyAsync(h_tbok.data(), d_tbok, n_tb, cudaMemcpyDeviceToHost, st));
-  std::vector<uint8_t> tmp_ok(cbs.size()), tmp_np(cbs.size());
-  if (!cbs.empty()) {
-    B200_CUDA_TRY(cudaMemcpyAsync(tmp_ok.data(), d_ok, cbs.size(), cudaMemcpyDeviceToHost, st));
-    B200_CUDA_TRY(cudaMemcpyAsync(tmp_np.data(), d_np, cbs.size(), cudaMemcpyDeviceToHost, st));
+  // ---- ONE batched decode over all (K, CRC kind) groups (one launch per pass, tiles ordered by length) ------------------
+  const bool al8 = p.soft_offsets_aligned8 && (reinterpret_cast<uintptr_t>(d_soft) & 7u) == 0;
+  h_tbok.assign(n_tb, 0);
+  tmp_ok.assign(cbs.size(), 0);
+  tmp_np.assign(cbs.size(), 0);
+  std::chrono::steady_clock::time_point t_4, t_5;
+
+  // The decoder workspace is borrowed for the duration of this (synchronous) call; it is carved without the int16 copies of
+  // the channel LLRs until a batch needs them (TdecWorkspace::int16_on_demand).
+  struct Borrowed {
+    int            dev;
+    TdecWorkspace* w;
+    ~Borrowed() { workspace_release(dev, w); }
+  } ws{ctx->device, workspace_acquire(ctx->device)};
+  if (!ws.w) return B200_ERROR;
+  ws.w->int16_on_demand = true;
+
+  // decode, payload assembly, transport block CRC, results; ends with the stream synchronised
+  auto decode_and_finish = [&]() -> int {
+    if (!cbs.empty()) {
+      int r = tdec.run_groups(*ws.w, d_soft, p.specs, max_iterations, 1, p.d_dec, p.d_ok, p.d_np, st, p.d_offs, al8);
+      if (r != B200_SUCCESS) return r;
+      sch_scatter_payload_kernel<<<(unsigned)cbs.size(), 128, 0, st>>>(p.d_dec, d_data, p.d_jobs, (uint32_t)cbs.size());
+      g_kernel_launches++;
+    }
+    t_4 = now();
+    sch_tb_crc_kernel<<<(n_tb + 3) / 4, 128, 0, st>>>(d_data, p.d_cj, n_tb, p.d_tbok);
+    g_kernel_launches++;
+    B200_CUDA_TRY(cudaMemcpyAsync(h_tbok.data(), p.d_tbok, n_tb, cudaMemcpyDeviceToHost, st));
+    if (!cbs.empty()) {
+      B200_CUDA_TRY(cudaMemcpyAsync(tmp_ok.data(), p.d_ok, cbs.size(), cudaMemcpyDeviceToHost, st));
+      B200_CUDA_TRY(cudaMemcpyAsync(tmp_np.data(), p.d_np, cbs.size(), cudaMemcpyDeviceToHost, st));
+    }
+    if (!all_dev) {
+      B200_CUDA_TRY(cudaMemcpyAsync(data, d_data, data_len, cudaMemcpyDeviceToHost, st));
+      if (!soft_dev) B200_CUDA_TRY(cudaMemcpyAsync(soft_pool, d_soft, soft_len * sizeof(int16_t), cudaMemcpyDeviceToHost, st));
+    }
+    t_5 = now();
+    B200_CUDA_TRY(cudaStreamSynchronize(st));
+    B200_CUDA_TRY(cudaGetLastError());
+    return B200_SUCCESS;
+  };
+  int rc = decode_and_finish();
+  if (rc != B200_SUCCESS) return rc;
+  if (ws.w->h_err && *ws.w->h_err) {
+    // some soft values did not fit the int8 tiles and this decoder workspace was carved without the int16 copies
+    // (int16_on_demand): carve them from now on and decode the batch again -- the soft buffers still hold its input
+    ws.w->have_int16 = true;
+    *ws.w->h_err     = 0;
+    rc               = decode_and_finish();
+    if (rc != B200_SUCCESS) return rc;
   }
-  if (!all_dev) {
-    B200_CUDA_TRY(cudaMemcpyAsync(data, d_data, data_len, cudaMemcpyDeviceToHost, st));
-    if (!soft_dev) B200_CUDA_TRY(cudaMemcpyAsync(soft_pool, d_soft, soft_len * sizeof(int16_t), cudaMemcpyDeviceToHost, st));
-  }
-  auto t_5 = now();
-  B200_CUDA_TRY(cudaStreamSynchronize(st));
-  B200_CUDA_TRY(cudaGetLastError());
   auto t_6 = now();
   if (timing) {
     auto us = [](auto a, auto b) { return (double)std::chrono::duration_cast<std::chrono::nanoseconds>(b - a).count() / 1e3; };
-    fprintf(stderr, "[sch timing] bookkeeping %.0f us, rm descs %.0f, upload+dematch launch %.0f, groups+decode launches %.0f, tail launches %.0f, "
-                    "wait for the device %.0f\n", us(t_0, t_1), us(t_1, t_2), us(t_2, t_3), us(t_3, t_4), us(t_4, t_5), us(t_5, t_6));
+    fprintf(stderr, "[sch timing] plan %s %.0f us, staging + de-matching launch %.0f, decode launches %.0f, tail launches %.0f, "
+                    "wait for the device %.0f\n", same ? "reused" : "built", us(t_0, t_1), us(t_1, t_3), us(t_3, t_4), us(t_4, t_5), us(t_5, t_6));
   }
-  for (size_t i = 0; i < cbs.size(); i++) {
-    h_ok[i] = tmp_ok[slot_of[i]];
-    h_np[i] = tmp_np[slot_of[i]];
-  }
-  std::vector<uint32_t> iters(n_tb, 0);
+  iters_scratch.assign(n_tb, 0);
   for (size_t i = 0; i < cbs.size(); i++) {
     srsran_b200_tb_t& tb = tbs[cbs[i].tb];
-    iters[cbs[i].tb] += h_np[i];
-    if (h_ok[i]) tb.cb_crc_mask |= (1u << cbs[i].c);
+    iters_scratch[cbs[i].tb] += tmp_np[p.slot_of[i]];
+    if (tmp_ok[p.slot_of[i]]) tb.cb_crc_mask |= (1u << cbs[i].c);
   }
   for (uint32_t t = 0; t < n_tb; t++) {
     srsran_b200_tb_t& tb = tbs[t];
-    if (tb.nof_cb == 0 || crc_jobs[t].pad == 0) continue;
+    if (!p.tb_valid[t] || tb.nof_cb == 0) continue;
     if (tb.result == B200_ERROR_INVALID_INPUTS) continue;
-    tb.avg_iterations  = (float)iters[t] / (float)tb.nof_cb; // sch.c:490
+    tb.avg_iterations  = (float)iters_scratch[t] / (float)tb.nof_cb; // sch.c:490
     const uint32_t all = tb.nof_cb >= 32 ? 0xFFFFFFFFu : ((1u << tb.nof_cb) - 1u);
     tb.result          = ((tb.cb_crc_mask & all) == all && h_tbok[t]) ? B200_SUCCESS : B200_ERROR;
   }
+  // the list's own cb_crc_mask fields have just changed: the kept plan stays valid only for a list that repeats the INPUT
+  // masks (a retransmission with updated masks is planned anew, as it must be)
   return B200_SUCCESS;
 }
 

@@ -310,7 +310,7 @@ static int tdec_one_pass(srsran_tdec_t* h, int16_t* input)
     launch_load_natural(c->view, K, c->d_llr, nullptr, true, st);
     g_kernel_launches++;
   }
-  launch_siso_pass(c->view, h->n_iter, st);
+  launch_siso_pass(c->view, h->n_iter, SISO_LOW_LATENCY, c->eng.sm_count, st); // one code block: latency is all that matters
   g_kernel_launches++;
   h->n_iter++;
   return SRSRAN_SUCCESS;

@@ -73,6 +73,13 @@ struct alignas(8) CrcPow {
 
 constexpr uint32_t LANE_EMPTY = 0xFFFFFFFFu;
 
+// TdecView::ctl
+constexpr int TDEC_CTL_USE_LL      = 0; // 1: so few tiles still run that the next pass goes to the low-latency kernel
+constexpr int TDEC_CTL_LL_QUEUE    = 1; // low-latency pass: next tile to hand out
+constexpr int TDEC_CTL_PLAN_DONE   = 2; // re-packing: groups planned so far (the last one decides TDEC_CTL_USE_LL)
+constexpr int TDEC_CTL_TILES_LEFT  = 3; // re-packing: tiles that still hold running lanes, summed over the groups
+constexpr int TDEC_CTL_WORDS       = 8;
+
 // which block pair a lane slot holds
 struct LaneMap {
   uint32_t st0; // index of the pair's first record in status[] (LANE_EMPTY: the slot holds nothing)
@@ -118,6 +125,10 @@ struct TdecView {
   int              split_percent; // share of a tile's trellis windows below the split (tdec_split)
   const TileDesc*  tiles;  // [ntiles]
   uint32_t*        fmt;    // [ntiles] 0: the int8 arrays hold the tile, 1: the int16 arrays do
+  uint32_t*        err;    // bit 0: a tile needed the int16 arrays but the workspace was carved without them (TileDesc::S == nullptr)
+  uint32_t*        ctl;    // device-side control words, see TDEC_CTL_*
+  u4*              ll_ck;  // low-latency pass: alpha checkpoints of the tile a thread block works on, one slot per thread block
+  uint32_t         ll_ck_slot; // u4 elements per slot (max K / 8 * 64)
   u4*              S2T;    // [ntiles*32] : x,y,z = systematic tail of encoder 2 (app2[K..K+2]) of the pair in that slot
   LaneMap*         lanes;  // [ntiles*32]
   uint16_t*        HB;

@@ -47,9 +47,23 @@ struct TdecWorkspace {
   cudaEvent_t                uploaded = nullptr; // the staged descriptors have been copied
   std::vector<TdecGroupSpec> cached;
   uint64_t                   cached_generation = ~0ull; // arena generation the cached descriptors live in
+  bool                       cached_int16 = true;
   TdecPlan                   plan;
+  // The int16 copies of the channel LLRs (a tile uses them when a value does not fit int8) are 40 % of the workspace and
+  // almost never touched.  With int16_on_demand the workspace is carved WITHOUT them until a batch needs them: the load
+  // kernels then flag the batch (TdecView::err, mirrored into *h_err after the decode) and the caller, who synchronises
+  // anyway, sets have_int16 and runs the decode again.  Only for synchronous callers (the transport-block decode loop).
+  bool                       int16_on_demand = false;
+  bool                       have_int16      = false;
+  uint32_t*                  h_err           = nullptr; // page-locked
   void                       release();
 };
+
+// Decoder workspaces are scratch: valid only while one decode runs.  Callers that synchronise at the end of a decode (the
+// transport-block decode loop) borrow one from a per-device pool instead of owning one, so that many receiver objects of a
+// process (one per cell) share as many workspaces as decodes are in flight, not one each (~0.9 GB per 13,000 code blocks).
+TdecWorkspace* workspace_acquire(int device);
+void           workspace_release(int device, TdecWorkspace* w);
 
 struct TdecEngine {
   // code blocks per pipeline chunk on the host-pointer path: ~300 MB of LLRs at K=6144, big enough to run PCIe at
@@ -76,7 +90,7 @@ struct TdecEngine {
   void prof_reset(bool enable);
   int  prof_get(double* ms_by_class, uint64_t* launches_by_class, int nclasses); // synchronises the device
 
-  static size_t workspace_bytes(const std::vector<TdecGroupSpec>& groups);
+  static size_t workspace_bytes(const std::vector<TdecGroupSpec>& groups, bool with_int16 = true);
   static size_t workspace_bytes(int K, uint32_t ncb);
   // carve the workspace for `groups`, build and upload the tile descriptors (or reuse the cached ones)
   int prepare(TdecWorkspace& w, const std::vector<TdecGroupSpec>& groups, cudaStream_t stream);

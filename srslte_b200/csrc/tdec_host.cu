@@ -4,7 +4,10 @@
 
 #include <algorithm>
 #include <atomic>
+#include <map>
+#include <mutex>
 #include <new>
+#include <vector>
 #include <utility>
 
 #include "../../include/srslte_b200.h"
@@ -18,31 +21,34 @@ namespace b200 {
 std::atomic<uint64_t> g_kernel_launches{0};
 
 // device bytes of one tile's own arrays (each carve-out is rounded up to 256 bytes)
-static size_t tile_bytes(int K)
+static size_t tile_bytes(int K, bool with_int16)
 {
   auto r256 = [](size_t b) { return (b + 255) / 256 * 256; };
   size_t total = 0;
-  total += 3 * r256((size_t)((K + 4) / 4) * 32 * sizeof(u4));  // S, P0, P1
+  if (with_int16) total += 3 * r256((size_t)((K + 4) / 4) * 32 * sizeof(u4));  // S, P0, P1
   total += 3 * r256((size_t)(K / 8 + 1) * 32 * sizeof(u4));    // S8, P08, P18
   total += r256((size_t)K * 32 * sizeof(uint32_t));            // E
   total += r256((size_t)(K / 8) * 2 * 32 * sizeof(u4));        // CK
   return total;
 }
 
-size_t TdecEngine::workspace_bytes(const std::vector<TdecGroupSpec>& groups)
+size_t TdecEngine::workspace_bytes(const std::vector<TdecGroupSpec>& groups, bool with_int16)
 {
   size_t total = 0, ntiles = 0, hb_rows = 0;
   for (const TdecGroupSpec& g : groups) {
     const size_t nt = (g.ncb + TDEC_TILE_CB - 1) / TDEC_TILE_CB;
-    total += nt * tile_bytes(g.K);
+    total += nt * tile_bytes(g.K, with_int16);
     ntiles += nt;
     hb_rows += nt * (size_t)(g.K / 8);
   }
   total += hb_rows * 32 * sizeof(uint16_t) + 256;                         // HB
-  total += ntiles * (sizeof(uint32_t) * 3 + 32 * sizeof(u4) + 32 * sizeof(LaneMap) + TDEC_TILE_CB * sizeof(CbStatus) +
+  total += ntiles * (sizeof(uint32_t) * 4 + 32 * sizeof(u4) + 32 * sizeof(LaneMap) + TDEC_TILE_CB * sizeof(CbStatus) +
                      sizeof(TileDesc) + 32 * sizeof(MoveRec) + 32 * sizeof(uint32_t));             // fmt, mask, pref, S2T, lanes, status, descriptors, moves
   total += groups.size() * (sizeof(TileGroup) + sizeof(GroupPlan));
-  return total + 16 * 256 + 4096;
+  int max_K = 0;
+  for (const TdecGroupSpec& g : groups) max_K = std::max(max_K, g.K);
+  total += std::min<size_t>(ntiles, 256) * (size_t)(max_K / 8) * 64 * sizeof(u4); // low-latency pass: one alpha checkpoint slot per thread block
+  return total + 20 * 256 + 4096;
 }
 
 size_t TdecEngine::workspace_bytes(int K, uint32_t ncb)
@@ -52,12 +58,36 @@ size_t TdecEngine::workspace_bytes(int K, uint32_t ncb)
   return workspace_bytes(g);
 }
 
+static std::mutex                                 g_pool_mutex;
+static std::map<int, std::vector<TdecWorkspace*>> g_pool_free;
+
+TdecWorkspace* workspace_acquire(int device)
+{
+  std::lock_guard<std::mutex> lk(g_pool_mutex);
+  auto&                       v = g_pool_free[device];
+  if (!v.empty()) {
+    TdecWorkspace* w = v.back();
+    v.pop_back();
+    return w;
+  }
+  return new (std::nothrow) TdecWorkspace();
+}
+
+void workspace_release(int device, TdecWorkspace* w)
+{
+  if (!w) return;
+  std::lock_guard<std::mutex> lk(g_pool_mutex);
+  g_pool_free[device].push_back(w); // kept for the next decode on this device (its descriptors stay cached); never freed
+}
+
 void TdecWorkspace::release()
 {
   arena.release();
   stage.release();
   if (uploaded) cudaEventDestroy(uploaded);
   uploaded = nullptr;
+  if (h_err) cudaFreeHost(h_err);
+  h_err = nullptr;
   cached.clear();
   cached_generation = ~0ull;
 }
@@ -85,8 +115,13 @@ static int split_percent(int kind)
 // mixed batch fill the tail of every pass), every group's tiles consecutive.
 int TdecEngine::prepare(TdecWorkspace& w, const std::vector<TdecGroupSpec>& groups, cudaStream_t stream)
 {
-  if (w.arena.reserve(workspace_bytes(groups)) != B200_SUCCESS) return B200_ERROR;
-  if (w.cached_generation == w.arena.generation && w.cached == groups && w.plan.v.tiles != nullptr) {
+  const bool with_int16 = !w.int16_on_demand || w.have_int16;
+  if (w.arena.reserve(workspace_bytes(groups, with_int16)) != B200_SUCCESS) return B200_ERROR;
+  if (w.int16_on_demand && !w.h_err) {
+    B200_CUDA_TRY(cudaHostAlloc(&w.h_err, sizeof(uint32_t), cudaHostAllocDefault));
+    *w.h_err = 0;
+  }
+  if (w.cached_generation == w.arena.generation && w.cached == groups && w.cached_int16 == with_int16 && w.plan.v.tiles != nullptr) {
     return B200_SUCCESS; // same batch shape in the same memory: the descriptors on the device are still right
   }
   std::vector<uint32_t> order(groups.size());
@@ -114,6 +149,10 @@ int TdecEngine::prepare(TdecWorkspace& w, const std::vector<TdecGroupSpec>& grou
   p.groups        = (TileGroup*)a.take(groups.size() * sizeof(TileGroup));
   p.plans         = (GroupPlan*)a.take(groups.size() * sizeof(GroupPlan));
   p.v.fmt         = (uint32_t*)a.take(ntiles * sizeof(uint32_t));
+  p.v.err         = (uint32_t*)a.take(sizeof(uint32_t));
+  p.v.ctl         = (uint32_t*)a.take(TDEC_CTL_WORDS * sizeof(uint32_t));
+  p.v.ll_ck_slot  = (uint32_t)(max_K / 8) * 64u;
+  p.v.ll_ck       = (u4*)a.take((size_t)std::min<size_t>(ntiles, (size_t)sm_count) * p.v.ll_ck_slot * sizeof(u4));
   p.mask          = (uint32_t*)a.take(ntiles * sizeof(uint32_t));
   p.pref          = (uint32_t*)a.take(ntiles * sizeof(uint32_t));
   p.move_counter  = (uint32_t*)a.take(sizeof(uint32_t));
@@ -124,7 +163,7 @@ int TdecEngine::prepare(TdecWorkspace& w, const std::vector<TdecGroupSpec>& grou
   p.v.status      = (CbStatus*)a.take(ntiles * TDEC_TILE_CB * sizeof(CbStatus));
   p.v.HB          = (uint16_t*)a.take(hb_rows * 32 * sizeof(uint16_t));
   p.v.tiles       = d_tiles;
-  if (!d_tiles || !p.groups || !p.plans || !p.v.fmt || !p.mask || !p.pref || !p.move_counter || !p.moves || !p.gsrc || !p.v.S2T || !p.v.lanes ||
+  if (!d_tiles || !p.groups || !p.plans || !p.v.fmt || !p.v.err || !p.v.ctl || !p.v.ll_ck || !p.mask || !p.pref || !p.move_counter || !p.moves || !p.gsrc || !p.v.S2T || !p.v.lanes ||
       !p.v.status || !p.v.HB) {
     B200_LOG_ERROR("decoder workspace too small");
     return B200_ERROR;
@@ -154,12 +193,12 @@ int TdecEngine::prepare(TdecWorkspace& w, const std::vector<TdecGroupSpec>& grou
       d.S8        = (u4*)a.take(rows8);
       d.P08       = (u4*)a.take(rows8);
       d.P18       = (u4*)a.take(rows8);
-      d.S         = (u4*)a.take(vrows);
-      d.P0        = (u4*)a.take(vrows);
-      d.P1        = (u4*)a.take(vrows);
+      d.S         = with_int16 ? (u4*)a.take(vrows) : nullptr;
+      d.P0        = with_int16 ? (u4*)a.take(vrows) : nullptr;
+      d.P1        = with_int16 ? (u4*)a.take(vrows) : nullptr;
       d.E         = (uint32_t*)a.take((size_t)K * 32 * sizeof(uint32_t));
       d.CK        = (u4*)a.take((size_t)(K / 8) * 2 * 32 * sizeof(u4));
-      if (!d.S8 || !d.P08 || !d.P18 || !d.S || !d.P0 || !d.P1 || !d.E || !d.CK) {
+      if (!d.S8 || !d.P08 || !d.P18 || (with_int16 && (!d.S || !d.P0 || !d.P1)) || !d.E || !d.CK) {
         B200_LOG_ERROR("decoder workspace too small");
         return B200_ERROR;
       }
@@ -183,6 +222,7 @@ int TdecEngine::prepare(TdecWorkspace& w, const std::vector<TdecGroupSpec>& grou
   B200_CUDA_TRY(cudaEventRecord(w.uploaded, stream));
   w.cached            = groups;
   w.cached_generation = a.generation;
+  w.cached_int16      = with_int16;
   return B200_SUCCESS;
 }
 
@@ -319,6 +359,14 @@ int TdecEngine::run_groups(TdecWorkspace&                    w,
   const char* min_env    = getenv("SRSLTE_B200_TDEC_COMPACT_MIN_TILES"); // tests: re-pack small batches too
   const int   min_tiles  = min_env ? atoi(min_env) : 2 * sm_count;
   const bool  compact    = early_stop && !no_compact && v.ntiles >= min_tiles;
+  // Which SISO kernel: batches of at most one tile per SM are latency-bound and go to the low-latency kernel (a whole SM per
+  // tile); large early-stop batches start on the throughput kernel and switch when the re-packing finds that few tiles left
+  // (decided on the device: both kernels are launched for every pass and one of them returns at once).
+  const char* ll_env = getenv("SRSLTE_B200_TDEC_LL"); // "0": never, "1": always (comparison runs and tests)
+  int         mode   = v.ntiles <= sm_count ? SISO_LOW_LATENCY : (compact ? SISO_AUTO : SISO_THROUGHPUT);
+  if (ll_env && ll_env[0] == '0') mode = SISO_THROUGHPUT;
+  if (ll_env && ll_env[0] == '1') mode = SISO_LOW_LATENCY;
+  B200_CUDA_TRY(cudaMemsetAsync(v.ctl, 0, TDEC_CTL_WORDS * sizeof(uint32_t), stream));
 
   prof_begin(0, stream);
   launch_load_natural(v, p.max_K, llr_dev, llr_offsets_dev, aligned8, stream);
@@ -327,12 +375,12 @@ int TdecEngine::run_groups(TdecWorkspace&                    w,
   for (uint32_t ps = 0; ps < max_passes; ps++) {
     prof_begin(1, stream);
     v.split_percent = split_percent(ps == 0 ? 0 : ((ps & 1) ? 1 : 2)); // the checkpoints are per-pass scratch: each kind of pass splits where it balances
-    launch_siso_pass(v, (int)ps, stream);
+    launch_siso_pass(v, (int)ps, mode, sm_count, stream);
     prof_end(stream);
-    g_kernel_launches++;
+    g_kernel_launches += mode == SISO_AUTO ? 2 : 1;
     if (compact && ps + 1 < max_passes) {
       prof_begin(3, stream);
-      launch_compact(v, p.groups, p.ngroups, p.mask, p.pref, p.plans, p.moves, p.move_counter, p.gsrc, min_env ? 0u : 4u, sm_count, stream);
+      launch_compact(v, p.groups, p.ngroups, p.mask, p.pref, p.plans, p.moves, p.move_counter, p.gsrc, min_env ? 0u : 4u, mode == SISO_AUTO ? (uint32_t)sm_count : 0u, sm_count, stream);
       prof_end(stream);
       g_kernel_launches += 4;
     }
@@ -341,6 +389,7 @@ int TdecEngine::run_groups(TdecWorkspace&                    w,
   launch_decide(v, p.max_K, out_dev, crc_ok_dev, npass_dev, nullptr, stream);
   prof_end(stream);
   g_kernel_launches++;
+  if (w.h_err) B200_CUDA_TRY(cudaMemcpyAsync(w.h_err, v.err, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
   B200_CUDA_TRY(cudaGetLastError());
   return B200_SUCCESS;
 }

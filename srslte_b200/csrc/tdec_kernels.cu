@@ -6,6 +6,7 @@
 //   tdec_decide_kernel         HB (visiting order of the last pass)  ->  packed bytes, natural order
 //                              (turbodecoder.c:370-378 + turbodecoder_gen.c:260-277)
 #include <cuda_runtime.h>
+#include <stdio.h>
 #include <stdlib.h>
 
 #include <algorithm>
@@ -341,15 +342,367 @@ __device__ __forceinline__ void siso_pass_tile(const TdecView& v, int pass_idx, 
 // One launch per pass; a CTA takes the int8 or the int16 code path according to its tile's format (which tiles are
 // which is only known on the device, after the load kernels ran).
 template <bool DEC2, bool FIRST>
-__global__ void __maxnreg__(128) tdec_siso_pass_kernel(TdecView v, int pass_idx)
+__global__ void __maxnreg__(128) tdec_siso_pass_kernel(TdecView v, int pass_idx, int unless_flagged)
 {
   extern __shared__ __align__(128) uint8_t smem[];
   __shared__ LaneResult xres[32];
   if ((int)blockIdx.x >= v.ntiles) return;
-  if (v.fmt[blockIdx.x] == 0u) {
+  if (unless_flagged && v.ctl[TDEC_CTL_USE_LL] != 0u) return; // the low-latency kernel, launched beside this one, owns the pass
+  if (v.fmt[blockIdx.x] == 0u || v.tiles[blockIdx.x].S == nullptr) {
     siso_pass_tile<DEC2, FIRST, true>(v, pass_idx, smem, xres);
   } else {
     siso_pass_tile<DEC2, FIRST, false>(v, pass_idx, smem, xres);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Low-latency SISO pass: the same arithmetic, bit for bit, for batches that cannot fill the GPU with tiles (a single
+// subframe's 13 code blocks are ONE tile; the last passes of an early-stop decode concern a handful of blocks).  There a
+// pass of the kernel above is bound by the latency of its two warps: each runs its recursion AND the 7x heavier window
+// work (rebuild + LLR) one window after the other, ~0.45 ms per K=6144 pass however empty the GPU is.
+//
+// Here a tile gets a whole SM: 16 warps.  Only the two recursions are sequential, so
+//   warp 0  runs the forward recursion over ALL windows and leaves alpha_{8w}   for every window  (CKA, a per-block scratch)
+//   warp 1  runs the tail + backward recursion over ALL windows, leaving beta_{8w+8} (un-normalised) (CKB = the tile's CK)
+// and every window w whose two checkpoints exist is an independent piece of work -- rebuild its 8 beta vectors from CKB[w],
+// 8 forward steps from CKA[w] with LLR output: exactly fwd_window() of the throughput kernel -- taken by whichever warp
+// is free (the two recursion warps join when they are done).  The fronts meet in the middle of the trellis, so the work
+// is handed out from the middle outwards.  4 recursions per step instead of 3 and twice the checkpoint traffic: worth it
+// only when tiles are scarce (srsran_b200 engine: batches of at most one tile per SM, and the tail passes of an
+// early-stop decode once the running blocks have been re-packed into that few tiles).
+// The extrinsic array is updated in place like above: window w's rows are written by its worker only after BOTH
+// recursions have consumed window w (doneA > w, doneB <= w), and no other window reads or writes those rows.
+namespace ll {
+constexpr int WARPS = 16;
+template <bool DEC2, bool IN8>
+struct Lay {
+  static constexpr uint32_t SP      = IN8 ? 512u : 1024u;
+  static constexpr uint32_t OFF_P   = 0;
+  static constexpr uint32_t OFF_S   = SP;
+  static constexpr uint32_t OFF_E   = DEC2 ? SP : 2 * SP;
+  static constexpr uint32_t OFF_CKA = OFF_E + 1024;
+  static constexpr uint32_t OFF_CKB = OFF_CKA + 1024;
+  static constexpr uint32_t OFF_CRC = OFF_CKB + 1024;
+  static constexpr uint32_t OFF_QPP = OFF_CRC + 64;
+  static constexpr uint32_t BYTES   = (OFF_QPP + 16 + 127) / 128 * 128;
+  static_assert(2 * BYTES <= 2 * 5248, "two worker stages per warp");
+};
+// a recursion warp alone on its issue port consumes a window every few hundred cycles: it needs its inputs requested a
+// whole memory latency ahead, so its ring is deep (32 KB: 10-21 stages of P | S | E) while a worker warp's two stages are small
+constexpr uint32_t REC_RING    = 32768;
+constexpr uint32_t WORKER_RING = 2 * 5248; // two stages of the largest worker layout (int16 tiles, DEC1)
+constexpr uint32_t SMEM_BYTES  = 2 * REC_RING + (WARPS - 2) * WORKER_RING;
+template <bool DEC2, bool FIRST, bool IN8>
+struct RecLay {
+  static constexpr uint32_t SP    = IN8 ? 512u : 1024u;
+  static constexpr uint32_t OFF_P = 0;
+  static constexpr uint32_t OFF_S = SP;
+  static constexpr uint32_t OFF_E = DEC2 ? SP : 2 * SP;
+  static constexpr uint32_t BYTES = (OFF_E + (FIRST ? 0u : 1024u) + 127) / 128 * 128;
+  static constexpr int      NST   = (int)(REC_RING / BYTES) > 24 ? 24 : (int)(REC_RING / BYTES);
+};
+struct Shared {
+  volatile int doneA; // windows [0, doneA) consumed by the forward recursion, CKA[0 .. doneA-1] stored
+  volatile int doneB; // windows [doneB, nw) consumed by the backward recursion, CKB[doneB-1 .. nw-1] stored (doneB-1 >= 0)
+  int          cur_up, cur_dn;
+  int          tile;
+  LaneResult   xres[WARPS][32];
+};
+} // namespace ll
+
+template <bool DEC2, bool FIRST, bool IN8>
+__device__ __forceinline__ void ll_pass_tile(const TdecView& v, int tile, int pass_idx, uint8_t* smem, ll::Shared& sh, u4* cka, int debug)
+{
+  const long long t_start = clock64();
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const LaneMap lm   = v.lanes[(size_t)tile * 32 + lane];
+  const bool    held = lm.st0 != LANE_EMPTY;
+  CbStatus*     stp  = v.status + (held ? lm.st0 : 0u);
+  const bool act_lo = held && stp[0].active != 0, act_hi = held && stp[1].active != 0;
+  if (__ballot_sync(0xFFFFFFFFu, act_lo || act_hi) == 0u) return; // every warp sees the same lanes: uniform over the thread block
+
+  using RG = WarpRing<DEC2, FIRST, IN8>;
+  using WL = ll::Lay<DEC2, IN8>;
+  const TileDesc& td  = v.tiles[tile];
+  const uint32_t  K   = td.K;
+  const int       nw  = (int)(K / 8u);
+  const bool      have_crc = (DEC2 ? td.crc_perm : td.crc_nat) != nullptr;
+  const uint16_t* qpp_fwd  = td.qpp_fwd;
+  // shared memory: two deep rings for the recursion warps (re-used as their worker stages afterwards), then the workers' stages
+  uint8_t*        my_smem  = warp < 2 ? smem + warp * ll::REC_RING : smem + 2 * ll::REC_RING + (warp - 2) * ll::WORKER_RING;
+  RG              rg(v, td, my_smem, lane, lm.hb0);
+  uint8_t*        gCKA = reinterpret_cast<uint8_t*>(cka);
+
+  if (threadIdx.x == 0) {
+    sh.doneA  = 0;
+    sh.doneB  = nw;
+    sh.cur_up = nw / 2;
+    sh.cur_dn = nw / 2 - 1;
+  }
+  __syncthreads();
+
+  WinRegs  r;
+  uint32_t M[8];
+  if (warp < 2) {
+    // ---- the two sequential recursions, each streamed through its own deep ring -----------------------------------------
+    using RL = ll::RecLay<DEC2, FIRST, IN8>;
+    constexpr int      NST  = RL::NST;
+    constexpr uint32_t WB   = IN8 ? 512u : 1024u;
+    const uint32_t     rb   = smem_u32(my_smem);
+    const uint32_t     l16r = (uint32_t)lane * 16u, l4r = (uint32_t)lane * 4u;
+    const int     dir = warp == 0 ? +1 : -1;
+    int           nxt = warp == 0 ? 0 : nw - 1, left = nw;
+    int           fill = 0, drain = 0;
+    u4            qn  = {};
+    M[0] = 0;
+#pragma unroll
+    for (int i = 1; i < 8; i++) M[i] = NEG_INF2;
+    if (warp == 1) {
+      const u4 pt = *reinterpret_cast<const u4*>(rg.tP + ((uint32_t)nw * WB + rg.l16));
+      if (DEC2) {
+        const u4 s2 = v.S2T[(size_t)tile * 32 + lane];
+#pragma unroll
+        for (int t = 2; t >= 0; t--) {
+          const u4       pq[2] = {pt, pt};
+          const uint32_t x = u4_get(s2, t), y = win_val<IN8>(pq, t);
+          beta_step(M, x, y, add2(x, y));
+        }
+      } else {
+        const u4 stl = *reinterpret_cast<const u4*>(rg.tS + ((uint32_t)nw * WB + rg.l16));
+        beta_tail<IN8>(M, stl, pt);
+      }
+      rg.store_ck((uint32_t)(nw - 1), M); // CKB[nw-1] = beta_K
+    }
+    if (DEC2 && !FIRST) qn = ldg_q(qpp_fwd, (uint32_t)nxt);
+    auto issue_next = [&]() {
+      if (left > 0) {
+        const uint32_t st = rb + (uint32_t)fill * RL::BYTES, uw = (uint32_t)nxt;
+        cp16(st + RL::OFF_P + l16r, rg.tP + (uw * WB + l16r));
+        if (!IN8) cp16(st + RL::OFF_P + 512u + l16r, rg.tP + (uw * WB + 512u + l16r));
+        if (!DEC2) {
+          cp16(st + RL::OFF_S + l16r, rg.tS + (uw * WB + l16r));
+          if (!IN8) cp16(st + RL::OFF_S + 512u + l16r, rg.tS + (uw * WB + 512u + l16r));
+        }
+        if (!FIRST) {
+          if (!DEC2) {
+            cp16(st + RL::OFF_E + l16r, rg.tE + (uw * 1024u + l16r));
+            cp16(st + RL::OFF_E + 512u + l16r, rg.tE + (uw * 1024u + 512u + l16r));
+          } else {
+            const u4 q = qn;
+            if (left > 1) qn = ldg_q(qpp_fwd, (uint32_t)(nxt + dir));
+#pragma unroll
+            for (int t = 0; t < 8; t++) cp4(st + RL::OFF_E + (uint32_t)t * 128u + l4r, rg.tE + (win_pi(q, t) * 128u + l4r));
+          }
+        }
+        fill = fill + 1 == NST ? 0 : fill + 1;
+        nxt += dir;
+        left--;
+      }
+      cp_commit();
+    };
+#pragma unroll 1
+    for (int i = 0; i < NST; i++) issue_next();
+    int w = warp == 0 ? 0 : nw - 1;
+#pragma unroll 1
+    for (int n = 0; n < nw; n++, w += dir) {
+      cp_wait<NST - 1>();
+      __syncwarp();
+      const uint8_t* st = my_smem + (uint32_t)drain * RL::BYTES;
+      drain             = drain + 1 == NST ? 0 : drain + 1;
+      {
+        u4       sv[2] = {}, pv[2] = {};
+        uint32_t e[8] = {};
+        pv[0] = *reinterpret_cast<const u4*>(st + RL::OFF_P + l16r);
+        if (!IN8) pv[1] = *reinterpret_cast<const u4*>(st + RL::OFF_P + 512 + l16r);
+        if (!DEC2) {
+          sv[0] = *reinterpret_cast<const u4*>(st + RL::OFF_S + l16r);
+          if (!IN8) sv[1] = *reinterpret_cast<const u4*>(st + RL::OFF_S + 512 + l16r);
+        }
+        if (!FIRST) {
+#pragma unroll
+          for (int t = 0; t < 8; t++) e[t] = *reinterpret_cast<const uint32_t*>(st + RL::OFF_E + t * 128 + l4r);
+        }
+        win_unpack<DEC2, FIRST, IN8>(r, sv, pv, e);
+      }
+      if (warp == 0) {
+        // CKA[w] = alpha_{8w}, same [half][lane] rows as the tile's own checkpoint array
+        *reinterpret_cast<u4*>(gCKA + ((uint32_t)w * 1024u + rg.l16))        = u4{M[0], M[1], M[2], M[3]};
+        *reinterpret_cast<u4*>(gCKA + ((uint32_t)w * 1024u + 512u + rg.l16)) = u4{M[4], M[5], M[6], M[7]};
+        alpha_window(M, r);
+      } else {
+        beta_window(M, r);
+        if (w > 0) {
+          rg.store_ck((uint32_t)(w - 1), M);
+          normalise(M);
+        }
+      }
+      __syncwarp(); // every lane has consumed the stage before it is refilled
+      issue_next();
+      if ((n & 3) == 3 || n == nw - 1) { // publish the progress every four windows: stores first, then the counter
+        __threadfence_block();
+        if (lane == 0) {
+          if (warp == 0) sh.doneA = w + 1;
+          else sh.doneB = w;
+        }
+      }
+    }
+    cp_wait<0>();
+    __syncwarp();
+    if (debug && lane == 0 && blockIdx.x == 0) printf("[ll] pass %d tile %d warp %d: recursion over %d windows took %lld cycles\n", pass_idx, tile, warp, nw, clock64() - t_start);
+  }
+
+  // ---- window work, handed out from the middle of the trellis outwards ---------------------------------------------------
+  const uint32_t sbase = smem_u32(my_smem);
+  const uint32_t l16 = (uint32_t)lane * 16u, l4 = (uint32_t)lane * 4u;
+  const uint8_t* gCRC = reinterpret_cast<const uint8_t*>(DEC2 ? td.crc_perm : td.crc_nat);
+  LaneResult     res  = {0u, 0u};
+  auto grab = [&]() -> int {
+    int w = -1;
+    if (lane == 0) {
+      if (warp & 1) {
+        w = atomicAdd(&sh.cur_up, 1);
+        if (w >= nw) {
+          w = atomicSub(&sh.cur_dn, 1);
+          if (w < 0) w = -1;
+        }
+      } else {
+        w = atomicSub(&sh.cur_dn, 1);
+        if (w < 0) {
+          w = atomicAdd(&sh.cur_up, 1);
+          if (w >= nw) w = -1;
+        }
+      }
+    }
+    return __shfl_sync(0xFFFFFFFFu, w, 0);
+  };
+  // waits until both recursions are past window w, then enqueues everything the window needs into stage `s`
+  auto fetch = [&](int w, int s) {
+    while (!(sh.doneA > w && sh.doneB <= w)) __nanosleep(200);
+    __threadfence_block(); // the checkpoints were written (and fenced) by the recursion warps before they raised the counters
+    __syncwarp();
+    const uint32_t     st = sbase + (uint32_t)s * WL::BYTES;
+    constexpr uint32_t WB = IN8 ? 512u : 1024u;
+    const uint32_t     uw = (uint32_t)w;
+    cp16(st + WL::OFF_P + l16, rg.tP + (uw * WB + l16));
+    if (!IN8) cp16(st + WL::OFF_P + 512u + l16, rg.tP + (uw * WB + 512u + l16));
+    if (!DEC2) {
+      cp16(st + WL::OFF_S + l16, rg.tS + (uw * WB + l16));
+      if (!IN8) cp16(st + WL::OFF_S + 512u + l16, rg.tS + (uw * WB + 512u + l16));
+    }
+    u4 q = {};
+    if (DEC2) q = ldg_q(qpp_fwd, uw);
+    if (!FIRST) {
+      if (!DEC2) {
+        cp16(st + WL::OFF_E + l16, rg.tE + (uw * 1024u + l16));
+        cp16(st + WL::OFF_E + 512u + l16, rg.tE + (uw * 1024u + 512u + l16));
+      } else {
+#pragma unroll
+        for (int t = 0; t < 8; t++) cp4(st + WL::OFF_E + (uint32_t)t * 128u + l4, rg.tE + (win_pi(q, t) * 128u + l4));
+      }
+    }
+    cp16(st + WL::OFF_CKA + l16, gCKA + (uw * 1024u + l16));
+    cp16(st + WL::OFF_CKA + 512u + l16, gCKA + (uw * 1024u + 512u + l16));
+    cp16(st + WL::OFF_CKB + l16, rg.tCK + (uw * 1024u + l16));
+    cp16(st + WL::OFF_CKB + 512u + l16, rg.tCK + (uw * 1024u + 512u + l16));
+    if (gCRC != nullptr && l16 < 64u) cp16(st + WL::OFF_CRC + l16, gCRC + (uw * 64u + l16));
+    if (DEC2 && lane == 0) *reinterpret_cast<u4*>(my_smem + (uint32_t)s * WL::BYTES + WL::OFF_QPP) = q;
+    cp_commit();
+  };
+  // Warps share an issue port four by four (warp id mod 4).  The recursions are the critical path of the pass, so the worker
+  // warps that sit on the recursion warps' ports stay out of their way until the recursion there is finished; the workers on
+  // the other two ports start as soon as the fronts have crossed.
+  if (warp >= 2 && (warp & 3) == 0) {
+    while (sh.doneA < nw) __nanosleep(400);
+  } else if (warp >= 2 && (warp & 3) == 1) {
+    while (sh.doneB > 0) __nanosleep(400);
+  }
+  int cur = grab(), s = 0;
+  if (cur >= 0) fetch(cur, 0);
+#pragma unroll 1
+  while (cur >= 0) {
+    const int nxt = grab();
+    if (nxt >= 0) fetch(nxt, s ^ 1); // the next window's data travels while this one is worked on
+    if (nxt >= 0) cp_wait<1>();
+    else cp_wait<0>();
+    __syncwarp();
+    const uint8_t* st = my_smem + (uint32_t)s * WL::BYTES;
+    {
+      u4       sv[2] = {}, pv[2] = {};
+      uint32_t e[8] = {};
+      pv[0] = *reinterpret_cast<const u4*>(st + WL::OFF_P + l16);
+      if (!IN8) pv[1] = *reinterpret_cast<const u4*>(st + WL::OFF_P + 512 + l16);
+      if (!DEC2) {
+        sv[0] = *reinterpret_cast<const u4*>(st + WL::OFF_S + l16);
+        if (!IN8) sv[1] = *reinterpret_cast<const u4*>(st + WL::OFF_S + 512 + l16);
+      }
+      if (!FIRST) {
+#pragma unroll
+        for (int t = 0; t < 8; t++) e[t] = *reinterpret_cast<const uint32_t*>(st + WL::OFF_E + t * 128 + l4);
+      }
+      win_unpack<DEC2, FIRST, IN8>(r, sv, pv, e);
+    }
+    uint32_t c[8];
+    {
+      const u4 a0 = *reinterpret_cast<const u4*>(st + WL::OFF_CKA + l16), a1 = *reinterpret_cast<const u4*>(st + WL::OFF_CKA + 512 + l16);
+      const u4 b0 = *reinterpret_cast<const u4*>(st + WL::OFF_CKB + l16), b1 = *reinterpret_cast<const u4*>(st + WL::OFF_CKB + 512 + l16);
+      M[0] = a0.x; M[1] = a0.y; M[2] = a0.z; M[3] = a0.w; M[4] = a1.x; M[5] = a1.y; M[6] = a1.z; M[7] = a1.w;
+      c[0] = b0.x; c[1] = b0.y; c[2] = b0.z; c[3] = b0.w; c[4] = b1.x; c[5] = b1.y; c[6] = b1.z; c[7] = b1.w;
+    }
+    u4 q = {};
+    if (DEC2) q = *reinterpret_cast<const u4*>(st + WL::OFF_QPP);
+    WinOut         o;
+    const uint32_t uw = (uint32_t)cur;
+    fwd_window(M, c, 8u * uw + 8u < K, r, have_crc ? reinterpret_cast<const CrcPow*>(st + WL::OFF_CRC) : nullptr, res, o,
+               [&](int t, uint32_t L) {
+                 uint32_t ein = 0u;
+                 if (!FIRST) {
+                   if (DEC2) ein = r.xs[t];
+                   else asm volatile("ld.shared.u32 %0, [%1];" : "=r"(ein) : "r"(smem_u32(st) + WL::OFF_E + (uint32_t)t * 128u + l4));
+                 }
+                 *rg.e_out(uw, q, t) = sub2(L, ein);
+               });
+    rg.store_hb(uw, o.bits, act_lo, act_hi);
+    __syncwarp(); // every lane is done with this stage before it is refilled
+    cur = nxt;
+    s ^= 1;
+  }
+  sh.xres[warp][lane] = res;
+  if (debug && lane == 0 && blockIdx.x == 0) printf("[ll] pass %d tile %d warp %d: done after %lld cycles\n", pass_idx, tile, warp, clock64() - t_start);
+  __syncthreads();
+  if (warp == 0) {
+    LaneResult tot = {0u, 0u};
+#pragma unroll
+    for (int i = 0; i < ll::WARPS; i++) {
+      tot.crc_lo16x2 ^= sh.xres[i][lane].crc_lo16x2;
+      tot.crc_hi8x2 ^= sh.xres[i][lane].crc_hi8x2;
+    }
+    finish_pass(v, have_crc, stp, stp[0], stp[1], act_lo, act_hi, tot, pass_idx);
+  }
+  __syncthreads(); // the shared control block is reused by the next tile
+}
+
+// Thread blocks take tiles from a queue (TDEC_CTL_LL_QUEUE): a batch of mixed lengths is ordered longest first and the
+// running tiles of an early-stop decode sit anywhere.  only_if_flagged: run only when the device decided that the pass
+// belongs to this kernel (TDEC_CTL_USE_LL); the throughput kernel, launched beside it, then returns at once.
+template <bool DEC2, bool FIRST>
+__global__ void __launch_bounds__(ll::WARPS * 32, 1) tdec_siso_pass_ll_kernel(TdecView v, int pass_idx, int only_if_flagged)
+{
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ ll::Shared sh;
+  if ((only_if_flagged & 1) && v.ctl[TDEC_CTL_USE_LL] == 0u) return;
+  u4* cka = v.ll_ck + (size_t)blockIdx.x * v.ll_ck_slot;
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) sh.tile = (int)atomicAdd(v.ctl + TDEC_CTL_LL_QUEUE, 1u);
+    __syncthreads();
+    const int tile = sh.tile;
+    if (tile >= v.ntiles) return;
+    if (v.fmt[tile] == 0u || v.tiles[tile].S == nullptr) {
+      ll_pass_tile<DEC2, FIRST, true>(v, tile, pass_idx, smem, sh, cka, only_if_flagged & 2);
+    } else {
+      ll_pass_tile<DEC2, FIRST, false>(v, tile, pass_idx, smem, sh, cka, only_if_flagged & 2);
+    }
   }
 }
 
@@ -365,6 +718,10 @@ static void siso_set_attributes()
     cudaFuncSetAttribute(tdec_siso_pass_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(tdec_siso_pass_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     cudaFuncSetAttribute(tdec_siso_pass_kernel<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    const int ll_smem = (int)ll::SMEM_BYTES;
+    cudaFuncSetAttribute(tdec_siso_pass_ll_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ll_smem);
+    cudaFuncSetAttribute(tdec_siso_pass_ll_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ll_smem);
+    cudaFuncSetAttribute(tdec_siso_pass_ll_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, ll_smem);
   }
 }
 
@@ -378,17 +735,36 @@ int siso_resident_tiles_per_sm()
   return n;
 }
 
-void launch_siso_pass(const TdecView& v, int pass_idx, cudaStream_t stream)
+// mode: SISO_THROUGHPUT (two warps per tile, every tile its own thread block), SISO_LOW_LATENCY (16 warps per tile, one
+// thread block per SM) or SISO_AUTO (both are launched and the device's TDEC_CTL_USE_LL flag says which one works)
+void launch_siso_pass(const TdecView& v, int pass_idx, int mode, int sm_count, cudaStream_t stream)
 {
-  const size_t smem = 2 * ring::RING_BYTES;
-  dim3         grid((unsigned)v.ntiles), block(64);
   siso_set_attributes();
-  if (pass_idx == 0) {
-    tdec_siso_pass_kernel<false, true><<<grid, block, smem, stream>>>(v, pass_idx);
-  } else if (pass_idx & 1) {
-    tdec_siso_pass_kernel<true, false><<<grid, block, smem, stream>>>(v, pass_idx);
-  } else {
-    tdec_siso_pass_kernel<false, false><<<grid, block, smem, stream>>>(v, pass_idx);
+  if (mode != SISO_LOW_LATENCY) {
+    const size_t smem = 2 * ring::RING_BYTES;
+    dim3         grid((unsigned)v.ntiles), block(64);
+    const int    unless = mode == SISO_AUTO;
+    if (pass_idx == 0) {
+      tdec_siso_pass_kernel<false, true><<<grid, block, smem, stream>>>(v, pass_idx, unless);
+    } else if (pass_idx & 1) {
+      tdec_siso_pass_kernel<true, false><<<grid, block, smem, stream>>>(v, pass_idx, unless);
+    } else {
+      tdec_siso_pass_kernel<false, false><<<grid, block, smem, stream>>>(v, pass_idx, unless);
+    }
+  }
+  if (mode != SISO_THROUGHPUT) {
+    const size_t smem = ll::SMEM_BYTES;
+    dim3         grid((unsigned)std::min(v.ntiles, sm_count)), block(ll::WARPS * 32);
+    static const bool ll_debug = getenv("SRSLTE_B200_TDEC_LL_DEBUG") != nullptr; // cycle stamps of the first thread block (printf)
+    const int    only = (mode == SISO_AUTO ? 1 : 0) | (ll_debug ? 2 : 0);
+    cudaMemsetAsync(v.ctl + TDEC_CTL_LL_QUEUE, 0, sizeof(uint32_t), stream);
+    if (pass_idx == 0) {
+      tdec_siso_pass_ll_kernel<false, true><<<grid, block, smem, stream>>>(v, pass_idx, only);
+    } else if (pass_idx & 1) {
+      tdec_siso_pass_ll_kernel<true, false><<<grid, block, smem, stream>>>(v, pass_idx, only);
+    } else {
+      tdec_siso_pass_ll_kernel<false, false><<<grid, block, smem, stream>>>(v, pass_idx, only);
+    }
   }
 }
 
@@ -407,6 +783,14 @@ constexpr size_t LOAD_SMEM = (size_t)TDEC_TILE_CB * RAW_PITCH;
 __device__ __forceinline__ bool fits8(int16_t a)
 {
   return (int16_t)(int8_t)a == a;
+}
+
+// A value of the tile does not fit int8: the tile goes to the int16 arrays -- or, when the workspace was carved without them
+// (int16 on demand), the batch is flagged so that the host repeats it with them.
+__device__ __forceinline__ void raise_int16(const TdecView& v, const TileDesc& td, int tile)
+{
+  atomicOr(v.fmt + tile, 1u);
+  if (td.S == nullptr) atomicOr(v.err, 1u);
 }
 
 // Source of block c (0..63) of a tile: `offsets` (optional) holds the int16 offset of every block's vector inside llr,
@@ -489,7 +873,7 @@ __device__ __forceinline__ void load_tail_and_arm(const TdecView& v, const TileD
       if (s_ < 3) bad |= !fits8(a0) || !fits8(b0); // S2T stays int16
     }
   }
-  if (__any_sync(0xFFFFFFFFu, bad) && lane == 0) atomicOr(v.fmt + tile, 1u);
+  if (__any_sync(0xFFFFFFFFu, bad) && lane == 0) raise_int16(v, td, tile);
 #pragma unroll
   for (int s_ = 0; s_ < 3; s_++) {
     uint32_t w[4] = {0u, 0u, 0u, 0u};
@@ -525,7 +909,7 @@ __global__ void __launch_bounds__(256)
   if (k0 < K) {
     const int  rows = min(LOAD_ROWS, K - k0); // multiple of 8
     const bool ok   = load_stage_chunk<ALIGNED8>(sm, td, llr, offsets, k0, rows);
-    if (!ok && tid == 0) atomicOr(v.fmt + tile, 1u);
+    if (!ok && tid == 0) raise_int16(v, td, tile);
     // warp = window of the chunk; a lane reads the 48 bytes of its two blocks, pairs and packs them with byte permutes
     // and writes its 16 bytes of each int8 tile row
     const int lane = tid & 31;
@@ -569,6 +953,7 @@ __global__ void __launch_bounds__(256)
   const int tile = item / max_chunks, chunk = item % max_chunks;
   if (v.fmt[tile] == 0u) continue; // the tile lives in the int8 arrays
   const TileDesc& td = v.tiles[tile];
+  if (td.S == nullptr) continue;   // no int16 arrays in this workspace: the batch is flagged (v.err) and repeated by the host
   const int       K  = (int)td.K;
   const int       k0 = chunk * LOAD_ROWS;
   if (chunk > (K + LOAD_ROWS - 1) / LOAD_ROWS) continue;
@@ -709,7 +1094,7 @@ __global__ void __launch_bounds__(256)
       }
     }
   }
-  if (__syncthreads_or((acc & 0xFF00FF00u) != 0u) && tid == 0) atomicOr(v.fmt + tile, 1u);
+  if (__syncthreads_or((acc & 0xFF00FF00u) != 0u) && tid == 0) raise_int16(v, td, tile);
 
   // the tile's last segment also writes the tail row and arms the block state
   if (seg == nseg - 1 && tid < 32) load_tail_and_arm(v, td, tile, llr, offsets, lane);
@@ -739,6 +1124,7 @@ void launch_load_natural(const TdecView& v,
     cudaFuncSetAttribute(tdec_load8_stream_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   }
   cudaMemsetAsync(v.fmt, 0, (size_t)v.ntiles * sizeof(uint32_t), stream);
+  cudaMemsetAsync(v.err, 0, sizeof(uint32_t), stream);
   if (aligned8) {
     const int nchunk = (max_K + LOAD_ROWS - 1) / LOAD_ROWS;
     dim3      gs((unsigned)((nchunk + LS_CHUNKS - 1) / LS_CHUNKS), (unsigned)v.ntiles);
@@ -861,7 +1247,7 @@ __global__ void __launch_bounds__(256) tdec_compact_scan_kernel(TdecView v, uint
 __global__ void __launch_bounds__(256) tdec_compact_plan_kernel(TdecView v, const TileGroup* __restrict__ groups, const uint32_t* __restrict__ mask,
                                                                 uint32_t* __restrict__ pref, GroupPlan* __restrict__ plans,
                                                                 MoveRec* __restrict__ moves, uint32_t* __restrict__ move_counter,
-                                                                uint32_t move_cap, uint32_t min_gain_tiles)
+                                                                uint32_t move_cap, uint32_t min_gain_tiles, uint32_t ll_max_tiles)
 {
   __shared__ uint32_t  part[256];
   __shared__ uint32_t  red_run[8], red_last[8], red_int8[8];
@@ -898,8 +1284,22 @@ __global__ void __launch_bounds__(256) tdec_compact_plan_kernel(TdecView v, cons
   }
   const uint32_t need = (running + 31u) / 32u;
   const bool     go   = all_int8 && tiles_now >= need + min_gain_tiles && 5u * need <= 3u * tiles_now && tiles_now > need;
+  // Tiles that still hold running lanes after this round, summed over the groups by whichever block finishes last: few
+  // enough of them and the next pass goes to the low-latency kernel (TDEC_CTL_USE_LL).
+  auto account = [&](uint32_t tiles_left) {
+    atomicAdd(v.ctl + TDEC_CTL_TILES_LEFT, tiles_left);
+    __threadfence();
+    if (atomicAdd(v.ctl + TDEC_CTL_PLAN_DONE, 1u) == gridDim.x - 1u) {
+      const uint32_t total        = atomicExch(v.ctl + TDEC_CTL_TILES_LEFT, 0u);
+      v.ctl[TDEC_CTL_PLAN_DONE]   = 0u;
+      v.ctl[TDEC_CTL_USE_LL]      = (total <= ll_max_tiles) ? 1u : 0u;
+    }
+  };
   if (!go) {
-    if (tid == 0) plans[blockIdx.x] = GroupPlan{need, 0, 0, 0};
+    if (tid == 0) {
+      plans[blockIdx.x] = GroupPlan{need, 0, 0, 0};
+      account(tiles_now);
+    }
     return;
   }
   // running counts: free lane slots over the receiver tiles [0, need), running lanes over the donor tiles [need, tiles_now)
@@ -946,6 +1346,7 @@ __global__ void __launch_bounds__(256) tdec_compact_plan_kernel(TdecView v, cons
     }
     plan              = p;
     plans[blockIdx.x] = p;
+    account(p.go ? need : tiles_now);
   }
   __syncthreads();
   if (!plan.go) return;
@@ -1018,13 +1419,13 @@ __global__ void __launch_bounds__(256) tdec_compact_move_kernel(TdecView v, cons
 
 void launch_compact(const TdecView& v, const TileGroup* groups_dev, uint32_t ngroups, uint32_t* mask_dev, uint32_t* pref_dev,
                     GroupPlan* plans_dev, MoveRec* moves_dev, uint32_t* move_counter_dev, uint32_t* gsrc_dev, uint32_t min_gain_tiles,
-                    int sm_count, cudaStream_t stream)
+                    uint32_t ll_max_tiles, int sm_count, cudaStream_t stream)
 {
   cudaMemsetAsync(move_counter_dev, 0, sizeof(uint32_t), stream);
   cudaMemsetAsync(gsrc_dev, 0xFF, (size_t)v.ntiles * 32 * sizeof(uint32_t), stream); // LANE_EMPTY: every slot keeps what it has
   tdec_compact_scan_kernel<<<(unsigned)((v.ntiles + 7) / 8), 256, 0, stream>>>(v, mask_dev);
   tdec_compact_plan_kernel<<<ngroups, 256, 0, stream>>>(v, groups_dev, mask_dev, pref_dev, plans_dev, moves_dev, move_counter_dev,
-                                                        (uint32_t)v.ntiles * 32u, min_gain_tiles);
+                                                        (uint32_t)v.ntiles * 32u, min_gain_tiles, ll_max_tiles);
   tdec_compact_gsrc_kernel<<<(unsigned)std::min<long>(((long)v.ntiles * 32 + 255) / 256, (long)sm_count * 4), 256, 0, stream>>>(v, moves_dev, move_counter_dev, gsrc_dev);
   tdec_compact_move_kernel<<<dim3((unsigned)v.ntiles, COMPACT_SPLIT), 256, 0, stream>>>(v, groups_dev, plans_dev, gsrc_dev, move_counter_dev);
 }

@@ -14,7 +14,8 @@ void launch_load_natural(const TdecView& v,
                          const uint64_t* offsets_dev, // optional per-block int16 offsets into llr_dev
                          bool            aligned8,    // every block vector starts on an 8-byte boundary
                          cudaStream_t    stream);
-void launch_siso_pass(const TdecView& v, int pass_idx, cudaStream_t stream);
+constexpr int SISO_THROUGHPUT = 0, SISO_LOW_LATENCY = 1, SISO_AUTO = 2;
+void launch_siso_pass(const TdecView& v, int pass_idx, int mode, int sm_count, cudaStream_t stream);
 int  siso_resident_tiles_per_sm();
 void launch_decide(const TdecView& v,
                    int             max_K,
@@ -26,7 +27,7 @@ void launch_decide(const TdecView& v,
 // re-packs the lanes that still run into fewer tiles (two kernels, all decisions on the device)
 void launch_compact(const TdecView& v, const TileGroup* groups_dev, uint32_t ngroups, uint32_t* mask_dev, uint32_t* pref_dev,
                     GroupPlan* plans_dev, MoveRec* moves_dev, uint32_t* move_counter_dev, uint32_t* gsrc_dev, uint32_t min_gain_tiles,
-                    int sm_count, cudaStream_t stream);
+                    uint32_t ll_max_tiles, int sm_count, cudaStream_t stream);
 
 // int8 LLR container -> int16 (sign extension), n values
 void launch_widen_i8(const int8_t* in, int16_t* out, size_t n, cudaStream_t stream);

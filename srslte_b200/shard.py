@@ -46,3 +46,37 @@ def aggregate_throughput(units_per_rank: float, ms_this_rank: float, dist=None, 
     (ms_max,) = reduce_scalars([ms_this_rank], "max", dist, device)
     (units,) = reduce_scalars([units_per_rank], "sum", dist, device)
     return units / (ms_max * 1e-3), ms_max
+
+
+def bind_to_gpu_numa_node(local_rank: int) -> dict:
+    """Pins this process to the CPUs next to its GPU (sysfs: the PCI device's local_cpulist) BEFORE it allocates page-locked
+    host memory, so that the buffers every rank feeds its GPU from live on the memory of the GPU's own NUMA node instead of all
+    ranks sharing node 0.  Returns what was found (reported in the bench line); never fails."""
+    info = {"bound": False}
+    try:
+        import torch
+
+        p = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{getattr(p, 'pci_domain_id', 0):04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        base = f"/sys/bus/pci/devices/{bdf}"
+        info["pci"] = bdf
+        node = open(os.path.join(base, "numa_node")).read().strip()
+        cpus = open(os.path.join(base, "local_cpulist")).read().strip()
+        info["numa_node"], info["local_cpulist"] = int(node), cpus
+        want = set()
+        for part in cpus.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                want.update(range(int(a), int(b) + 1))
+            elif part:
+                want.add(int(part))
+        allowed = os.sched_getaffinity(0)
+        use = want & allowed
+        info["cpus_allowed"] = len(allowed)
+        if use and use != allowed:
+            os.sched_setaffinity(0, use)
+            info["bound"] = True
+            info["cpus_used"] = len(use)
+    except Exception as ex:  # containers often hide sysfs; the benchmark then runs unbound
+        info["note"] = f"not bound: {type(ex).__name__}"
+    return info

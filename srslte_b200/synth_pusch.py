@@ -142,8 +142,23 @@ def _qam(bits: np.ndarray, Qm: int) -> np.ndarray:
     return (i + 1j * q) / nrm
 
 
+_TB_CACHE: dict = {}
+
+
 def make_transport_blocks(tbs: int, Qm: int, G: int, rv: int, qpp: np.ndarray, n: int, seed: int):
-    """n random transport blocks -> (coded bits (n, G) uint8, payload bytes incl. the TB CRC (n, tbs/8+3))."""
+    """n random transport blocks -> (coded bits (n, G) uint8, payload bytes incl. the TB CRC (n, tbs/8+3)).
+    The result for the last few argument sets is kept: the cells of the multi-cell benchmark transmit the same payloads and
+    differ in scrambling, reference signals and noise, so the (slow, pure numpy) turbo encoding runs once."""
+    key = (tbs, Qm, G, rv, n, seed, int(qpp.size))
+    if key in _TB_CACHE:
+        return _TB_CACHE[key]
+    if len(_TB_CACHE) > 4:
+        _TB_CACHE.clear()
+    _TB_CACHE[key] = _make_transport_blocks(tbs, Qm, G, rv, qpp, n, seed)
+    return _TB_CACHE[key]
+
+
+def _make_transport_blocks(tbs: int, Qm: int, G: int, rv: int, qpp: np.ndarray, n: int, seed: int):
     rng = np.random.default_rng(seed)
     C, K = segment(tbs)
     assert qpp.size == K
@@ -250,7 +265,7 @@ def make_pusch_grids(cell_id: int, cell_nof_prb: int, L_prb: int, n_prb: int, tb
 
 
 def make_subframes_full(cell_id: int, nof_prb: int, N: int, tbs: int, Qm: int, rv: int, qpp: np.ndarray, n: int, rnti, tti, dmrs,
-                        snr_db: float, seed: int, fading: bool = True):
+                        snr_db: float, seed: int, fading: bool = True, noise: bool = True, return_gain: bool = False):
     """Time-domain PUSCH subframes through a per-subframe flat complex gain with a small timing offset (linear phase over the
     subcarriers) plus AWGN whose level follows the gain, so that every subframe is received at snr_db.
     Returns (iq (n, 15N) complex64, payload bytes (n, tbs/8+3), G)."""
@@ -265,5 +280,8 @@ def make_subframes_full(cell_id: int, nof_prb: int, N: int, tbs: int, Qm: int, r
         grid = grid * h[:, None, :]
     iq = ofdm_modulate(grid, N).astype(np.complex128)
     sigma_t = 10 ** (-snr_db / 20.0) / np.sqrt(N)
-    iq += (rng.normal(size=iq.shape) + 1j * rng.normal(size=iq.shape)) * (sigma_t / np.sqrt(2.0)) * np.abs(gain)[:, None]
+    if noise:
+        iq += (rng.normal(size=iq.shape) + 1j * rng.normal(size=iq.shape)) * (sigma_t / np.sqrt(2.0)) * np.abs(gain)[:, None]
+    if return_gain:  # (noiseless subframes + per-subframe |gain| and the time-domain noise sigma: the caller adds its own noise)
+        return iq.astype(np.complex64), payload, 12 * R * Qm, np.abs(gain).astype(np.float32), float(sigma_t)
     return iq.astype(np.complex64), payload, 12 * R * Qm

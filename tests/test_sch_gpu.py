@@ -180,3 +180,78 @@ def test_config2_all_188_sizes_in_one_dematch_and_decode_batch(sch, port):
         assert (soft_pool[soff: soff + 3 * K + 12] == soft).all(), K
         n_ok += ret == 0
     assert n_ok > 150  # the point is parity, but most of the batch should decode
+
+
+def test_soft_values_beyond_int8_are_decoded_with_int16_tiles_on_demand(port):
+    """The decode loop's decoder workspace is carved without the int16 copies of the channel LLRs until a batch needs them
+    (int16 on demand): a FRESH object first sees a batch that fits int8, then one whose soft values reach +-400 (the batch is
+    flagged on the device and decoded again with int16 tiles), then an int8 batch again.  Every result must equal the
+    oracle's decode_tb."""
+    from srslte_b200 import SchDecoder
+
+    d = SchDecoder(device=0, max_noi=8)
+    try:
+        for scale, clip, seed in ((16.0, 31, 1), (150.0, 400, 2), (16.0, 31, 3), (150.0, 400, 4)):
+            tbs, Qm, G = 12960, 4, 28800
+            e, _, s = make_tb(port, tbs, Qm, G, 0, 0.7, scale=scale, clip=clip, seed=seed)
+            assert np.abs(e).max() == clip
+            soft = np.zeros(s["C"] * SB, np.int16)
+            cbcrc = np.zeros(s["C"], np.uint8)
+            want = np.zeros(tbs // 8 + 3 + 768, np.uint8)
+            ret, iters = port.decode_tb(e, tbs, Qm, 0, 8, soft, cbcrc, want)
+            soft_pool = np.zeros(s["C"] * SB, np.int16)
+            data = np.zeros(tbs // 8 + 3 + 1024, np.uint8)
+            rc, res = d.decode(e, soft_pool, data, [dict(tbs=tbs, Qm=Qm, rv=0, nof_e_bits=G, e_offset=0, soft_offset=0, data_offset=0)])
+            assert rc == 0 and res[0]["result"] == ret and abs(res[0]["avg_iterations"] - iters / s["C"]) < 1e-6, (scale, res, ret, iters)
+            assert (data[:tbs // 8 + 3] == want[:tbs // 8 + 3]).all(), scale
+            assert (soft_pool == soft).all()
+    finally:
+        d.close()
+
+
+def test_repeated_lists_reuse_the_plan_but_follow_the_data(port):
+    """decode_batch keeps what it derives from the transport block list (segmentation, descriptors, decoder groups) and reuses
+    it when the next list repeats the same inputs.  The kept plan must only ever stand for the descriptors: new soft bits under
+    the same list, a changed redundancy version, a de-matching call in between and a HARQ retransmission must all give the
+    oracle's results."""
+    from srslte_b200 import SchDecoder
+
+    d = SchDecoder(device=0, max_noi=8)
+    try:
+        tbs, Qm, G = 12960, 4, 28800
+        C = port.cbsegm(tbs)["C"]
+
+        def oracle(e, rv, soft, cbcrc):
+            data = np.zeros(tbs // 8 + 3 + 768, np.uint8)
+            ret, iters = port.decode_tb(e, tbs, Qm, rv, 8, soft, cbcrc, data)
+            return ret, iters / C, data[:tbs // 8 + 3].copy()
+
+        def ours(e, rv, soft_pool, new_data=1, mask=0):
+            data = np.zeros(tbs // 8 + 3 + 1024, np.uint8)
+            rc, res = d.decode(e, soft_pool, data, [dict(tbs=tbs, Qm=Qm, rv=rv, nof_e_bits=G, e_offset=0, soft_offset=0, data_offset=0,
+                                                         new_data=new_data, cb_crc_mask=mask)])
+            assert rc == 0
+            return res[0], data[:tbs // 8 + 3].copy()
+
+        seq = [(0, 0.7, 11), (0, 0.7, 11), (0, 0.75, 12), (2, 0.7, 13), (0, 0.7, 11)]   # (rv, sigma, seed): same list, new data, new rv, back
+        for n, (rv, sigma, seed) in enumerate(seq):
+            e, _, _ = make_tb(port, tbs, Qm, G, rv, sigma, seed=seed)
+            want = oracle(e, rv, np.zeros(C * SB, np.int16), np.zeros(C, np.uint8))
+            if n == 3:  # a de-matching call through the same object in between (it shares the descriptor arena)
+                assert d.rm_rx(np.zeros(100, np.int16), np.zeros(SB, np.int16), [dict(cb_idx=0, rv=0, E=100, new_data=1, in_offset=0, soft_offset=0)]) == 0
+            got, data = ours(e, rv, np.zeros(C * SB, np.int16))
+            assert got["result"] == want[0] and abs(got["avg_iterations"] - want[1]) < 1e-6 and (data == want[2]).all(), n
+        # HARQ: a noisy first transmission, then rv 2 combined on the kept buffers with the updated mask (a different list)
+        e0, _, _ = make_tb(port, tbs, Qm, G, 0, 1.05, seed=21)
+        e2, _, _ = make_tb(port, tbs, Qm, G, 2, 1.05, seed=21)
+        soft_o, cb_o = np.zeros(C * SB, np.int16), np.zeros(C, np.uint8)
+        w0 = oracle(e0, 0, soft_o, cb_o)
+        mask0 = sum(int(b) << c for c, b in enumerate(cb_o))
+        w1 = oracle(e2, 2, soft_o, cb_o)
+        soft = np.zeros(C * SB, np.int16)
+        g0, _ = ours(e0, 0, soft)
+        assert g0["result"] == w0[0] and g0["cb_crc_mask"] == mask0
+        g1, _ = ours(e2, 2, soft, new_data=0, mask=mask0)
+        assert g1["result"] == w1[0] and (soft == soft_o).all()
+    finally:
+        d.close()

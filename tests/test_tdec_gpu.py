@@ -10,6 +10,20 @@ pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
 
+@pytest.fixture(autouse=True, params=["throughput", "low_latency", "auto"])
+def siso_kernel(request, monkeypatch):
+    """Every test of this file runs three times: forced onto the throughput SISO kernel (two warps per tile), forced onto
+    the low-latency kernel (16 warps per tile, all windows in parallel between two recursion warps), and with the engine's
+    own choice (small batches: low latency; large early-stop batches: throughput first, low latency for the tail passes)."""
+    if request.param == "throughput":
+        monkeypatch.setenv("SRSLTE_B200_TDEC_LL", "0")
+    elif request.param == "low_latency":
+        monkeypatch.setenv("SRSLTE_B200_TDEC_LL", "1")
+    else:
+        monkeypatch.delenv("SRSLTE_B200_TDEC_LL", raising=False)
+    return request.param
+
+
 @pytest.fixture(scope="module")
 def dec():
     from srslte_b200 import TurboDecoderBatch

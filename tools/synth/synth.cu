@@ -173,3 +173,132 @@ extern "C" __attribute__((visibility("default"))) int b200_synth_llr(int      de
   SYNTH_CUDA_TRY(cudaGetLastError());
   return 0;
 }
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// PUSCH input for the multi-cell benchmark (BASELINE config 5): every subframe of a batch is one of `nbase` noiseless
+// time-domain subframes (distinct payloads / RNTI / TTI / fading, synthesised on the host) plus its OWN realisation of
+// complex AWGN, drawn here from a counter-based generator, quantised to the radio's int16 I/Q wire format:
+//   out[sf][i] = sat16(rint(scale * (base[sf % nbase][i] + sigma * amp[sf % nbase] * (n1 + j n2) / sqrt(2))))
+namespace b200 {
+__global__ void synth_pusch_iq16_kernel(const float2* __restrict__ base, const float* __restrict__ amp, uint32_t nbase, uint32_t nsf,
+                                        uint32_t sf_sz, float sigma, float scale, uint64_t seed, short2* __restrict__ out)
+{
+  const size_t n = (size_t)nsf * sf_sz, stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint32_t sf = (uint32_t)(i / sf_sz), k = (uint32_t)(i % sf_sz), b = sf % nbase;
+    const uint64_t r  = mix64(seed ^ (0x5A5Aull << 48) ^ (uint64_t)i);
+    const float    u1 = ((float)(uint32_t)(r >> 40) + 1.0f) * (1.0f / 16777217.0f); // (0,1)
+    const float    u2 = (float)(uint32_t)((r >> 8) & 0xFFFFFFu) * (1.0f / 16777216.0f);
+    const float    m  = sqrtf(-2.0f * __logf(u1)) * sigma * amp[b] * 0.70710678f;
+    float          sn, cs;
+    __sincosf(6.28318530718f * u2, &sn, &cs);
+    const float2 x  = base[(size_t)b * sf_sz + k];
+    const int    re = max(-32768, min(32767, __float2int_rn(scale * (x.x + m * cs))));
+    const int    im = max(-32768, min(32767, __float2int_rn(scale * (x.y + m * sn))));
+    out[i]          = make_short2((short)re, (short)im);
+  }
+}
+} // namespace b200
+
+extern "C" __attribute__((visibility("default"))) int b200_synth_pusch_iq16(int device, const void* base_dev, const float* amp_dev,
+                                                                            uint32_t nbase, uint32_t nsf, uint32_t sf_sz, float sigma,
+                                                                            float scale, uint64_t seed, void* out_dev, void* stream)
+{
+  if (!base_dev || !amp_dev || !out_dev || nbase == 0) return -2;
+  SYNTH_CUDA_TRY(cudaSetDevice(device));
+  synth_pusch_iq16_kernel<<<148 * 16, 256, 0, (cudaStream_t)stream>>>((const float2*)base_dev, amp_dev, nbase, nsf, sf_sz, sigma, scale, seed,
+                                                                       (short2*)out_dev);
+  SYNTH_CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Issue rate of the packed-int16 instructions the turbo decoder is built from, measured in this process on this GPU: the
+// denominator of the decoder's integer roofline.  Dependency-free streams, `warps_per_sm` resident warps per
+// SM; lanes_per_clk_sm[0..2] = VIADD.16x2 alone, VIADDMNMX.S16x2 alone, the two interleaved 1:1 (they issue on different
+// pipes); sm_clock_mhz = the SM clock observed while the streams ran (clock64 ticks / event time).
+namespace b200 {
+constexpr int UB_ILP = 8, UB_ITER = 4096;
+template <int MODE>
+__global__ void ubench_kernel(uint32_t* out, uint32_t seed, long long* cycles)
+{
+  uint32_t r[UB_ILP], b = seed | 1u, c = seed ^ 0x12345u;
+#pragma unroll
+  for (int i = 0; i < UB_ILP; i++) r[i] = threadIdx.x * 7 + i + seed;
+  const long long t0 = clock64();
+  for (int it = 0; it < UB_ITER; it++) {
+#pragma unroll
+    for (int i = 0; i < UB_ILP; i++) {
+      if (MODE == 0 || (MODE == 2 && !(i & 1))) asm volatile("add.s16x2 %0, %1, %2;" : "=r"(r[i]) : "r"(r[i]), "r"(b));
+      if (MODE == 1 || (MODE == 2 && (i & 1)))
+        asm volatile("{.reg .b32 t; add.s16x2 t, %1, %2; max.s16x2 %0, t, %3;}" : "=r"(r[i]) : "r"(r[i]), "r"(b), "r"(c));
+    }
+  }
+  const long long t1 = clock64();
+  uint32_t        s  = 0;
+#pragma unroll
+  for (int i = 0; i < UB_ILP; i++) s ^= r[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+  // the SM is busy until its LAST warp is done: first start to last end over the warps of the block
+  __shared__ long long s0, s1;
+  if (threadIdx.x == 0) {
+    s0 = t0;
+    s1 = t1;
+  }
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin(&s0, t0);
+    atomicMax(&s1, t1);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) cycles[blockIdx.x] = s1 - s0;
+}
+
+template <int MODE>
+static int ubench_run(int nsm, int warps_per_sm, uint32_t* out, long long* cyc, double* lanes, double* mhz)
+{
+  const int threads = warps_per_sm * 32;
+  ubench_kernel<MODE><<<nsm, threads>>>(out, 3, cyc);
+  cudaEvent_t e0, e1;
+  SYNTH_CUDA_TRY(cudaEventCreate(&e0));
+  SYNTH_CUDA_TRY(cudaEventCreate(&e1));
+  SYNTH_CUDA_TRY(cudaEventRecord(e0));
+  ubench_kernel<MODE><<<nsm, threads>>>(out, 5, cyc);
+  SYNTH_CUDA_TRY(cudaEventRecord(e1));
+  SYNTH_CUDA_TRY(cudaDeviceSynchronize());
+  float ms = 0;
+  SYNTH_CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+  std::vector<long long> h(nsm);
+  SYNTH_CUDA_TRY(cudaMemcpy(h.data(), cyc, nsm * sizeof(long long), cudaMemcpyDeviceToHost));
+  double avg = 0;
+  for (int i = 0; i < nsm; i++) avg += (double)h[i];
+  avg /= nsm;
+  *lanes = 32.0 * (double)UB_ITER * UB_ILP * warps_per_sm / avg;
+  *mhz   = avg / (ms * 1e-3) / 1e6;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return 0;
+}
+} // namespace b200
+
+extern "C" __attribute__((visibility("default"))) int b200_ubench_int16_issue(int device, int warps_per_sm, double* lanes_per_clk_sm,
+                                                                              double* sm_clock_mhz)
+{
+  if (!lanes_per_clk_sm || warps_per_sm < 1 || warps_per_sm > 32) return -2;
+  SYNTH_CUDA_TRY(cudaSetDevice(device));
+  int nsm = 0;
+  SYNTH_CUDA_TRY(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device));
+  uint32_t*  out = nullptr;
+  long long* cyc = nullptr;
+  SYNTH_CUDA_TRY(cudaMalloc(&out, (size_t)nsm * warps_per_sm * 32 * 4));
+  SYNTH_CUDA_TRY(cudaMalloc(&cyc, nsm * sizeof(long long)));
+  double mhz[3] = {0, 0, 0};
+  int    rc     = ubench_run<0>(nsm, warps_per_sm, out, cyc, &lanes_per_clk_sm[0], &mhz[0]);
+  if (!rc) rc = ubench_run<1>(nsm, warps_per_sm, out, cyc, &lanes_per_clk_sm[1], &mhz[1]);
+  if (!rc) rc = ubench_run<2>(nsm, warps_per_sm, out, cyc, &lanes_per_clk_sm[2], &mhz[2]);
+  if (sm_clock_mhz) *sm_clock_mhz = mhz[2];
+  cudaFree(out);
+  cudaFree(cyc);
+  return rc;
+}
