@@ -161,9 +161,12 @@ SRSRAN_B200_API uint32_t srsran_tdec_autoimp_get_subblocks_8bit(uint32_t long_cb
 SRSRAN_B200_API void srsran_tdec_iteration(srsran_tdec_t* h, int16_t* input, uint8_t* output);
 /* nof_iterations passes (at least one, turbodecoder.c:536-549) + hard decision */
 SRSRAN_B200_API int srsran_tdec_run_all(srsran_tdec_t* h, int16_t* input, uint8_t* output, uint32_t nof_iterations, uint32_t long_cb);
-SRSRAN_B200_API void srsran_tdec_iteration_8bit(srsran_tdec_t* h, int8_t* input, uint8_t* output); /* no-op: out of scope */
+SRSRAN_B200_API void srsran_tdec_iteration_8bit(srsran_tdec_t* h, int8_t* input, uint8_t* output); /* widened to int16, see below */
 SRSRAN_B200_API int
-srsran_tdec_run_all_8bit(srsran_tdec_t* h, int8_t* input, uint8_t* output, uint32_t nof_iterations, uint32_t long_cb); /* SRSRAN_ERROR */
+srsran_tdec_run_all_8bit(srsran_tdec_t* h, int8_t* input, uint8_t* output, uint32_t nof_iterations, uint32_t long_cb);
+/* 8-bit entries: the int8 values are widened and decoded with the generic int16 arithmetic -- the route the reference itself takes
+ * for the lengths its 8-bit window decoders cannot handle (convert_8_to_16, turbodecoder.c:441-470).  Bit-exact with
+ * srsran_tdec_run_all on the widened values; not with the reference's approximate saturating 8-bit decoders. */
 
 /* ---- DFT plans: lib/include/srsran/phy/dft/dft.h ------------------------------------------------------------------------ */
 #ifndef SRSRAN_DFT_H

@@ -188,10 +188,24 @@ int srsran_rm_turbo_rx_lut(int16_t* input, int16_t* output, uint32_t in_len, uin
   return srsran_rm_turbo_rx_lut_(input, output, in_len, cb_idx, rv_idx, true);
 }
 
-int srsran_rm_turbo_rx_lut_8bit(int8_t*, int8_t*, uint32_t, uint32_t, uint32_t)
+// The reference's 8-bit soft-bit container (rm_turbo.c:447-483): output[deinter[i % out_len]] += input[i] in int8, which wraps
+// modulo 256.  Computed here with the int16 kernel on widened values and narrowed again: the low byte of the wrapped 16-bit
+// sum IS the wrapped 8-bit sum, so the result equals the reference's scalar form (natural layout, like the 16-bit entry).
+int srsran_rm_turbo_rx_lut_8bit(int8_t* input, int8_t* output, uint32_t in_len, uint32_t cb_idx, uint32_t rv_idx)
 {
-  B200_LOG_ERROR("8-bit LLR rate de-matching is not part of the GPU path");
-  return SRSRAN_ERROR;
+  if (rv_idx >= 4 || cb_idx >= (uint32_t)NOF_CB_SIZES) {
+    printf("Invalid inputs rv_idx=%d, cb_idx=%d\n", rv_idx, cb_idx);
+    return SRSRAN_ERROR_INVALID_INPUTS;
+  }
+  if (!input || !output) return SRSRAN_ERROR_INVALID_INPUTS;
+  const uint32_t       n = 3 * (uint32_t)cb_size(cb_idx) + 12;
+  std::vector<int16_t> in16(in_len), out16(n);
+  for (uint32_t i = 0; i < in_len; i++) in16[i] = (int16_t)input[i];
+  for (uint32_t i = 0; i < n; i++) out16[i] = (int16_t)output[i];
+  const int rc = srsran_rm_turbo_rx_lut_(in16.data(), out16.data(), in_len, cb_idx, rv_idx, false);
+  if (rc != SRSRAN_SUCCESS) return rc;
+  for (uint32_t i = 0; i < n; i++) output[i] = (int8_t)(uint8_t)(uint16_t)out16[i];
+  return SRSRAN_SUCCESS;
 }
 
 } // extern "C"
@@ -205,6 +219,7 @@ struct CompatTdec {
   int        cb_idx = -1;
   uint8_t *  d_out = nullptr;
   int16_t*   d_llr = nullptr;
+  std::vector<int16_t> wide; // 8-bit entries: the input widened to int16
 };
 
 static CompatTdec* tdec_of(srsran_tdec_t* h)
@@ -343,12 +358,34 @@ int srsran_tdec_run_all(srsran_tdec_t* h, int16_t* input, uint8_t* output, uint3
   return tdec_decide(h, output);
 }
 
-void srsran_tdec_iteration_8bit(srsran_tdec_t*, int8_t*, uint8_t*) {}
-
-int srsran_tdec_run_all_8bit(srsran_tdec_t*, int8_t*, uint8_t*, uint32_t, uint32_t)
+// 8-bit LLR input (turbodecoder.c:410-484,551-577).  The reference sends int8 inputs either to its saturating 8-bit window
+// decoders or -- for every length those cannot take -- through convert_8_to_16 into a 16-bit decoder (turbodecoder.c:441-470).
+// This library always takes the second route: the values are widened and decoded with the generic int16 arithmetic, i.e. the
+// result is bit-exact with srsran_tdec_run_all on the widened values (and NOT with the reference's approximate 8-bit window
+// decoders, which differ from its own 16-bit decoders as well; tests/test_compat_8bit_gpu.py compares block error rates).
+static void widen8(CompatTdec* c, const int8_t* in, uint32_t n)
 {
-  B200_LOG_ERROR("8-bit LLR decoding is not part of the GPU path");
-  return SRSRAN_ERROR;
+  c->wide.resize(n);
+  for (uint32_t i = 0; i < n; i++) c->wide[i] = (int16_t)in[i];
+}
+
+void srsran_tdec_iteration_8bit(srsran_tdec_t* h, int8_t* input, uint8_t* output)
+{
+  if (!h || !tdec_of(h) || h->current_cbidx < 0 || !input) return; // turbodecoder.c:553
+  CompatTdec* c = tdec_of(h);
+  if (h->n_iter == 0) widen8(c, input, 3 * h->current_long_cb + 12); // only the first iteration reads the input (:466)
+  if (tdec_one_pass(h, c->wide.data()) == SRSRAN_SUCCESS) tdec_decide(h, output);
+}
+
+int srsran_tdec_run_all_8bit(srsran_tdec_t* h, int8_t* input, uint8_t* output, uint32_t nof_iterations, uint32_t long_cb)
+{
+  if (!input || srsran_tdec_new_cb(h, long_cb)) return SRSRAN_ERROR;
+  CompatTdec* c = tdec_of(h);
+  widen8(c, input, 3 * long_cb + 12);
+  do {
+    if (tdec_one_pass(h, c->wide.data()) != SRSRAN_SUCCESS) return SRSRAN_ERROR;
+  } while (h->n_iter < (int)nof_iterations);
+  return tdec_decide(h, output);
 }
 
 } // extern "C"
