@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "tdec_core.h"
+
 namespace b200 {
 
 // One code block's de-matching job, device-side view
@@ -17,5 +19,11 @@ struct RmDescDev {
 };
 
 int launch_rm_rx(const int16_t* e_bits_dev, int16_t* soft_pool_dev, const RmDescDev* descs_dev, uint32_t n, cudaStream_t stream);
+
+// De-matching fused with the decoder's tile layout: one thread block per lane slot of `v` (ntiles * 32).  pairs_dev: two int32
+// per slot = index into descs_dev of the slot's low / high block, -1 for none.  Every soft buffer must start on an 8-byte
+// boundary.  Leaves the tiles, S2T, lane map and block state of `v` as the decoder's own load kernels would.
+int launch_rm_rx_tiles(const int16_t* e_bits_dev, int16_t* soft_pool_dev, const RmDescDev* descs_dev, const void* pairs_dev,
+                       const TdecView& v, int max_K, uint32_t max_E, cudaStream_t stream);
 
 } // namespace b200

@@ -7,6 +7,7 @@
 // Code blocks of all transport blocks are pooled, grouped by (K, CRC kind) and each group runs as ONE batched decode.
 #include <string.h>
 
+#include <algorithm>
 #include <chrono>
 #include <map>
 #include <new>
@@ -140,6 +141,9 @@ struct SchPlan {
   ScatterJob* d_jobs  = nullptr;
   TbCrcJob*   d_cj    = nullptr;
   uint8_t *   d_dec = nullptr, *d_ok = nullptr, *d_np = nullptr, *d_tbok = nullptr;
+  uint32_t    max_E   = 0;       // longest received block of the list (sizes the fused kernel's staging)
+  int32_t*    d_pairs = nullptr; // fused de-matching: de-matching job of every lane slot's two blocks (-1: none), [ntiles*32][2]
+  uint32_t    ntiles  = 0;
 };
 
 // the input fields only, compared one by one: the caller's structs may carry anything in their output fields and padding
@@ -368,6 +372,8 @@ int SchEngine::build_plan(SchPlan& p, uint64_t e_len, uint64_t soft_len, uint64_
   }
   const std::vector<CbRec>& cbs = p.cbs;
   last_ncb                      = cbs.size();
+  p.max_E                       = 0;
+  for (const CbRec& r : cbs) p.max_E = std::max(p.max_E, r.E);
   // ---- de-matching descriptors, decoder groups (K, CRC kind), payload assembly -------------------------------------------
   std::vector<RmDescDev> descs;
   int                    rc = build_rm_descs(ctx, rm.data(), (uint32_t)rm.size(), e_len, soft_len, descs);
@@ -401,12 +407,12 @@ int SchEngine::build_plan(SchPlan& p, uint64_t e_len, uint64_t soft_len, uint64_
   }
   // ---- upload ------------------------------------------------------------------------------------------------------------
   size_t meta_need = descs.size() * sizeof(RmDescDev) + cbs.size() * (sizeof(uint64_t) + sizeof(ScatterJob) + 8) +
-                     n_tb * (sizeof(TbCrcJob) + 8) + p.dec_bytes + (size_t(2) << 20);
+                     n_tb * (sizeof(TbCrcJob) + 8) + p.dec_bytes + (cbs.size() + 64 * groups.size()) * 2 * sizeof(int32_t) + (size_t(2) << 20);
   if (meta.reserve(meta_need) != B200_SUCCESS) return B200_ERROR;
   meta.reset();
   // the previous call ended with a stream synchronisation, so its staged descriptors are free again
   if (hmeta.reserve(descs.size() * sizeof(RmDescDev) + cbs.size() * (sizeof(uint64_t) + sizeof(ScatterJob)) + n_tb * sizeof(TbCrcJob) +
-                    (size_t(1) << 20)) != B200_SUCCESS) {
+                    (cbs.size() + 64 * groups.size()) * 2 * sizeof(int32_t) + (size_t(1) << 20)) != B200_SUCCESS) {
     return B200_ERROR;
   }
   hmeta.reset();
@@ -421,6 +427,25 @@ int SchEngine::build_plan(SchPlan& p, uint64_t e_len, uint64_t soft_len, uint64_
     p.d_ok  = (uint8_t*)meta.take(cbs.size());
     p.d_np  = (uint8_t*)meta.take(cbs.size());
     if (!p.d_dec || !p.d_ok || !p.d_np) return B200_ERROR;
+  }
+  {
+    // which de-matching job fills which lane slot of the decoder: code block i sits at position slot_of[i] - cb0 of its group
+    std::vector<uint32_t> first_tile;
+    TdecEngine::tile_layout(p.specs, first_tile);
+    p.ntiles = 0;
+    for (const TdecGroupSpec& g : p.specs) p.ntiles += (g.ncb + TDEC_TILE_CB - 1) / TDEC_TILE_CB;
+    std::vector<int32_t> pairs((size_t)p.ntiles * 64, -1);
+    uint32_t             gi = 0;
+    for (auto& g : groups) {
+      const TdecGroupSpec& sp = p.specs[gi];
+      for (uint32_t i : g.second) {
+        const uint32_t idx = p.slot_of[i] - sp.cb0;
+        pairs[((size_t)first_tile[gi] + idx / TDEC_TILE_CB) * 64 + idx % TDEC_TILE_CB] = (int32_t)i; // [tile][lane][half] = [tile][block]
+      }
+      gi++;
+    }
+    p.d_pairs = nullptr;
+    if (!pairs.empty() && upload(meta, pairs, &p.d_pairs, st, &hmeta) != B200_SUCCESS) return B200_ERROR;
   }
   if (upload(meta, crc_jobs, &p.d_cj, st, &hmeta) != B200_SUCCESS) return B200_ERROR;
   p.d_tbok = (uint8_t*)meta.take(n_tb);
@@ -499,20 +524,6 @@ int SchEngine::decode_batch(const int16_t* e_bits, uint64_t e_len, int16_t* soft
     }
   }
 
-  // ---- rate de-matching of every pending code block -------------------------------------------------------------------
-  if (!cbs.empty()) {
-    if (launch_rm_rx(d_e, d_soft, p.d_descs, (uint32_t)cbs.size(), st) != B200_SUCCESS) return B200_ERROR;
-    g_kernel_launches++;
-  }
-  auto t_3 = now();
-
-  // ---- ONE batched decode over all (K, CRC kind) groups (one launch per pass, tiles ordered by length) ------------------
-  const bool al8 = p.soft_offsets_aligned8 && (reinterpret_cast<uintptr_t>(d_soft) & 7u) == 0;
-  h_tbok.assign(n_tb, 0);
-  tmp_ok.assign(cbs.size(), 0);
-  tmp_np.assign(cbs.size(), 0);
-  std::chrono::steady_clock::time_point t_4, t_5;
-
   // The decoder workspace is borrowed for the duration of this (synchronous) call; it is carved without the int16 copies of
   // the channel LLRs until a batch needs them (TdecWorkspace::int16_on_demand).
   struct Borrowed {
@@ -523,10 +534,37 @@ int SchEngine::decode_batch(const int16_t* e_bits, uint64_t e_len, int16_t* soft
   if (!ws.w) return B200_ERROR;
   ws.w->int16_on_demand = true;
 
+  // ---- rate de-matching of every pending code block -------------------------------------------------------------------
+  // Two forms.  Default: de-match into the natural soft buffers, then the decoder's load kernel turns them into tiles (it owns a
+  // whole tile and writes full 512-byte rows).  SRSLTE_B200_RM_FUSED=1: the de-matching kernel writes the decoder's int8 tiles
+  // itself (one thread block per lane slot) -- bit-identical, one kernel and one read of every soft buffer less, but measured
+  // SLOWER (1.40 ms against 0.67 + 0.59 ms for 53,248 blocks, profiles/README.md): a lane slot owns only 16 bytes of every tile
+  // row, so its 2,300 row pieces are scattered partial-sector stores.  Kept for the record and for the tests.
+  const bool  al8       = p.soft_offsets_aligned8 && (reinterpret_cast<uintptr_t>(d_soft) & 7u) == 0;
+  const char* fused_env = getenv("SRSLTE_B200_RM_FUSED");
+  const bool  fused     = al8 && !cbs.empty() && p.d_pairs != nullptr && fused_env != nullptr && fused_env[0] == '1';
+  if (fused) {
+    int r = tdec.begin_batch(*ws.w, p.specs, st);
+    if (r != B200_SUCCESS) return r;
+    if (launch_rm_rx_tiles(d_e, d_soft, p.d_descs, p.d_pairs, ws.w->plan.v, ws.w->plan.max_K, p.max_E, st) != B200_SUCCESS) return B200_ERROR;
+    g_kernel_launches++;
+  } else if (!cbs.empty()) {
+    if (launch_rm_rx(d_e, d_soft, p.d_descs, (uint32_t)cbs.size(), st) != B200_SUCCESS) return B200_ERROR;
+    g_kernel_launches++;
+  }
+  auto t_3 = now();
+
+  // ---- ONE batched decode over all (K, CRC kind) groups (one launch per pass, tiles ordered by length) ------------------
+  h_tbok.assign(n_tb, 0);
+  tmp_ok.assign(cbs.size(), 0);
+  tmp_np.assign(cbs.size(), 0);
+  std::chrono::steady_clock::time_point t_4, t_5;
+
   // decode, payload assembly, transport block CRC, results; ends with the stream synchronised
+  bool preloaded = fused;
   auto decode_and_finish = [&]() -> int {
     if (!cbs.empty()) {
-      int r = tdec.run_groups(*ws.w, d_soft, p.specs, max_iterations, 1, p.d_dec, p.d_ok, p.d_np, st, p.d_offs, al8);
+      int r = tdec.run_groups(*ws.w, d_soft, p.specs, max_iterations, 1, p.d_dec, p.d_ok, p.d_np, st, p.d_offs, al8, preloaded);
       if (r != B200_SUCCESS) return r;
       sch_scatter_payload_kernel<<<(unsigned)cbs.size(), 128, 0, st>>>(p.d_dec, d_data, p.d_jobs, (uint32_t)cbs.size());
       g_kernel_launches++;
@@ -555,6 +593,7 @@ int SchEngine::decode_batch(const int16_t* e_bits, uint64_t e_len, int16_t* soft
     // (int16_on_demand): carve them from now on and decode the batch again -- the soft buffers still hold its input
     ws.w->have_int16 = true;
     *ws.w->h_err     = 0;
+    preloaded        = false; // the workspace is carved anew: the tiles are loaded again from the soft buffers
     rc               = decode_and_finish();
     if (rc != B200_SUCCESS) return rc;
   }

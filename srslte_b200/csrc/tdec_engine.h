@@ -94,6 +94,11 @@ struct TdecEngine {
   static size_t workspace_bytes(int K, uint32_t ncb);
   // carve the workspace for `groups`, build and upload the tile descriptors (or reuse the cached ones)
   int prepare(TdecWorkspace& w, const std::vector<TdecGroupSpec>& groups, cudaStream_t stream);
+  // first tile of every group in the order prepare() lays the tiles out (descending K, stable)
+  static void tile_layout(const std::vector<TdecGroupSpec>& groups, std::vector<uint32_t>& first_tile);
+  // prepare() + the per-decode flags cleared: for a producer that fills the tiles itself (the fused de-matching kernel) and
+  // then calls run_groups(.., tiles_preloaded = true)
+  int begin_batch(TdecWorkspace& w, const std::vector<TdecGroupSpec>& groups, cudaStream_t stream);
 
   int  init(int device, uint32_t max_cb_hint);
   void destroy();
@@ -109,7 +114,8 @@ struct TdecEngine {
                  uint8_t*                          npass_dev,
                  cudaStream_t                      stream,
                  const uint64_t*                   llr_offsets_dev  = nullptr,
-                 bool                              offsets_aligned8 = false);
+                 bool                              offsets_aligned8 = false,
+                 bool                              tiles_preloaded  = false);
 
   // one group of equal-K blocks, contiguous vectors
   int run_device(TdecWorkspace& w,

@@ -330,6 +330,29 @@ int TdecEngine::prof_get(double* ms_by_class, uint64_t* launches_by_class, int n
   return B200_SUCCESS;
 }
 
+void TdecEngine::tile_layout(const std::vector<TdecGroupSpec>& groups, std::vector<uint32_t>& first_tile)
+{
+  std::vector<uint32_t> order(groups.size());
+  for (uint32_t i = 0; i < order.size(); i++) order[i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return groups[a].K > groups[b].K; });
+  first_tile.assign(groups.size(), 0);
+  uint32_t tile = 0;
+  for (uint32_t oi = 0; oi < order.size(); oi++) {
+    first_tile[order[oi]] = tile;
+    tile += (groups[order[oi]].ncb + TDEC_TILE_CB - 1) / TDEC_TILE_CB;
+  }
+}
+
+int TdecEngine::begin_batch(TdecWorkspace& w, const std::vector<TdecGroupSpec>& groups, cudaStream_t stream)
+{
+  int rc = prepare(w, groups, stream);
+  if (rc != B200_SUCCESS) return rc;
+  const TdecView& v = w.plan.v;
+  B200_CUDA_TRY(cudaMemsetAsync(v.fmt, 0, (size_t)v.ntiles * sizeof(uint32_t), stream));
+  B200_CUDA_TRY(cudaMemsetAsync(v.err, 0, sizeof(uint32_t), stream));
+  return B200_SUCCESS;
+}
+
 // Everything on `stream`, all pointers device memory.
 int TdecEngine::run_groups(TdecWorkspace&                    w,
                            const int16_t*                    llr_dev,
@@ -341,7 +364,8 @@ int TdecEngine::run_groups(TdecWorkspace&                    w,
                            uint8_t*                          npass_dev,
                            cudaStream_t                      stream,
                            const uint64_t*                   llr_offsets_dev,
-                           bool                              offsets_aligned8)
+                           bool                              offsets_aligned8,
+                           bool                              tiles_preloaded)
 {
   int rc = prepare(w, groups, stream);
   if (rc != B200_SUCCESS) return rc;
@@ -369,9 +393,9 @@ int TdecEngine::run_groups(TdecWorkspace&                    w,
   B200_CUDA_TRY(cudaMemsetAsync(v.ctl, 0, TDEC_CTL_WORDS * sizeof(uint32_t), stream));
 
   prof_begin(0, stream);
-  launch_load_natural(v, p.max_K, llr_dev, llr_offsets_dev, aligned8, stream);
+  launch_load_natural(v, p.max_K, llr_dev, llr_offsets_dev, aligned8, stream, tiles_preloaded);
   prof_end(stream);
-  g_kernel_launches += 2;
+  g_kernel_launches += tiles_preloaded ? 1 : 2;
   for (uint32_t ps = 0; ps < max_passes; ps++) {
     prof_begin(1, stream);
     v.split_percent = split_percent(ps == 0 ? 0 : ((ps & 1) ? 1 : 2)); // the checkpoints are per-pass scratch: each kind of pass splits where it balances

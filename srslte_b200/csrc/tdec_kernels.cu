@@ -1106,7 +1106,8 @@ void launch_load_natural(const TdecView& v,
                          const int16_t*  llr_dev,
                          const uint64_t* offsets_dev,
                          bool            aligned8,
-                         cudaStream_t    stream)
+                         cudaStream_t    stream,
+                         bool            int8_tiles_done)
 {
   const int chunks = (max_K + LOAD_ROWS - 1) / LOAD_ROWS + 1; // +1: the tail chunk
   dim3      grid((unsigned)chunks, (unsigned)v.ntiles), block(256);
@@ -1122,6 +1123,11 @@ void launch_load_natural(const TdecView& v,
     cudaFuncSetAttribute(tdec_load16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LOAD_SMEM);
     cudaFuncSetAttribute(tdec_load8_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LS_SMEM);
     cudaFuncSetAttribute(tdec_load8_stream_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  }
+  if (int8_tiles_done) { // the fused de-matching kernel wrote the int8 tiles and raised the format flags: only the raised tiles are left
+    if (aligned8) tdec_load16_kernel<true><<<grid16, block, LOAD_SMEM, stream>>>(v, llr_dev, offsets_dev, chunks);
+    else tdec_load16_kernel<false><<<grid16, block, LOAD_SMEM, stream>>>(v, llr_dev, offsets_dev, chunks);
+    return;
   }
   cudaMemsetAsync(v.fmt, 0, (size_t)v.ntiles * sizeof(uint32_t), stream);
   cudaMemsetAsync(v.err, 0, sizeof(uint32_t), stream);

@@ -13,7 +13,8 @@ void launch_load_natural(const TdecView& v,
                          const int16_t*  llr_dev,
                          const uint64_t* offsets_dev, // optional per-block int16 offsets into llr_dev
                          bool            aligned8,    // every block vector starts on an 8-byte boundary
-                         cudaStream_t    stream);
+                         cudaStream_t    stream,
+                         bool            int8_tiles_done = false); // only rebuild the tiles whose format flag is raised, in int16
 constexpr int SISO_THROUGHPUT = 0, SISO_LOW_LATENCY = 1, SISO_AUTO = 2;
 void launch_siso_pass(const TdecView& v, int pass_idx, int mode, int sm_count, cudaStream_t stream);
 int  siso_resident_tiles_per_sm();

@@ -8,6 +8,17 @@ pytestmark = pytest.mark.gpu
 SB = 18600
 
 
+@pytest.fixture(autouse=True, params=["fused", "unfused"])
+def dematching_kernel(request, monkeypatch):
+    """Every test of this file runs with the separate de-matching + load kernels (the default) and with the de-matching kernel that
+    writes the decoder's tiles itself (SRSLTE_B200_RM_FUSED=1)."""
+    if request.param == "fused":
+        monkeypatch.setenv("SRSLTE_B200_RM_FUSED", "1")
+    else:
+        monkeypatch.delenv("SRSLTE_B200_RM_FUSED", raising=False)
+    return request.param
+
+
 @pytest.fixture(scope="module")
 def sch():
     from srslte_b200 import SchDecoder
