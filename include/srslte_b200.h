@@ -292,8 +292,8 @@ SRSRAN_B200_API int srsran_b200_pusch_demap_batch(int         device,
  *   DMRS least-squares estimate, 3-tap smoothing, noise / SNR / CFO  ->  MMSE equaliser (srsran_predecoding_single)
  *   ->  transform de-precoding (srsran_dft_precoding, backward DFT of 12*L_prb points / sqrt(N))  ->  int16 soft
  *   demapping  ->  descrambling (srsran_sequence_pusch_apply_s)  ->  UL-SCH de-interleaving.
- * Scope: one receive antenna; no RI / ACK / CQI multiplexed into the PUSCH; no intra-subframe hopping; L_prb >= 3 and
- * 12*L_prb = 2^a 3^b 5^c (srsran_dft_precoding_valid_prb).  All data pointers are DEVICE memory (flags must carry
+ * Scope: one receive antenna; no RI / ACK / CQI multiplexed into the PUSCH; no intra-subframe hopping; L_prb >= 1 with
+ * 12*L_prb = 2^a 3^b 5^c (srsran_dft_precoding_valid_prb; 1 and 2 PRB use the phi(n) tables of TS 36.211 5.5.1.2).  All data pointers are DEVICE memory (flags must carry
  * SRSRAN_B200_FLAG_DEVICE_PTRS), the per-subframe parameter arrays (rnti, tti, n_dmrs) are HOST memory; every call is
  * enqueued on `stream` and returns without synchronising.
  */

@@ -985,14 +985,15 @@ static uint32_t orc_prime_lower_than(uint32_t n) /* primes.c: largest prime < n 
 }
 
 /* refsignal_ul.c:95-181,227-249,337-357 + zc_sequence.c:205-235,273-300 + phy_common.c:471-489.
- * PUSCH DMRS of one subframe, r[2][12*L_prb] (slot-major).  Only M_sc >= 36 (L_prb >= 3): the 1- and 2-PRB base
- * sequences are table look-ups of TS 36.211 5.5.1.2 and are not restated. */
+ * PUSCH DMRS of one subframe, r[2][12*L_prb] (slot-major).  M_sc >= 36 is the Zadoff-Chu form; the 1- and 2-PRB base
+ * sequences are the phi(n) pi/4 table look-ups of TS 36.211 5.5.1.2 (zc_sequence.c:175-183,232-247). */
+#include "phi_table.inc"
 int orc_dmrs_pusch_gen(const uint32_t* p, float complex* r)
 {
   static const uint32_t n_dmrs_1[8] = {0, 2, 3, 4, 6, 8, 9, 10}, n_dmrs_2[8] = {0, 6, 3, 4, 2, 8, 10, 9}; /* 36.211 5.5.2.1.1 */
   const uint32_t cell_id = p[OP_CELL_ID], L = p[OP_L_PRB], sf_idx = p[OP_TTI] % 10, dss = p[OP_DELTA_SS];
   const uint32_t nsymb = p[OP_CP_EXT] ? 6 : 7, M = 12 * L;
-  if (L < 3 || p[OP_CSHIFT] > 7 || p[OP_N_DMRS] > 7 || dss > 29) return -1;
+  if (L < 1 || p[OP_CSHIFT] > 7 || p[OP_N_DMRS] > 7 || dss > 29) return -1;
   uint8_t        c[8 * 7 * 20];
   const uint32_t c_init = ((cell_id / 30) << 5) + (((cell_id % 30) + dss) % 30);
   orc_gold(c_init, c, 8 * nsymb * 20);
@@ -1016,8 +1017,11 @@ int orc_dmrs_pusch_gen(const uint32_t* p, float complex* r)
     else qf = q_hat + 0.5 - v;
     const float q = (float)(uint32_t)qf;
     for (uint32_t i = 0; i < M; i++) {
-      const float m   = (float)(i % Nzc);
-      const float arg = (float)(-M_PI * q * m * (m + 1) / n_sz); /* double expression rounded into a float (cf_t) */
+      const float m = (float)(i % (Nzc ? Nzc : 1));
+      float       arg;
+      if (M == 12) arg = (float)orc_phi12[u][i] * (float)M_PI_4; /* srsran_vec_sc_prod_fcc: float times float */
+      else if (M == 24) arg = (float)orc_phi24[u][i] * (float)M_PI_4;
+      else arg = (float)(-M_PI * q * m * (m + 1) / n_sz); /* double expression rounded into a float (cf_t) */
       /* the reference is built with -mfma and GCC contracts arg + alpha*i into one fused multiply-add (oracle/Makefile
        * uses the reference's own ISA flags); restated explicitly so that this file does not depend on its own flags */
       r[(ns % 2) * M + i] = cexpf(I * fmaf(alpha, (float)i, arg));

@@ -29,6 +29,8 @@
 
 namespace b200 {
 
+#include "dmrs_phi_table.inc"
+
 struct PuschSfParam {
   uint32_t c_init;   // scrambling seed of the subframe: (rnti << 14) + (sf_idx << 9) + cell_id  (sequences.c:120-123)
   uint32_t dmrs_idx; // n_dmrs * 10 + sf_idx: row of the DMRS table
@@ -285,8 +287,15 @@ struct PuschRx {
           else qf = (float)((double)q_hat + 0.5 - (double)v);
           const float q = (float)(uint32_t)qf;
           for (int i = 0; i < M; i++) {
-            const float m   = (float)((uint32_t)i % Nzc);
-            const float arg = (float)(-M_PI * (double)q * (double)m * (double)(m + 1) / (double)n_sz);
+            float arg;
+            if (M <= 24) { // 1 and 2 PRB: phi(n) pi / 4 from the tables of TS 36.211 5.5.1.2 (zc_sequence.c:175-183, float product)
+              const uint64_t w   = (M == 12 ? g_phi12 : g_phi24)[u];
+              const float    phi = (float)(2 * (int)((w >> (2 * i)) & 3u) - 3);
+              arg                = phi * (float)M_PI_4;
+            } else {
+              const float m = (float)((uint32_t)i % Nzc);
+              arg           = (float)(-M_PI * (double)q * (double)m * (double)(m + 1) / (double)n_sz);
+            }
             const float a   = fmaf(alpha, (float)i, arg);
             float       sn, cs;
             sincosf(a, &sn, &cs);
@@ -308,7 +317,7 @@ struct PuschRx {
     Qm   = 2 * c.modulation;
     int       radix[OFDM_MAX_PASSES];
     const int npass = fft_factorise(M, radix);
-    if (c.modulation < 1 || c.modulation > 3 || c.L_prb < 3 || c.n_prb + c.L_prb > c.cell_nof_prb || c.cell_nof_prb > 110 || npass == 0 ||
+    if (c.modulation < 1 || c.modulation > 3 || c.L_prb < 1 || c.n_prb + c.L_prb > c.cell_nof_prb || c.cell_nof_prb > 110 || npass == 0 ||
         c.dmrs_cyclic_shift > 7 || c.dmrs_delta_ss > 29 || c.cell_id > 503 || c.llr_shift > 15) {
       // dft_precoding.c:88-104 accepts exactly the allocations whose 12 L_prb is 2^a 3^b 5^c
       B200_LOG_ERROR("unsupported PUSCH configuration (L_prb=%u n_prb=%u cell_nof_prb=%u mod=%d)", c.L_prb, c.n_prb, c.cell_nof_prb, c.modulation);

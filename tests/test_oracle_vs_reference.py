@@ -120,7 +120,7 @@ def test_pusch_descrambling_and_deinterleave(port, ref):
         assert (ref.ulsch_deinterleave(q, Qm, nsym) == port.ulsch_deinterleave(q, Qm, nsym)).all()
 
 
-@pytest.mark.parametrize("L", [3, 5, 6, 25, 27, 60, 81, 100])
+@pytest.mark.parametrize("L", [1, 2, 3, 5, 6, 25, 27, 60, 81, 100])
 def test_dft_precoding(port, ref, L):
     rng = np.random.default_rng(L)
     z = (rng.standard_normal(12 * 12 * L) + 1j * rng.standard_normal(12 * 12 * L)).astype(np.complex64)
@@ -143,7 +143,10 @@ def test_predecoding_single(port, ref):
 
 PUSCH_LINKS = [dict(), dict(cell_id=301, tti=7, n_dmrs=3, cyclic_shift=5, delta_ss=11), dict(L_prb=6, group_hopping=1, tti=4, tbs=2216, mod=2),
                dict(L_prb=50, n_prb=20, sequence_hopping=1, tti=9, cell_id=77, tbs=14112, mod=2), dict(L_prb=3, nof_prb=6, cell_id=9, tbs=392, mod=1),
-               dict(L_prb=5, nof_prb=15, cell_id=42, cp_ext=1, tti=12, tbs=1000, mod=2), dict(L_prb=81, n_prb=3, cell_id=503, delta_ss=29, tti=5, tbs=51024)]
+               dict(L_prb=5, nof_prb=15, cell_id=42, cp_ext=1, tti=12, tbs=1000, mod=2), dict(L_prb=81, n_prb=3, cell_id=503, delta_ss=29, tti=5, tbs=51024),
+               # 1 and 2 PRB: the base sequences are the phi(n) tables of TS 36.211 5.5.1.2 instead of Zadoff-Chu
+               dict(L_prb=1, nof_prb=6, n_prb=4, cell_id=12, tti=3, tbs=136, mod=1), dict(L_prb=2, nof_prb=25, n_prb=11, cell_id=250, tti=8, tbs=328, mod=2, n_dmrs=5),
+               dict(L_prb=1, nof_prb=15, n_prb=0, cell_id=499, group_hopping=1, delta_ss=17, tti=6, tbs=56, mod=1), dict(L_prb=2, nof_prb=6, n_prb=2, cell_id=88, cp_ext=1, cyclic_shift=2, tbs=256, mod=1)]
 
 
 @pytest.mark.parametrize("kw", PUSCH_LINKS)

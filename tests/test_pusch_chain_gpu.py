@@ -28,6 +28,10 @@ CONFIGS = [
     dict(cell_id=503, cell_nof_prb=100, L_prb=81, n_prb=3, mod=3, sequence_hopping=True, delta_ss=29),
     dict(cell_id=9, cell_nof_prb=6, L_prb=3, n_prb=2, mod=2),
     dict(cell_id=42, cell_nof_prb=15, L_prb=5, n_prb=0, mod=3, cp_ext=True),
+    # 1 and 2 PRB: table base sequences (TS 36.211 5.5.1.2), 12- and 24-point transforms
+    dict(cell_id=12, cell_nof_prb=6, L_prb=1, n_prb=4, mod=1),
+    dict(cell_id=250, cell_nof_prb=25, L_prb=2, n_prb=11, mod=2, group_hopping=True, delta_ss=17),
+    dict(cell_id=88, cell_nof_prb=6, L_prb=2, n_prb=2, mod=1, cp_ext=True, cyclic_shift=2),
 ]
 
 
@@ -137,7 +141,7 @@ def test_demod_descramble_deinterleave_is_bit_exact(port, kw, shift):
 def test_unsupported_configurations_fail_cleanly():
     from srslte_b200.pusch import PuschChain
 
-    for kw in (dict(L_prb=7, cell_nof_prb=25), dict(L_prb=2, cell_nof_prb=6), dict(L_prb=50, n_prb=60), dict(mod=4)):
+    for kw in (dict(L_prb=7, cell_nof_prb=25), dict(L_prb=0, cell_nof_prb=6), dict(L_prb=50, n_prb=60), dict(mod=4)):
         with pytest.raises(RuntimeError):
             PuschChain(**kw)
 
@@ -146,7 +150,9 @@ def test_unsupported_configurations_fail_cleanly():
                                     (dict(cell_id=150, cell_nof_prb=50, L_prb=24, n_prb=13, mod=2, cyclic_shift=3), 9912),
                                     (dict(cell_id=7, cell_nof_prb=25, L_prb=10, n_prb=5, mod=1), 1544),
                                     (dict(cell_id=42, cell_nof_prb=15, L_prb=15, n_prb=0, mod=2, cp_ext=True, delta_ss=7), 4584),
-                                    (dict(cell_id=333, cell_nof_prb=75, L_prb=72, n_prb=2, mod=3, group_hopping=True), 46888)])
+                                    (dict(cell_id=333, cell_nof_prb=75, L_prb=72, n_prb=2, mod=3, group_hopping=True), 46888),
+                                    (dict(cell_id=12, cell_nof_prb=6, L_prb=1, n_prb=4, mod=1), 136),
+                                    (dict(cell_id=250, cell_nof_prb=25, L_prb=2, n_prb=11, mod=2, cyclic_shift=6), 328)])
 def test_chain_against_the_reference_link(ref, port, kw, tbs):
     """Reference transmitter (srsran_pusch_encode + DMRS) -> flat fading + AWGN -> GPU chain, compared with the buffers of the
     reference receiver (chest + srsran_pusch_decode) and decoded down to the transport block."""
