@@ -292,7 +292,8 @@ SRSRAN_B200_API int srsran_b200_pusch_demap_batch(int         device,
  *   DMRS least-squares estimate, 3-tap smoothing, noise / SNR / CFO  ->  MMSE equaliser (srsran_predecoding_single)
  *   ->  transform de-precoding (srsran_dft_precoding, backward DFT of 12*L_prb points / sqrt(N))  ->  int16 soft
  *   demapping  ->  descrambling (srsran_sequence_pusch_apply_s)  ->  UL-SCH de-interleaving.
- * Scope: one receive antenna; no RI / ACK / CQI multiplexed into the PUSCH; no intra-subframe hopping; L_prb >= 1 with
+ * Scope: one receive antenna (as srsran_pusch_decode, pusch.c:413); control information through the _uci_ entries below;
+ * no intra-subframe hopping; L_prb >= 1 with
  * 12*L_prb = 2^a 3^b 5^c (srsran_dft_precoding_valid_prb; 1 and 2 PRB use the phi(n) tables of TS 36.211 5.5.1.2).  All data pointers are DEVICE memory (flags must carry
  * SRSRAN_B200_FLAG_DEVICE_PTRS), the per-subframe parameter arrays (rnti, tti, n_dmrs) are HOST memory; every call is
  * enqueued on `stream` and returns without synchronising.
@@ -349,6 +350,55 @@ SRSRAN_B200_API int srsran_b200_pusch_rx_batch(srsran_b200_pusch_t* q, const voi
                                                void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Uplink control information multiplexed into the PUSCH (TS 36.212 5.2.2.6-5.2.2.8).  Replaces, per subframe, what
+ * srsran_ulsch_decode does before decode_tb (lib/src/phy/phch/sch.c:1121-1190): uci_decode_ri_ack (sch.c:1022-1119,
+ * srsran_uci_decode_ack_ri uci.c:637-713), ulsch_deinterleave with the RI positions left out (sch.c:993-1020) and
+ * srsran_uci_decode_cqi_pusch (uci.c:289-330) on the front of the de-interleaved stream.  The kernel that demaps, descrambles
+ * and de-interleaves also finds the three fields' soft bits (reference scale, before llr_shift) and zeroes the HARQ-ACK
+ * positions; the decisions (1 bit, 2 bits, (32,O) block code, CRC-8 + tail-biting convolutional code) run on the host on those
+ * few soft bits in srsran_b200_pusch_uci_collect.  g keeps the reference's layout and its one quirk: element 0 of the stream
+ * holds the soft bit of the LAST RI position whenever RI is present (sch.c:672-674 maps every RI position to index 0 and
+ * srsran_vec_lut_sis scatters in order).  The UL-SCH bits of subframe i start at g + i*nof_bits + e_offset and are nof_e_bits long.
+ */
+#define SRSRAN_B200_UCI_MAX_ACK_BITS 10 /* SRSRAN_UCI_MAX_ACK_BITS (uci_cfg.h:27) */
+#define SRSRAN_B200_UCI_MAX_CQI_BITS 64 /* SRSRAN_CQI_MAX_BITS (cqi.h:38) */
+
+typedef struct {
+  uint32_t nof_ack;      /* srsran_uci_cfg_total_ack(&cfg->uci_cfg), 0 = no HARQ-ACK field */
+  uint32_t ri_len;       /* cfg->uci_cfg.cqi.ri_len: 0 or 1 (the reference carries a 1-bit RI, uci.c:635) */
+  uint32_t cqi_len;      /* srsran_cqi_size(&cfg->uci_cfg.cqi) when cqi.data_enable, else 0 */
+  uint32_t I_offset_ack; /* srsran_uci_offset_cfg_t: indices into TS 36.213 Tables 8.6.3-1..3 (sch.c:41-95) */
+  uint32_t I_offset_ri;
+  uint32_t I_offset_cqi;
+} srsran_b200_uci_cfg_t;
+
+typedef struct {
+  uint8_t  ack_value[SRSRAN_B200_UCI_MAX_ACK_BITS]; /* srsran_uci_value_t.ack.ack_value; bits not carried stay 2 (srsran_uci_data_reset) */
+  uint8_t  ack_valid;                               /* ack.valid: correlation above the reference's threshold (uci.c:694-710) */
+  uint8_t  ri;
+  uint8_t  cqi_crc;                                 /* cqi.data_crc: 1 for the block-coded form, the CRC-8 verdict above 11 bits */
+  uint8_t  reserved;
+  uint8_t  cqi_bits[SRSRAN_B200_UCI_MAX_CQI_BITS];  /* the cqi_len payload bits, one per byte: input of srsran_cqi_value_unpack */
+  uint32_t Q_prime_ack, Q_prime_ri, Q_prime_cqi;    /* coded modulation symbols of each field */
+  uint32_t e_offset, nof_e_bits;                    /* the UL-SCH part of the subframe's g: arguments of the transport-block decode */
+} srsran_b200_uci_value_t;
+
+/* Host only: Q' of the three fields and the UL-SCH span for a grant of transport block size tbs on this object's allocation
+ * (Q_prime_ri_ack / Q_prime_cqi, uci.c:172-190,395-418, with K_segm from srsran_cbsegm).  Fills the last five members of out. */
+SRSRAN_B200_API int srsran_b200_pusch_uci_geometry(const srsran_b200_pusch_t* q, uint32_t tbs, const srsran_b200_uci_cfg_t* uci,
+                                                   srsran_b200_uci_value_t* out);
+
+/* srsran_b200_pusch_rx_batch for subframes that carry control information: tbs[nsf] and uci[nsf] are host arrays (an all-zero
+ * uci[i] is a subframe without control information).  Enqueues the kernels and the copy of the fields' soft bits on `stream`. */
+SRSRAN_B200_API int srsran_b200_pusch_rx_uci_batch(srsran_b200_pusch_t* q, const void* grid, int16_t* g, float* meas, uint32_t nsf,
+                                                   const uint32_t* rnti, const uint32_t* tti, const uint32_t* n_dmrs, const uint32_t* tbs,
+                                                   const srsran_b200_uci_cfg_t* uci, uint32_t flags, void* stream);
+
+/* Waits for the soft bits of every srsran_b200_pusch_rx_uci_batch call since the last collect and decides them, in call order:
+ * out[0 .. sum of those calls' nsf).  nof_out must equal that sum; out = NULL discards what is pending. */
+SRSRAN_B200_API int srsran_b200_pusch_uci_collect(srsran_b200_pusch_t* q, srsran_b200_uci_value_t* out, uint32_t nof_out);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * One cell's PUSCH receiver for a batch of subframes in ONE call: time samples in, transport-block bytes out.  Replaces, per
  * subframe, srsran_enb_ul_fft (lib/src/phy/enb/enb_ul.c:151-154) and get_pusch (enb_ul.c:262-290: srsran_chest_ul_estimate_pusch +
  * srsran_pusch_decode) for subframes that all carry the configured allocation.  The object owns the three engines above, the
@@ -397,6 +447,13 @@ SRSRAN_B200_API int  srsran_b200_enb_ul_geometry(const srsran_b200_enb_ul_t* q, 
 SRSRAN_B200_API int srsran_b200_enb_ul_pusch_batch(srsran_b200_enb_ul_t* q, const void* samples, uint32_t nsf, const uint32_t* rnti,
                                                    const uint32_t* tti, const uint32_t* n_dmrs, const uint32_t* rv, const uint32_t* new_data,
                                                    uint8_t* data, srsran_b200_pusch_res_t* res, uint32_t flags);
+
+/* The same call for subframes that carry control information (get_pusch with cfg->uci_cfg set, enb_ul.c:262-290): uci[nsf] in,
+ * uci_out[nsf] out; the UL-SCH bits are de-matched from what is left of each subframe after the RI and CQI symbols. */
+SRSRAN_B200_API int srsran_b200_enb_ul_pusch_uci_batch(srsran_b200_enb_ul_t* q, const void* samples, uint32_t nsf, const uint32_t* rnti,
+                                                       const uint32_t* tti, const uint32_t* n_dmrs, const uint32_t* rv,
+                                                       const uint32_t* new_data, const srsran_b200_uci_cfg_t* uci, uint8_t* data,
+                                                       srsran_b200_pusch_res_t* res, srsran_b200_uci_value_t* uci_out, uint32_t flags);
 
 #ifdef __cplusplus
 }

@@ -281,6 +281,45 @@ class _Api:
         assert r == 0, r
         return grid.reshape(nsym, -1).copy()
 
+    def pusch_encode_uci(self, link: np.ndarray, uci: np.ndarray, data: np.ndarray) -> np.ndarray:
+        """Reference only: srsran_pusch_encode with control information (pusch_uci) multiplexed in, + DMRS."""
+        assert self.which == "ref"
+        link = np.ascontiguousarray(link, np.uint32)
+        uci = np.ascontiguousarray(uci, np.uint32)
+        nsym = 12 if link[2] else 14
+        data = np.concatenate([np.ascontiguousarray(data, np.uint8), np.zeros(8, np.uint8)])
+        grid = _aligned(nsym * 12 * int(link[1]), np.complex64)
+        r = self.lib.ref_pusch_encode_uci(_p(link), _p(uci), _p(data), _p(grid))
+        assert r == 0, r
+        return grid.reshape(nsym, -1).copy()
+
+    def pusch_decode_uci(self, link: np.ndarray, uci: np.ndarray, grid: np.ndarray, identity_ce: bool = False) -> dict:
+        """Reference only: (chest +) srsran_pusch_decode of one subframe that carries HARQ-ACK / RI / CQI."""
+        assert self.which == "ref"
+        link = np.ascontiguousarray(link, np.uint32)
+        uci = np.ascontiguousarray(uci, np.uint32)
+        Qm = {1: 2, 2: 4, 3: 6}[int(link[11])]
+        nsym = 12 if link[2] else 14
+        nre = (nsym - 2) * 12 * int(link[9])
+        grid = _aligned_copy(grid, np.complex64)
+        data = np.zeros(int(link[12]) // 8 + 16, np.uint8)
+        crc = C.c_int(0)
+        meas = np.zeros(8, np.float32)
+        q = _aligned(nre * Qm, np.int16)
+        g = _aligned(nre * Qm, np.int16)
+        out = np.zeros(14 + 64, np.int32)
+        r = self.lib.ref_pusch_decode_uci(_p(link), _p(uci), _p(grid), C.c_int(int(identity_ce)), _p(data), C.byref(crc), _p(meas),
+                                          _p(q), _p(g), _p(out))
+        return dict(ret=r, crc=bool(crc.value), data=data[:int(link[12]) // 8].copy(), noise=float(meas[0]), q=q.copy(), g=g.copy(),
+                    ack=out[:10].copy(), ack_valid=bool(out[10]), ri=int(out[11]), cqi_crc=bool(out[12]),
+                    cqi_bits=out[14:14 + int(out[13])].astype(np.uint8))
+
+    def qprime_ack(self, L_prb: int, nof_symbols: int, K_segm: int, nof_ack: int, beta: float) -> int:
+        assert self.which == "ref"
+        f = self.lib.ref_qprime_ack
+        f.restype = C.c_uint32
+        return int(f(C.c_uint32(L_prb), C.c_uint32(nof_symbols), C.c_uint32(K_segm), C.c_uint32(nof_ack), C.c_float(beta)))
+
     def pusch_decode(self, link: np.ndarray, grid: np.ndarray, identity_ce: bool = False) -> dict:
         """Reference only: (chest +) srsran_pusch_decode of one subframe, with the object's intermediate buffers."""
         assert self.which == "ref"
@@ -320,6 +359,12 @@ def pusch_link(cell_id=1, nof_prb=100, cp_ext=0, cyclic_shift=0, delta_ss=0, gro
     """The uint32 parameter block shared by ref_harness.c and oracle_port.c (mod: 1 QPSK, 2 16QAM, 3 64QAM)."""
     return np.array([cell_id, nof_prb, cp_ext, cyclic_shift, delta_ss, group_hopping, sequence_hopping, rnti, tti, L_prb, n_prb, mod,
                      tbs, rv, n_dmrs, max_iter], np.uint32)
+
+
+def pusch_uci(nof_ack=0, ack_bits=0, ri_len=0, ri=0, cqi_kind=0, cqi_N=0, cqi_wb=0, cqi_sb=0, I_offset_ack=9, I_offset_ri=5,
+              I_offset_cqi=6) -> np.ndarray:
+    """The uint32 UCI parameter block of ref_harness.c (cqi_kind: 0 none, 1 wideband, 2 wideband + PMI, 3 higher-layer subband)."""
+    return np.array([nof_ack, ack_bits, ri_len, ri, cqi_kind, cqi_N, cqi_wb, cqi_sb, I_offset_ack, I_offset_ri, I_offset_cqi], np.uint32)
 
 
 def _aligned(n: int, dtype, align: int = 64) -> np.ndarray:

@@ -748,3 +748,149 @@ int ref_pusch_rx_bench(const uint32_t* p, cf_t* grids, uint32_t nsf, int nthread
   free(jobs);
   return err;
 }
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * PUSCH with control information multiplexed into it (TS 36.212 5.2.2.6-5.2.2.8; sch.c:1022-1195, uci.c).
+ * UCI parameters, all uint32:
+ *  0 nof_ack (uci_cfg.ack[0].nof_acks)  1 ack bits (bit a = ack_value[a])  2 ri_len  3 ri
+ *  4 cqi kind: 0 none, 1 wideband (4 bits), 2 wideband + PMI, 2 ports, rank 1 (6 bits), 3 higher-layer subband (4 + 2N bits)
+ *  5 N (kind 3)  6 wideband cqi  7 subband differential cqi (kind 3) / pmi (kind 2)
+ *  8 I_offset_ack  9 I_offset_ri  10 I_offset_cqi */
+enum { U_NOF_ACK, U_ACK_BITS, U_RI_LEN, U_RI, U_CQI_KIND, U_CQI_N, U_CQI_WB, U_CQI_SB, U_IOFF_ACK, U_IOFF_RI, U_IOFF_CQI, U_COUNT };
+
+static void link_uci(const uint32_t* u, srsran_pusch_cfg_t* cfg, srsran_uci_value_t* val)
+{
+  memset(val, 0, sizeof(*val));
+  cfg->uci_cfg.ack[0].nof_acks = u[U_NOF_ACK];
+  for (uint32_t a = 0; a < u[U_NOF_ACK]; a++) val->ack.ack_value[a] = (u[U_ACK_BITS] >> a) & 1u;
+  cfg->uci_cfg.cqi.ri_len = u[U_RI_LEN];
+  val->ri                 = (uint8_t)u[U_RI];
+  if (u[U_CQI_KIND]) {
+    cfg->uci_cfg.cqi.data_enable = true;
+    if (u[U_CQI_KIND] == 3) {
+      cfg->uci_cfg.cqi.type                   = SRSRAN_CQI_TYPE_SUBBAND_HL;
+      cfg->uci_cfg.cqi.N                      = u[U_CQI_N];
+      val->cqi.subband_hl.wideband_cqi_cw0     = (uint8_t)u[U_CQI_WB];
+      val->cqi.subband_hl.subband_diff_cqi_cw0 = u[U_CQI_SB];
+    } else {
+      cfg->uci_cfg.cqi.type          = SRSRAN_CQI_TYPE_WIDEBAND;
+      cfg->uci_cfg.cqi.pmi_present   = u[U_CQI_KIND] == 2;
+      val->cqi.wideband.wideband_cqi = (uint8_t)u[U_CQI_WB];
+      val->cqi.wideband.pmi          = (uint8_t)u[U_CQI_SB];
+    }
+  }
+  cfg->uci_offset.I_offset_ack = u[U_IOFF_ACK];
+  cfg->uci_offset.I_offset_ri  = u[U_IOFF_RI];
+  cfg->uci_offset.I_offset_cqi = u[U_IOFF_CQI];
+}
+
+/* srsran_pusch_encode with pdata.uci set + DMRS, like ref_pusch_encode */
+int ref_pusch_encode_uci(const uint32_t* p, const uint32_t* u, uint8_t* data, cf_t* grid)
+{
+  srsran_cell_t                     cell = link_cell(p);
+  srsran_pusch_cfg_t                cfg;
+  srsran_ul_sf_cfg_t                sf;
+  srsran_refsignal_dmrs_pusch_cfg_t dmrs;
+  srsran_pusch_t                    tx;
+  srsran_softbuffer_tx_t            sb;
+  srsran_refsignal_ul_t             rs;
+  srsran_pusch_data_t               pdata;
+  link_cfg(p, &cell, &cfg, &sf, &dmrs);
+  memset(&pdata, 0, sizeof(pdata));
+  link_uci(u, &cfg, &pdata.uci);
+  ensure_tables();
+  if (srsran_pusch_init_ue(&tx, cell.nof_prb)) return -1;
+  if (srsran_pusch_set_cell(&tx, cell)) return -2;
+  if (srsran_softbuffer_tx_init(&sb, cell.nof_prb)) return -3;
+  srsran_softbuffer_tx_reset(&sb);
+  cfg.softbuffers.tx = &sb;
+  pdata.ptr          = data;
+  uint32_t nre       = 2 * SRSRAN_CP_NSYMB(cell.cp) * 12 * cell.nof_prb;
+  memset(grid, 0, sizeof(cf_t) * nre);
+  int r = srsran_pusch_encode(&tx, &sf, &cfg, &pdata, grid);
+  if (r == 0) {
+    cf_t* rp = srsran_vec_cf_malloc(2 * 12 * p[P_L_PRB]);
+    memset(&rs, 0, sizeof(rs));
+    if (srsran_refsignal_ul_set_cell(&rs, cell)) r = -4;
+    else if (srsran_refsignal_dmrs_pusch_gen(&rs, &dmrs, p[P_L_PRB], p[P_TTI] % 10, p[P_N_DMRS], rp)) r = -5;
+    else srsran_refsignal_dmrs_pusch_put(&rs, &cfg, rp, grid);
+    free(rp);
+  }
+  srsran_softbuffer_tx_free(&sb);
+  srsran_pusch_free(&tx);
+  return r;
+}
+
+/* chest + srsran_pusch_decode with the same UCI configuration.  uci_out (int32):
+ *  0..9 ack_value  10 ack.valid  11 ri  12 cqi.data_crc  13 cqi_len  14.. the cqi payload bits (srsran_cqi_value_pack of what was decoded)
+ * q_out: the object's q->q after the call (descrambled, HARQ-ACK positions zeroed), g_out: q->g */
+int ref_pusch_decode_uci(const uint32_t* p, const uint32_t* u, cf_t* grid, int use_identity_ce, uint8_t* data, int* crc_ok, float* meas,
+                         int16_t* q_out, int16_t* g_out, int32_t* uci_out)
+{
+  srsran_cell_t                     cell = link_cell(p);
+  srsran_pusch_cfg_t                cfg;
+  srsran_ul_sf_cfg_t                sf;
+  srsran_refsignal_dmrs_pusch_cfg_t dmrs;
+  srsran_pusch_t                    rx;
+  srsran_softbuffer_rx_t            sb;
+  srsran_chest_ul_t                 chest;
+  srsran_chest_ul_res_t             res;
+  srsran_uci_value_t                sent;
+  link_cfg(p, &cell, &cfg, &sf, &dmrs);
+  link_uci(u, &cfg, &sent);
+  ensure_tables();
+  if (srsran_pusch_init_enb(&rx, cell.nof_prb)) return -1;
+  if (srsran_pusch_set_cell(&rx, cell)) return -2;
+  if (srsran_softbuffer_rx_init(&sb, cell.nof_prb)) return -3;
+  srsran_softbuffer_rx_reset(&sb);
+  cfg.softbuffers.rx = &sb;
+  if (srsran_chest_ul_res_init(&res, cell.nof_prb)) return -4;
+  if (use_identity_ce) {
+    srsran_chest_ul_res_set_identity(&res);
+    res.noise_estimate = 0;
+  } else {
+    if (srsran_chest_ul_init(&chest, cell.nof_prb)) return -5;
+    if (srsran_chest_ul_set_cell(&chest, cell)) return -6;
+    srsran_chest_ul_pregen(&chest, &dmrs, NULL);
+    memset(res.ce, 0, sizeof(cf_t) * res.nof_re);
+    if (srsran_chest_ul_estimate_pusch(&chest, &sf, &cfg, grid, &res)) return -7;
+    srsran_chest_ul_free(&chest);
+  }
+  if (meas) {
+    meas[0] = res.noise_estimate;
+    meas[1] = res.snr;
+    meas[2] = res.cfo_hz;
+    meas[3] = res.ta_us;
+  }
+  srsran_pusch_res_t out;
+  memset(&out, 0, sizeof(out));
+  out.data = data;
+  memset(out.uci.ack.ack_value, 2, SRSRAN_UCI_MAX_ACK_BITS);
+  int r = srsran_pusch_decode(&rx, &sf, &cfg, &res, grid, &out);
+  if (crc_ok) *crc_ok = out.crc ? 1 : 0;
+  if (meas) meas[4] = out.avg_iterations_block;
+  if (q_out) memcpy(q_out, rx.q, sizeof(int16_t) * cfg.grant.tb.nof_bits);
+  if (g_out) memcpy(g_out, rx.g, sizeof(int16_t) * cfg.grant.tb.nof_bits);
+  for (int a = 0; a < 10; a++) uci_out[a] = out.uci.ack.ack_value[a];
+  uci_out[10] = out.uci.ack.valid ? 1 : 0;
+  uci_out[11] = out.uci.ri;
+  uci_out[12] = out.uci.cqi.data_crc ? 1 : 0;
+  uci_out[13] = 0;
+  if (cfg.uci_cfg.cqi.data_enable) {
+    uint8_t buff[SRSRAN_CQI_MAX_BITS];
+    memset(buff, 0, sizeof(buff));
+    int n       = srsran_cqi_value_pack(&cfg.uci_cfg.cqi, &out.uci.cqi, buff);
+    uci_out[13] = n;
+    for (int i = 0; i < n; i++) uci_out[14 + i] = buff[i];
+  }
+  srsran_chest_ul_res_free(&res);
+  srsran_softbuffer_rx_free(&sb);
+  srsran_pusch_free(&rx);
+  return r;
+}
+
+/* uci.c:395-427 through its exported wrappers (K_segm = the argument named tbs there) */
+uint32_t ref_qprime_ack(uint32_t L_prb, uint32_t nof_symbols, uint32_t K_segm, uint32_t nof_ack, float beta)
+{
+  return srsran_qprime_ack_ext(L_prb, nof_symbols, K_segm, nof_ack, beta);
+}

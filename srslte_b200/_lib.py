@@ -76,6 +76,10 @@ def lib() -> C.CDLL:
     L.srsran_b200_pusch_equalize_deprecode_batch.argtypes = [vp, vp, vp, vp, vp, u32, u32, vp]
     L.srsran_b200_pusch_demod_descramble_batch.argtypes = [vp, vp, vp, u32, vp, vp, u32, vp]
     L.srsran_b200_pusch_rx_batch.argtypes = [vp, vp, vp, vp, u32, vp, vp, vp, u32, vp]
+    L.srsran_b200_pusch_uci_geometry.argtypes = [vp, u32, vp, vp]
+    L.srsran_b200_pusch_rx_uci_batch.argtypes = [vp, vp, vp, vp, u32, vp, vp, vp, vp, vp, u32, vp]
+    L.srsran_b200_pusch_uci_collect.argtypes = [vp, vp, u32]
+    L.srsran_b200_enb_ul_pusch_uci_batch.argtypes = [vp, vp, u32, vp, vp, vp, vp, vp, vp, vp, vp, vp, u32]
     L.srsran_b200_enb_ul_init.argtypes = [C.POINTER(vp), C.c_int, vp]
     L.srsran_b200_enb_ul_free.argtypes = [vp]
     L.srsran_b200_enb_ul_free.restype = None
@@ -106,6 +110,10 @@ EXPORTED_SYMBOLS = [
     "srsran_b200_pusch_equalize_deprecode_batch",
     "srsran_b200_pusch_demod_descramble_batch",
     "srsran_b200_pusch_rx_batch",
+    "srsran_b200_pusch_uci_geometry",
+    "srsran_b200_pusch_rx_uci_batch",
+    "srsran_b200_pusch_uci_collect",
+    "srsran_b200_enb_ul_pusch_uci_batch",
     "srsran_b200_enb_ul_init",
     "srsran_b200_enb_ul_free",
     "srsran_b200_enb_ul_geometry",

@@ -23,13 +23,13 @@ SOURCES = [
     "b200_runtime.cu",
     "tdec_kernels.cu",
     "tdec_host.cu",
-    "tdec_ll.cu",
     "rm_kernels.cu",
     "sch_host.cu",
     "ofdm_kernels.cu",
     "ofdm_host.cu",
     "demod_kernels.cu",
     "pusch_kernels.cu",
+    "uci_host.cu",
     "enb_ul.cu",
     "srsran_compat.cu",
 ]

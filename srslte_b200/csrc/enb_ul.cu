@@ -36,6 +36,7 @@ struct EnbUl {
   uint8_t* d_data = nullptr;
   float*   d_meas = nullptr;
   std::vector<srsran_b200_tb_t> tbs;
+  std::vector<uint32_t>         tbs_vec; // the configured size once per subframe: argument of the UCI entry
   std::vector<uint32_t>         crc_mask; // per slot, carried across retransmissions (sch.c:474-488)
   std::vector<float>            h_meas;
 
@@ -145,9 +146,10 @@ struct EnbUl {
   }
 
   int run(const void* samples, uint32_t nsf, const uint32_t* rnti, const uint32_t* tti, const uint32_t* n_dmrs, const uint32_t* rv,
-          const uint32_t* new_data, uint8_t* data, srsran_b200_pusch_res_t* res, uint32_t flags)
+          const uint32_t* new_data, uint8_t* data, srsran_b200_pusch_res_t* res, uint32_t flags, const srsran_b200_uci_cfg_t* uci = nullptr,
+          srsran_b200_uci_value_t* uci_out = nullptr)
   {
-    if (!samples || !data || !res) return B200_ERROR_INVALID_INPUTS;
+    if (!samples || !data || !res || (uci && !uci_out)) return B200_ERROR_INVALID_INPUTS;
     if (nsf == 0) return B200_SUCCESS;
     B200_CUDA_TRY(cudaSetDevice(device));
     const bool   dev_ptrs = (flags & SRSRAN_B200_FLAG_DEVICE_PTRS) != 0;
@@ -162,6 +164,19 @@ struct EnbUl {
       cap_iq = cap_sf;
     }
     const uint32_t fe_flags = SRSRAN_B200_FLAG_DEVICE_PTRS | (iq16 ? SRSRAN_B200_FLAG_IQ_INT16 : 0u);
+    // where the UL-SCH bits of each subframe lie: everything, or what the RI and CQI symbols leave (sch.c:1186-1190)
+    if (uci) tbs_vec.assign(nsf, cfg.tbs);
+    for (uint32_t i = 0; i < nsf; i++) {
+      uint32_t e_off = 0, e_bits = nbits;
+      if (uci) {
+        srsran_b200_uci_value_t span;
+        if ((rc = srsran_b200_pusch_uci_geometry(pusch, cfg.tbs, &uci[i], &span)) != B200_SUCCESS) return rc;
+        e_off  = span.e_offset;
+        e_bits = span.nof_e_bits;
+      }
+      tbs[i].e_offset   = (uint64_t)i * nbits + e_off;
+      tbs[i].nof_e_bits = e_bits;
+    }
 
     // ---- front end, chunk by chunk -----------------------------------------------------------------------------------------
     const uint32_t chunk   = dev_ptrs ? nsf : (nsf > 1024 ? 512u : (nsf + 1) / 2);
@@ -184,9 +199,16 @@ struct EnbUl {
       }
       float2* grid_c = d_grid + (size_t)first * nsym * nre;
       if ((rc = srsran_b200_ofdm_rx_sf_batch(ofdm, d_in, grid_c, n, fe_flags, compute)) != B200_SUCCESS) return rc;
-      if ((rc = srsran_b200_pusch_rx_batch(pusch, grid_c, d_llr + (size_t)first * nbits, d_meas + (size_t)first * 4, n, rnti ? rnti + first : nullptr,
-                                           tti ? tti + first : nullptr, n_dmrs ? n_dmrs + first : nullptr, SRSRAN_B200_FLAG_DEVICE_PTRS,
-                                           compute)) != B200_SUCCESS) {
+      if (uci) {
+        rc = srsran_b200_pusch_rx_uci_batch(pusch, grid_c, d_llr + (size_t)first * nbits, d_meas + (size_t)first * 4, n, rnti ? rnti + first : nullptr,
+                                            tti ? tti + first : nullptr, n_dmrs ? n_dmrs + first : nullptr, tbs_vec.data() + first, uci + first,
+                                            SRSRAN_B200_FLAG_DEVICE_PTRS, compute);
+      } else {
+        rc = srsran_b200_pusch_rx_batch(pusch, grid_c, d_llr + (size_t)first * nbits, d_meas + (size_t)first * 4, n, rnti ? rnti + first : nullptr,
+                                        tti ? tti + first : nullptr, n_dmrs ? n_dmrs + first : nullptr, SRSRAN_B200_FLAG_DEVICE_PTRS, compute);
+      }
+      if (rc != B200_SUCCESS) {
+        if (uci) srsran_b200_pusch_uci_collect(pusch, nullptr, 0); // drop the chunks already queued
         return rc;
       }
     }
@@ -211,6 +233,7 @@ struct EnbUl {
       B200_CUDA_TRY(cudaMemcpy2DAsync(data, out_b, d_data, data_stride, out_b, nsf, cudaMemcpyDeviceToHost, compute));
     }
     B200_CUDA_TRY(cudaStreamSynchronize(compute));
+    if (uci && (rc = srsran_b200_pusch_uci_collect(pusch, uci_out, nsf)) != B200_SUCCESS) return rc;
     for (uint32_t i = 0; i < nsf; i++) {
       crc_mask[i]           = tbs[i].cb_crc_mask;
       res[i].crc_ok         = tbs[i].result == B200_SUCCESS ? 1 : 0;
@@ -257,6 +280,15 @@ extern "C" SRSRAN_B200_API int srsran_b200_enb_ul_geometry(const srsran_b200_enb
   if (sf_sz) *sf_sz = q->e.sf_sz;
   if (tb_bytes) *tb_bytes = q->e.cfg.tbs / 8 + 3;
   return B200_SUCCESS;
+}
+
+extern "C" SRSRAN_B200_API int srsran_b200_enb_ul_pusch_uci_batch(srsran_b200_enb_ul_t* q, const void* samples, uint32_t nsf, const uint32_t* rnti,
+                                                                 const uint32_t* tti, const uint32_t* n_dmrs, const uint32_t* rv,
+                                                                 const uint32_t* new_data, const srsran_b200_uci_cfg_t* uci, uint8_t* data,
+                                                                 srsran_b200_pusch_res_t* res, srsran_b200_uci_value_t* uci_out, uint32_t flags)
+{
+  if (!q || !uci || !uci_out) return B200_ERROR_INVALID_INPUTS;
+  return q->e.run(samples, nsf, rnti, tti, n_dmrs, rv, new_data, data, res, flags, uci, uci_out);
 }
 
 extern "C" SRSRAN_B200_API int srsran_b200_enb_ul_pusch_batch(srsran_b200_enb_ul_t* q, const void* samples, uint32_t nsf, const uint32_t* rnti,

@@ -11,9 +11,9 @@
 //   UL-SCH de-interleaving     ulsch_deinterleave                    lib/src/phy/phch/sch.c:660-681,993-1020     }
 //
 // in the order lib/src/phy/phch/pusch.c:392-456 (srsran_pusch_decode) and sch.c:1121-1190 (srsran_ulsch_decode) call them.
-// Scope: one receive antenna, no uplink control information multiplexed into the PUSCH (no RI / ACK / CQI bits), no
-// intra-subframe hopping (the reference's estimator refuses it too, chest_ul.c:276), allocations of >= 3 PRB (the 1- and
-// 2-PRB DMRS base sequences are table look-ups of TS 36.211 5.5.1.2 that are not carried here).
+//   control information        uci_decode_ri_ack, ulsch_deinterleave  lib/src/phy/phch/sch.c:993-1119 (UCI = true instantiation + uci_host.cu)
+// Scope: one receive antenna (like pusch.c:413), no intra-subframe hopping (the reference's estimator refuses it too,
+// chest_ul.c:330), every allocation srsran_dft_precoding_valid_prb accepts.
 #include <cuda_runtime.h>
 #include <math.h>
 #include <string.h>
@@ -25,7 +25,9 @@
 #include "b200_runtime.h"
 #include "demod_core.h"
 #include "ofdm_kernels.h"
+#include "lte_tables.h"
 #include "tdec_engine.h"
+#include "uci_host.h"
 
 namespace b200 {
 
@@ -139,10 +141,40 @@ __global__ void __launch_bounds__(256) pusch_gold_kernel(const PuschSfParam* __r
 // at g[(j*nd + i)*Qm + k] (sch.c:660-681 with rows = M, cols = nd, no RI bits).  A block stages a tile of 64 subcarriers x nd
 // symbols in shared memory (coalesced row reads), then walks it in output order so the stores are contiguous.
 constexpr int DEMOD_TJ = 64;
-template <int MOD, int ND> // srsran_mod_t 1..3; data symbols per subframe 12 (normal CP) or 10 (extended): constants, so no run-time divisions
+//
+// UCI = true (TS 36.212 5.2.2.7-5.2.2.8; sch.c:993-1119, uci.c:346-393,637-690): the interleaver matrix has M rows (subcarriers) and
+// nd columns (data symbols).  HARQ-ACK symbol a sits in row M-1-a/4 of the column set {2,3,8,9} ({1,2,6,7} with the extended
+// prefix) taken in the order (3a)%4, RI symbol r likewise in {1,4,7,10} ({0,3,5,8}).  The de-interleaved stream leaves the RI
+// positions out (everything after them moves up) and carries zeros at the HARQ-ACK positions; the fields' own soft bits go, at
+// the demapper's scale (no llr_shift), to the subframe's row of `uci_llr`: [Q_ack*Qm | Q_ri*Qm | Q_cqi*Qm], the last being a copy of
+// the front of the stream.  In the 1-bit forms the repeated bit's scrambling is undone here (uci.c:678-682: it was scrambled
+// like its predecessor).  Element 0 of the stream repeats the reference's scatter quirk: see include/srslte_b200.h.
+struct PuschUciSf {
+  uint32_t Q_ack, Q_ri, Q_cqi;
+  uint32_t flags; // bit 0: 1-bit HARQ-ACK, bit 1: 1-bit RI
+};
+struct PuschUciArgs {
+  const PuschUciSf* sf;      // [nsf]
+  int16_t*          llr;     // [nsf][stride]
+  uint32_t          stride;  // int16 per subframe
+  uint32_t          off_ri, off_cqi;
+};
+
+template <int ND>
+__device__ __forceinline__ int uci_col_order(uint32_t col, bool ri) // position of `col` in the field's filling order, -1 = not its column
+{
+  if (ND > 10) {
+    if (ri) return col == 1 ? 0 : col == 10 ? 1 : col == 7 ? 2 : col == 4 ? 3 : -1;
+    return col == 2 ? 0 : col == 9 ? 1 : col == 8 ? 2 : col == 3 ? 3 : -1;
+  }
+  if (ri) return col == 0 ? 0 : col == 8 ? 1 : col == 5 ? 2 : col == 3 ? 3 : -1;
+  return col == 1 ? 0 : col == 7 ? 1 : col == 6 ? 2 : col == 2 ? 3 : -1;
+}
+
+template <int MOD, int ND, bool UCI = false> // srsran_mod_t 1..3; data symbols per subframe 12 (normal CP) or 10 (extended): constants, so no run-time divisions
 __global__ void __launch_bounds__(256) pusch_demod_descramble_kernel(const float2* __restrict__ d, const uint32_t* __restrict__ seq,
                                                                      int16_t* __restrict__ g, uint32_t M, uint32_t nwords, int shift,
-                                                                     float qpsk_scale)
+                                                                     float qpsk_scale, PuschUciArgs uci)
 {
   constexpr int      mod = MOD;
   constexpr uint32_t nd  = ND;
@@ -168,6 +200,52 @@ __global__ void __launch_bounds__(256) pusch_demod_descramble_kernel(const float
     const uint32_t n = pos * (uint32_t)Qm, wd = n >> 5, sh = n & 31u;
     uint32_t       bits = sq[wd] >> sh;
     if (sh + (uint32_t)Qm > 32u) bits |= sq[wd + 1] << (32u - sh);
+    if (UCI) {
+      const PuschUciSf u  = uci.sf[sf];
+      const uint32_t   jr = M - 1u - j; // rows counted from the bottom, where both fields start
+      const int        o_ri = uci_col_order<ND>(i, true), o_ack = uci_col_order<ND>(i, false);
+      const bool       is_ri = o_ri >= 0 && 4u * jr + (uint32_t)o_ri < u.Q_ri, is_ack = o_ack >= 0 && 4u * jr + (uint32_t)o_ack < u.Q_ack;
+      // RI symbols in the rows above this one, plus those of this row in earlier columns
+      uint32_t before = u.Q_ri > 4u * (jr + 1u) ? u.Q_ri - 4u * (jr + 1u) : 0u;
+#pragma unroll
+      for (uint32_t c = 0; c < nd; c++) {
+        const int o = uci_col_order<ND>(c, true);
+        if (o >= 0 && c < i && 4u * jr + (uint32_t)o < u.Q_ri) before++;
+      }
+      const uint32_t sym  = j * nd + i - before; // index of this symbol in the de-interleaved stream (unless it is RI)
+      int16_t*       row  = uci.llr + (size_t)sf * uci.stride;
+      int16_t*       gs   = g + (size_t)sf * per_sf * Qm;
+      const bool     last_ri = is_ri && jr == 0u && o_ri == (u.Q_ri >= 2u ? 1 : 0); // the largest RI position of the matrix
+#pragma unroll
+      for (int k = 0; k < Qm; k++) {
+        int v = (int)o[k];
+        if ((bits >> k) & 1u) v = -v;
+        const int16_t raw = (int16_t)v;                       // reference scale, int16 wrap like srsran_sequence_pusch_apply_s
+        int           vs  = (int)o[k] >> shift;
+        if ((bits >> k) & 1u) vs = -vs;
+        const int16_t sh = (int16_t)vs;
+        if (is_ri) {
+          int16_t f = raw;
+          if (k == 1 && (u.flags & 2u) && (((bits >> 1) ^ bits) & 1u)) f = (int16_t)(-(int)raw);
+          row[uci.off_ri + (4u * jr + (uint32_t)o_ri) * Qm + k] = f;
+          if (last_ri && k == Qm - 1) {
+            gs[0] = sh;
+            if (u.Q_cqi) row[uci.off_cqi] = raw;
+          }
+        } else {
+          if (is_ack) {
+            int16_t f = raw;
+            if (k == 1 && (u.flags & 1u) && (((bits >> 1) ^ bits) & 1u)) f = (int16_t)(-(int)raw);
+            row[(4u * jr + (uint32_t)o_ack) * Qm + k] = f;
+          }
+          if (!(sym == 0u && k == 0 && u.Q_ri)) {
+            gs[(size_t)sym * Qm + k] = is_ack ? (int16_t)0 : sh;
+            if (sym < u.Q_cqi) row[uci.off_cqi + sym * Qm + k] = is_ack ? (int16_t)0 : raw;
+          }
+        }
+      }
+      continue;
+    }
     const size_t ow = ((size_t)j * nd + i) * (size_t)mod;
 #pragma unroll
     for (int w = 0; w < 3; w++) {
@@ -240,10 +318,36 @@ struct PuschRx {
   cudaEvent_t   prm_ev[2]  = {nullptr, nullptr};
   uint32_t      h_prm_cap  = 0;
   int           prm_cur    = 0;
+  // control information: one buffer set per rx_uci_batch call that has not been collected yet (srsran_b200_pusch_uci_collect)
+  struct UciBatch {
+    PuschUciSf* d_sf = nullptr; // device and page-locked host copies of the per-subframe field sizes
+    PuschUciSf* h_sf = nullptr;
+    int16_t*    d_llr = nullptr; // the fields' soft bits, [nsf][stride]
+    int16_t*    h_llr = nullptr;
+    size_t      cap_sf = 0, cap_llr = 0;
+    cudaEvent_t done = nullptr;
+    bool        pending = false;
+    uint32_t    nsf = 0, stride = 0, off_ri = 0, off_cqi = 0;
+    std::vector<UciGeometry>           geo;
+    std::vector<srsran_b200_uci_cfg_t> cfg;
+  };
+  std::vector<UciBatch*> uci_pool;
+  std::vector<UciBatch*> uci_pending; // in call order
 
   ~PuschRx()
   {
     if (ctx) cudaSetDevice(ctx->device);
+    for (UciBatch* b : uci_pool) {
+      if (b->done) {
+        cudaEventSynchronize(b->done);
+        cudaEventDestroy(b->done);
+      }
+      if (b->d_sf) cudaFree(b->d_sf);
+      if (b->d_llr) cudaFree(b->d_llr);
+      if (b->h_sf) cudaFreeHost(b->h_sf);
+      if (b->h_llr) cudaFreeHost(b->h_llr);
+      delete b;
+    }
     for (void* p : {(void*)dW, (void*)d_dmrs, (void*)d_x1w, (void*)d_jump, (void*)d_prm, (void*)d_seq, (void*)d_ce, (void*)d_d, (void*)d_meas}) {
       if (p) cudaFree(p);
     }
@@ -462,7 +566,124 @@ struct PuschRx {
     return B200_SUCCESS;
   }
 
-  int demod(const float2* d, int16_t* g, uint32_t nsf, cudaStream_t st)
+  // field sizes and the UL-SCH span of one grant (uci.c:172-190,395-418; sch.c:1136,1186-1190)
+  int uci_span(uint32_t tbs, const srsran_b200_uci_cfg_t& c, UciGeometry* geo, uint32_t* e_offset, uint32_t* nof_e_bits) const
+  {
+    CbSegm seg;
+    if (cb_segmentation(tbs, seg) != 0) return B200_ERROR_INVALID_INPUTS;
+    const int rc = uci_geometry(c, seg.C1 * seg.K1 + seg.C2 * seg.K2, (uint32_t)M, (uint32_t)nd, geo);
+    if (rc != B200_SUCCESS) return rc;
+    if (geo->Q_ri + geo->Q_cqi >= (uint32_t)(nd * M)) {
+      B200_LOG_ERROR("control information leaves no room for the transport block (Q'_ri=%u Q'_cqi=%u of %d symbols)", geo->Q_ri, geo->Q_cqi, nd * M);
+      return B200_ERROR_INVALID_INPUTS;
+    }
+    if (e_offset) *e_offset = geo->Q_cqi * (uint32_t)Qm;
+    if (nof_e_bits) *nof_e_bits = ((uint32_t)(nd * M) - geo->Q_ri - geo->Q_cqi) * (uint32_t)Qm;
+    return B200_SUCCESS;
+  }
+
+  // buffers of one rx_uci_batch call: field sizes to the device now, soft bits back after the kernel
+  int uci_begin(uint32_t nsf, const uint32_t* tbs, const srsran_b200_uci_cfg_t* uci, cudaStream_t st, UciBatch** out)
+  {
+    UciBatch* b = nullptr;
+    for (UciBatch* c : uci_pool) {
+      if (!c->pending) {
+        b = c;
+        break;
+      }
+    }
+    if (!b) {
+      b = new (std::nothrow) UciBatch();
+      if (!b) return B200_ERROR;
+      uci_pool.push_back(b);
+      B200_CUDA_TRY(cudaEventCreateWithFlags(&b->done, cudaEventDisableTiming));
+    }
+    b->geo.assign(nsf, UciGeometry());
+    b->cfg.assign(uci, uci + nsf);
+    uint32_t qa = 0, qr = 0, qc = 0;
+    for (uint32_t i = 0; i < nsf; i++) {
+      const int rc = uci_span(tbs[i], uci[i], &b->geo[i], nullptr, nullptr);
+      if (rc != B200_SUCCESS) return rc;
+      qa = b->geo[i].Q_ack > qa ? b->geo[i].Q_ack : qa;
+      qr = b->geo[i].Q_ri > qr ? b->geo[i].Q_ri : qr;
+      qc = b->geo[i].Q_cqi > qc ? b->geo[i].Q_cqi : qc;
+    }
+    b->nsf     = nsf;
+    b->off_ri  = qa * (uint32_t)Qm;
+    b->off_cqi = (qa + qr) * (uint32_t)Qm;
+    b->stride  = ((qa + qr + qc) * (uint32_t)Qm + 7u) & ~7u;
+    if (b->stride == 0) b->stride = 8;
+    if (nsf > b->cap_sf) {
+      if (b->d_sf) cudaFree(b->d_sf);
+      if (b->h_sf) cudaFreeHost(b->h_sf);
+      b->d_sf = nullptr; b->h_sf = nullptr; b->cap_sf = 0;
+      B200_CUDA_TRY(cudaMalloc(&b->d_sf, (size_t)nsf * sizeof(PuschUciSf)));
+      B200_CUDA_TRY(cudaHostAlloc((void**)&b->h_sf, (size_t)nsf * sizeof(PuschUciSf), cudaHostAllocDefault));
+      b->cap_sf = nsf;
+    }
+    const size_t need = (size_t)nsf * b->stride;
+    if (need > b->cap_llr) {
+      if (b->d_llr) cudaFree(b->d_llr);
+      if (b->h_llr) cudaFreeHost(b->h_llr);
+      b->d_llr = nullptr; b->h_llr = nullptr; b->cap_llr = 0;
+      B200_CUDA_TRY(cudaMalloc(&b->d_llr, need * sizeof(int16_t)));
+      B200_CUDA_TRY(cudaHostAlloc((void**)&b->h_llr, need * sizeof(int16_t), cudaHostAllocDefault));
+      b->cap_llr = need;
+    }
+    for (uint32_t i = 0; i < nsf; i++) {
+      b->h_sf[i] = PuschUciSf{b->geo[i].Q_ack, b->geo[i].Q_ri, b->geo[i].Q_cqi, (b->geo[i].ack_one_bit ? 1u : 0u) | (b->geo[i].ri_one_bit ? 2u : 0u)};
+    }
+    B200_CUDA_TRY(cudaMemcpyAsync(b->d_sf, b->h_sf, (size_t)nsf * sizeof(PuschUciSf), cudaMemcpyHostToDevice, st));
+    *out = b;
+    return B200_SUCCESS;
+  }
+
+  int uci_end(UciBatch* b, cudaStream_t st)
+  {
+    B200_CUDA_TRY(cudaMemcpyAsync(b->h_llr, b->d_llr, (size_t)b->nsf * b->stride * sizeof(int16_t), cudaMemcpyDeviceToHost, st));
+    B200_CUDA_TRY(cudaEventRecord(b->done, st));
+    b->pending = true;
+    uci_pending.push_back(b);
+    return B200_SUCCESS;
+  }
+
+  int uci_collect(srsran_b200_uci_value_t* out, uint32_t nof_out)
+  {
+    uint32_t total = 0;
+    for (UciBatch* b : uci_pending) total += b->nsf;
+    if (!out) { // discard: the caller gave up on the batch
+      for (UciBatch* b : uci_pending) {
+        cudaEventSynchronize(b->done);
+        b->pending = false;
+      }
+      uci_pending.clear();
+      return B200_SUCCESS;
+    }
+    if (total != nof_out) {
+      B200_LOG_ERROR("uci_collect: %u subframes pending, room for %u", total, nof_out);
+      return B200_ERROR_INVALID_INPUTS;
+    }
+    uint32_t o = 0;
+    int      rc = B200_SUCCESS;
+    for (UciBatch* b : uci_pending) {
+      if (cudaEventSynchronize(b->done) != cudaSuccess) rc = B200_ERROR;
+      for (uint32_t i = 0; i < b->nsf && rc == B200_SUCCESS; i++, o++) {
+        const int16_t*     row = b->h_llr + (size_t)i * b->stride;
+        const UciGeometry& g   = b->geo[i];
+        uci_decide(b->cfg[i], g, (uint32_t)Qm, row, row + b->off_ri, row + b->off_cqi, &out[o]);
+        out[o].Q_prime_ack = g.Q_ack;
+        out[o].Q_prime_ri  = g.Q_ri;
+        out[o].Q_prime_cqi = g.Q_cqi;
+        out[o].e_offset    = g.Q_cqi * (uint32_t)Qm;
+        out[o].nof_e_bits  = ((uint32_t)(nd * M) - g.Q_ri - g.Q_cqi) * (uint32_t)Qm;
+      }
+      b->pending = false;
+    }
+    uci_pending.clear();
+    return rc;
+  }
+
+  int demod(const float2* d, int16_t* g, uint32_t nsf, cudaStream_t st, const UciBatch* ub = nullptr)
   {
     pusch_gold_kernel<<<(nsf + 7) / 8, 256, 0, st>>>(d_prm, d_x1w, d_jump, d_seq, nsf, nwords, wpl);
     g_kernel_launches++;
@@ -470,7 +691,13 @@ struct PuschRx {
     dim3 grid((unsigned)((M + DEMOD_TJ - 1) / DEMOD_TJ), nsf);
     const float qs = (float)(-100.0 * M_SQRT2);
     const int   sh = (int)cfg.llr_shift;
-#define B200_DEMOD(MOD, ND) pusch_demod_descramble_kernel<MOD, ND><<<grid, 256, 0, st>>>(d, d_seq, g, (uint32_t)M, nwords, sh, qs)
+    PuschUciArgs ua{};
+    if (ub) ua = PuschUciArgs{ub->d_sf, ub->d_llr, ub->stride, ub->off_ri, ub->off_cqi};
+#define B200_DEMOD(MOD, ND)                                                                                                            \
+  do {                                                                                                                                 \
+    if (ub) pusch_demod_descramble_kernel<MOD, ND, true><<<grid, 256, 0, st>>>(d, d_seq, g, (uint32_t)M, nwords, sh, qs, ua);          \
+    else pusch_demod_descramble_kernel<MOD, ND, false><<<grid, 256, 0, st>>>(d, d_seq, g, (uint32_t)M, nwords, sh, qs, ua);            \
+  } while (0)
     if (nd == 12) {
       if (cfg.modulation == 1) B200_DEMOD(1, 12);
       else if (cfg.modulation == 2) B200_DEMOD(2, 12);
@@ -601,4 +828,46 @@ extern "C" SRSRAN_B200_API int srsran_b200_pusch_rx_batch(srsran_b200_pusch_t* q
   if ((rc = rx.chest((const float2*)grid, rx.d_ce, m, nsf, st)) != B200_SUCCESS) return rc;
   if ((rc = rx.equalize_deprecode((const float2*)grid, rx.d_ce, m, rx.d_d, nsf, st)) != B200_SUCCESS) return rc;
   return rx.demod(rx.d_d, g, nsf, st);
+}
+
+extern "C" SRSRAN_B200_API int srsran_b200_pusch_uci_geometry(const srsran_b200_pusch_t* q, uint32_t tbs, const srsran_b200_uci_cfg_t* uci,
+                                                             srsran_b200_uci_value_t* out)
+{
+  if (!q || !uci || !out) return B200_ERROR_INVALID_INPUTS;
+  UciGeometry g;
+  const int   rc = q->rx.uci_span(tbs, *uci, &g, &out->e_offset, &out->nof_e_bits);
+  if (rc != B200_SUCCESS) return rc;
+  out->Q_prime_ack = g.Q_ack;
+  out->Q_prime_ri  = g.Q_ri;
+  out->Q_prime_cqi = g.Q_cqi;
+  return B200_SUCCESS;
+}
+
+extern "C" SRSRAN_B200_API int srsran_b200_pusch_rx_uci_batch(srsran_b200_pusch_t* q, const void* grid, int16_t* g, float* meas, uint32_t nsf,
+                                                             const uint32_t* rnti, const uint32_t* tti, const uint32_t* n_dmrs,
+                                                             const uint32_t* tbs, const srsran_b200_uci_cfg_t* uci, uint32_t flags, void* stream)
+{
+  if (!q || !grid || !g || !tbs || !uci) return B200_ERROR_INVALID_INPUTS;
+  if (need_device(flags, "srsran_b200_pusch_rx_uci_batch")) return B200_ERROR_INVALID_INPUTS;
+  if (nsf == 0) return B200_SUCCESS;
+  PuschRx&     rx = q->rx;
+  cudaStream_t st = (cudaStream_t)stream;
+  B200_CUDA_TRY(cudaSetDevice(rx.ctx->device));
+  if (rx.reserve(nsf) != B200_SUCCESS) return B200_ERROR;
+  PuschRx::UciBatch* ub = nullptr;
+  int                rc = rx.uci_begin(nsf, tbs, uci, st, &ub); // validates every grant before anything is enqueued
+  if (rc != B200_SUCCESS) return rc;
+  if ((rc = rx.upload_params(nsf, rnti, tti, n_dmrs, st)) != B200_SUCCESS) return rc;
+  float* m = meas ? meas : rx.d_meas;
+  if ((rc = rx.chest((const float2*)grid, rx.d_ce, m, nsf, st)) != B200_SUCCESS) return rc;
+  if ((rc = rx.equalize_deprecode((const float2*)grid, rx.d_ce, m, rx.d_d, nsf, st)) != B200_SUCCESS) return rc;
+  if ((rc = rx.demod(rx.d_d, g, nsf, st, ub)) != B200_SUCCESS) return rc;
+  return rx.uci_end(ub, st);
+}
+
+extern "C" SRSRAN_B200_API int srsran_b200_pusch_uci_collect(srsran_b200_pusch_t* q, srsran_b200_uci_value_t* out, uint32_t nof_out)
+{
+  if (!q) return B200_ERROR_INVALID_INPUTS;
+  B200_CUDA_TRY(cudaSetDevice(q->rx.ctx->device));
+  return q->rx.uci_collect(out, nof_out);
 }

@@ -107,6 +107,23 @@ class PuschCfg(C.Structure):
                 ("group_hopping_en", C.c_int), ("sequence_hopping_en", C.c_int)]
 
 
+# srsran_b200_uci_cfg_t / srsran_b200_uci_value_t (include/srslte_b200.h)
+UCI_CFG_DTYPE = np.dtype([("nof_ack", "<u4"), ("ri_len", "<u4"), ("cqi_len", "<u4"), ("I_offset_ack", "<u4"), ("I_offset_ri", "<u4"),
+                          ("I_offset_cqi", "<u4")])
+UCI_VALUE_DTYPE = np.dtype([("ack_value", "u1", (10,)), ("ack_valid", "u1"), ("ri", "u1"), ("cqi_crc", "u1"), ("reserved", "u1"),
+                            ("cqi_bits", "u1", (64,)), ("Q_prime_ack", "<u4"), ("Q_prime_ri", "<u4"), ("Q_prime_cqi", "<u4"),
+                            ("e_offset", "<u4"), ("nof_e_bits", "<u4")], align=True)
+assert UCI_VALUE_DTYPE.itemsize == 100
+
+
+def uci_cfg(nsf: int = 1, nof_ack=0, ri_len=0, cqi_len=0, I_offset_ack=9, I_offset_ri=5, I_offset_cqi=6) -> np.ndarray:
+    """nsf equal srsran_b200_uci_cfg_t entries (edit single rows afterwards for a mixed batch)."""
+    a = np.zeros(nsf, UCI_CFG_DTYPE)
+    a["nof_ack"], a["ri_len"], a["cqi_len"] = nof_ack, ri_len, cqi_len
+    a["I_offset_ack"], a["I_offset_ri"], a["I_offset_cqi"] = I_offset_ack, I_offset_ri, I_offset_cqi
+    return a
+
+
 class PuschChain:
     """Mirror of the srsran_b200_pusch_* entries: channel estimation -> equaliser + transform de-precoding -> soft demapping +
     descrambling + UL-SCH de-interleaving for a batch of subframes sharing one allocation (chest_ul.c:370, pusch.c:392-443,
@@ -212,6 +229,40 @@ class PuschChain:
         return g
 
 
+    def uci_geometry(self, tbs: int, uci: np.ndarray) -> np.ndarray:
+        """Q' of the three fields and the UL-SCH span (e_offset, nof_e_bits) of one grant; host only."""
+        uci = np.ascontiguousarray(uci, UCI_CFG_DTYPE).reshape(-1)
+        out = np.zeros(1, UCI_VALUE_DTYPE)
+        rc = self._lib.srsran_b200_pusch_uci_geometry(self._h, tbs, uci.ctypes.data, out.ctypes.data)
+        if rc != _lib.SUCCESS:
+            raise RuntimeError(f"srsran_b200_pusch_uci_geometry failed ({rc})")
+        return out[0]
+
+    def rx_uci(self, grid, rnti, tti, n_dmrs, tbs, uci: np.ndarray, out=None, meas=None):
+        """rx() for subframes with HARQ-ACK / RI / CQI multiplexed in: uci = UCI_CFG_DTYPE array (nsf,), tbs scalar or (nsf,).
+        Returns g; the decided values come from uci_collect()."""
+        t = self.torch
+        nsf = grid.shape[0]
+        g = out if out is not None else t.zeros((nsf, self.nof_bits), dtype=t.int16, device=self.dev)
+        k1, p1 = self._u32(rnti, nsf)
+        k2, p2 = self._u32(tti, nsf)
+        k3, p3 = self._u32(n_dmrs, nsf)
+        k4, p4 = self._u32(tbs, nsf)
+        uci = np.ascontiguousarray(uci, UCI_CFG_DTYPE).reshape(nsf)
+        rc = self._lib.srsran_b200_pusch_rx_uci_batch(self._h, grid.data_ptr(), g.data_ptr(), meas.data_ptr() if meas is not None else None,
+                                                      nsf, p1, p2, p3, p4, uci.ctypes.data, _lib.FLAG_DEVICE_PTRS, self._st())
+        if rc != _lib.SUCCESS:
+            raise RuntimeError(f"srsran_b200_pusch_rx_uci_batch failed ({rc})")
+        return g
+
+    def uci_collect(self, nsf: int) -> np.ndarray:
+        out = np.zeros(nsf, UCI_VALUE_DTYPE)
+        rc = self._lib.srsran_b200_pusch_uci_collect(self._h, out.ctypes.data, nsf)
+        if rc != _lib.SUCCESS:
+            raise RuntimeError(f"srsran_b200_pusch_uci_collect failed ({rc})")
+        return out
+
+
 class PuschRxFull(PuschRx):
     """Complete PUSCH receive pipeline on device buffers, one full-band allocation per (cell, subframe):
 
@@ -294,12 +345,22 @@ class EnbUl:
         if rc != _lib.SUCCESS:
             raise RuntimeError(f"srsran_b200_enb_ul_pusch_batch failed ({rc})")
 
-    def run(self, samples: np.ndarray, rnti, tti, n_dmrs=None, rv=None, new_data=None):
-        """samples: (nsf, sf_sz) complex64 or (nsf, sf_sz, 2) int16 host array.  Returns (bytes (nsf, tb_bytes) uint8, results)."""
+    def run(self, samples: np.ndarray, rnti, tti, n_dmrs=None, rv=None, new_data=None, uci: np.ndarray | None = None):
+        """samples: (nsf, sf_sz) complex64 or (nsf, sf_sz, 2) int16 host array.  Returns (bytes (nsf, tb_bytes) uint8, results)
+        and, with uci (UCI_CFG_DTYPE array (nsf,)), the decided control information (UCI_VALUE_DTYPE array) as a third item."""
         samples = np.ascontiguousarray(samples)
         nsf = samples.shape[0]
         fl = _lib.FLAG_IQ_INT16 if samples.dtype == np.int16 else 0
         data = np.zeros((nsf, self.tb_bytes), np.uint8)
         res = np.zeros(nsf, PUSCH_RES_DTYPE)
-        self.run_ptr(samples.ctypes.data, nsf, rnti, tti, data.ctypes.data, res, n_dmrs, rv, new_data, fl)
-        return data, res
+        if uci is None:
+            self.run_ptr(samples.ctypes.data, nsf, rnti, tti, data.ctypes.data, res, n_dmrs, rv, new_data, fl)
+            return data, res
+        uci = np.ascontiguousarray(uci, UCI_CFG_DTYPE).reshape(nsf)
+        val = np.zeros(nsf, UCI_VALUE_DTYPE)
+        k = [PuschChain._u32(a, nsf) for a in (rnti, tti, n_dmrs, rv, new_data)]
+        rc = self._lib.srsran_b200_enb_ul_pusch_uci_batch(self._h, samples.ctypes.data, nsf, k[0][1], k[1][1], k[2][1], k[3][1], k[4][1],
+                                                          uci.ctypes.data, data.ctypes.data, res.ctypes.data, val.ctypes.data, fl)
+        if rc != _lib.SUCCESS:
+            raise RuntimeError(f"srsran_b200_enb_ul_pusch_uci_batch failed ({rc})")
+        return data, res, val
