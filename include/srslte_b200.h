@@ -144,6 +144,9 @@ SRSRAN_B200_API void srsran_b200_sch_set_max_noi(srsran_b200_sch_t* q, uint32_t 
  * (e.g. the soft bits of srsran_b200_pusch_rx_batch): its kernels are ordered after everything queued on that stream at
  * the time of the call, so the caller need not synchronise first and the call's host-side bookkeeping overlaps the producer. */
 SRSRAN_B200_API void srsran_b200_sch_decode_after(srsran_b200_sch_t* q, void* producer_stream);
+/* The same with a cudaEvent_t the caller has recorded behind the producing work: the next call waits for that event only,
+ * not for what was queued on the producer stream after it (a later chunk of a pipelined batch). */
+SRSRAN_B200_API void srsran_b200_sch_decode_after_event(srsran_b200_sch_t* q, void* event);
 
 /* One srsran_rm_turbo_rx_lut_(input, output, in_len, cb_idx, rv_idx, enable_input_tdec=false) call (rm_turbo.c:403) */
 typedef struct {
@@ -208,6 +211,15 @@ SRSRAN_B200_API int srsran_b200_sch_decode_batch(srsran_b200_sch_t* q,
                                                  srsran_b200_tb_t*  tbs,
                                                  uint32_t           n_tb,
                                                  uint32_t           flags);
+
+/* The same call in two halves, for a caller thread that keeps several batches in flight (one object per batch): _begin plans
+ * and queues the whole batch on the object's stream and returns; _finish waits for it and fills tbs[] (which, like the
+ * buffers, must stay valid and untouched in between).  Device buffers only (SRSRAN_B200_FLAG_DEVICE_PTRS).  One batch per
+ * object at a time; srsran_b200_sch_decode_batch is _begin followed by _finish. */
+SRSRAN_B200_API int srsran_b200_sch_decode_begin(srsran_b200_sch_t* q, const int16_t* e_bits, uint64_t e_len, int16_t* soft_pool,
+                                                 uint64_t soft_len, uint8_t* data, uint64_t data_len, srsran_b200_tb_t* tbs, uint32_t n_tb,
+                                                 uint32_t flags);
+SRSRAN_B200_API int srsran_b200_sch_decode_finish(srsran_b200_sch_t* q);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Batched OFDM demodulation: srsran_ofdm_rx_sf (lib/src/phy/dft/ofdm.c:453-466) for many subframes per call.

@@ -55,6 +55,10 @@ def lib() -> C.CDLL:
     L.srsran_b200_sch_set_max_noi.restype = None
     L.srsran_b200_sch_decode_after.argtypes = [vp, vp]
     L.srsran_b200_sch_decode_after.restype = None
+    L.srsran_b200_sch_decode_after_event.argtypes = [vp, vp]
+    L.srsran_b200_sch_decode_begin.argtypes = [vp, vp, u64, vp, u64, vp, u64, vp, u32, u32]
+    L.srsran_b200_sch_decode_finish.argtypes = [vp]
+    L.srsran_b200_sch_decode_after_event.restype = None
     L.srsran_b200_rm_turbo_rx_batch.argtypes = [vp, vp, u64, vp, u64, vp, u32, u32, vp]
     L.srsran_b200_sch_decode_batch.argtypes = [vp, vp, u64, vp, u64, vp, u64, vp, u32, u32]
     L.srsran_b200_use_standard_symbol_size.argtypes = [C.c_int]
@@ -121,6 +125,9 @@ EXPORTED_SYMBOLS = [
     "srsran_b200_sch_init",
     "srsran_b200_sch_free",
     "srsran_b200_sch_decode_after",
+    "srsran_b200_sch_decode_after_event",
+    "srsran_b200_sch_decode_begin",
+    "srsran_b200_sch_decode_finish",
     "srsran_b200_sch_set_max_noi",
     "srsran_b200_rm_turbo_rx_batch",
     "srsran_b200_sch_decode_batch",

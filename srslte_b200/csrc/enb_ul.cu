@@ -7,7 +7,11 @@
 // while its host-side bookkeeping overlaps the tail of the front end.  HARQ soft buffers live in the object, one slot per
 // subframe index of the batch (the caller maps (UE, HARQ process) to slots).
 #include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
+
+#include <chrono>
 
 #include <new>
 #include <vector>
@@ -24,7 +28,14 @@ struct EnbUl {
   srsran_b200_ofdm_t*       ofdm  = nullptr;
   srsran_b200_pusch_t*      pusch = nullptr;
   srsran_b200_sch_t*        sch   = nullptr;
-  cudaStream_t              compute = nullptr, copy = nullptr;
+  // With host samples a large batch is decoded in groups, each as soon as its front end is done, so that the decoder works
+  // while the later groups' samples are still crossing PCIe.  One decode object per group: each keeps the cached plan of its
+  // own slice of the transport-block list.
+  static constexpr uint32_t MAX_GROUPS = 8, MIN_GROUP_SF = 1024;
+  srsran_b200_sch_t*        sch_g[MAX_GROUPS] = {};
+  cudaEvent_t               ev_g[MAX_GROUPS]  = {};
+  cudaEvent_t               ev_t0 = nullptr; // SRSLTE_B200_ENB_UL_TIMING
+  cudaStream_t              compute = nullptr, copy = nullptr, out_st = nullptr;
   std::vector<cudaEvent_t>  ev;
   uint32_t sf_sz = 0, nsym = 0, nre = 0, nbits = 0, ncb = 0, data_stride = 0;
   // device buffers, grow-only
@@ -46,6 +57,13 @@ struct EnbUl {
     if (ofdm) srsran_b200_ofdm_rx_free(ofdm);
     if (pusch) srsran_b200_pusch_free(pusch);
     if (sch) srsran_b200_sch_free(sch);
+    for (uint32_t g = 1; g < MAX_GROUPS; g++) {
+      if (sch_g[g]) srsran_b200_sch_free(sch_g[g]);
+    }
+    for (cudaEvent_t e : ev_g) {
+      if (e) cudaEventDestroy(e);
+    }
+    if (out_st) cudaStreamDestroy(out_st);
     for (void* p : {d_iq, (void*)d_grid, (void*)d_llr, (void*)d_soft, (void*)d_data, (void*)d_meas}) {
       if (p) cudaFree(p);
     }
@@ -96,6 +114,8 @@ struct EnbUl {
     data_stride      = (c.tbs / 8 + 3 + 768 + 15) / 16 * 16;
     B200_CUDA_TRY(cudaStreamCreateWithFlags(&compute, cudaStreamNonBlocking));
     B200_CUDA_TRY(cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking));
+    B200_CUDA_TRY(cudaStreamCreateWithFlags(&out_st, cudaStreamNonBlocking));
+    sch_g[0] = sch;
     return B200_SUCCESS;
   }
 
@@ -181,9 +201,33 @@ struct EnbUl {
     // ---- front end, chunk by chunk -----------------------------------------------------------------------------------------
     const uint32_t chunk   = dev_ptrs ? nsf : (nsf > 1024 ? 512u : (nsf + 1) / 2);
     const uint32_t nchunks = (nsf + chunk - 1) / chunk;
+    // decode groups: whole chunks, at least MIN_GROUP_SF subframes each (a smaller group leaves most SMs without a tile)
+    static const bool no_groups = getenv("SRSLTE_B200_ENB_UL_NO_GROUPS") != nullptr;
+    static const bool timing    = getenv("SRSLTE_B200_ENB_UL_TIMING") != nullptr; // where a call's time goes: host stamps + event times
+    const unsigned    ev_flags  = timing ? cudaEventDefault : cudaEventDisableTiming;
+    auto              now       = [] { return std::chrono::steady_clock::now(); };
+    auto              us        = [](auto a, auto b) { return (double)std::chrono::duration_cast<std::chrono::nanoseconds>(b - a).count() / 1e3; };
+    const auto        h0        = now();
+    if (timing) {
+      if (!ev_t0) B200_CUDA_TRY(cudaEventCreate(&ev_t0));
+      B200_CUDA_TRY(cudaEventRecord(ev_t0, copy));
+    }
+    static const char* gsf_env  = getenv("SRSLTE_B200_ENB_UL_GROUP_SF");
+    const uint32_t    group_sf  = gsf_env && atoi(gsf_env) >= 64 ? (uint32_t)atoi(gsf_env) : MIN_GROUP_SF;
+    uint32_t          ngroups   = (dev_ptrs || no_groups) ? 1u : nsf / group_sf;
+    ngroups                     = ngroups < 1 ? 1 : ngroups > MAX_GROUPS ? MAX_GROUPS : ngroups;
+    const uint32_t cpg          = (nchunks + ngroups - 1) / ngroups; // chunks per group
+    ngroups                     = (nchunks + cpg - 1) / cpg;
+    for (uint32_t g = 0; g < ngroups; g++) {
+      if (!sch_g[g]) {
+        if ((rc = srsran_b200_sch_init(&sch_g[g], device)) != B200_SUCCESS) return rc;
+        srsran_b200_sch_set_max_noi(sch_g[g], cfg.max_iterations ? cfg.max_iterations : 8);
+      }
+      if (!ev_g[g]) B200_CUDA_TRY(cudaEventCreateWithFlags(&ev_g[g], ev_flags));
+    }
     while (ev.size() < nchunks) {
       cudaEvent_t e;
-      B200_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      B200_CUDA_TRY(cudaEventCreateWithFlags(&e, ev_flags));
       ev.push_back(e);
     }
     for (uint32_t c = 0; c < nchunks; c++) {
@@ -211,28 +255,73 @@ struct EnbUl {
         if (uci) srsran_b200_pusch_uci_collect(pusch, nullptr, 0); // drop the chunks already queued
         return rc;
       }
+      if ((c + 1) % cpg == 0 || c + 1 == nchunks) B200_CUDA_TRY(cudaEventRecord(ev_g[c / cpg], compute));
     }
 
-    // ---- decode loop over the whole batch ------------------------------------------------------------------------------------
+    // ---- decode, group by group; the bytes of a group travel back while the next one is decoded ---------------------------------
     for (uint32_t i = 0; i < nsf; i++) {
       const bool fresh   = new_data ? new_data[i] != 0 : true;
       tbs[i].rv          = rv ? rv[i] : 0u;
       tbs[i].new_data    = fresh ? 1u : 0u;
       tbs[i].cb_crc_mask = fresh ? 0u : crc_mask[i];
     }
-    srsran_b200_sch_decode_after(sch, compute);
-    rc = srsran_b200_sch_decode_batch(sch, d_llr, (uint64_t)nsf * nbits, d_soft, (uint64_t)cap_sf * ncb * SRSRAN_B200_SOFTBUFFER_SIZE, d_data,
-                                      (uint64_t)cap_sf * data_stride, tbs.data(), nsf, SRSRAN_B200_FLAG_DEVICE_PTRS);
-    if (rc != B200_SUCCESS) return rc;
-    // (the decode call has synchronised its stream, which was ordered after `compute`: front end, meas copy and decode are done)
-    B200_CUDA_TRY(cudaMemcpyAsync(h_meas.data(), d_meas, (size_t)nsf * 4 * sizeof(float), cudaMemcpyDeviceToHost, compute));
     const size_t out_b = (size_t)cfg.tbs / 8 + 3;
-    if (dev_ptrs) {
-      B200_CUDA_TRY(cudaMemcpy2DAsync(data, out_b, d_data, data_stride, out_b, nsf, cudaMemcpyDeviceToDevice, compute));
-    } else {
-      B200_CUDA_TRY(cudaMemcpy2DAsync(data, out_b, d_data, data_stride, out_b, nsf, cudaMemcpyDeviceToHost, compute));
+    const auto h1 = now();
+    // every group is queued behind its own front end right away (the groups' kernels share the SMs as their inputs arrive) ...
+    auto span = [&](uint32_t g, uint32_t* first, uint32_t* last) {
+      *first = g * cpg * chunk;
+      *last  = (g + 1) * cpg * chunk < nsf ? (g + 1) * cpg * chunk : nsf;
+    };
+    uint32_t begun = 0;
+    for (uint32_t g = 0; g < ngroups && rc == B200_SUCCESS; g++) {
+      uint32_t first, last;
+      span(g, &first, &last);
+      srsran_b200_sch_decode_after_event(sch_g[g], ev_g[g]);
+      rc = srsran_b200_sch_decode_begin(sch_g[g], d_llr, (uint64_t)nsf * nbits, d_soft, (uint64_t)cap_sf * ncb * SRSRAN_B200_SOFTBUFFER_SIZE, d_data,
+                                        (uint64_t)cap_sf * data_stride, tbs.data() + first, last - first, SRSRAN_B200_FLAG_DEVICE_PTRS);
+      if (rc == B200_SUCCESS) begun++;
     }
+    const auto h2 = now();
+    double     fin_us[MAX_GROUPS] = {};
+    // ... and finished in order; the bytes of a group travel back while the next ones are still being decoded
+    for (uint32_t g = 0; g < begun; g++) {
+      uint32_t first, last;
+      span(g, &first, &last);
+      const int r = srsran_b200_sch_decode_finish(sch_g[g]);
+      fin_us[g]   = us(h0, now());
+      if (r != B200_SUCCESS && rc == B200_SUCCESS) rc = r;
+      if (rc == B200_SUCCESS) {
+        const cudaError_t ce = cudaMemcpy2DAsync(data + (size_t)first * out_b, out_b, d_data + (size_t)first * data_stride, data_stride, out_b,
+                                                 last - first, dev_ptrs ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, out_st);
+        if (ce != cudaSuccess) rc = B200_ERROR;
+      }
+    }
+    if (rc != B200_SUCCESS) {
+      if (uci) srsran_b200_pusch_uci_collect(pusch, nullptr, 0);
+      cudaStreamSynchronize(out_st);
+      return rc;
+    }
+    B200_CUDA_TRY(cudaMemcpyAsync(h_meas.data(), d_meas, (size_t)nsf * 4 * sizeof(float), cudaMemcpyDeviceToHost, compute));
+    B200_CUDA_TRY(cudaStreamSynchronize(out_st));
     B200_CUDA_TRY(cudaStreamSynchronize(compute));
+    if (timing && !dev_ptrs) {
+      fprintf(stderr, "[enb_ul timing] nsf %u chunks %u groups %u: host enqueue front end %.0f us, begin %.0f; copies done at", nsf, nchunks, ngroups,
+              us(h0, h1), us(h0, h2));
+      for (uint32_t c = 0; c < nchunks; c++) {
+        float t = 0;
+        cudaEventElapsedTime(&t, ev_t0, ev[c]);
+        fprintf(stderr, " %.2f", t);
+      }
+      fprintf(stderr, " ms; front end of group done at");
+      for (uint32_t g = 0; g < ngroups; g++) {
+        float t = 0;
+        cudaEventElapsedTime(&t, ev_t0, ev_g[g]);
+        fprintf(stderr, " %.2f", t);
+      }
+      fprintf(stderr, " ms; decode finished (host) at");
+      for (uint32_t g = 0; g < ngroups; g++) fprintf(stderr, " %.2f", fin_us[g] / 1e3);
+      fprintf(stderr, " ms; end %.2f ms\n", us(h0, now()) / 1e3);
+    }
     if (uci && (rc = srsran_b200_pusch_uci_collect(pusch, uci_out, nsf)) != B200_SUCCESS) return rc;
     for (uint32_t i = 0; i < nsf; i++) {
       crc_mask[i]           = tbs[i].cb_crc_mask;

@@ -16,6 +16,7 @@
 // chest_ul.c:330), every allocation srsran_dft_precoding_valid_prb accepts.
 #include <cuda_runtime.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -37,6 +38,16 @@ struct PuschSfParam {
   uint32_t c_init;   // scrambling seed of the subframe: (rnti << 14) + (sf_idx << 9) + cell_id  (sequences.c:120-123)
   uint32_t dmrs_idx; // n_dmrs * 10 + sf_idx: row of the DMRS table
 };
+
+// Small per-call parameter arrays reach the device through this kernel, which reads the page-locked host buffer directly
+// (unified addressing), NOT through a host-to-device copy: a copy would queue on the one H2D engine behind the megabytes of
+// samples that a pipelining caller has already submitted for its later chunks, and the chunk's kernels would wait for all of
+// them (measured: the front end of a 4096-subframe batch started only after the last sample copy, enb_ul.cu).
+__global__ void pusch_words_to_device_kernel(const uint32_t* __restrict__ host_mapped, uint32_t* __restrict__ dev, uint32_t nwords)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nwords) dev[i] = host_mapped[i];
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 // Channel estimation: one block per subframe.  LS estimates of the two DMRS symbols (received x conj(known)), 3-tap
@@ -108,30 +119,38 @@ __global__ void __launch_bounds__(256) pusch_chest_kernel(const float2* __restri
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Scrambling sequences: one warp per subframe.  c(n) = x1(n+1600) ^ x2(n+1600) (TS 36.211 7.2; sequence.c:33-120).
-// x1 does not depend on the seed: its words come from a table.  x2 is linear in the 31 seed bits, so lane l starts at its
+// Scrambling sequences: GOLD_CHUNKS threads per subframe.  c(n) = x1(n+1600) ^ x2(n+1600) (TS 36.211 7.2; sequence.c:33-120).
+// x1 does not depend on the seed: its words come from a table.  x2 is linear in the 31 seed bits, so every thread starts at its
 // own chunk of the sequence from the XOR of per-seed-bit jump states, then steps 16 bits at a time (all taps of the
-// recurrence x2(n+31) = x2(n+3)^x2(n+2)^x2(n+1)^x2(n) lie inside the 31-bit state for 16 new bits).
+// recurrence x2(n+31) = x2(n+3)^x2(n+2)^x2(n+1)^x2(n) lie inside the 31-bit state for 16 new bits).  The chunks are short
+// (a 20 MHz 64QAM subframe is 2701 words: 22 per thread) because the per-thread chain is serial.
+constexpr uint32_t GOLD_CHUNKS = 128;
 __global__ void __launch_bounds__(256) pusch_gold_kernel(const PuschSfParam* __restrict__ prm, const uint32_t* __restrict__ x1w,
                                                          const uint32_t* __restrict__ jump, uint32_t* __restrict__ seq, uint32_t nsf,
                                                          uint32_t nwords, uint32_t wpl)
 {
-  const uint32_t sf = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (sf >= nsf) return;
-  const uint32_t seed = prm[sf].c_init;
-  uint32_t       s    = 0;
+  extern __shared__ uint32_t gold_stage[]; // [2][nwords]: the block's two subframes, written out coalesced at the end
+  const uint32_t half = threadIdx.x / GOLD_CHUNKS, lane = threadIdx.x % GOLD_CHUNKS, sf = blockIdx.x * 2u + half;
+  if (sf < nsf) {
+    const uint32_t seed = prm[sf].c_init;
+    uint32_t       s    = 0;
 #pragma unroll
-  for (int b = 0; b < 31; b++) s ^= ((seed >> b) & 1u) ? jump[lane * 31 + b] : 0u;
-  const uint32_t w0 = lane * wpl, w1 = min(w0 + wpl, nwords);
-  for (uint32_t w = w0; w < w1; w++) {
-    uint32_t out = s & 0xFFFFu;
-    uint32_t f   = (s ^ (s >> 1) ^ (s >> 2) ^ (s >> 3)) & 0xFFFFu;
-    s            = (s >> 16) | (f << 15);
-    out |= (s & 0xFFFFu) << 16;
-    f = (s ^ (s >> 1) ^ (s >> 2) ^ (s >> 3)) & 0xFFFFu;
-    s = (s >> 16) | (f << 15);
-    seq[(size_t)sf * nwords + w] = out ^ x1w[w];
+    for (int b = 0; b < 31; b++) s ^= ((seed >> b) & 1u) ? jump[lane * 31 + b] : 0u;
+    const uint32_t w0 = lane * wpl, w1 = min(w0 + wpl, nwords);
+    for (uint32_t w = w0; w < w1; w++) {
+      uint32_t out = s & 0xFFFFu;
+      uint32_t f   = (s ^ (s >> 1) ^ (s >> 2) ^ (s >> 3)) & 0xFFFFu;
+      s            = (s >> 16) | (f << 15);
+      out |= (s & 0xFFFFu) << 16;
+      f = (s ^ (s >> 1) ^ (s >> 2) ^ (s >> 3)) & 0xFFFFu;
+      s = (s >> 16) | (f << 15);
+      gold_stage[half * nwords + w] = out;
+    }
   }
+  __syncthreads();
+  const uint32_t n = min(2u, nsf - blockIdx.x * 2u) * nwords;
+  uint32_t*      o = seq + (size_t)blockIdx.x * 2u * nwords;
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) o[i] = gold_stage[i] ^ x1w[i < nwords ? i : i - nwords];
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -259,6 +278,65 @@ __global__ void __launch_bounds__(256) pusch_demod_descramble_kernel(const float
   }
 }
 
+// The same stage without control information, vectorised: a thread owns G consecutive data symbols of one subcarrier (4 with the
+// normal prefix, 2 with the extended one), i.e. G*Qm consecutive soft bits of the de-interleaved stream, and writes them as
+// 16-byte (8-byte) vectors; consecutive threads write consecutive chunks.  The tile's scrambling bits are staged in shared memory
+// once per row instead of one scattered word load per symbol.  d and g must be 16-byte aligned (the host picks the kernel).
+template <int MOD, int ND>
+__global__ void __launch_bounds__(192) pusch_demod_descramble_vec_kernel(const float2* __restrict__ d, const uint32_t* __restrict__ seq,
+                                                                         int16_t* __restrict__ g, uint32_t M, uint32_t nwords, int shift,
+                                                                         float qpsk_scale)
+{
+  constexpr int Qm = 2 * MOD, G = (ND % 4 == 0) ? 4 : 2, NG = ND / G, TJ = DEMOD_TJ, TP = TJ + 2;
+  constexpr int SW = (TJ * Qm + 31) / 32 + 2; // a row's scrambling bits: TJ*Qm of them, not word aligned, plus the funnel shift's upper word
+  __shared__ __align__(16) float2 tile[ND][TP];
+  __shared__ uint32_t sbits[ND][SW];
+  const uint32_t  sf = blockIdx.y, j0 = blockIdx.x * TJ;
+  const uint32_t  per_sf = (uint32_t)ND * M;
+  const float2*   src = d + (size_t)sf * per_sf;
+  const uint32_t* sq  = seq + (size_t)sf * nwords;
+  for (uint32_t idx = threadIdx.x; idx < (uint32_t)(ND * (TJ / 2)); idx += blockDim.x) {
+    const uint32_t i = idx / (TJ / 2), jl = 2u * (idx % (TJ / 2));
+    if (j0 + jl < M) *reinterpret_cast<float4*>(&tile[i][jl]) = __ldcs(reinterpret_cast<const float4*>(&src[(size_t)i * M + j0 + jl]));
+  }
+  for (uint32_t idx = threadIdx.x; idx < (uint32_t)(ND * SW); idx += blockDim.x) {
+    const uint32_t i = idx / SW, t = idx % SW, w = (((i * M + j0) * (uint32_t)Qm) >> 5) + t;
+    sbits[i][t] = w < nwords ? sq[w] : 0u;
+  }
+  __syncthreads();
+  const uint32_t body = 4u * (per_sf / 4u), fbody = 16u * (2u * per_sf / 16u);
+  uint32_t*      dst  = reinterpret_cast<uint32_t*>(g + (size_t)sf * per_sf * Qm);
+  for (uint32_t item = threadIdx.x; item < (uint32_t)(TJ * NG); item += blockDim.x) {
+    const uint32_t jl = item / NG, iq = item % NG, j = j0 + jl;
+    if (j >= M) break;
+    uint32_t words[G * MOD];
+#pragma unroll
+    for (int r = 0; r < G; r++) {
+      const uint32_t i = iq * G + r, pos = i * M + j;
+      int16_t        o[6];
+      demod_one(MOD, tile[i][jl], pos < body, 2u * pos, fbody, qpsk_scale, o);
+      const uint32_t rel  = (((i * M + j0) * (uint32_t)Qm) & 31u) + jl * (uint32_t)Qm;
+      const uint32_t bits = __funnelshift_r(sbits[i][rel >> 5], sbits[i][(rel >> 5) + 1], rel & 31u);
+#pragma unroll
+      for (int w = 0; w < MOD; w++) {
+        int lo = (int)o[2 * w] >> shift, hi = (int)o[2 * w + 1] >> shift;
+        if ((bits >> (2 * w)) & 1u) lo = -lo;
+        if ((bits >> (2 * w + 1)) & 1u) hi = -hi;
+        words[r * MOD + w] = (uint32_t)(uint16_t)(int16_t)lo | ((uint32_t)(uint16_t)(int16_t)hi << 16);
+      }
+    }
+    if (G == 4) {
+      uint4* o4 = reinterpret_cast<uint4*>(dst) + ((size_t)j * (ND / 4) + iq) * MOD;
+#pragma unroll
+      for (int q = 0; q < MOD; q++) o4[q] = make_uint4(words[4 * q], words[4 * q + 1], words[4 * q + 2], words[4 * q + 3]);
+    } else {
+      uint2* o2 = reinterpret_cast<uint2*>(dst) + ((size_t)j * (ND / 2) + iq) * MOD;
+#pragma unroll
+      for (int q = 0; q < MOD; q++) o2[q] = make_uint2(words[2 * q], words[2 * q + 1]);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // host side
 
@@ -312,10 +390,13 @@ struct PuschRx {
   float2*       d_d   = nullptr;
   float*        d_meas = nullptr;
   uint32_t      cap_sf = 0;
-  // per-subframe parameters are staged in two page-locked buffers used in turn (a copy from pageable memory would first
-  // synchronise the stream, i.e. wait for the OFDM kernel queued just before this call)
-  PuschSfParam* h_prm[2]   = {nullptr, nullptr};
-  cudaEvent_t   prm_ev[2]  = {nullptr, nullptr};
+  // per-subframe parameters are staged in a ring of page-locked buffers (a copy from pageable memory would first
+  // synchronise the stream, i.e. wait for the OFDM kernel queued just before this call).  The ring is deep because a caller
+  // that pipelines a batch chunk by chunk queues all its chunks before the first one's samples have arrived: with two
+  // buffers the third call waited for the first chunk's copy and the host fell into step with PCIe (enb_ul.cu).
+  static constexpr int PRM_RING = 16;
+  PuschSfParam* h_prm[PRM_RING]  = {};
+  cudaEvent_t   prm_ev[PRM_RING] = {};
   uint32_t      h_prm_cap  = 0;
   int           prm_cur    = 0;
   // control information: one buffer set per rx_uci_batch call that has not been collected yet (srsran_b200_pusch_uci_collect)
@@ -351,7 +432,7 @@ struct PuschRx {
     for (void* p : {(void*)dW, (void*)d_dmrs, (void*)d_x1w, (void*)d_jump, (void*)d_prm, (void*)d_seq, (void*)d_ce, (void*)d_d, (void*)d_meas}) {
       if (p) cudaFree(p);
     }
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < PRM_RING; i++) {
       if (h_prm[i]) cudaFreeHost(h_prm[i]);
       if (prm_ev[i]) cudaEventDestroy(prm_ev[i]);
     }
@@ -465,8 +546,8 @@ struct PuschRx {
     // scrambling tables: x1 words and the jump states of the 31 seed bits at every lane's chunk start
     const uint32_t nbits = (uint32_t)(nd * M * Qm);
     nwords               = (nbits + 31) / 32 + 1; // one spare word: the kernel may look one word ahead
-    wpl                  = (nwords + 31) / 32;
-    std::vector<uint32_t> x1w(nwords, 0u), jump(32 * 31, 0u);
+    wpl                  = (nwords + GOLD_CHUNKS - 1) / GOLD_CHUNKS;
+    std::vector<uint32_t> x1w(nwords, 0u), jump(GOLD_CHUNKS * 31, 0u);
     {
       uint32_t x1 = 1;
       for (uint32_t n = 0; n < 1600; n++) x1 = Gold31::step1(x1);
@@ -481,7 +562,7 @@ struct PuschRx {
       for (int b = 0; b < 31; b++) {
         uint32_t x2 = 1u << b;
         for (uint32_t n = 0; n < 1600; n++) x2 = Gold31::step2(x2);
-        for (uint32_t lane = 0; lane < 32; lane++) {
+        for (uint32_t lane = 0; lane < GOLD_CHUNKS; lane++) {
           jump[lane * 31 + b] = x2;
           for (uint32_t n = 0; n < 32 * wpl; n++) x2 = Gold31::step2(x2);
         }
@@ -515,7 +596,7 @@ struct PuschRx {
   int upload_params(uint32_t nsf, const uint32_t* rnti, const uint32_t* tti, const uint32_t* n_dmrs, cudaStream_t st)
   {
     if (nsf > h_prm_cap) {
-      for (int i = 0; i < 2; i++) {
+      for (int i = 0; i < PRM_RING; i++) {
         if (prm_ev[i]) B200_CUDA_TRY(cudaEventSynchronize(prm_ev[i]));
         if (h_prm[i]) cudaFreeHost(h_prm[i]);
         h_prm[i] = nullptr;
@@ -524,7 +605,7 @@ struct PuschRx {
       }
       h_prm_cap = nsf;
     }
-    prm_cur ^= 1;
+    prm_cur = (prm_cur + 1) % PRM_RING;
     B200_CUDA_TRY(cudaEventSynchronize(prm_ev[prm_cur])); // the copy that last read this buffer has completed
     PuschSfParam* hp = h_prm[prm_cur];
     for (uint32_t i = 0; i < nsf; i++) {
@@ -536,7 +617,9 @@ struct PuschRx {
       hp[i].c_init   = ((r & 0xFFFFu) << 14) + (sf_idx << 9) + cfg.cell_id;
       hp[i].dmrs_idx = nd_ * 10 + sf_idx;
     }
-    B200_CUDA_TRY(cudaMemcpyAsync(d_prm, hp, (size_t)nsf * sizeof(PuschSfParam), cudaMemcpyHostToDevice, st));
+    const uint32_t nw = nsf * (uint32_t)(sizeof(PuschSfParam) / 4);
+    pusch_words_to_device_kernel<<<(nw + 255) / 256, 256, 0, st>>>((const uint32_t*)hp, (uint32_t*)d_prm, nw);
+    B200_CUDA_TRY(cudaGetLastError());
     B200_CUDA_TRY(cudaEventRecord(prm_ev[prm_cur], st));
     return B200_SUCCESS;
   }
@@ -633,7 +716,9 @@ struct PuschRx {
     for (uint32_t i = 0; i < nsf; i++) {
       b->h_sf[i] = PuschUciSf{b->geo[i].Q_ack, b->geo[i].Q_ri, b->geo[i].Q_cqi, (b->geo[i].ack_one_bit ? 1u : 0u) | (b->geo[i].ri_one_bit ? 2u : 0u)};
     }
-    B200_CUDA_TRY(cudaMemcpyAsync(b->d_sf, b->h_sf, (size_t)nsf * sizeof(PuschUciSf), cudaMemcpyHostToDevice, st));
+    const uint32_t nw = nsf * (uint32_t)(sizeof(PuschUciSf) / 4);
+    pusch_words_to_device_kernel<<<(nw + 255) / 256, 256, 0, st>>>((const uint32_t*)b->h_sf, (uint32_t*)b->d_sf, nw);
+    B200_CUDA_TRY(cudaGetLastError());
     *out = b;
     return B200_SUCCESS;
   }
@@ -685,7 +770,7 @@ struct PuschRx {
 
   int demod(const float2* d, int16_t* g, uint32_t nsf, cudaStream_t st, const UciBatch* ub = nullptr)
   {
-    pusch_gold_kernel<<<(nsf + 7) / 8, 256, 0, st>>>(d_prm, d_x1w, d_jump, d_seq, nsf, nwords, wpl);
+    pusch_gold_kernel<<<(nsf + 1) / 2, 2 * GOLD_CHUNKS, (size_t)2 * nwords * sizeof(uint32_t), st>>>(d_prm, d_x1w, d_jump, d_seq, nsf, nwords, wpl);
     g_kernel_launches++;
     B200_CUDA_TRY(cudaGetLastError());
     dim3 grid((unsigned)((M + DEMOD_TJ - 1) / DEMOD_TJ), nsf);
@@ -698,7 +783,19 @@ struct PuschRx {
     if (ub) pusch_demod_descramble_kernel<MOD, ND, true><<<grid, 256, 0, st>>>(d, d_seq, g, (uint32_t)M, nwords, sh, qs, ua);          \
     else pusch_demod_descramble_kernel<MOD, ND, false><<<grid, 256, 0, st>>>(d, d_seq, g, (uint32_t)M, nwords, sh, qs, ua);            \
   } while (0)
-    if (nd == 12) {
+    const bool vec = !ub && ((((uintptr_t)d | (uintptr_t)g) & 15u) == 0) && !getenv("SRSLTE_B200_PUSCH_DEMOD_SCALAR");
+#define B200_DEMODV(MOD, ND) pusch_demod_descramble_vec_kernel<MOD, ND><<<grid, 192, 0, st>>>(d, d_seq, g, (uint32_t)M, nwords, sh, qs)
+    if (vec) {
+      if (nd == 12) {
+        if (cfg.modulation == 1) B200_DEMODV(1, 12);
+        else if (cfg.modulation == 2) B200_DEMODV(2, 12);
+        else B200_DEMODV(3, 12);
+      } else {
+        if (cfg.modulation == 1) B200_DEMODV(1, 10);
+        else if (cfg.modulation == 2) B200_DEMODV(2, 10);
+        else B200_DEMODV(3, 10);
+      }
+    } else if (nd == 12) {
       if (cfg.modulation == 1) B200_DEMOD(1, 12);
       else if (cfg.modulation == 2) B200_DEMOD(2, 12);
       else B200_DEMOD(3, 12);
@@ -708,6 +805,7 @@ struct PuschRx {
       else B200_DEMOD(3, 10);
     }
 #undef B200_DEMOD
+#undef B200_DEMODV
     g_kernel_launches++;
     B200_CUDA_TRY(cudaGetLastError());
     return B200_SUCCESS;

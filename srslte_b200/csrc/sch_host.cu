@@ -165,9 +165,35 @@ struct SchEngine {
   cudaStream_t   after  = nullptr;    // srsran_b200_sch_decode_after: producer stream of the next decode_batch's device inputs
   bool           have_after = false;
   cudaEvent_t    after_ev = nullptr;
+  cudaEvent_t    after_ext = nullptr; // srsran_b200_sch_decode_after_event: the caller's own event
   SchPlan        plan;                // of the last transport block list (reused when the next list repeats it)
-  std::vector<uint8_t>          h_tbok, tmp_ok, tmp_np;
+  PinnedArena                   hres; // page-locked home of the per-batch verdicts (truly asynchronous copies back)
+  uint8_t *                     h_tbok = nullptr, *tmp_ok = nullptr, *tmp_np = nullptr;
   std::vector<uint32_t>         iters_scratch;
+  // a batch between decode_begin and decode_finish (decode_batch is the two back to back)
+  struct Pending {
+    bool              active = false, all_dev = false, soft_dev = false, al8 = false, preloaded = false, same = false;
+    srsran_b200_tb_t* tbs    = nullptr;
+    uint32_t          n_tb   = 0;
+    const int16_t*    d_e    = nullptr;
+    int16_t*          d_soft = nullptr;
+    uint8_t*          d_data = nullptr;
+    int16_t*          soft_pool = nullptr; // the caller's buffers (host or device)
+    uint8_t*          data      = nullptr;
+    uint64_t          soft_len = 0, data_len = 0;
+    TdecWorkspace*    ws = nullptr;
+    std::chrono::steady_clock::time_point t_0, t_1, t_3, t_4, t_5;
+  } pend;
+  int  enqueue_decode();           // decoder passes, payload, TB CRC, copies back: everything but the wait
+  int  decode_begin(const int16_t* e_bits, uint64_t e_len, int16_t* soft_pool, uint64_t soft_len, uint8_t* data, uint64_t data_len,
+                    srsran_b200_tb_t* tbs, uint32_t n_tb, uint32_t flags);
+  int  decode_finish();
+  void drop_pending()
+  {
+    if (pend.ws) workspace_release(ctx->device, pend.ws);
+    pend.ws     = nullptr;
+    pend.active = false;
+  }
 
   int init(int device)
   {
@@ -185,6 +211,8 @@ struct SchEngine {
     io.release();
     meta.release();
     hmeta.release();
+    hres.release();
+    if (pend.ws) drop_pending();
     tdec.destroy();
   }
 
@@ -462,7 +490,21 @@ int SchEngine::build_plan(SchPlan& p, uint64_t e_len, uint64_t soft_len, uint64_
 int SchEngine::decode_batch(const int16_t* e_bits, uint64_t e_len, int16_t* soft_pool, uint64_t soft_len, uint8_t* data,
                             uint64_t data_len, srsran_b200_tb_t* tbs, uint32_t n_tb, uint32_t flags)
 {
+  const int rc = decode_begin(e_bits, e_len, soft_pool, soft_len, data, data_len, tbs, n_tb, flags);
+  if (rc != B200_SUCCESS) return rc;
+  return decode_finish();
+}
+
+// Everything of a batch except the wait: plan (reused when the list repeats), staging, de-matching, decoder launches, payload,
+// transport-block CRC and the copies back.  Returns with the work queued on the engine's stream.
+int SchEngine::decode_begin(const int16_t* e_bits, uint64_t e_len, int16_t* soft_pool, uint64_t soft_len, uint8_t* data,
+                            uint64_t data_len, srsran_b200_tb_t* tbs, uint32_t n_tb, uint32_t flags)
+{
   if (!e_bits || !soft_pool || !data || (!tbs && n_tb)) return B200_ERROR_INVALID_INPUTS;
+  if (pend.active) {
+    B200_LOG_ERROR("srsran_b200_sch_decode_begin: the previous batch has not been finished");
+    return B200_ERROR_INVALID_INPUTS;
+  }
   if (n_tb == 0) return B200_SUCCESS;
   B200_CUDA_TRY(cudaSetDevice(ctx->device));
   const bool   all_dev  = (flags & SRSRAN_B200_FLAG_DEVICE_PTRS) != 0;
@@ -473,10 +515,15 @@ int SchEngine::decode_batch(const int16_t* e_bits, uint64_t e_len, int16_t* soft
     B200_CUDA_TRY(cudaStreamWaitEvent(st, after_ev, 0));
     have_after = false;
   }
+  if (after_ext) {
+    B200_CUDA_TRY(cudaStreamWaitEvent(st, after_ext, 0));
+    after_ext = nullptr;
+  }
 
   static const bool timing = getenv("SRSLTE_B200_SCH_TIMING") != nullptr;
   auto              now    = [] { return std::chrono::steady_clock::now(); };
-  auto              t_0    = now();
+  pend                     = Pending();
+  pend.t_0                 = now();
   // ---- the plan of this list: taken over from the previous call when nothing it depends on has changed -------------------
   SchPlan& p    = plan;
   bool     same = p.valid && p.key.size() == n_tb && p.e_len == e_len && p.soft_len == soft_len && p.data_len == data_len &&
@@ -500,7 +547,7 @@ int SchEngine::decode_batch(const int16_t* e_bits, uint64_t e_len, int16_t* soft
     tbs[t].nof_cb         = p.tb_nof_cb[t];
     tbs[t].avg_iterations = 0;
   }
-  auto t_1 = now();
+  pend.t_1 = now();
 
   // ---- stage buffers ---------------------------------------------------------------------------------------------------
   const int16_t* d_e    = e_bits;
@@ -523,16 +570,34 @@ int SchEngine::decode_batch(const int16_t* e_bits, uint64_t e_len, int16_t* soft
       B200_CUDA_TRY(cudaMemcpyAsync(d_soft, soft_pool, soft_len * sizeof(int16_t), cudaMemcpyHostToDevice, st));
     }
   }
+  // the verdicts come back into page-locked memory, so that their copies are plain enqueues
+  if (hres.reserve((size_t)n_tb + 2 * cbs.size() + 256) != B200_SUCCESS) return B200_ERROR;
+  hres.reset();
+  h_tbok = (uint8_t*)hres.take(n_tb);
+  tmp_ok = (uint8_t*)hres.take(cbs.size() + 1);
+  tmp_np = (uint8_t*)hres.take(cbs.size() + 1);
+  if (!h_tbok || !tmp_ok || !tmp_np) return B200_ERROR;
+  memset(h_tbok, 0, n_tb);
+  memset(tmp_ok, 0, cbs.size());
+  memset(tmp_np, 0, cbs.size());
 
-  // The decoder workspace is borrowed for the duration of this (synchronous) call; it is carved without the int16 copies of
-  // the channel LLRs until a batch needs them (TdecWorkspace::int16_on_demand).
-  struct Borrowed {
-    int            dev;
-    TdecWorkspace* w;
-    ~Borrowed() { workspace_release(dev, w); }
-  } ws{ctx->device, workspace_acquire(ctx->device)};
-  if (!ws.w) return B200_ERROR;
-  ws.w->int16_on_demand = true;
+  // The decoder workspace is borrowed until decode_finish; it is carved without the int16 copies of the channel LLRs until a
+  // batch needs them (TdecWorkspace::int16_on_demand).
+  pend.ws = workspace_acquire(ctx->device);
+  if (!pend.ws) return B200_ERROR;
+  pend.ws->int16_on_demand = true;
+  pend.all_dev   = all_dev;
+  pend.soft_dev  = soft_dev;
+  pend.same      = same;
+  pend.tbs       = tbs;
+  pend.n_tb      = n_tb;
+  pend.d_e       = d_e;
+  pend.d_soft    = d_soft;
+  pend.d_data    = d_data;
+  pend.soft_pool = soft_pool;
+  pend.data      = data;
+  pend.soft_len  = soft_len;
+  pend.data_len  = data_len;
 
   // ---- rate de-matching of every pending code block -------------------------------------------------------------------
   // Two forms.  Default: de-match into the natural soft buffers, then the decoder's load kernel turns them into tiles (it owns a
@@ -540,69 +605,96 @@ int SchEngine::decode_batch(const int16_t* e_bits, uint64_t e_len, int16_t* soft
   // itself (one thread block per lane slot) -- bit-identical, one kernel and one read of every soft buffer less, but measured
   // SLOWER (1.40 ms against 0.67 + 0.59 ms for 53,248 blocks, profiles/README.md): a lane slot owns only 16 bytes of every tile
   // row, so its 2,300 row pieces are scattered partial-sector stores.  Kept for the record and for the tests.
-  const bool  al8       = p.soft_offsets_aligned8 && (reinterpret_cast<uintptr_t>(d_soft) & 7u) == 0;
+  pend.al8              = p.soft_offsets_aligned8 && (reinterpret_cast<uintptr_t>(d_soft) & 7u) == 0;
   const char* fused_env = getenv("SRSLTE_B200_RM_FUSED");
-  const bool  fused     = al8 && !cbs.empty() && p.d_pairs != nullptr && fused_env != nullptr && fused_env[0] == '1';
+  const bool  fused     = pend.al8 && !cbs.empty() && p.d_pairs != nullptr && fused_env != nullptr && fused_env[0] == '1';
+  int         rc        = B200_SUCCESS;
   if (fused) {
-    int r = tdec.begin_batch(*ws.w, p.specs, st);
-    if (r != B200_SUCCESS) return r;
-    if (launch_rm_rx_tiles(d_e, d_soft, p.d_descs, p.d_pairs, ws.w->plan.v, ws.w->plan.max_K, p.max_E, st) != B200_SUCCESS) return B200_ERROR;
+    rc = tdec.begin_batch(*pend.ws, p.specs, st);
+    if (rc == B200_SUCCESS && launch_rm_rx_tiles(d_e, d_soft, p.d_descs, p.d_pairs, pend.ws->plan.v, pend.ws->plan.max_K, p.max_E, st) != B200_SUCCESS) {
+      rc = B200_ERROR;
+    }
     g_kernel_launches++;
   } else if (!cbs.empty()) {
-    if (launch_rm_rx(d_e, d_soft, p.d_descs, (uint32_t)cbs.size(), st) != B200_SUCCESS) return B200_ERROR;
+    if (launch_rm_rx(d_e, d_soft, p.d_descs, (uint32_t)cbs.size(), st) != B200_SUCCESS) rc = B200_ERROR;
     g_kernel_launches++;
   }
-  auto t_3 = now();
+  pend.t_3       = now();
+  pend.preloaded = fused;
+  if (rc == B200_SUCCESS) rc = enqueue_decode();
+  if (rc != B200_SUCCESS) {
+    cudaStreamSynchronize(st);
+    drop_pending();
+    return rc;
+  }
+  pend.active = true;
+  return B200_SUCCESS;
+}
 
-  // ---- ONE batched decode over all (K, CRC kind) groups (one launch per pass, tiles ordered by length) ------------------
-  h_tbok.assign(n_tb, 0);
-  tmp_ok.assign(cbs.size(), 0);
-  tmp_np.assign(cbs.size(), 0);
-  std::chrono::steady_clock::time_point t_4, t_5;
-
-  // decode, payload assembly, transport block CRC, results; ends with the stream synchronised
-  bool preloaded = fused;
-  auto decode_and_finish = [&]() -> int {
-    if (!cbs.empty()) {
-      int r = tdec.run_groups(*ws.w, d_soft, p.specs, max_iterations, 1, p.d_dec, p.d_ok, p.d_np, st, p.d_offs, al8, preloaded);
-      if (r != B200_SUCCESS) return r;
-      sch_scatter_payload_kernel<<<(unsigned)cbs.size(), 128, 0, st>>>(p.d_dec, d_data, p.d_jobs, (uint32_t)cbs.size());
-      g_kernel_launches++;
-    }
-    t_4 = now();
-    sch_tb_crc_kernel<<<(n_tb + 3) / 4, 128, 0, st>>>(d_data, p.d_cj, n_tb, p.d_tbok);
+// ONE batched decode over all (K, CRC kind) groups (one launch per pass, tiles ordered by length), payload assembly, transport
+// block CRC and the copies back
+int SchEngine::enqueue_decode()
+{
+  SchPlan&                  p   = plan;
+  const std::vector<CbRec>& cbs = p.cbs;
+  cudaStream_t              st  = stream;
+  auto                      now = [] { return std::chrono::steady_clock::now(); };
+  if (!cbs.empty()) {
+    int r = tdec.run_groups(*pend.ws, pend.d_soft, p.specs, max_iterations, 1, p.d_dec, p.d_ok, p.d_np, st, p.d_offs, pend.al8, pend.preloaded);
+    if (r != B200_SUCCESS) return r;
+    sch_scatter_payload_kernel<<<(unsigned)cbs.size(), 128, 0, st>>>(p.d_dec, pend.d_data, p.d_jobs, (uint32_t)cbs.size());
     g_kernel_launches++;
-    B200_CUDA_TRY(cudaMemcpyAsync(h_tbok.data(), p.d_tbok, n_tb, cudaMemcpyDeviceToHost, st));
-    if (!cbs.empty()) {
-      B200_CUDA_TRY(cudaMemcpyAsync(tmp_ok.data(), p.d_ok, cbs.size(), cudaMemcpyDeviceToHost, st));
-      B200_CUDA_TRY(cudaMemcpyAsync(tmp_np.data(), p.d_np, cbs.size(), cudaMemcpyDeviceToHost, st));
-    }
-    if (!all_dev) {
-      B200_CUDA_TRY(cudaMemcpyAsync(data, d_data, data_len, cudaMemcpyDeviceToHost, st));
-      if (!soft_dev) B200_CUDA_TRY(cudaMemcpyAsync(soft_pool, d_soft, soft_len * sizeof(int16_t), cudaMemcpyDeviceToHost, st));
-    }
-    t_5 = now();
-    B200_CUDA_TRY(cudaStreamSynchronize(st));
-    B200_CUDA_TRY(cudaGetLastError());
-    return B200_SUCCESS;
-  };
-  int rc = decode_and_finish();
-  if (rc != B200_SUCCESS) return rc;
-  if (ws.w->h_err && *ws.w->h_err) {
+  }
+  pend.t_4 = now();
+  sch_tb_crc_kernel<<<(pend.n_tb + 3) / 4, 128, 0, st>>>(pend.d_data, p.d_cj, pend.n_tb, p.d_tbok);
+  g_kernel_launches++;
+  B200_CUDA_TRY(cudaMemcpyAsync(h_tbok, p.d_tbok, pend.n_tb, cudaMemcpyDeviceToHost, st));
+  if (!cbs.empty()) {
+    B200_CUDA_TRY(cudaMemcpyAsync(tmp_ok, p.d_ok, cbs.size(), cudaMemcpyDeviceToHost, st));
+    B200_CUDA_TRY(cudaMemcpyAsync(tmp_np, p.d_np, cbs.size(), cudaMemcpyDeviceToHost, st));
+  }
+  if (!pend.all_dev) {
+    B200_CUDA_TRY(cudaMemcpyAsync(pend.data, pend.d_data, pend.data_len, cudaMemcpyDeviceToHost, st));
+    if (!pend.soft_dev) B200_CUDA_TRY(cudaMemcpyAsync(pend.soft_pool, pend.d_soft, pend.soft_len * sizeof(int16_t), cudaMemcpyDeviceToHost, st));
+  }
+  pend.t_5 = now();
+  return B200_SUCCESS;
+}
+
+// Waits for the batch queued by decode_begin and writes the results into its transport-block list
+int SchEngine::decode_finish()
+{
+  if (!pend.active) return B200_SUCCESS; // an empty list, or nothing begun
+  static const bool timing = getenv("SRSLTE_B200_SCH_TIMING") != nullptr;
+  auto              now    = [] { return std::chrono::steady_clock::now(); };
+  cudaSetDevice(ctx->device);
+  cudaStream_t st = stream;
+  int          rc = B200_SUCCESS;
+  if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) rc = B200_ERROR;
+  if (rc == B200_SUCCESS && pend.ws->h_err && *pend.ws->h_err) {
     // some soft values did not fit the int8 tiles and this decoder workspace was carved without the int16 copies
     // (int16_on_demand): carve them from now on and decode the batch again -- the soft buffers still hold its input
-    ws.w->have_int16 = true;
-    *ws.w->h_err     = 0;
-    preloaded        = false; // the workspace is carved anew: the tiles are loaded again from the soft buffers
-    rc               = decode_and_finish();
-    if (rc != B200_SUCCESS) return rc;
+    pend.ws->have_int16 = true;
+    *pend.ws->h_err     = 0;
+    pend.preloaded      = false; // the workspace is carved anew: the tiles are loaded again from the soft buffers
+    rc                  = enqueue_decode();
+    if (rc == B200_SUCCESS && (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess)) rc = B200_ERROR;
+  }
+  if (rc != B200_SUCCESS) {
+    drop_pending();
+    return rc;
   }
   auto t_6 = now();
   if (timing) {
     auto us = [](auto a, auto b) { return (double)std::chrono::duration_cast<std::chrono::nanoseconds>(b - a).count() / 1e3; };
     fprintf(stderr, "[sch timing] plan %s %.0f us, staging + de-matching launch %.0f, decode launches %.0f, tail launches %.0f, "
-                    "wait for the device %.0f\n", same ? "reused" : "built", us(t_0, t_1), us(t_1, t_3), us(t_3, t_4), us(t_4, t_5), us(t_5, t_6));
+                    "wait for the device %.0f\n", pend.same ? "reused" : "built", us(pend.t_0, pend.t_1), us(pend.t_1, pend.t_3),
+            us(pend.t_3, pend.t_4), us(pend.t_4, pend.t_5), us(pend.t_5, t_6));
   }
+  SchPlan&                  p    = plan;
+  const std::vector<CbRec>& cbs  = p.cbs;
+  srsran_b200_tb_t*         tbs  = pend.tbs;
+  const uint32_t            n_tb = pend.n_tb;
   iters_scratch.assign(n_tb, 0);
   for (size_t i = 0; i < cbs.size(); i++) {
     srsran_b200_tb_t& tb = tbs[cbs[i].tb];
@@ -619,6 +711,7 @@ int SchEngine::decode_batch(const int16_t* e_bits, uint64_t e_len, int16_t* soft
   }
   // the list's own cb_crc_mask fields have just changed: the kept plan stays valid only for a list that repeats the INPUT
   // masks (a retransmission with updated masks is planned anew, as it must be)
+  drop_pending();
   return B200_SUCCESS;
 }
 
@@ -661,6 +754,28 @@ void srsran_b200_sch_decode_after(srsran_b200_sch_t* q, void* producer_stream)
     q->eng.after      = (cudaStream_t)producer_stream;
     q->eng.have_after = true;
   }
+}
+
+int srsran_b200_sch_decode_begin(srsran_b200_sch_t* q, const int16_t* e_bits, uint64_t e_len, int16_t* soft_pool, uint64_t soft_len, uint8_t* data,
+                                 uint64_t data_len, srsran_b200_tb_t* tbs, uint32_t n_tb, uint32_t flags)
+{
+  if (!q) return B200_ERROR_INVALID_INPUTS;
+  if (!(flags & SRSRAN_B200_FLAG_DEVICE_PTRS)) {
+    B200_LOG_ERROR("srsran_b200_sch_decode_begin works on device buffers (host buffers would be read and written behind the caller's back)");
+    return B200_ERROR_INVALID_INPUTS;
+  }
+  return q->eng.decode_begin(e_bits, e_len, soft_pool, soft_len, data, data_len, tbs, n_tb, flags);
+}
+
+int srsran_b200_sch_decode_finish(srsran_b200_sch_t* q)
+{
+  if (!q) return B200_ERROR_INVALID_INPUTS;
+  return q->eng.decode_finish();
+}
+
+void srsran_b200_sch_decode_after_event(srsran_b200_sch_t* q, void* event)
+{
+  if (q) q->eng.after_ext = (cudaEvent_t)event;
 }
 
 void srsran_b200_sch_set_max_noi(srsran_b200_sch_t* q, uint32_t max_iterations)

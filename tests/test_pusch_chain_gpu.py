@@ -283,6 +283,34 @@ def test_native_enb_ul_pipeline_with_harq(port):
     enb.close()
 
 
+def test_native_enb_ul_large_batch_is_decoded_in_groups(port):
+    """From 2048 subframes of host samples on, the one-call receiver decodes in groups while later samples are still being
+    copied (enb_ul.cu): same bytes and results as the same subframes in small batches, also on a second call (cached plans) and
+    for a batch small enough to run as one group."""
+    from srslte_b200 import synth_pusch as sp
+    from srslte_b200.pusch import EnbUl, PuschChain
+
+    tbs, nd, nsf = 1544, 24, 2560 + 37  # 15 PRB QPSK, one code block; 2597 subframes = 6 chunks in 2 groups, the last one ragged
+    ch = PuschChain(33, 15, False, 15, 0, 1, 1)
+    dm = {sf: ch.dmrs(sf, 0) for sf in range(10)}
+    ch.close()
+    rng = np.random.default_rng(4)
+    rnti_d = rng.integers(1, 65000, nd).astype(np.uint32)
+    tti_d = rng.integers(0, 10240, nd).astype(np.uint32)
+    qpp = sp.qpp_interleaver(1568)
+    iq_d, payload_d, _ = sp.make_subframes_full(33, 15, 256, tbs, 2, 0, qpp, nd, rnti_d, tti_d, lambda sf: dm[sf], 9.0, seed=5)
+    pick = rng.integers(0, nd, nsf)
+    iq, rnti, tti, want = np.ascontiguousarray(iq_d[pick]), rnti_d[pick], tti_d[pick], payload_d[pick]
+    enb = EnbUl(33, 15, tbs, 1, llr_shift=1, max_noi=8, symbol_sz=256)
+    for _ in range(2):
+        data, res = enb.run(iq, rnti, tti)
+        assert res["crc_ok"].all() and (data == want).all()
+    small, res_s = enb.run(iq[:nd], rnti[:nd], tti[:nd])
+    assert (small == want[:nd]).all()
+    assert (res["avg_iterations"][:nd] == res_s["avg_iterations"]).all() and np.allclose(res["snr"][:nd], res_s["snr"])
+    enb.close()
+
+
 def test_entries_reject_bad_arguments():
     """Error behaviour in the reference's style: SRSRAN_ERROR_INVALID_INPUTS (-2) for missing pointers, host pointers where the
     stage works on device buffers, and out-of-range per-subframe parameters; nothing is launched."""
