@@ -94,6 +94,27 @@ class PuschRx:
             raise RuntimeError(f"srsran_b200_sch_decode_batch failed ({rc})")
         return d["result"][:nsf] == 0, d["avg_iterations"][:nsf].copy()
 
+    def decode_begin(self, nsf: int, rv: int = 0):
+        """decode() without the wait (srsran_b200_sch_decode_begin): returns once the batch is queued behind the front end."""
+        t = self.torch
+        d = self.tb_np
+        d["rv"][:nsf], d["new_data"][:nsf], d["cb_crc_mask"][:nsf] = rv, 1, 0
+        self._lib.srsran_b200_sch_decode_after(self.sch._h, t.cuda.current_stream(self.dev).cuda_stream)
+        rc = self._lib.srsran_b200_sch_decode_begin(self.sch._h, self.llr.data_ptr(), nsf * self.G, self.soft.data_ptr(),
+                                                    nsf * self.soft.shape[1], self.data.data_ptr(), nsf * self.data_stride,
+                                                    d.ctypes.data, nsf, _lib.FLAG_DEVICE_PTRS)
+        if rc != _lib.SUCCESS:
+            raise RuntimeError(f"srsran_b200_sch_decode_begin failed ({rc})")
+        self._begun = nsf
+
+    def decode_finish(self):
+        """Waits for the batch of decode_begin; returns what decode() returns."""
+        rc = self._lib.srsran_b200_sch_decode_finish(self.sch._h)
+        if rc != _lib.SUCCESS:
+            raise RuntimeError(f"srsran_b200_sch_decode_finish failed ({rc})")
+        nsf, d = self._begun, self.tb_np
+        return d["result"][:nsf] == 0, d["avg_iterations"][:nsf].copy()
+
     def run(self, iq, nsf: int, rv: int = 0):
         """iq: torch CUDA complex64 (nsf, sf_sz).  Returns (tb_ok (nsf,), avg passes (nsf,)); bytes are in self.data[:, :tbs/8+3]."""
         self.front_end(iq, nsf)
@@ -296,6 +317,16 @@ class PuschRxFull(PuschRx):
     def run(self, iq, nsf: int, rnti=None, tti=None, n_dmrs=None, rv: int = 0):
         self.front_end(iq, nsf, rnti, tti, n_dmrs)
         return self.decode(nsf, rv)
+
+    def run_begin(self, iq, nsf: int, rnti=None, tti=None, n_dmrs=None, rv: int = 0):
+        """run() in two halves: a caller thread that alternates between two objects (each on its own torch stream) keeps two
+        batches in flight, so one batch's last passes -- a handful of blocks that fail their CRC and run all the passes -- overlap
+        the bulk of the other."""
+        self.front_end(iq, nsf, rnti, tti, n_dmrs)
+        self.decode_begin(nsf, rv)
+
+    def run_finish(self):
+        return self.decode_finish()
 
 
 class EnbUlCfg(C.Structure):
