@@ -406,6 +406,15 @@ SRSRAN_B200_API int srsran_b200_pusch_rx_uci_batch(srsran_b200_pusch_t* q, const
                                                    const uint32_t* rnti, const uint32_t* tti, const uint32_t* n_dmrs, const uint32_t* tbs,
                                                    const srsran_b200_uci_cfg_t* uci, uint32_t flags, void* stream);
 
+/* Host only, no GPU involved: the decisions of srsran_b200_pusch_uci_collect on soft bits the caller already has, in the order the
+ * reference walks them (field symbol by field symbol, Qm soft bits each; for the 1-bit forms with the repeated bit's scrambling
+ * already undone).  ack_llr: Q_prime_ack*Qm values, ri_llr: Q_prime_ri*Qm, cqi_llr: Q_prime_cqi*Qm (NULL where the field is absent).
+ * Fills the value members of out.  srsran_uci_decode_ack_ri / srsran_uci_decode_cqi_pusch (uci.c:289-330,637-713) without the
+ * position search. */
+SRSRAN_B200_API int srsran_b200_uci_decide(const srsran_b200_uci_cfg_t* uci, uint32_t Qm, uint32_t Q_prime_ack, uint32_t Q_prime_ri,
+                                           uint32_t Q_prime_cqi, const int16_t* ack_llr, const int16_t* ri_llr, const int16_t* cqi_llr,
+                                           srsran_b200_uci_value_t* out);
+
 /* Waits for the soft bits of every srsran_b200_pusch_rx_uci_batch call since the last collect and decides them, in call order:
  * out[0 .. sum of those calls' nsf).  nof_out must equal that sum; out = NULL discards what is pending. */
 SRSRAN_B200_API int srsran_b200_pusch_uci_collect(srsran_b200_pusch_t* q, srsran_b200_uci_value_t* out, uint32_t nof_out);

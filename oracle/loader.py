@@ -314,6 +314,28 @@ class _Api:
                     ack=out[:10].copy(), ack_valid=bool(out[10]), ri=int(out[11]), cqi_crc=bool(out[12]),
                     cqi_bits=out[14:14 + int(out[13])].astype(np.uint8))
 
+    def uci_decode_ack_ri(self, link: np.ndarray, q_bits: np.ndarray, c_seq: np.ndarray, beta: float, nof_bits: int, is_ri: bool):
+        """Reference only: srsran_uci_decode_ack_ri on a whole descrambled subframe.  Returns (Q', data bits, valid)."""
+        assert self.which == "ref"
+        link = np.ascontiguousarray(link, np.uint32)
+        q = _aligned_copy(q_bits, np.int16)
+        c = _aligned_copy(c_seq, np.uint8)
+        data = np.full(16, 2, np.uint8)
+        valid = C.c_int(0)
+        r = self.lib.ref_uci_decode_ack_ri(_p(link), _p(q), _p(c), C.c_float(beta), C.c_uint32(nof_bits), C.c_int(int(is_ri)), _p(data),
+                                           C.byref(valid))
+        return r, data[:nof_bits].copy(), bool(valid.value)
+
+    def uci_decode_cqi(self, link: np.ndarray, q_bits: np.ndarray, beta: float, Q_prime_ri: int, cqi_len: int):
+        """Reference only: srsran_uci_decode_cqi_pusch on the front of the de-interleaved stream.  Returns (Q', bits, crc)."""
+        assert self.which == "ref"
+        link = np.ascontiguousarray(link, np.uint32)
+        q = _aligned_copy(q_bits, np.int16)
+        data = np.zeros(64, np.uint8)
+        crc = C.c_int(0)
+        r = self.lib.ref_uci_decode_cqi(_p(link), _p(q), C.c_float(beta), C.c_uint32(Q_prime_ri), C.c_uint32(cqi_len), _p(data), C.byref(crc))
+        return r, data[:cqi_len].copy(), bool(crc.value)
+
     def qprime_ack(self, L_prb: int, nof_symbols: int, K_segm: int, nof_ack: int, beta: float) -> int:
         assert self.which == "ref"
         f = self.lib.ref_qprime_ack

@@ -894,3 +894,44 @@ uint32_t ref_qprime_ack(uint32_t L_prb, uint32_t nof_symbols, uint32_t K_segm, u
 {
   return srsran_qprime_ack_ext(L_prb, nof_symbols, K_segm, nof_ack, beta);
 }
+
+/* The two field decoders on their own (uci.c:289-330,637-713).  q_bits for the HARQ-ACK / RI form is the whole descrambled
+ * subframe (the function finds the field's positions itself), c_seq its scrambling sequence, one bit per byte; for the CQI form
+ * it is the front of the de-interleaved stream.  K_segm is set the way srsran_ulsch_decode does (sch.c:1136). */
+static void uci_only_cfg(const uint32_t* p, srsran_pusch_cfg_t* cfg)
+{
+  srsran_cell_t                     cell = link_cell(p);
+  srsran_ul_sf_cfg_t                sf;
+  srsran_refsignal_dmrs_pusch_cfg_t dmrs;
+  srsran_cbsegm_t                   seg;
+  link_cfg(p, &cell, cfg, &sf, &dmrs);
+  srsran_cbsegm(&seg, p[P_TBS]);
+  cfg->K_segm = seg.C1 * seg.K1 + seg.C2 * seg.K2;
+}
+
+int ref_uci_decode_ack_ri(const uint32_t* p, int16_t* q_bits, uint8_t* c_seq, float beta, uint32_t nof_bits, int is_ri, uint8_t* data,
+                          int* valid)
+{
+  srsran_pusch_cfg_t cfg;
+  uci_only_cfg(p, &cfg);
+  uint32_t          Qm   = srsran_mod_bits_x_symbol(cfg.grant.tb.mod);
+  srsran_uci_bit_t* bits = calloc(4 * 12 * 110 * 8, sizeof(srsran_uci_bit_t));
+  bool              v    = false;
+  int r = srsran_uci_decode_ack_ri(&cfg, q_bits, c_seq, beta, cfg.grant.tb.nof_bits / Qm, 0, bits, data, is_ri ? NULL : &v, nof_bits, is_ri != 0);
+  if (valid) *valid = v ? 1 : 0;
+  free(bits);
+  return r;
+}
+
+int ref_uci_decode_cqi(const uint32_t* p, int16_t* q_bits, float beta, uint32_t Q_prime_ri, uint32_t cqi_len, uint8_t* data, int* crc)
+{
+  srsran_pusch_cfg_t     cfg;
+  srsran_uci_cqi_pusch_t q;
+  uci_only_cfg(p, &cfg);
+  if (srsran_uci_cqi_init(&q)) return -100;
+  bool ok = false;
+  int  r  = srsran_uci_decode_cqi_pusch(&q, &cfg, q_bits, beta, Q_prime_ri, cqi_len, data, &ok);
+  if (crc) *crc = ok ? 1 : 0;
+  srsran_uci_cqi_free(&q);
+  return r;
+}

@@ -83,6 +83,7 @@ def lib() -> C.CDLL:
     L.srsran_b200_pusch_uci_geometry.argtypes = [vp, u32, vp, vp]
     L.srsran_b200_pusch_rx_uci_batch.argtypes = [vp, vp, vp, vp, u32, vp, vp, vp, vp, vp, u32, vp]
     L.srsran_b200_pusch_uci_collect.argtypes = [vp, vp, u32]
+    L.srsran_b200_uci_decide.argtypes = [vp, u32, u32, u32, u32, vp, vp, vp, vp]
     L.srsran_b200_enb_ul_pusch_uci_batch.argtypes = [vp, vp, u32, vp, vp, vp, vp, vp, vp, vp, vp, vp, u32]
     L.srsran_b200_enb_ul_init.argtypes = [C.POINTER(vp), C.c_int, vp]
     L.srsran_b200_enb_ul_free.argtypes = [vp]
@@ -117,6 +118,7 @@ EXPORTED_SYMBOLS = [
     "srsran_b200_pusch_uci_geometry",
     "srsran_b200_pusch_rx_uci_batch",
     "srsran_b200_pusch_uci_collect",
+    "srsran_b200_uci_decide",
     "srsran_b200_enb_ul_pusch_uci_batch",
     "srsran_b200_enb_ul_init",
     "srsran_b200_enb_ul_free",

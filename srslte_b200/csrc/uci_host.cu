@@ -160,40 +160,57 @@ static void conv_rm_rx(const int16_t* in, uint32_t in_len, int16_t* out, uint32_
   }
 }
 
-// Tail-biting Viterbi for the K = 7 code with generators 133, 171, 165 (octal).  Same scheme as decode37 (viterbi.c:50-78): the
-// block is decoded three times back to back from equal state metrics and the middle copy is kept.  Metrics are exact 32-bit
-// correlations here (the reference quantises to 16 bits and renormalises), so the survivor is the maximum-likelihood path.
-static void viterbi_tb(const int16_t* sym, uint32_t F, uint8_t* bits)
+// Tail-biting Viterbi decoder for the K = 7 code with generators 133, 171, 165 (octal): a scalar restatement of the decoder the
+// reference's x86 build selects, decode37_avx2_16bit (viterbi.c:129-157) over viterbi37_avx2_16bit.c:
+//  * soft bits -> unsigned 16-bit symbols, x + 32767 clipped to [0, 65535] (viterbi.c:599-601, vector.c:801-814);
+//  * the block is decoded three times back to back from all-zero path metrics and the middle copy is kept;
+//  * branch metric = avg(avg(s0 ^ b0, s1 ^ b1), s2 ^ b2) >> 3 with the rounding of _mm256_avg_epu16, its complement is
+//    8191 - metric (viterbi37_avx2_16bit.c:228-239);
+//  * path metrics are uint16 with wrap-around, compared through the sign of their 16-bit difference (:243-252);
+//  * the renormalisation never subtracts anything: its horizontal minimum shifts a 128-bit lane by 16 bytes, which yields zero (:279-303);
+//  * the traceback reads the decision of step n + 6 for bit n ("look past tail", :140-152) although no tail was sent: the last six
+//    bits of the third copy come out as zeros and the traceback enters the real decisions in state 0, whatever the best state was.
+// With all of that the decided bits are the reference's on every input, not only where the CRC passes.
+static void viterbi_tb(const int16_t* llr, uint32_t F, uint8_t* bits)
 {
-  static const uint32_t poly[3] = {0x6D, 0x4F, 0x57}; // uci.c:158, newest bit in the LSB
-  const uint32_t        T = 3 * F;
-  std::vector<uint8_t>  dec((size_t)T * 64);
-  int32_t               m[64] = {}, nm[64];
-  uint8_t               outb[128]; // encoder outputs of the 7-bit register value
-  for (uint32_t r = 0; r < 128; r++) {
-    outb[r] = 0;
-    for (int s = 0; s < 3; s++) outb[r] |= (uint8_t)(__builtin_parity(r & poly[s]) << s);
+  static const uint32_t poly[3] = {0x6D, 0x4F, 0x57}; // uci.c:158
+  const uint32_t        N = 3 * F;
+  std::vector<uint16_t> sym((size_t)3 * F);
+  for (uint32_t i = 0; i < 3 * F; i++) {
+    int32_t v = (int32_t)(32767.0f + (float)llr[i]);
+    v         = v < 0 ? 0 : v > 65535 ? 65535 : v;
+    sym[i]    = (uint16_t)v;
   }
-  for (uint32_t t = 0; t < T; t++) {
-    const int16_t* y = sym + (size_t)(t % F) * 3;
-    int32_t        bm[8];
-    for (int o = 0; o < 8; o++) bm[o] = ((o & 1) ? y[0] : -y[0]) + ((o & 2) ? y[1] : -y[1]) + ((o & 4) ? y[2] : -y[2]);
-    for (uint32_t ns = 0; ns < 64; ns++) { // ns = the six newest bits after the step; its predecessors differ in the oldest bit
-      const uint32_t r0 = ns, r1 = ns | 64u; // 7-bit register (newest in the LSB) for the two predecessors
-      const uint32_t p0 = r0 >> 1, p1 = r1 >> 1;
-      const int32_t  a = m[p0] + bm[outb[r0]], b = m[p1] + bm[outb[r1]];
-      nm[ns]                    = b > a ? b : a;
-      dec[(size_t)t * 64 + ns] = b > a ? 1 : 0;
+  uint16_t tab[3][32];
+  for (uint32_t st = 0; st < 32; st++) {
+    for (int k = 0; k < 3; k++) tab[k][st] = __builtin_parity((2u * st) & poly[k]) ? 65535 : 0;
+  }
+  std::vector<uint8_t> dec((size_t)N * 64);
+  uint16_t             a[64] = {}, b[64];
+  uint16_t *           old = a, *nw = b;
+  auto                 avg = [](uint32_t x, uint32_t y) { return (uint16_t)((x + y + 1u) >> 1); };
+  for (uint32_t t = 0; t < N; t++) {
+    const uint16_t* y = &sym[(size_t)(t % F) * 3];
+    for (uint32_t st = 0; st < 32; st++) {
+      const uint16_t metric = (uint16_t)(avg((uint16_t)(tab[2][st] ^ y[2]), avg((uint16_t)(tab[0][st] ^ y[0]), (uint16_t)(tab[1][st] ^ y[1]))) >> 3);
+      const uint16_t mm     = (uint16_t)(8191 - metric);
+      const uint16_t m0 = (uint16_t)(old[st] + metric), m1 = (uint16_t)(old[st + 32] + mm);
+      const uint16_t m2 = (uint16_t)(old[st] + mm), m3 = (uint16_t)(old[st + 32] + metric);
+      const bool     d0 = (int16_t)(uint16_t)(m0 - m1) > 0, d1 = (int16_t)(uint16_t)(m2 - m3) > 0;
+      nw[2 * st]      = d0 ? m1 : m0;
+      nw[2 * st + 1]  = d1 ? m3 : m2;
+      dec[(size_t)t * 64 + 2 * st]     = d0;
+      dec[(size_t)t * 64 + 2 * st + 1] = d1;
     }
-    memcpy(m, nm, sizeof(m));
+    uint16_t* tmp = old;
+    old           = nw;
+    nw            = tmp;
   }
-  uint32_t st = 0;
-  for (uint32_t s = 1; s < 64; s++)
-    if (m[s] > m[st]) st = s;
-  for (uint32_t t = T; t-- > 0;) {
-    const uint32_t bit = st & 1u; // the bit that entered at step t
-    if (t >= F && t < 2 * F) bits[t - F] = (uint8_t)bit;
-    st = (st >> 1) | ((uint32_t)dec[(size_t)t * 64 + st] << 5);
+  uint32_t state = 0; // (the six zero decisions beyond the last step have shifted the best state out)
+  for (uint32_t n = N - 6; n-- > 0;) {
+    const uint32_t k = dec[(size_t)(n + 6) * 64 + state];
+    state            = (state >> 1) | (k << 5);
+    if (n >= F && n < 2 * F) bits[n - F] = (uint8_t)k;
   }
 }
 
@@ -243,3 +260,23 @@ void uci_decide(const srsran_b200_uci_cfg_t& c, const UciGeometry& g, uint32_t Q
 }
 
 } // namespace b200
+
+extern "C" SRSRAN_B200_API int srsran_b200_uci_decide(const srsran_b200_uci_cfg_t* uci, uint32_t Qm, uint32_t Q_prime_ack, uint32_t Q_prime_ri,
+                                                     uint32_t Q_prime_cqi, const int16_t* ack_llr, const int16_t* ri_llr, const int16_t* cqi_llr,
+                                                     srsran_b200_uci_value_t* out)
+{
+  if (!uci || !out || (Qm != 2 && Qm != 4 && Qm != 6)) return B200_ERROR_INVALID_INPUTS;
+  if (uci->nof_ack > SRSRAN_B200_UCI_MAX_ACK_BITS || uci->ri_len > 1 || uci->cqi_len > SRSRAN_B200_UCI_MAX_CQI_BITS - 8) return B200_ERROR_INVALID_INPUTS;
+  if ((uci->nof_ack && !ack_llr) || (uci->ri_len && !ri_llr) || (uci->cqi_len && !cqi_llr)) return B200_ERROR_INVALID_INPUTS;
+  b200::UciGeometry g;
+  g.Q_ack = Q_prime_ack;
+  g.Q_ri  = Q_prime_ri;
+  g.Q_cqi = Q_prime_cqi;
+  b200::uci_decide(*uci, g, Qm, ack_llr, ri_llr, cqi_llr, out);
+  out->Q_prime_ack = Q_prime_ack;
+  out->Q_prime_ri  = Q_prime_ri;
+  out->Q_prime_cqi = Q_prime_cqi;
+  out->e_offset    = Q_prime_cqi * Qm;
+  out->nof_e_bits  = 0;
+  return B200_SUCCESS;
+}
