@@ -628,6 +628,37 @@ def pusch_e2e(torch, dev, steps, h_iq, x, run_fn, result_dev, h_data, barrier, m
     return max_over_ranks((time.perf_counter() - t0) * 1e3) / steps
 
 
+def ofdm_cpu_substitute(iq, cores: int, return_grid: bool = False):
+    """SURVEY 8(d): the reference's srsran_ofdm_rx_sf needs FFTW, which this image does not have, so its speed cannot be measured;
+    this is the SUBSTITUTE the survey asks for instead -- the same arithmetic (half-subcarrier shift over the subframe, the 14
+    windows advanced by half a CP, 2048-point transforms, the 1200 occupied bins in fftshift order, window-offset ramp) with
+    scipy.fft (pocketfft) on all host cores.  iq: (n, 30720) complex64.  Returns subframes/s."""
+    import numpy as np
+    import scipy.fft
+
+    n, N, R = iq.shape[0], 2048, 1200
+    cp = [160] + [144] * 6
+    noff = 72
+    starts, rel, t0 = [], np.zeros(15 * N), 0
+    for slot in range(2):
+        for l in range(7):
+            rel[t0:t0 + cp[l] + N] = np.arange(-cp[l], N)   # sample index relative to the end of the symbol's cyclic prefix (ofdm.c:347-355)
+            t0 += cp[l]
+            starts.append(t0 - noff)
+            t0 += N
+    shift = np.exp(-2j * np.pi * 0.5 * rel / N).astype(np.complex64)
+    ramp = np.exp(2j * np.pi * noff * (np.arange(R) - R // 2) / N).astype(np.complex64)
+    idx = (np.array(starts)[:, None] + np.arange(N)[None, :]).reshape(-1)
+    t_0 = time.perf_counter()
+    x = iq * shift[None, :]
+    w = x[:, idx].reshape(n, 14, N)
+    X = scipy.fft.fft(w, axis=2, workers=cores)
+    out = np.concatenate([X[:, :, N - R // 2:], X[:, :, :R // 2]], axis=2) * ramp[None, None, :]
+    sec = time.perf_counter() - t_0
+    assert out.shape == (n, 14, R)
+    return out if return_grid else n / sec
+
+
 def pusch_full_leg(args, R, hlp, peaks):
     """BASELINE configs[3] batched: the 20 MHz subframe through the COMPLETE receive chain: transmit side with channel interleaver,
     scrambling, transform precoding and DMRS; per-subframe flat fading + timing offset + AWGN (every one of the 4096 subframes of a
@@ -779,6 +810,7 @@ def pusch_full_leg(args, R, hlp, peaks):
         native[name] = {"value": world * nsf / (msn * 1e-3), "unit": "subframes/s", "ms_per_step": msn, "tb_ok_fraction": float(okm.mean()),
                         "crc_ok_blocks_equal_transmitted_bytes": okn}
     enb.close()
+    iq16_sample = h_iq16[:256].numpy().copy()   # for the CPU substitute of the OFDM stage below
     del h_iq, h_iq16
     # CPU baseline: the reference's own receiver after the OFDM demodulator (FFTW is not available to build its srsran_ofdm)
     cpu = None
@@ -792,7 +824,13 @@ def pusch_full_leg(args, R, hlp, peaks):
                 n_cpu = 16 * cores
                 lk = loader.pusch_link(cell_id=cell_id, rnti=int(rnti8[0]), tti=int(tti8[0]), tbs=tbs, max_iter=MAX_PASSES)
                 okc, sec = Rf.pusch_rx_bench(lk, np.ascontiguousarray(np.tile(grids8[:1], (n_cpu, 1, 1))), cores)
-                cpu = {"value": n_cpu / sec, "unit": "subframes/s", "cores": cores, "kind": "reference",
+                try:
+                    sub_iq = np.ascontiguousarray(iq16_sample.astype(np.float32) / np.float32(scale)).view(np.complex64).reshape(256, -1)
+                    ofdm_sub = {"value": ofdm_cpu_substitute(sub_iq, cores), "unit": "subframes/s", "cores": cores,
+                                "label": "FFTW not available; substitute: numpy + scipy.fft (pocketfft) doing what srsran_ofdm_rx_sf does, 256 subframes"}
+                except Exception as ex2:  # noqa: BLE001
+                    ofdm_sub = {"error": repr(ex2)}
+                cpu = {"value": n_cpu / sec, "unit": "subframes/s", "cores": cores, "kind": "reference", "ofdm_substitute": ofdm_sub,
                        "sample": f"{n_cpu} copies of one subframe's resource grid (demodulated on the GPU: the reference's OFDM needs FFTW, "
                                  f"absent here): srsran_chest_ul_estimate_pusch + srsran_pusch_decode per subframe, one object set per thread, "
                                  f"all crc ok = {bool(okc.all())}"}

@@ -89,3 +89,19 @@ def test_full_pusch_transmitter_matches_the_reference(ref):
         for s in range(2):
             want = ref.pusch_encode(links[s], payload[s, :tbs // 8])
             assert np.linalg.norm(grid[s] - want) / np.linalg.norm(want) < 1e-5
+
+
+def test_bench_ofdm_cpu_substitute_demodulates_what_the_synthesiser_sends():
+    """bench.py's labelled stand-in for the CPU speed of srsran_ofdm_rx_sf (FFTW is not available here) must at least
+    be the same arithmetic: eNB uplink settings, N = 2048, 100 PRB."""
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    from srslte_b200 import synth_pusch as sp
+
+    rng = np.random.default_rng(0)
+    g = (rng.standard_normal((3, 14, 1200)) + 1j * rng.standard_normal((3, 14, 1200))).astype(np.complex64)
+    out = bench.ofdm_cpu_substitute(sp.ofdm_modulate(g, 2048), 2, True)
+    assert np.abs(out - g).max() < 1e-5 * np.abs(g).max()
