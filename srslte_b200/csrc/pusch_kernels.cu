@@ -656,10 +656,8 @@ struct PuschRx {
     if (cb_segmentation(tbs, seg) != 0) return B200_ERROR_INVALID_INPUTS;
     const int rc = uci_geometry(c, seg.C1 * seg.K1 + seg.C2 * seg.K2, (uint32_t)M, (uint32_t)nd, geo);
     if (rc != B200_SUCCESS) return rc;
-    if (geo->Q_ri + geo->Q_cqi >= (uint32_t)(nd * M)) {
-      B200_LOG_ERROR("control information leaves no room for the transport block (Q'_ri=%u Q'_cqi=%u of %d symbols)", geo->Q_ri, geo->Q_cqi, nd * M);
-      return B200_ERROR_INVALID_INPUTS;
-    }
+    // (Q'_cqi is capped at what the RI symbols leave, uci.c:186: the transport block may be left with nothing -- the reference then
+    // de-matches zero soft bits and the block fails its CRC; the same happens here)
     if (e_offset) *e_offset = geo->Q_cqi * (uint32_t)Qm;
     if (nof_e_bits) *nof_e_bits = ((uint32_t)(nd * M) - geo->Q_ri - geo->Q_cqi) * (uint32_t)Qm;
     return B200_SUCCESS;
