@@ -266,3 +266,54 @@ def test_repeated_lists_reuse_the_plan_but_follow_the_data(port):
         assert g1["result"] == w1[0] and (soft == soft_o).all()
     finally:
         d.close()
+
+
+def test_decode_in_two_halves(port):
+    """srsran_b200_sch_decode_begin / _finish: two objects with a batch in flight each give what the one-shot call gives; a second
+    begin on a busy object, host pointers and a finish without a begin behave as documented."""
+    import torch
+    from srslte_b200 import SchDecoder, _lib
+    from srslte_b200.pusch import TB_DTYPE
+
+    L = _lib.lib()
+    tbs, Qm, G, ntb = 12960, 4, 28800, 6
+    C = port.cbsegm(tbs)["C"]
+    es, want = [], []
+    for t in range(ntb):
+        e, _, _ = make_tb(port, tbs, Qm, G, 0, 0.7 + 0.08 * t, seed=40 + t)
+        es.append(e)
+        data = np.zeros(tbs // 8 + 3 + 768, np.uint8)
+        ret, iters = port.decode_tb(e, tbs, Qm, 0, 8, np.zeros(C * SB, np.int16), np.zeros(C, np.uint8), data)
+        want.append((ret, iters / C, data[:tbs // 8 + 3].copy()))
+    stride = (tbs // 8 + 3 + 768 + 15) // 16 * 16
+    e_dev = torch.from_numpy(np.concatenate(es)).cuda()
+
+    def new_set():
+        tb = np.zeros(ntb, TB_DTYPE)
+        i = np.arange(ntb, dtype=np.uint64)
+        tb["tbs"], tb["Qm"], tb["nof_e_bits"], tb["new_data"] = tbs, Qm, G, 1
+        tb["e_offset"], tb["soft_offset"], tb["data_offset"] = i * np.uint64(G), i * np.uint64(C * SB), i * np.uint64(stride)
+        return dict(q=SchDecoder(device=0, max_noi=8), tb=tb, soft=torch.zeros(ntb * C * SB, dtype=torch.int16, device="cuda"),
+                    data=torch.zeros(ntb * stride, dtype=torch.uint8, device="cuda"))
+
+    def begin(s, flags=_lib.FLAG_DEVICE_PTRS):
+        return L.srsran_b200_sch_decode_begin(s["q"]._h, e_dev.data_ptr(), e_dev.numel(), s["soft"].data_ptr(), s["soft"].numel(),
+                                              s["data"].data_ptr(), s["data"].numel(), s["tb"].ctypes.data, ntb, flags)
+
+    a, b = new_set(), new_set()
+    try:
+        assert L.srsran_b200_sch_decode_finish(a["q"]._h) == 0          # nothing begun: nothing to wait for
+        assert begin(a, 0) == -2                                        # host pointers are refused
+        assert begin(a) == 0 and begin(b) == 0                          # two batches in flight
+        assert begin(a) == -2                                           # one batch per object at a time
+        assert L.srsran_b200_sch_decode_finish(a["q"]._h) == 0 and L.srsran_b200_sch_decode_finish(b["q"]._h) == 0
+        for s in (a, b):
+            d = s["data"].cpu().numpy().reshape(ntb, stride)
+            for t in range(ntb):
+                assert s["tb"]["result"][t] == want[t][0] and abs(s["tb"]["avg_iterations"][t] - want[t][1]) < 1e-6, t
+                assert (d[t, :tbs // 8 + 3] == want[t][2]).all(), t
+        assert begin(a) == 0 and L.srsran_b200_sch_decode_finish(a["q"]._h) == 0   # and again on the same object (cached plan)
+        assert (a["tb"]["result"] == [w[0] for w in want]).all()
+    finally:
+        a["q"].close()
+        b["q"].close()
