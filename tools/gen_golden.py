@@ -105,7 +105,10 @@ def main():
     pc = {}
     links = [loader.pusch_link(cell_id=301, nof_prb=25, L_prb=12, n_prb=7, mod=2, tbs=4584, tti=7, n_dmrs=3, cyclic_shift=5, delta_ss=11, rnti=4660),
              loader.pusch_link(cell_id=9, nof_prb=6, L_prb=3, n_prb=2, mod=1, tbs=392, tti=12, rnti=62),
-             loader.pusch_link(cell_id=77, nof_prb=15, L_prb=10, n_prb=0, mod=3, tbs=5160, tti=5, group_hopping=1, rnti=65535)]
+             loader.pusch_link(cell_id=77, nof_prb=15, L_prb=10, n_prb=0, mod=3, tbs=5160, tti=5, group_hopping=1, rnti=65535),
+             # 1 and 2 PRB: the phi(n) base sequences of TS 36.211 5.5.1.2 (appended: the vectors above do not change)
+             loader.pusch_link(cell_id=12, nof_prb=6, L_prb=1, n_prb=4, mod=1, tbs=136, tti=3, rnti=101),
+             loader.pusch_link(cell_id=250, nof_prb=25, L_prb=2, n_prb=11, mod=2, tbs=328, tti=8, n_dmrs=5, group_hopping=1, delta_ss=17, rnti=9)]
     for i, lk in enumerate(links):
         data = rng.integers(0, 256, int(lk[12]) // 8, dtype=np.uint8)
         tx = R.pusch_encode(lk, data)
