@@ -343,3 +343,35 @@ def test_entries_reject_bad_arguments():
     res = np.zeros(1, np.dtype([("a", "<i4"), ("b", "<f4"), ("c", "<f4"), ("d", "<f4"), ("e", "<f4")]))
     assert L.srsran_b200_enb_ul_pusch_batch(enb._h, None, 1, None, None, None, None, None, None, res.ctypes.data, 0) == -2
     enb.close()
+
+
+def test_chain_against_the_committed_golden_fixtures():
+    """tests/golden/pusch_chain.npz (the reference's receiver buffers, tools/gen_golden.py): needs neither oracle/_ref nor the
+    port at run time.  Five links, among them the 1- and 2-PRB allocations."""
+    import os
+    import torch
+    from srslte_b200.pusch import PuschChain
+
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "pusch_chain.npz"))
+    i = 0
+    while f"link{i}" in g:
+        lk = [int(v) for v in g[f"link{i}"]]
+        ch = PuschChain(cell_id=lk[0], cell_nof_prb=lk[1], cp_ext=bool(lk[2]), L_prb=lk[9], n_prb=lk[10], mod=lk[11], llr_shift=0,
+                        cyclic_shift=lk[3], delta_ss=lk[4], group_hopping=bool(lk[5]), sequence_hopping=bool(lk[6]))
+        rnti, tti, n_dmrs = np.array([lk[7]], np.uint32), np.array([lk[8]], np.uint32), np.array([lk[14]], np.uint32)
+        assert np.abs(ch.dmrs(lk[8] % 10, lk[14]).reshape(-1) - g[f"dmrs{i}"]).max() < 1e-6
+        grid = torch.from_numpy(g[f"rx{i}"][None]).cuda()
+        ce, meas = ch.chest(grid, tti, n_dmrs)
+        d = ch.equalize_deprecode(grid, ce, meas)
+        soft = ch.demod_descramble(d, rnti, tti)
+        torch.cuda.synchronize()
+        off, half = 12 * lk[10], ch.nsym // 2
+        for slot in range(2):
+            assert rel(ce[0, slot].cpu().numpy(), g[f"ce{i}"][(slot + 1) * half - 4, off:off + ch.M]) < 1e-5, (i, slot)
+        assert abs(float(meas[0, 0]) - g[f"meas{i}"][0]) <= 2e-4 * g[f"meas{i}"][0]
+        assert rel(d[0].cpu().numpy(), g[f"d{i}"]) < TOL, i
+        diff = np.abs(soft[0].cpu().numpy().astype(np.int32) - g[f"g{i}"].astype(np.int32))
+        assert diff.max() <= 1 and (diff != 0).mean() < 3e-3, (i, diff.max(), (diff != 0).mean())
+        ch.close()
+        i += 1
+    assert i >= 5
