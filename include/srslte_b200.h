@@ -324,6 +324,8 @@ typedef struct {
   uint32_t dmrs_delta_ss;
   int      group_hopping_en;
   int      sequence_hopping_en;
+  int      shortened;           /* srsran_ul_sf_cfg_t.shortened: the subframe's last symbol carries the SRS, the PUSCH has one data
+                                   symbol less (srsran_ra_ul_compute_nof_re with N_srs = 1, ra_ul.c:232; pusch.c:63-72) */
 } srsran_b200_pusch_cfg_t;
 
 SRSRAN_B200_API int  srsran_b200_pusch_init(srsran_b200_pusch_t** q, int device, const srsran_b200_pusch_cfg_t* cfg);
@@ -444,6 +446,7 @@ typedef struct {
   uint32_t tbs;                 /* transport block size in bits (a standard size: no filler bits) */
   uint32_t llr_shift;           /* see srsran_b200_pusch_cfg_t */
   uint32_t max_iterations;      /* decoder passes per code block, 0 = 8 */
+  int      shortened;           /* see srsran_b200_pusch_cfg_t: every subframe of the batch is an SRS subframe */
 } srsran_b200_enb_ul_cfg_t;
 
 typedef struct {

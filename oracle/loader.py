@@ -300,7 +300,7 @@ class _Api:
         uci = np.ascontiguousarray(uci, np.uint32)
         Qm = {1: 2, 2: 4, 3: 6}[int(link[11])]
         nsym = 12 if link[2] else 14
-        nre = (nsym - 2) * 12 * int(link[9])
+        nre = (nsym - 2 - (int(link[16]) if link.size > 16 else 0)) * 12 * int(link[9])
         grid = _aligned_copy(grid, np.complex64)
         data = np.zeros(int(link[12]) // 8 + 16, np.uint8)
         crc = C.c_int(0)
@@ -348,7 +348,7 @@ class _Api:
         link = np.ascontiguousarray(link, np.uint32)
         Qm = {1: 2, 2: 4, 3: 6}[int(link[11])]
         nsym = 12 if link[2] else 14
-        nre = (nsym - 2) * 12 * int(link[9])
+        nre = (nsym - 2 - (int(link[16]) if link.size > 16 else 0)) * 12 * int(link[9])
         grid = _aligned_copy(grid, np.complex64)
         data = np.zeros(int(link[12]) // 8 + 16, np.uint8)
         crc = C.c_int(0)
@@ -377,10 +377,10 @@ class _Api:
 
 
 def pusch_link(cell_id=1, nof_prb=100, cp_ext=0, cyclic_shift=0, delta_ss=0, group_hopping=0, sequence_hopping=0, rnti=62, tti=0,
-               L_prb=100, n_prb=0, mod=3, tbs=75376, rv=0, n_dmrs=0, max_iter=8) -> np.ndarray:
+               L_prb=100, n_prb=0, mod=3, tbs=75376, rv=0, n_dmrs=0, max_iter=8, shortened=0) -> np.ndarray:
     """The uint32 parameter block shared by ref_harness.c and oracle_port.c (mod: 1 QPSK, 2 16QAM, 3 64QAM)."""
     return np.array([cell_id, nof_prb, cp_ext, cyclic_shift, delta_ss, group_hopping, sequence_hopping, rnti, tti, L_prb, n_prb, mod,
-                     tbs, rv, n_dmrs, max_iter], np.uint32)
+                     tbs, rv, n_dmrs, max_iter, shortened], np.uint32)
 
 
 def pusch_uci(nof_ack=0, ack_bits=0, ri_len=0, ri=0, cqi_kind=0, cqi_N=0, cqi_wb=0, cqi_sb=0, I_offset_ack=9, I_offset_ri=5,

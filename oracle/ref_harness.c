@@ -485,9 +485,9 @@ int ref_predecoding_single(cf_t* y, cf_t* h, cf_t* x, int nof_symbols, float sca
 /* Link parameters, all uint32:
  *  0 cell_id  1 cell nof_prb  2 cp_ext  3 dmrs cyclic_shift  4 delta_ss  5 group_hopping  6 sequence_hopping
  *  7 rnti  8 tti  9 L_prb  10 n_prb  11 mod (srsran_mod_t)  12 tbs  13 rv  14 n_dmrs (cyclic shift for DMRS, 0..7)
- *  15 max_nof_iterations */
+ *  15 max_nof_iterations  16 shortened (the subframe's last symbol carries the SRS: srsran_ul_sf_cfg_t.shortened) */
 enum { P_CELL_ID, P_NOF_PRB, P_CP_EXT, P_CSHIFT, P_DELTA_SS, P_GH, P_SH, P_RNTI, P_TTI, P_L_PRB, P_N_PRB, P_MOD, P_TBS, P_RV,
-       P_N_DMRS, P_MAX_ITER, P_COUNT };
+       P_N_DMRS, P_MAX_ITER, P_SHORTENED, P_COUNT };
 
 static srsran_cell_t link_cell(const uint32_t* p)
 {
@@ -510,6 +510,7 @@ static void link_cfg(const uint32_t* p, srsran_cell_t* cell, srsran_pusch_cfg_t*
   memset(sf, 0, sizeof(*sf));
   memset(dmrs, 0, sizeof(*dmrs));
   sf->tti                   = p[P_TTI];
+  sf->shortened             = p[P_SHORTENED] != 0;
   dmrs->cyclic_shift        = p[P_CSHIFT];
   dmrs->delta_ss            = p[P_DELTA_SS];
   dmrs->group_hopping_en    = p[P_GH] != 0;
@@ -522,7 +523,7 @@ static void link_cfg(const uint32_t* p, srsran_cell_t* cell, srsran_pusch_cfg_t*
   cfg->grant.tb.tbs   = (int)p[P_TBS];
   cfg->grant.tb.rv    = (int)p[P_RV];
   cfg->grant.n_dmrs   = p[P_N_DMRS];
-  srsran_ra_ul_compute_nof_re(&cfg->grant, cell->cp, 0); /* ra_ul.c:230 */
+  srsran_ra_ul_compute_nof_re(&cfg->grant, cell->cp, p[P_SHORTENED] ? 1 : 0); /* ra_ul.c:230 */
   cfg->max_nof_iterations = p[P_MAX_ITER];
   cfg->enable_64qam       = true;
 }

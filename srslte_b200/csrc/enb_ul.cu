@@ -101,6 +101,7 @@ struct EnbUl {
     pc.dmrs_delta_ss       = c.dmrs_delta_ss;
     pc.group_hopping_en    = c.group_hopping_en;
     pc.sequence_hopping_en = c.sequence_hopping_en;
+    pc.shortened           = c.shortened;
     if ((rc = srsran_b200_pusch_init(&pusch, dev, &pc)) != B200_SUCCESS) return rc;
     if ((rc = srsran_b200_sch_init(&sch, dev)) != B200_SUCCESS) return rc;
     srsran_b200_sch_set_max_noi(sch, c.max_iterations ? c.max_iterations : 8);

@@ -496,7 +496,7 @@ struct PuschRx {
   {
     cfg  = c;
     nsym = c.cp_ext ? 12 : 14;
-    nd   = nsym - 2;
+    nd   = nsym - 2 - (c.shortened ? 1 : 0); // ra_ul.c:232: the last symbol of a shortened subframe carries the SRS
     M    = 12 * (int)c.L_prb;
     R    = 12 * (int)c.cell_nof_prb;
     Qm   = 2 * c.modulation;
@@ -526,7 +526,7 @@ struct PuschRx {
     plan.tps       = tps;
     plan.pusch_nd  = nd;
     for (int l = 0, k = 0; l < nsym; l++) {
-      if (l != nsym / 2 - 4 && l != nsym - 4) plan.pusch_l[k++] = (unsigned char)l;
+      if (l != nsym / 2 - 4 && l != nsym - 4 && !(c.shortened && l == nsym - 1)) plan.pusch_l[k++] = (unsigned char)l; // pusch.c:63-72
     }
     plan.grid_nsym = nsym;
     plan.grid_R    = R;
@@ -783,25 +783,19 @@ struct PuschRx {
   } while (0)
     const bool vec = !ub && ((((uintptr_t)d | (uintptr_t)g) & 15u) == 0) && !getenv("SRSLTE_B200_PUSCH_DEMOD_SCALAR");
 #define B200_DEMODV(MOD, ND) pusch_demod_descramble_vec_kernel<MOD, ND><<<grid, 192, 0, st>>>(d, d_seq, g, (uint32_t)M, nwords, sh, qs)
-    if (vec) {
-      if (nd == 12) {
-        if (cfg.modulation == 1) B200_DEMODV(1, 12);
-        else if (cfg.modulation == 2) B200_DEMODV(2, 12);
-        else B200_DEMODV(3, 12);
-      } else {
-        if (cfg.modulation == 1) B200_DEMODV(1, 10);
-        else if (cfg.modulation == 2) B200_DEMODV(2, 10);
-        else B200_DEMODV(3, 10);
-      }
-    } else if (nd == 12) {
-      if (cfg.modulation == 1) B200_DEMOD(1, 12);
-      else if (cfg.modulation == 2) B200_DEMOD(2, 12);
-      else B200_DEMOD(3, 12);
-    } else {
-      if (cfg.modulation == 1) B200_DEMOD(1, 10);
-      else if (cfg.modulation == 2) B200_DEMOD(2, 10);
-      else B200_DEMOD(3, 10);
-    }
+#define B200_DEMOD_MOD(KIND, ND)                                                                                                       \
+  do {                                                                                                                                 \
+    if (cfg.modulation == 1) KIND(1, ND);                                                                                              \
+    else if (cfg.modulation == 2) KIND(2, ND);                                                                                         \
+    else KIND(3, ND);                                                                                                                  \
+  } while (0)
+    if (vec && nd == 12) B200_DEMOD_MOD(B200_DEMODV, 12);
+    else if (vec && nd == 10) B200_DEMOD_MOD(B200_DEMODV, 10);
+    else if (nd == 12) B200_DEMOD_MOD(B200_DEMOD, 12);
+    else if (nd == 11) B200_DEMOD_MOD(B200_DEMOD, 11); // shortened subframes: one symbol per thread (11 and 9 do not split into vectors)
+    else if (nd == 10) B200_DEMOD_MOD(B200_DEMOD, 10);
+    else B200_DEMOD_MOD(B200_DEMOD, 9);
+#undef B200_DEMOD_MOD
 #undef B200_DEMOD
 #undef B200_DEMODV
     g_kernel_launches++;

@@ -125,7 +125,7 @@ class PuschCfg(C.Structure):
     """srsran_b200_pusch_cfg_t (include/srslte_b200.h)"""
     _fields_ = [("cell_id", C.c_uint32), ("cell_nof_prb", C.c_uint32), ("cp_ext", C.c_int), ("L_prb", C.c_uint32), ("n_prb", C.c_uint32),
                 ("modulation", C.c_int), ("llr_shift", C.c_uint32), ("dmrs_cyclic_shift", C.c_uint32), ("dmrs_delta_ss", C.c_uint32),
-                ("group_hopping_en", C.c_int), ("sequence_hopping_en", C.c_int)]
+                ("group_hopping_en", C.c_int), ("sequence_hopping_en", C.c_int), ("shortened", C.c_int)]
 
 
 # srsran_b200_uci_cfg_t / srsran_b200_uci_value_t (include/srslte_b200.h)
@@ -151,7 +151,7 @@ class PuschChain:
     sch.c:993).  All tensors are torch CUDA tensors; rnti / tti / n_dmrs are numpy uint32 arrays (host)."""
 
     def __init__(self, cell_id=1, cell_nof_prb=100, cp_ext=False, L_prb=100, n_prb=0, mod=3, llr_shift=0, cyclic_shift=0, delta_ss=0,
-                 group_hopping=False, sequence_hopping=False, device=0):
+                 group_hopping=False, sequence_hopping=False, device=0, shortened=False):
         import torch
 
         self.torch = torch
@@ -159,7 +159,7 @@ class PuschChain:
         self.dev = torch.device("cuda", device)
         self._lib = _lib.lib()
         self.cfg = PuschCfg(cell_id, cell_nof_prb, int(cp_ext), L_prb, n_prb, mod, llr_shift, cyclic_shift, delta_ss, int(group_hopping),
-                            int(sequence_hopping))
+                            int(sequence_hopping), int(shortened))
         self._h = C.c_void_p()
         rc = self._lib.srsran_b200_pusch_init(C.byref(self._h), device, C.byref(self.cfg))
         if rc != _lib.SUCCESS:
@@ -334,7 +334,7 @@ class EnbUlCfg(C.Structure):
     _fields_ = [("cell_id", C.c_uint32), ("cell_nof_prb", C.c_uint32), ("cp_ext", C.c_int), ("symbol_sz", C.c_uint32),
                 ("dmrs_cyclic_shift", C.c_uint32), ("dmrs_delta_ss", C.c_uint32), ("group_hopping_en", C.c_int),
                 ("sequence_hopping_en", C.c_int), ("L_prb", C.c_uint32), ("n_prb", C.c_uint32), ("modulation", C.c_int), ("tbs", C.c_uint32),
-                ("llr_shift", C.c_uint32), ("max_iterations", C.c_uint32)]
+                ("llr_shift", C.c_uint32), ("max_iterations", C.c_uint32), ("shortened", C.c_int)]
 
 
 PUSCH_RES_DTYPE = np.dtype([("crc_ok", "<i4"), ("avg_iterations", "<f4"), ("noise_estimate", "<f4"), ("snr", "<f4"), ("cfo_hz", "<f4")])
@@ -344,10 +344,10 @@ class EnbUl:
     """srsran_b200_enb_ul_*: the native one-call PUSCH receiver (time samples in, transport-block bytes out)."""
 
     def __init__(self, cell_id=1, nof_prb=100, tbs=75376, mod=3, llr_shift=4, max_noi=8, device=0, symbol_sz=0, L_prb=None, n_prb=0,
-                 cyclic_shift=0, delta_ss=0, cp_ext=False):
+                 cyclic_shift=0, delta_ss=0, cp_ext=False, shortened=False):
         self._lib = _lib.lib()
         self.cfg = EnbUlCfg(cell_id, nof_prb, int(cp_ext), symbol_sz, cyclic_shift, delta_ss, 0, 0, L_prb if L_prb is not None else nof_prb,
-                            n_prb, mod, tbs, llr_shift, max_noi)
+                            n_prb, mod, tbs, llr_shift, max_noi, int(shortened))
         self._h = C.c_void_p()
         rc = self._lib.srsran_b200_enb_ul_init(C.byref(self._h), device, C.byref(self.cfg))
         if rc != _lib.SUCCESS:

@@ -18,7 +18,7 @@ def rel(a, b):
 def link_of(loader, ch, rnti=0, tti=0, n_dmrs=0, tbs=0):
     c = ch.cfg
     return loader.pusch_link(c.cell_id, c.cell_nof_prb, c.cp_ext, c.dmrs_cyclic_shift, c.dmrs_delta_ss, c.group_hopping_en,
-                             c.sequence_hopping_en, rnti, tti, c.L_prb, c.n_prb, c.modulation, tbs, 0, n_dmrs, 8)
+                             c.sequence_hopping_en, rnti, tti, c.L_prb, c.n_prb, c.modulation, tbs, 0, n_dmrs, 8, c.shortened)
 
 
 CONFIGS = [
@@ -152,7 +152,10 @@ def test_unsupported_configurations_fail_cleanly():
                                     (dict(cell_id=42, cell_nof_prb=15, L_prb=15, n_prb=0, mod=2, cp_ext=True, delta_ss=7), 4584),
                                     (dict(cell_id=333, cell_nof_prb=75, L_prb=72, n_prb=2, mod=3, group_hopping=True), 46888),
                                     (dict(cell_id=12, cell_nof_prb=6, L_prb=1, n_prb=4, mod=1), 136),
-                                    (dict(cell_id=250, cell_nof_prb=25, L_prb=2, n_prb=11, mod=2, cyclic_shift=6), 328)])
+                                    (dict(cell_id=250, cell_nof_prb=25, L_prb=2, n_prb=11, mod=2, cyclic_shift=6), 328),
+                                    # SRS subframes: the last symbol is not PUSCH (11 / 9 data symbols)
+                                    (dict(cell_id=61, cell_nof_prb=50, L_prb=20, n_prb=8, mod=3, shortened=True), 11448),
+                                    (dict(cell_id=42, cell_nof_prb=15, L_prb=12, n_prb=1, mod=1, cp_ext=True, shortened=True), 1000)])
 def test_chain_against_the_reference_link(ref, port, kw, tbs):
     """Reference transmitter (srsran_pusch_encode + DMRS) -> flat fading + AWGN -> GPU chain, compared with the buffers of the
     reference receiver (chest + srsran_pusch_decode) and decoded down to the transport block."""

@@ -9,7 +9,7 @@ pytestmark = pytest.mark.gpu
 
 def link_of(loader, kw, rnti, tti, n_dmrs, tbs):
     return loader.pusch_link(kw["cell_id"], kw["cell_nof_prb"], int(kw.get("cp_ext", False)), kw.get("cyclic_shift", 0), kw.get("delta_ss", 0),
-                             0, 0, rnti, tti, kw["L_prb"], kw["n_prb"], kw["mod"], tbs, 0, n_dmrs, 8)
+                             0, 0, rnti, tti, kw["L_prb"], kw["n_prb"], kw["mod"], tbs, 0, n_dmrs, 8, int(kw.get("shortened", False)))
 
 
 # harness parameter block (oracle/loader.py: pusch_uci) and the cqi payload length it stands for
@@ -66,6 +66,8 @@ CONFIGS = [
     (dict(cell_id=42, cell_nof_prb=15, L_prb=15, n_prb=0, mod=1, cp_ext=True, delta_ss=7), 1544),
     (dict(cell_id=200, cell_nof_prb=50, L_prb=4, n_prb=30, mod=2, cyclic_shift=4), 1000),
     (dict(cell_id=5, cell_nof_prb=6, L_prb=2, n_prb=1, mod=1), 208),   # 24 subcarriers: the fields fill whole columns of the matrix
+    (dict(cell_id=61, cell_nof_prb=50, L_prb=20, n_prb=8, mod=2, shortened=True), 5160),               # SRS subframe: 11 columns
+    (dict(cell_id=42, cell_nof_prb=15, L_prb=12, n_prb=1, mod=1, cp_ext=True, shortened=True), 1000),  # ... and 9
 ]
 
 
