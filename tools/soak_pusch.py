@@ -17,7 +17,7 @@ budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
 rng = np.random.default_rng(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
 port = loader.api("port")
 valid = []
-for _L in range(3, 101):  # srsran_dft_precoding_valid_prb: 12 L = 2^a 3^b 5^c
+for _L in range(1, 101):  # srsran_dft_precoding_valid_prb: 12 L = 2^a 3^b 5^c
     _n = _L
     for _f in (2, 3, 5):
         while _n % _f == 0:
@@ -39,7 +39,7 @@ while time.time() - t0 < budget:
     cp_ext = bool(rng.integers(0, 4) == 0)
     kw = dict(cell_id=int(rng.integers(0, 504)), cell_nof_prb=cell_prb, cp_ext=cp_ext, L_prb=L, n_prb=n_prb, mod=mod, llr_shift=shift,
               cyclic_shift=int(rng.integers(0, 8)), delta_ss=int(rng.integers(0, 30)), group_hopping=bool(rng.integers(0, 2)),
-              sequence_hopping=bool(rng.integers(0, 2)))
+              sequence_hopping=bool(rng.integers(0, 2)), shortened=bool(rng.integers(0, 3) == 0))
     ch = PuschChain(**kw)
     nsf = int(rng.integers(1, 6))
     rnti = rng.integers(0, 65536, nsf).astype(np.uint32)
@@ -53,7 +53,7 @@ while time.time() - t0 < budget:
     torch.cuda.synchronize()
     ce, meas, d, g = ce.cpu().numpy(), meas.cpu().numpy(), d.cpu().numpy(), g.cpu().numpy()
     off, half = 12 * n_prb, ch.nsym // 2
-    data_syms = [l for l in range(ch.nsym) if l not in (half - 4, ch.nsym - 4)]
+    data_syms = [l for l in range(ch.nsym) if l not in (half - 4, ch.nsym - 4) and not (kw["shortened"] and l == ch.nsym - 1)]
     for s in range(nsf):
         lk = loader.pusch_link(kw["cell_id"], cell_prb, int(cp_ext), kw["cyclic_shift"], kw["delta_ss"], int(kw["group_hopping"]),
                                int(kw["sequence_hopping"]), int(rnti[s]), int(tti[s]), L, n_prb, mod, 0, 0, int(n_dmrs[s]), 8)
