@@ -479,6 +479,16 @@ SRSRAN_B200_API int srsran_b200_enb_ul_pusch_uci_batch(srsran_b200_enb_ul_t* q, 
                                                        const uint32_t* new_data, const srsran_b200_uci_cfg_t* uci, uint8_t* data,
                                                        srsran_b200_pusch_res_t* res, srsran_b200_uci_value_t* uci_out, uint32_t flags);
 
+/* The call in two halves, for ONE caller thread that serves several cells (one object each) or keeps two batches of a cell in
+ * flight: _begin queues the sample copies, the front end and every decode group on the object's own streams and returns; _finish
+ * waits and fills data, res and uci_out (which must stay valid in between; uci and uci_out may be NULL for subframes without control
+ * information).  One batch per object at a time.  srsran_b200_enb_ul_pusch_batch is _begin followed by _finish. */
+SRSRAN_B200_API int srsran_b200_enb_ul_pusch_batch_begin(srsran_b200_enb_ul_t* q, const void* samples, uint32_t nsf, const uint32_t* rnti,
+                                                         const uint32_t* tti, const uint32_t* n_dmrs, const uint32_t* rv,
+                                                         const uint32_t* new_data, const srsran_b200_uci_cfg_t* uci, uint8_t* data,
+                                                         srsran_b200_pusch_res_t* res, srsran_b200_uci_value_t* uci_out, uint32_t flags);
+SRSRAN_B200_API int srsran_b200_enb_ul_pusch_batch_finish(srsran_b200_enb_ul_t* q);
+
 #ifdef __cplusplus
 }
 #endif

@@ -85,6 +85,8 @@ def lib() -> C.CDLL:
     L.srsran_b200_pusch_uci_collect.argtypes = [vp, vp, u32]
     L.srsran_b200_uci_decide.argtypes = [vp, u32, u32, u32, u32, vp, vp, vp, vp]
     L.srsran_b200_enb_ul_pusch_uci_batch.argtypes = [vp, vp, u32, vp, vp, vp, vp, vp, vp, vp, vp, vp, u32]
+    L.srsran_b200_enb_ul_pusch_batch_begin.argtypes = [vp, vp, u32, vp, vp, vp, vp, vp, vp, vp, vp, vp, u32]
+    L.srsran_b200_enb_ul_pusch_batch_finish.argtypes = [vp]
     L.srsran_b200_enb_ul_init.argtypes = [C.POINTER(vp), C.c_int, vp]
     L.srsran_b200_enb_ul_free.argtypes = [vp]
     L.srsran_b200_enb_ul_free.restype = None
@@ -120,6 +122,8 @@ EXPORTED_SYMBOLS = [
     "srsran_b200_pusch_uci_collect",
     "srsran_b200_uci_decide",
     "srsran_b200_enb_ul_pusch_uci_batch",
+    "srsran_b200_enb_ul_pusch_batch_begin",
+    "srsran_b200_enb_ul_pusch_batch_finish",
     "srsran_b200_enb_ul_init",
     "srsran_b200_enb_ul_free",
     "srsran_b200_enb_ul_geometry",

@@ -54,6 +54,7 @@ struct EnbUl {
   ~EnbUl()
   {
     cudaSetDevice(device);
+    if (pend.active) finish();
     if (ofdm) srsran_b200_ofdm_rx_free(ofdm);
     if (pusch) srsran_b200_pusch_free(pusch);
     if (sch) srsran_b200_sch_free(sch);
@@ -166,11 +167,35 @@ struct EnbUl {
     return B200_SUCCESS;
   }
 
+  // a batch between begin() and finish(): run() is the two back to back
+  struct Pending {
+    bool                     active = false, dev_ptrs = false, uci = false;
+    uint32_t                 nsf = 0, chunk = 0, nchunks = 0, cpg = 0, ngroups = 0, begun = 0;
+    uint8_t*                 data    = nullptr;
+    srsran_b200_pusch_res_t* res     = nullptr;
+    srsran_b200_uci_value_t* uci_out = nullptr;
+    std::chrono::steady_clock::time_point h0, h1, h2;
+  } pend;
+
   int run(const void* samples, uint32_t nsf, const uint32_t* rnti, const uint32_t* tti, const uint32_t* n_dmrs, const uint32_t* rv,
           const uint32_t* new_data, uint8_t* data, srsran_b200_pusch_res_t* res, uint32_t flags, const srsran_b200_uci_cfg_t* uci = nullptr,
           srsran_b200_uci_value_t* uci_out = nullptr)
   {
+    const int rc = begin(samples, nsf, rnti, tti, n_dmrs, rv, new_data, data, res, flags, uci, uci_out);
+    if (rc != B200_SUCCESS) return rc;
+    return finish();
+  }
+
+  // Queues the whole batch (sample copies, front end, every decode group) and returns; data / res / uci_out are written by finish()
+  int begin(const void* samples, uint32_t nsf, const uint32_t* rnti, const uint32_t* tti, const uint32_t* n_dmrs, const uint32_t* rv,
+            const uint32_t* new_data, uint8_t* data, srsran_b200_pusch_res_t* res, uint32_t flags, const srsran_b200_uci_cfg_t* uci = nullptr,
+            srsran_b200_uci_value_t* uci_out = nullptr)
+  {
     if (!samples || !data || !res || (uci && !uci_out)) return B200_ERROR_INVALID_INPUTS;
+    if (pend.active) {
+      B200_LOG_ERROR("srsran_b200_enb_ul_pusch_batch_begin: the previous batch has not been finished");
+      return B200_ERROR_INVALID_INPUTS;
+    }
     if (nsf == 0) return B200_SUCCESS;
     B200_CUDA_TRY(cudaSetDevice(device));
     const bool   dev_ptrs = (flags & SRSRAN_B200_FLAG_DEVICE_PTRS) != 0;
@@ -207,7 +232,6 @@ struct EnbUl {
     static const bool timing    = getenv("SRSLTE_B200_ENB_UL_TIMING") != nullptr; // where a call's time goes: host stamps + event times
     const unsigned    ev_flags  = timing ? cudaEventDefault : cudaEventDisableTiming;
     auto              now       = [] { return std::chrono::steady_clock::now(); };
-    auto              us        = [](auto a, auto b) { return (double)std::chrono::duration_cast<std::chrono::nanoseconds>(b - a).count() / 1e3; };
     const auto        h0        = now();
     if (timing) {
       if (!ev_t0) B200_CUDA_TRY(cudaEventCreate(&ev_t0));
@@ -266,7 +290,6 @@ struct EnbUl {
       tbs[i].new_data    = fresh ? 1u : 0u;
       tbs[i].cb_crc_mask = fresh ? 0u : crc_mask[i];
     }
-    const size_t out_b = (size_t)cfg.tbs / 8 + 3;
     const auto h1 = now();
     // every group is queued behind its own front end right away (the groups' kernels share the SMs as their inputs arrive) ...
     auto span = [&](uint32_t g, uint32_t* first, uint32_t* last) {
@@ -282,9 +305,42 @@ struct EnbUl {
                                         (uint64_t)cap_sf * data_stride, tbs.data() + first, last - first, SRSRAN_B200_FLAG_DEVICE_PTRS);
       if (rc == B200_SUCCESS) begun++;
     }
-    const auto h2 = now();
-    double     fin_us[MAX_GROUPS] = {};
-    // ... and finished in order; the bytes of a group travel back while the next ones are still being decoded
+    pend          = Pending();
+    pend.dev_ptrs = dev_ptrs;
+    pend.uci      = uci != nullptr;
+    pend.nsf = nsf; pend.chunk = chunk; pend.nchunks = nchunks; pend.cpg = cpg; pend.ngroups = ngroups; pend.begun = begun;
+    pend.data = data; pend.res = res; pend.uci_out = uci_out;
+    pend.h0 = h0; pend.h1 = h1; pend.h2 = now();
+    pend.active = true;
+    if (rc != B200_SUCCESS) { // some group could not be queued: wait for the others and give up
+      finish();
+      return rc;
+    }
+    return B200_SUCCESS;
+  }
+
+  // Waits for the batch of begin(): the groups are finished in order, the bytes of a group travel back while the next ones decode
+  int finish()
+  {
+    if (!pend.active) return B200_SUCCESS;
+    cudaSetDevice(device);
+    static const bool timing = getenv("SRSLTE_B200_ENB_UL_TIMING") != nullptr;
+    auto              now    = [] { return std::chrono::steady_clock::now(); };
+    auto              us     = [](auto a, auto b) { return (double)std::chrono::duration_cast<std::chrono::nanoseconds>(b - a).count() / 1e3; };
+    const uint32_t nsf = pend.nsf, chunk = pend.chunk, nchunks = pend.nchunks, cpg = pend.cpg, ngroups = pend.ngroups, begun = pend.begun;
+    const bool     dev_ptrs = pend.dev_ptrs, uci = pend.uci;
+    uint8_t*       data = pend.data;
+    srsran_b200_pusch_res_t* res     = pend.res;
+    srsran_b200_uci_value_t* uci_out = pend.uci_out;
+    const auto     h0 = pend.h0, h1 = pend.h1, h2 = pend.h2;
+    const size_t   out_b = (size_t)cfg.tbs / 8 + 3;
+    int            rc    = begun == ngroups ? B200_SUCCESS : B200_ERROR;
+    pend.active          = false;
+    auto span = [&](uint32_t g, uint32_t* first, uint32_t* last) {
+      *first = g * cpg * chunk;
+      *last  = (g + 1) * cpg * chunk < nsf ? (g + 1) * cpg * chunk : nsf;
+    };
+    double fin_us[MAX_GROUPS] = {};
     for (uint32_t g = 0; g < begun; g++) {
       uint32_t first, last;
       span(g, &first, &last);
@@ -370,6 +426,21 @@ extern "C" SRSRAN_B200_API int srsran_b200_enb_ul_geometry(const srsran_b200_enb
   if (sf_sz) *sf_sz = q->e.sf_sz;
   if (tb_bytes) *tb_bytes = q->e.cfg.tbs / 8 + 3;
   return B200_SUCCESS;
+}
+
+extern "C" SRSRAN_B200_API int srsran_b200_enb_ul_pusch_batch_begin(srsran_b200_enb_ul_t* q, const void* samples, uint32_t nsf, const uint32_t* rnti,
+                                                                   const uint32_t* tti, const uint32_t* n_dmrs, const uint32_t* rv,
+                                                                   const uint32_t* new_data, const srsran_b200_uci_cfg_t* uci, uint8_t* data,
+                                                                   srsran_b200_pusch_res_t* res, srsran_b200_uci_value_t* uci_out, uint32_t flags)
+{
+  if (!q) return B200_ERROR_INVALID_INPUTS;
+  return q->e.begin(samples, nsf, rnti, tti, n_dmrs, rv, new_data, data, res, flags, uci, uci_out);
+}
+
+extern "C" SRSRAN_B200_API int srsran_b200_enb_ul_pusch_batch_finish(srsran_b200_enb_ul_t* q)
+{
+  if (!q) return B200_ERROR_INVALID_INPUTS;
+  return q->e.finish();
 }
 
 extern "C" SRSRAN_B200_API int srsran_b200_enb_ul_pusch_uci_batch(srsran_b200_enb_ul_t* q, const void* samples, uint32_t nsf, const uint32_t* rnti,

@@ -376,6 +376,21 @@ class EnbUl:
         if rc != _lib.SUCCESS:
             raise RuntimeError(f"srsran_b200_enb_ul_pusch_batch failed ({rc})")
 
+    def begin_ptr(self, samples_ptr: int, nsf: int, rnti, tti, data_ptr: int, res: np.ndarray, n_dmrs=None, rv=None, new_data=None,
+                  flags: int = 0):
+        """run_ptr without the wait (srsran_b200_enb_ul_pusch_batch_begin); finish() completes it.  The buffers behind data_ptr and
+        res must stay alive until then."""
+        k = [PuschChain._u32(a, nsf) for a in (rnti, tti, n_dmrs, rv, new_data)]
+        rc = self._lib.srsran_b200_enb_ul_pusch_batch_begin(self._h, samples_ptr, nsf, k[0][1], k[1][1], k[2][1], k[3][1], k[4][1], None,
+                                                            data_ptr, res.ctypes.data, None, flags)
+        if rc != _lib.SUCCESS:
+            raise RuntimeError(f"srsran_b200_enb_ul_pusch_batch_begin failed ({rc})")
+
+    def finish(self):
+        rc = self._lib.srsran_b200_enb_ul_pusch_batch_finish(self._h)
+        if rc != _lib.SUCCESS:
+            raise RuntimeError(f"srsran_b200_enb_ul_pusch_batch_finish failed ({rc})")
+
     def run(self, samples: np.ndarray, rnti, tti, n_dmrs=None, rv=None, new_data=None, uci: np.ndarray | None = None):
         """samples: (nsf, sf_sz) complex64 or (nsf, sf_sz, 2) int16 host array.  Returns (bytes (nsf, tb_bytes) uint8, results)
         and, with uci (UCI_CFG_DTYPE array (nsf,)), the decided control information (UCI_VALUE_DTYPE array) as a third item."""

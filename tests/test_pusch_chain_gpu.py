@@ -348,6 +348,42 @@ def test_entries_reject_bad_arguments():
     enb.close()
 
 
+def test_native_enb_ul_two_cells_from_one_thread(port):
+    """srsran_b200_enb_ul_pusch_batch_begin / _finish: one thread queues the batches of two cells (two objects) before it waits for
+    either; same bytes and results as the one-shot call; a second begin on a busy object is refused; finish without begin is a no-op."""
+    import torch
+    from srslte_b200 import synth_pusch as sp
+    from srslte_b200.pusch import EnbUl, PUSCH_RES_DTYPE, PuschChain
+
+    tbs, nsf = 4584, 40
+    cells = []
+    for cell_id in (42, 43):
+        ch = PuschChain(cell_id, 25, False, 25, 0, 2, 3)
+        dm = {sf: ch.dmrs(sf, 0) for sf in range(10)}
+        ch.close()
+        rnti = (np.arange(nsf, dtype=np.uint32) * 31 + cell_id) % 65000 + 1
+        tti = (np.arange(nsf, dtype=np.uint32) * 7 + cell_id) % 10240
+        enb = EnbUl(cell_id, 25, tbs, 2, llr_shift=3, max_noi=8)
+        iq, payload, _ = sp.make_subframes_full(cell_id, 25, enb.sf_sz // 15, tbs, 4, 0, sp.qpp_interleaver(port.cbsegm(tbs)["K1"]), nsf, rnti, tti,
+                                                lambda sf: dm[sf], 16.0, seed=cell_id)
+        want_data, want_res = enb.run(iq, rnti, tti)
+        assert want_res["crc_ok"].all() and (want_data == payload).all()
+        h_iq = torch.from_numpy(iq).pin_memory()
+        cells.append(dict(enb=enb, iq=h_iq, rnti=rnti, tti=tti, want=want_data, want_res=want_res,
+                          data=torch.zeros((nsf, enb.tb_bytes), dtype=torch.uint8).pin_memory(), res=np.zeros(nsf, PUSCH_RES_DTYPE)))
+    assert cells[0]["enb"].finish() is None  # nothing begun
+    for c in cells:
+        c["enb"].begin_ptr(c["iq"].data_ptr(), nsf, c["rnti"], c["tti"], c["data"].data_ptr(), c["res"])
+    with pytest.raises(RuntimeError):
+        c = cells[0]
+        c["enb"].begin_ptr(c["iq"].data_ptr(), nsf, c["rnti"], c["tti"], c["data"].data_ptr(), c["res"])
+    for c in cells:
+        c["enb"].finish()
+        assert (c["data"].numpy() == c["want"]).all()
+        assert (c["res"]["crc_ok"] == 1).all() and (c["res"]["avg_iterations"] == c["want_res"]["avg_iterations"]).all()
+        c["enb"].close()
+
+
 def test_chain_against_the_committed_golden_fixtures():
     """tests/golden/pusch_chain.npz (the reference's receiver buffers, tools/gen_golden.py): needs neither oracle/_ref nor the
     port at run time.  Five links, among them the 1- and 2-PRB allocations."""
