@@ -1019,8 +1019,8 @@ int orc_dmrs_pusch_gen(const uint32_t* p, float complex* r)
     for (uint32_t i = 0; i < M; i++) {
       const float m = (float)(i % (Nzc ? Nzc : 1));
       float       arg;
-      if (M == 12) arg = (float)orc_phi12[u][i] * (float)M_PI_4; /* srsran_vec_sc_prod_fcc: float times float */
-      else if (M == 24) arg = (float)orc_phi24[u][i] * (float)M_PI_4;
+      if (M == 12) arg = (float)(2 * (orc_phi12[u][i] - '0') - 3) * (float)M_PI_4; /* srsran_vec_sc_prod_fcc: float times float */
+      else if (M == 24) arg = (float)(2 * (orc_phi24[u][i] - '0') - 3) * (float)M_PI_4;
       else arg = (float)(-M_PI * q * m * (m + 1) / n_sz); /* double expression rounded into a float (cf_t) */
       /* the reference is built with -mfma and GCC contracts arg + alpha*i into one fused multiply-add (oracle/Makefile
        * uses the reference's own ISA flags); restated explicitly so that this file does not depend on its own flags */
