@@ -306,13 +306,17 @@ int launch_rm_rx_tiles(const int16_t* e_bits_dev, int16_t* soft_pool_dev, const 
   return B200_SUCCESS;
 }
 
-int launch_rm_rx(const int16_t* e_bits_dev, int16_t* soft_pool_dev, const RmDescDev* descs_dev, uint32_t n, cudaStream_t stream)
+int launch_rm_rx(const int16_t* e_bits_dev, int16_t* soft_pool_dev, const RmDescDev* descs_dev, uint32_t n, cudaStream_t stream, uint32_t max_E)
 {
   if (n == 0) return B200_SUCCESS;
   static std::atomic<uint64_t> attr{0}; // function attributes are per device
-  const size_t smem = RM_MAX_STAGE * sizeof(int16_t);
+  // a wrap stages min(n_out, E - base) values: when the caller knows the longest E of the list (punctured blocks: E is a third of
+  // the circular buffer at 64QAM rate 0.87) the stage shrinks and eight blocks fit an SM instead of six
+  size_t stage_len = RM_MAX_STAGE;
+  if (max_E && max_E < (uint32_t)RM_MAX_STAGE) stage_len = ((size_t)max_E + 7) / 8 * 8;
+  const size_t smem = stage_len * sizeof(int16_t);
   if (once_per_device(attr)) {
-    B200_CUDA_TRY(cudaFuncSetAttribute(rm_rx_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    B200_CUDA_TRY(cudaFuncSetAttribute(rm_rx_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(RM_MAX_STAGE * sizeof(int16_t))));
   }
   rm_rx_gather_kernel<<<n, RM_THREADS, smem, stream>>>(e_bits_dev, soft_pool_dev, descs_dev, n);
   B200_CUDA_TRY(cudaGetLastError());

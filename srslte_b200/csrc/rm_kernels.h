@@ -18,7 +18,8 @@ struct RmDescDev {
   uint32_t        pad;
 };
 
-int launch_rm_rx(const int16_t* e_bits_dev, int16_t* soft_pool_dev, const RmDescDev* descs_dev, uint32_t n, cudaStream_t stream);
+// max_E: the longest E of the list when known (sizes the staging), 0 = unknown
+int launch_rm_rx(const int16_t* e_bits_dev, int16_t* soft_pool_dev, const RmDescDev* descs_dev, uint32_t n, cudaStream_t stream, uint32_t max_E = 0);
 
 // De-matching fused with the decoder's tile layout: one thread block per lane slot of `v` (ntiles * 32).  pairs_dev: two int32
 // per slot = index into descs_dev of the slot's low / high block, -1 for none.  Every soft buffer must start on an 8-byte

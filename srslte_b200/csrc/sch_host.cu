@@ -616,7 +616,7 @@ int SchEngine::decode_begin(const int16_t* e_bits, uint64_t e_len, int16_t* soft
     }
     g_kernel_launches++;
   } else if (!cbs.empty()) {
-    if (launch_rm_rx(d_e, d_soft, p.d_descs, (uint32_t)cbs.size(), st) != B200_SUCCESS) rc = B200_ERROR;
+    if (launch_rm_rx(d_e, d_soft, p.d_descs, (uint32_t)cbs.size(), st, p.max_E) != B200_SUCCESS) rc = B200_ERROR;
     g_kernel_launches++;
   }
   pend.t_3       = now();
