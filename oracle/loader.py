@@ -307,7 +307,7 @@ class _Api:
         meas = np.zeros(8, np.float32)
         q = _aligned(nre * Qm, np.int16)
         g = _aligned(nre * Qm, np.int16)
-        out = np.zeros(14 + 64, np.int32)
+        out = np.zeros(14 + 256, np.int32)
         r = self.lib.ref_pusch_decode_uci(_p(link), _p(uci), _p(grid), C.c_int(int(identity_ce)), _p(data), C.byref(crc), _p(meas),
                                           _p(q), _p(g), _p(out))
         return dict(ret=r, crc=bool(crc.value), data=data[:int(link[12]) // 8].copy(), noise=float(meas[0]), q=q.copy(), g=g.copy(),

@@ -823,7 +823,8 @@ int ref_pusch_encode_uci(const uint32_t* p, const uint32_t* u, uint8_t* data, cf
 }
 
 /* chest + srsran_pusch_decode with the same UCI configuration.  uci_out (int32):
- *  0..9 ack_value  10 ack.valid  11 ri  12 cqi.data_crc  13 cqi_len  14.. the cqi payload bits (srsran_cqi_value_pack of what was decoded)
+ *  0..9 ack_value  10 ack.valid  11 ri  12 cqi.data_crc  13 number of packed bits  14.. the cqi payload bits (srsran_cqi_value_pack of what was
+ *  decoded; room for 14 + 200 values)
  * q_out: the object's q->q after the call (descrambled, HARQ-ACK positions zeroed), g_out: q->g */
 int ref_pusch_decode_uci(const uint32_t* p, const uint32_t* u, cf_t* grid, int use_identity_ce, uint8_t* data, int* crc_ok, float* meas,
                          int16_t* q_out, int16_t* g_out, int32_t* uci_out)
@@ -878,9 +879,12 @@ int ref_pusch_decode_uci(const uint32_t* p, const uint32_t* u, cf_t* grid, int u
   uci_out[12] = out.uci.cqi.data_crc ? 1 : 0;
   uci_out[13] = 0;
   if (cfg.uci_cfg.cqi.data_enable) {
-    uint8_t buff[SRSRAN_CQI_MAX_BITS];
+    /* the packer writes a second codeword once the decoded RI says rank > 1 (cqi.c: higher-layer subband reports), i.e. up to
+     * 2 * (4 + 2N) bits: more than SRSRAN_CQI_MAX_BITS for N > 14 -- give it room; the caller compares the first cqi_len bits */
+    uint8_t buff[512];
     memset(buff, 0, sizeof(buff));
     int n       = srsran_cqi_value_pack(&cfg.uci_cfg.cqi, &out.uci.cqi, buff);
+    if (n > 200) n = 200;
     uci_out[13] = n;
     for (int i = 0; i < n; i++) uci_out[14 + i] = buff[i];
   }
